@@ -1,0 +1,147 @@
+/* rt_b200.h — C-ABI of librt_b200.so, the B200 (sm_100a) replacement for the reference's
+ * RayTrace / ResetAccumulated compute kernels.
+ *
+ * The boundary it replaces is the Unity ComputeShader / ComputeBuffer / RenderTexture API exactly
+ * as RayComputeManager drives it through ComputeHelper.  Every entry point below
+ * names the reference call it stands in for (paths relative to the reference repo root:
+ *   RCM = Assets/Scripts/Tracer/RayComputeManager.cs, CH = Assets/Scripts/Helpers/ComputeHelper.cs,
+ *   RC  = Assets/Scripts/Tracer/RayCompute.compute,   HL = Assets/Scripts/Tracer/RayCommon.hlsl).
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in any signature (streams and device pointers travel as void*).
+ *   - every function returns 0 on success, a negative RT_E_* code on failure; rtLastError() gives text.
+ *     Nothing throws or exits across the ABI.
+ *   - copy-in semantics: host arrays are copied before the call returns (ComputeBuffer.SetData
+ *     semantics, CH:83-153); the caller may mutate them afterwards.
+ *   - single caller thread per context (Unity main thread, RCM:78); rtDispatch is asynchronous
+ *     w.r.t. the CPU, rtReadback / rtSynchronize synchronise.
+ *   - there is NO CPU fallback: without a CUDA device rtCreate fails with RT_E_NO_DEVICE.
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "rt_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct RtContext RtContext;
+
+enum {
+    RT_OK              =  0,
+    RT_E_INVALID       = -1,  /* bad argument (NULL, negative count, wrong stride, wrong size) */
+    RT_E_UNKNOWN_NAME  = -2,  /* uniform / buffer / texture / option name not part of the kernel's interface */
+    RT_E_NO_DEVICE     = -3,  /* no usable CUDA device — there is no CPU path */
+    RT_E_CUDA          = -4,  /* a CUDA runtime call failed; see rtLastError */
+    RT_E_STATE         = -5   /* call sequence error (e.g. dispatch before rtResize / buffers) */
+};
+
+enum { RT_KERNEL_RAYTRACE = 0, RT_KERNEL_RESET_ACCUMULATED = 1 };  /* RC:1-2, RCM:57-58 */
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+
+/* Replaces: the ComputeShader asset reference + lazily created GPU objects (RCM:34,126-161).
+ * device = CUDA ordinal this context renders on (one context per GPU / per process). */
+int rtCreate(RtContext** out, int device);
+
+/* Replaces: OnDestroy → ComputeHelper.Release(buffers, textures) (RCM:238-247, CH:209-247). */
+int rtDestroy(RtContext* ctx);
+
+/* Text of the last error on this context (never NULL). ctx may be NULL → last rtCreate error. */
+const char* rtLastError(const RtContext* ctx);
+
+/* ---- structured buffers ------------------------------------------------------------------------ */
+
+/* Replaces: ComputeHelper.CreateStructuredBuffer(ref buf, data) + cs.SetBuffer(kernel, name, buf)
+ * (RCM:151-160,201-202; CH:83-153).  name ∈ {"Triangles"(72), "Nodes"(32), "ModelInfo"(224),
+ * "Spheres"(104, extension)}; stride is validated against the element size in rt_types.h exactly as
+ * Unity validates it against the HLSL struct.  The allocation is re-used when count is unchanged
+ * (CH:86-92).  count == 0 (data may be NULL) empties the buffer. */
+int rtSetBuffer(RtContext* ctx, const char* name, const void* data, int count, int stride);
+
+/* ---- uniforms (same names as the HLSL globals, HL:5-26,120-121, RC:7-8) --------------------------- */
+
+int rtSetInt   (RtContext* ctx, const char* name, int value);               /* cs.SetInt    RCM:156,165-169,178-179,203 */
+int rtSetInts  (RtContext* ctx, const char* name, const int* values, int n);/* cs.SetInts   RCM:139 ("Resolution")      */
+int rtSetFloat (RtContext* ctx, const char* name, float value);             /* cs.SetFloat  RCM:170-174                 */
+int rtSetVector(RtContext* ctx, const char* name, const float value[4]);    /* cs.SetVector RCM:140,175-176,188         */
+int rtSetMatrix(RtContext* ctx, const char* name, const float value[16]);   /* cs.SetMatrix RCM:189 (column-major)      */
+int rtSetBool  (RtContext* ctx, const char* name, int value);               /* cs.SetBool   RCM:180 ("accumulate")      */
+
+/* ---- render targets ------------------------------------------------------------------------------ */
+
+/* Replaces: CreateRenderTexture(ref raytraceFrameTex / accumulatedResult, w, h, R32G32B32A32_SFloat)
+ * + SetTexture ×3 + SetInts("Resolution") (RCM:126-139, CH:303-323).  Re-allocates only when the size
+ * changes; new textures are zero-filled (a fresh RenderTexture), unchanged size keeps their content. */
+int rtResize(RtContext* ctx, int width, int height);
+
+/* Replaces: cs.Dispatch(kernelIndex, groupsX, groupsY, groupsZ) (CH:25-32, RCM:75,90).
+ * Thread groups are 8×8×1 (RC:10,26): pixels with x >= min(W, 8·groupsX) or y >= min(H, 8·groupsY)
+ * are left untouched, like threads that were never launched.  Asynchronous. */
+int rtDispatch(RtContext* ctx, int kernelIndex, int groupsX, int groupsY, int groupsZ);
+
+/* Replaces: reading the RenderTexture back (ComputeHelper.ReadbackData / AsyncGPUReadback; the
+ * reference itself only samples it on-GPU in Display.shader).  tex ∈ {"FrameRender",
+ * "AccumulatedRender"}; dst receives W·H float4 in [y][x] order (row 0 = bottom of the view plane),
+ * bytes must equal W·H·16.  Synchronises. */
+int rtReadback(RtContext* ctx, const char* tex, float* dst, size_t bytes);
+
+/* Block until all work queued on this context has finished. */
+int rtSynchronize(RtContext* ctx);
+
+/* ---- extensions (no counterpart in the reference) ------------------------------------------------------- */
+
+/* Run the context's work on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL = the
+ * context's own stream).  Lets a host that owns streams (e.g. torch) time and order the dispatches. */
+int rtSetStream(RtContext* ctx, void* cudaStream);
+
+/* Row-band tiling for multi-GPU rendering: the image is cut into bands of bandRows
+ * rows; band b belongs to rank (b mod worldSize).  After this call rtDispatch(RAYTRACE) traces only
+ * this rank's bands (pixels keep their GLOBAL index, so seeds and results equal the 1-GPU run) and
+ * writes them into the textures at their global position.  rank 0 / worldSize 1 = whole image. */
+int rtSetTile(RtContext* ctx, int rank, int worldSize, int bandRows);
+
+/* Gather / scatter staging for the per-frame all-gather of finished tiles.
+ * rtPackTile   : copies this rank's bands of FrameRender and AccumulatedRender into the contiguous
+ *                "TileSend" buffer ([frame bands | accumulated bands]).
+ * rtUnpackTiles: scatters "TileRecv" (worldSize × TileSend, rank-major — what ncclAllGather produces)
+ *                back into the two full-size textures.  Both are asynchronous on the context stream. */
+int rtPackTile(RtContext* ctx);
+int rtUnpackTiles(RtContext* ctx);
+
+/* Device address + size of a named device object, for zero-copy plumbing (NCCL, torch views).
+ * name ∈ {"FrameRender","AccumulatedRender","TileSend","TileRecv"}. */
+int rtGetDevicePointer(RtContext* ctx, const char* name, void** devPtr, size_t* bytes);
+
+/* Tuning / instrumentation switches.  name ∈
+ *   "kernel"      0 = reference-shaped per-pixel megakernel, 1 = persistent-thread wavefront (default)
+ *   "countStats"  1 = also count box / triangle tests (HL:254,271) — slower, off by default
+ *   "smemNodes"   number of top-of-tree node pairs staged in shared memory by TMA bulk copy (0 = off)
+ * Unknown names return RT_E_UNKNOWN_NAME. */
+int rtSetOption(RtContext* ctx, const char* name, int value);
+
+typedef struct RtStats {
+    uint64_t rays;          /* CalculateRayCollision calls (HL:487) since the last rtResetStats          */
+    uint64_t boxTests;      /* stats[1] (HL:271), only when "countStats" = 1                               */
+    uint64_t triTests;      /* stats[0] (HL:254), only when "countStats" = 1                               */
+    uint64_t sphereTests;   /* RaySphere calls (extension), only when "countStats" = 1                     */
+    uint64_t dispatches;    /* RAYTRACE dispatches since the last reset                                    */
+    double   kernelMs;      /* CUDA-event time of the RAYTRACE kernels since the last reset (sum)          */
+} RtStats;
+
+/* Synchronises, then reports the counters accumulated since the last rtResetStats. */
+int rtGetStats(RtContext* ctx, RtStats* out);
+int rtResetStats(RtContext* ctx);
+
+/* ABI version of this header: (major << 16) | minor. */
+int rtGetVersion(void);
+#define RT_B200_VERSION ((1 << 16) | 0)
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* RT_B200_H */

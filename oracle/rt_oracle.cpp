@@ -1,0 +1,886 @@
+/* rt_oracle.cpp — TEST INFRASTRUCTURE.  CPU restatement ("oracle") of the reference's path-tracing
+ * hot path: Assets/Scripts/Tracer/RayCompute.compute:10-32 and Assets/Scripts/Tracer/RayCommon.hlsl:1-582
+ * of SebLague/Ray-Tracing, transcribed function by function, line by line (each function cites the
+ * lines it follows; identifiers are the reference's).
+ *
+ * PARITY UNPINNED against the real reference: the reference ships no tests, golden images or
+ * known-answer vectors and neither its HLSL nor its C# can run in this image
+ * (no Unity / dxc / dotnet / mono).  What pins this oracle instead: the integer RNG known-answer
+ * vectors hand-derived from RayCommon.hlsl:127-137 (tests/golden/pcg_kat.json), analytic checks
+ * (sphere hit distances, furnace test), BVH-vs-brute-force equality, and the arithmetic contract
+ * in rt_oracle_math.h.
+ *
+ * Who may use this file: tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs — as the checker and as the reported CPU baseline.  The product
+ * (ray_tracing_b200/csrc, librt_b200.so) never includes, links or calls anything in oracle/.
+ *
+ * It exports the same C-ABI as include/rt_b200.h (so the same host call sequence drives either
+ * implementation) plus or* helpers for tests.  Plain C-style C++; std::thread over rows.
+ */
+#include "../include/rt_b200.h"
+#include "rt_oracle_math.h"
+
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace orc;
+
+namespace {
+
+/* ======================================================================================================
+ *  The shader.  One instance = one thread's view of the HLSL global scope (uniforms + buffers).
+ * ====================================================================================================== */
+struct Shader
+{
+    // --- Settings and constants ---                                           RayCommon.hlsl:1-31
+    static constexpr float PI = 3.1415f;                                     // :2  (sic)
+
+    // Raytracing Settings                                                      :4-8
+    int MaxBounceCount = 0;
+    int NumRaysPerPixel = 0;
+    int Frame = 0;
+    int renderSeed = 0;
+
+    // Camera settings                                                          :10-14
+    float DefocusStrength = 0;
+    float DivergeStrength = 0;
+    float3 ViewParams = {0, 0, 0};
+    float4x4 CamLocalToWorldMatrix = {{1,0,0,0, 0,1,0,0, 0,0,1,0, 0,0,0,1}};
+
+    // Sky settings                                                             :16-21
+    int UseSky = 0;
+    float3 SunColour = {0, 0, 0};
+    float SunFocus = 0;      // HLSL initialisers (:19-20) are ignored for cbuffer globals; host always sets them
+    float SunIntensity = 0;
+    float3 dirToSun = {0, 0, 0};
+
+    // Constants                                                                :28-31
+    static constexpr int MATERIAL_CHECKERED = 1;
+    static constexpr int MATERIAL_GLASS = 2;
+
+    // RayCompute.compute:7-8
+    uint Resolution[2] = {0, 0};
+    bool accumulate = false;
+
+    // --- Buffers ---                                                          :115-121
+    const RtModel* ModelInfo = nullptr;
+    const RtTriangle* Triangles = nullptr;
+    const RtNode* Nodes = nullptr;
+    int modelCount = 0;
+    // extension: Sphere structured buffer
+    const RtSphere* Spheres = nullptr;
+    int sphereCount = 0;
+
+    // work counters (the reference's `stats`, :254,271, plus rays = CalculateRayCollision calls)
+    unsigned long long nTri = 0, nBox = 0, nRays = 0, nSphere = 0;
+
+    // ---- Structures ----                                                     :33-113
+    struct Ray
+    {
+        float3 pos;
+        float3 dir;
+        float3 invDir;
+        float3 transmittance;
+        int bounceCount;
+    };
+
+    struct TriangleHitInfo
+    {
+        bool didHit;
+        bool isBackface;
+        float dst;
+        float3 hitPoint;
+        float3 normal;
+    };
+
+    struct ModelHitInfo
+    {
+        bool didHit;
+        bool isBackface;
+        float3 normal;
+        float3 pos;
+        float dst;
+        RtMaterial material;
+    };
+
+    struct LightResponse
+    {
+        float3 reflectDir;
+        float3 refractDir;
+        float reflectWeight;
+        float refractWeight;
+    };
+
+    // ---- RNG Functions ----                                                  :123-164
+    static uint NextRandom(uint& state)                                      // :127-133
+    {
+        state = state * 747796405u + 2891336453u;
+        uint result = ((state >> ((state >> 28) + 4)) ^ state) * 277803737u;
+        result = (result >> 22) ^ result;
+        return result;
+    }
+
+    static float RandomValue(uint& state)                                    // :135-138
+    {
+        // the literal 4294967295.0 is a float: it rounds to 2^32
+        return (float)NextRandom(state) / 4294967296.0f;
+    }
+
+    static float RandomValueNormalDistribution(uint& state)                  // :141-147
+    {
+        float theta = (2.0f * 3.1415926f) * RandomValue(state);
+        float rho = orc::sqrt(-2.0f * orc::log(RandomValue(state)));
+        return rho * orc::cos(theta);
+    }
+
+    static float3 RandomDirection(uint& state)                               // :150-157
+    {
+        float x = RandomValueNormalDistribution(state);
+        float y = RandomValueNormalDistribution(state);
+        float z = RandomValueNormalDistribution(state);
+        return normalize(mk3(x, y, z));
+    }
+
+    static float2 RandomPointInCircle(uint& rngState)                        // :159-164
+    {
+        float angle = RandomValue(rngState) * 2.0f * PI;
+        float2 pointOnCircle = mk2(orc::cos(angle), orc::sin(angle));
+        return pointOnCircle * orc::sqrt(RandomValue(rngState));
+    }
+
+    float3 GetEnvironmentLight(float3 dir) const                             // :167-183
+    {
+        if (UseSky == 0) return mk3(0.0f);
+        const float3 GroundColour = mk3(0.35f, 0.3f, 0.35f);
+        const float3 SkyColourHorizon = mk3(1.0f, 1.0f, 1.0f);
+        const float3 SkyColourZenith = mk3(0.08f, 0.37f, 0.73f);
+
+        float skyGradientT = orc::pow(smoothstep(0.0f, 0.4f, dir.y), 0.35f);
+        float groundToSkyT = smoothstep(-0.01f, 0.0f, dir.y);
+        float3 skyGradient = lerp(SkyColourHorizon, SkyColourZenith, skyGradientT);
+        float s = 1000.0f * 1.0f / SunFocus;
+        float sun = orc::pow(orc::max(0.0f, dot(dir, dirToSun)), s) * SunIntensity;
+        // Combine ground, sky, and sun
+        float3 composite = lerp(GroundColour, skyGradient, groundToSkyT) + sun * SunColour * (groundToSkyT >= 1.0f ? 1.0f : 0.0f);
+        return composite;
+    }
+
+    // --- Ray Intersection Functions ---
+    static TriangleHitInfo RayTriangle(const Ray& ray, const RtTriangle& tri, bool cullBackface)   // :188-215
+    {
+        float3 posA = mk3(tri.posA), posB = mk3(tri.posB), posC = mk3(tri.posC);
+        float3 edgeAB = posB - posA;
+        float3 edgeAC = posC - posA;
+        float3 triFaceVector = cross(edgeAB, edgeAC);
+        float3 vertRayOffset = ray.pos - posA;
+        float3 rayOffsetPerp = cross(vertRayOffset, ray.dir);
+        float determinant = -dot(ray.dir, triFaceVector);
+        float invDet = 1.0f / determinant;
+
+        // Calculate hit-dst and barycentric coordinates
+        float dst = dot(vertRayOffset, triFaceVector) * invDet;
+        float u = dot(edgeAC, rayOffsetPerp) * invDet;
+        float v = -dot(edgeAB, rayOffsetPerp) * invDet;
+        float w = 1.0f - u - v;
+
+        // Initialize hit info
+        TriangleHitInfo hitInfo;
+        bool keep = cullBackface ? determinant >= 1E-8f : orc::abs(determinant) >= 1E-8f;
+        hitInfo.didHit = keep && dst > 0.0f && u >= 0.0f && v >= 0.0f && w >= 0.0f;
+        float3 smoothNormal = normalize(mk3(tri.normA) * w + mk3(tri.normB) * u + mk3(tri.normC) * v);
+        hitInfo.normal = smoothNormal * sign(determinant);
+        hitInfo.isBackface = determinant < 0.0f;
+        hitInfo.hitPoint = ray.pos + ray.dir * dst;
+        hitInfo.dst = dst;
+        return hitInfo;
+    }
+
+    static float RayBoundingBoxDst(const Ray& ray, float3 boxMin, float3 boxMax)     // :219-231
+    {
+        float3 tMin = (boxMin - ray.pos) * ray.invDir;
+        float3 tMax = (boxMax - ray.pos) * ray.invDir;
+        float3 t1 = orc::min(tMin, tMax);
+        float3 t2 = orc::max(tMin, tMax);
+        float tNear = orc::max(orc::max(t1.x, t1.y), t1.z);
+        float tFar = orc::min(orc::min(t2.x, t2.y), t2.z);
+
+        bool hit = tFar >= tNear && tFar > 0.0f;
+        float dst = hit ? tNear > 0.0f ? tNear : 0.0f : rt_inf();
+        return dst;
+    }
+
+    TriangleHitInfo RayTriangleBVH(Ray& ray, float rayLength, int nodeOffset, int triOffset, bool cullBackface)   // :234-287
+    {
+        TriangleHitInfo result;
+        result.didHit = false; result.isBackface = false;          // (uninitialised in the HLSL; never read unless dst improved)
+        result.hitPoint = mk3(0.0f); result.normal = mk3(0.0f);
+        result.dst = rayLength;
+
+        // the reference declares int stack[32] (:239) but its builder's MaxDepth = 32 (BVH.cs:91) can
+        // need 33 entries; 64 here — identical whenever the reference does not overflow.
+        int stack[64];
+        int stackCount = 0;
+        stack[stackCount++] = nodeOffset + 0;
+
+        while (stackCount > 0)
+        {
+            const RtNode& node = Nodes[stack[--stackCount]];
+            bool isLeaf = node.triangleCount > 0;
+
+            if (isLeaf)
+            {
+                for (int i = 0; i < node.triangleCount; i++)
+                {
+                    const RtTriangle& tri = Triangles[triOffset + node.startIndex + i];
+                    TriangleHitInfo triHitInfo = RayTriangle(ray, tri, cullBackface);
+                    nTri++; // count triangle intersection tests                       :254
+
+                    if (triHitInfo.didHit && triHitInfo.dst < result.dst)
+                    {
+                        result = triHitInfo;
+                    }
+                }
+            }
+            else
+            {
+                int childIndexA = nodeOffset + node.startIndex + 0;
+                int childIndexB = nodeOffset + node.startIndex + 1;
+                const RtNode& childA = Nodes[childIndexA];
+                const RtNode& childB = Nodes[childIndexB];
+
+                float dstA = RayBoundingBoxDst(ray, mk3(childA.boundsMin), mk3(childA.boundsMax));
+                float dstB = RayBoundingBoxDst(ray, mk3(childB.boundsMin), mk3(childB.boundsMax));
+                nBox += 2; // count bounding box intersection tests                   :271
+
+                // We want to look at closest child node first, so push it last
+                bool isNearestA = dstA <= dstB;
+                float dstNear = isNearestA ? dstA : dstB;
+                float dstFar = isNearestA ? dstB : dstA;
+                int childIndexNear = isNearestA ? childIndexA : childIndexB;
+                int childIndexFar = isNearestA ? childIndexB : childIndexA;
+
+                if (dstFar < result.dst) stack[stackCount++] = childIndexFar;
+                if (dstNear < result.dst) stack[stackCount++] = childIndexNear;
+            }
+        }
+
+        return result;
+    }
+
+    // :289-332, with the hard-coded debug material (:321-327) replaced by the sphere's own (extension)
+    static ModelHitInfo RaySphere(float3 rayPos, float3 rayDir, float3 sphereCentre, float sphereRadius)
+    {
+        ModelHitInfo hitInfo;
+        memset(&hitInfo, 0, sizeof(hitInfo));
+        hitInfo.dst = rt_inf();
+
+        float3 offsetRayOrigin = rayPos - sphereCentre;
+        float a = dot(rayDir, rayDir);
+        float b = 2.0f * dot(offsetRayOrigin, rayDir);
+        float c = dot(offsetRayOrigin, offsetRayOrigin) - sphereRadius * sphereRadius;
+        float discriminant = b * b - 4.0f * a * c;
+
+        if (discriminant >= 0.0f)
+        {
+            float s = orc::sqrt(discriminant);
+            float dstNear = orc::max(0.0f, (-b - s) / (2.0f * a));
+            float dstFar = (-b + s) / (2.0f * a);
+
+            if (dstFar >= 0.0f)
+            {
+                hitInfo.didHit = true;
+                bool isInside = dstNear == 0.0f;
+                hitInfo.isBackface = isInside;
+                hitInfo.dst = isInside ? dstFar : dstNear;
+
+                hitInfo.pos = rayPos + rayDir * hitInfo.dst;
+                hitInfo.normal = normalize(hitInfo.pos - sphereCentre) * (isInside ? -1.0f : 1.0f);
+            }
+        }
+
+        return hitInfo;
+    }
+
+    ModelHitInfo CalculateRayCollision(const Ray& worldRay, bool forceDontCullBack)      // :335-374
+    {
+        ModelHitInfo result;
+        memset(&result, 0, sizeof(result));
+        result.dst = rt_inf();
+        nRays++;
+
+        // Sphere extension: analytic spheres are tested in world space before the model loop, where the
+        // reference's commented-out call sits (:341); first index wins ties (strict <).
+        for (int i = 0; i < sphereCount; i++)
+        {
+            const RtSphere& sphere = Spheres[i];
+            ModelHitInfo s = RaySphere(worldRay.pos, worldRay.dir, mk3(sphere.centre), sphere.radius);
+            nSphere++;
+            if (s.didHit && s.dst < result.dst)
+            {
+                result = s;
+                result.material = sphere.material;
+            }
+        }
+
+        Ray localRay;
+        localRay.transmittance = mk3(0.0f);
+        localRay.bounceCount = 0;
+
+        for (int i = 0; i < modelCount; i++)
+        {
+            const RtModel& model = ModelInfo[i];
+            float4x4 worldToLocalMatrix, localToWorldMatrix;
+            memcpy(worldToLocalMatrix.m, model.worldToLocal, 64);
+            memcpy(localToWorldMatrix.m, model.localToWorld, 64);
+            // Transform ray into model's local coordinate space
+            localRay.pos = mul_xyz(worldToLocalMatrix, mk4(worldRay.pos, 1.0f));
+            localRay.dir = mul_xyz(worldToLocalMatrix, mk4(worldRay.dir, 0.0f));
+            localRay.invDir = 1.0f / localRay.dir;
+
+            bool cullBackface = model.material.flag != MATERIAL_GLASS;
+            if (forceDontCullBack) cullBackface = false;
+            // Traverse bvh to find closest triangle intersection with current model
+            TriangleHitInfo hit = RayTriangleBVH(localRay, result.dst, model.nodeOffset, model.triOffset, cullBackface);
+
+            // Record closest hit
+            if (hit.dst < result.dst)
+            {
+                result.didHit = true;
+                result.isBackface = hit.isBackface;
+                result.dst = hit.dst;
+                result.normal = normalize(mul_xyz(localToWorldMatrix, mk4(hit.normal, 0.0f)));
+                result.pos = worldRay.pos + worldRay.dir * hit.dst;
+                result.material = model.material;
+            }
+        }
+
+        return result;
+    }
+
+    static float2 mod2(float2 x, float y)                                      // :376-379
+    {
+        return mk2(x.x - y * orc::floor(x.x / y), x.y - y * orc::floor(x.y / y));
+    }
+
+    static float CalculateReflectance(float3 inDir, float3 normal, float iorA, float iorB)   // :383-405
+    {
+        float refractRatio = iorA / iorB;
+        float cosAngleIn = -dot(inDir, normal);
+        float sinSqrAngleOfRefraction = refractRatio * refractRatio * (1.0f - cosAngleIn * cosAngleIn);
+        if (sinSqrAngleOfRefraction >= 1.0f) return 1.0f; // Ray is fully reflected, no refraction occurs
+
+        float cosAngleOfRefraction = orc::sqrt(1.0f - sinSqrAngleOfRefraction);
+        float denominatorPerpendicular = iorA * cosAngleIn + iorB * cosAngleOfRefraction;
+        float denominatorParallel = iorA * cosAngleIn + iorB * cosAngleOfRefraction;    // (sic, :392)
+
+        if (orc::min(denominatorPerpendicular, denominatorParallel) < 1E-8f) return 1.0f;
+
+        // Perpendicular polarization
+        float rPerpendicular = (iorA * cosAngleIn - iorB * cosAngleOfRefraction) / denominatorPerpendicular;
+        rPerpendicular *= rPerpendicular;
+        // Parallel polarization
+        float rParallel = (iorB * cosAngleIn - iorA * cosAngleOfRefraction) / denominatorParallel;
+        rParallel *= rParallel;
+
+        // Return the average of the perpendicular and parallel polarizations
+        return (rPerpendicular + rParallel) / 2.0f;
+    }
+
+    static float3 Refract(float3 inDir, float3 normal, float iorA, float iorB)        // :408-417
+    {
+        float refractRatio = iorA / iorB;
+        float cosAngleIn = -dot(inDir, normal);
+        float sinSqrAngleOfRefraction = refractRatio * refractRatio * (1.0f - cosAngleIn * cosAngleIn);
+        if (sinSqrAngleOfRefraction > 1.0f) return mk3(0.0f); // Ray is fully reflected, no refraction occurs
+
+        float3 refractDir = refractRatio * inDir + (refractRatio * cosAngleIn - orc::sqrt(1.0f - sinSqrAngleOfRefraction)) * normal;
+        return refractDir;
+    }
+
+    static float3 Reflect(float3 inDir, float3 normal)                              // :419-422
+    {
+        return inDir - 2.0f * dot(inDir, normal) * normal;
+    }
+
+    static LightResponse CalculateReflectionAndRefraction(float3 inDir, float3 normal, float iorA, float iorB)   // :424-437
+    {
+        LightResponse result;
+
+        // Calculate the two directions that light can take
+        result.reflectDir = Reflect(inDir, normal);
+        result.refractDir = Refract(inDir, normal, iorA, iorB);
+
+        // Calculate the proportion of light [0, 1] that takes each path
+        result.reflectWeight = CalculateReflectance(inDir, normal, iorA, iorB);
+        result.refractWeight = 1.0f - result.reflectWeight;
+
+        return result;
+    }
+
+    static Ray CreateRay(float3 origin, float3 dir, float3 transmittance, int bounceIndex)   // :439-448
+    {
+        Ray ray;
+        ray.pos = origin;
+        ray.dir = dir;
+        ray.invDir = 1.0f / dir;
+        ray.transmittance = transmittance;
+        ray.bounceCount = bounceIndex;
+        return ray;
+    }
+
+    static float3 GetMaterialColour(const RtMaterial& mat, float3 pos, float3 normal, bool isSpecularBounce)   // :450-466
+    {
+        float3 col = mk3(mat.diffuseCol);
+
+        if (mat.flag == MATERIAL_CHECKERED)
+        {
+            float2 checkerPoint = mk2(pos.x, pos.z);
+            if (orc::abs(normal.x) > orc::abs(normal.y)) checkerPoint = mk2(pos.z, pos.y);
+            if (orc::abs(normal.z) > orc::max(orc::abs(normal.x), orc::abs(normal.y))) checkerPoint = mk2(pos.x, pos.y);
+
+            checkerPoint = checkerPoint * 1.5f;
+            float2 c = mod2(mk2(orc::floor(checkerPoint.x), orc::floor(checkerPoint.y)), 2.0f);
+            col = c.x == c.y ? col : mk3(mat.emissionCol);
+        }
+
+        return lerp(col, mk3(mat.specularCol), isSpecularBounce ? 1.0f : 0.0f);
+    }
+
+    static constexpr float epsilon = 0.001f;                                    // :468
+
+    float3 Trace(Ray initialRay, uint& rngState)                             // :479-542
+    {
+        float3 totalLight = mk3(0.0f);
+        Ray ray = initialRay;
+
+        // Bounce the ray around the world to gather light
+        for (int i = ray.bounceCount; i <= MaxBounceCount; i++)
+        {
+            ModelHitInfo hit = CalculateRayCollision(ray, false);
+            if (!hit.didHit)
+            {
+                if (UseSky)
+                {
+                    totalLight += ray.transmittance * GetEnvironmentLight(ray.dir);
+                }
+                break;
+            }
+
+            const RtMaterial& material = hit.material;
+
+            if (material.flag == MATERIAL_GLASS) // Glass-like material
+            {
+                // Absorb some amount of light as it travels through the object
+                if (hit.isBackface) ray.transmittance *= orc::exp(-hit.dst * mk3(material.absorption) * material.absorptionStrength);
+
+                float iorCurrent = hit.isBackface ? material.ior : 1.0f;
+                float iorNext = hit.isBackface ? 1.0f : material.ior;
+                LightResponse lr = CalculateReflectionAndRefraction(ray.dir, hit.normal, iorCurrent, iorNext);
+
+                // Calculate random direction in hemisphere around surface normal (cosine-weighted)
+                float3 diffuseDir = normalize(hit.normal + RandomDirection(rngState));
+                // Randomize the reflect/refract directions based on smoothness for a frosted effect
+                lr.reflectDir = normalize(lerp(diffuseDir, lr.reflectDir, material.specularProbability));
+                lr.refractDir = normalize(lerp(-diffuseDir, lr.refractDir, material.smoothness));
+
+                // Choose between reflection and refraction probabilistically based on proportion of light going each way
+                bool followReflection = RandomValue(rngState) <= lr.reflectWeight;
+                ray.dir = followReflection ? lr.reflectDir : lr.refractDir;
+                ray.pos = hit.pos + epsilon * hit.normal * sign(dot(hit.normal, ray.dir));
+            }
+            else
+            {
+                bool isSpecularBounce = material.specularProbability >= RandomValue(rngState);
+
+                // Redirect ray based on collision info
+                ray.pos = hit.pos + (hit.normal * epsilon);
+                float3 diffuseDir = normalize(hit.normal + RandomDirection(rngState));
+                float3 specularDir = reflect(ray.dir, hit.normal);
+                ray.dir = normalize(lerp(diffuseDir, specularDir, material.smoothness * (isSpecularBounce ? 1.0f : 0.0f)));
+
+                // Update light info
+                float3 emittedLight = mk3(material.emissionCol) * material.emissionStrength;
+                totalLight += emittedLight * ray.transmittance;
+                ray.transmittance *= GetMaterialColour(material, hit.pos, hit.normal, isSpecularBounce);
+            }
+
+            // Randomly early-exit paths, with probability based on how little light can be transmitted along it
+            float p = orc::max(ray.transmittance.x, orc::max(ray.transmittance.y, ray.transmittance.z));
+            if (RandomValue(rngState) >= p) break;
+            ray.transmittance *= 1.0f / p; // scale by inverse probability so result averages out over many iterations
+        }
+
+        return totalLight;
+    }
+
+    float3 RayTrace(float2 uv, const uint numPixels[2])                      // :545-582
+    {
+        float3 camOrigin = mul_xyz(CamLocalToWorldMatrix, mk4(mk3(0.0f, 0.0f, 0.0f), 1.0f));
+
+        // Create seed for random number generator
+        uint pixelCoordX = (uint)(uv.x * (float)numPixels[0]);
+        uint pixelCoordY = (uint)(uv.y * (float)numPixels[1]);
+        uint pixelIndex = pixelCoordY * numPixels[0] + pixelCoordX;
+        uint rngState = pixelIndex + (uint)Frame * 719393u + (uint)renderSeed;
+
+        // Calculate focus point
+        float3 focusPointLocal = mk3(uv.x - 0.5f, uv.y - 0.5f, 1.0f) * ViewParams;
+        float3 focusPoint = mul_xyz(CamLocalToWorldMatrix, mk4(focusPointLocal, 1.0f));
+        float3 camRight = mk3(M(CamLocalToWorldMatrix,0,0), M(CamLocalToWorldMatrix,1,0), M(CamLocalToWorldMatrix,2,0));
+        float3 camUp = mk3(M(CamLocalToWorldMatrix,0,1), M(CamLocalToWorldMatrix,1,1), M(CamLocalToWorldMatrix,2,1));
+
+        // Trace multiple rays and average together
+        float3 totalIncomingLight = mk3(0.0f);
+
+        for (int rayIndex = 0; rayIndex < NumRaysPerPixel; rayIndex++)
+        {
+            // -- Calculate ray origin and direction --
+            float2 defocusJitter = RandomPointInCircle(rngState) * DefocusStrength / (float)numPixels[0];
+            float3 rayOrigin = camOrigin + camRight * defocusJitter.x + camUp * defocusJitter.y;
+
+            float2 jitter = RandomPointInCircle(rngState) * DivergeStrength / (float)numPixels[0];
+            float3 jitteredFocusPoint = focusPoint + camRight * jitter.x + camUp * jitter.y;
+            float3 rayDir = normalize(jitteredFocusPoint - rayOrigin);
+
+            Ray ray = CreateRay(rayOrigin, rayDir, mk3(1.0f), 0);
+
+            totalIncomingLight += Trace(ray, rngState);
+        }
+
+        return totalIncomingLight / (float)NumRaysPerPixel;
+    }
+
+    // kernel RayTrace, RayCompute.compute:10-24 (one invocation = one thread id)
+    void Kernel_RayTrace(uint idx, uint idy, float* FrameRender, float* AccumulatedRender)
+    {
+        if (idx >= Resolution[0] || idy >= Resolution[1]) return;
+
+        float2 uv = mk2((float)idx / ((float)Resolution[0] - 1.0f), (float)idy / ((float)Resolution[1] - 1.0f));
+        float3 pixelCol = RayTrace(uv, Resolution);
+
+        size_t o = ((size_t)idy * Resolution[0] + idx) * 4;
+        FrameRender[o + 0] = pixelCol.x; FrameRender[o + 1] = pixelCol.y; FrameRender[o + 2] = pixelCol.z; FrameRender[o + 3] = 1.0f;
+
+        if (accumulate)
+        {
+            AccumulatedRender[o + 0] += pixelCol.x; AccumulatedRender[o + 1] += pixelCol.y;
+            AccumulatedRender[o + 2] += pixelCol.z; AccumulatedRender[o + 3] += 1.0f;
+        }
+    }
+};
+
+} // namespace
+
+/* ======================================================================================================
+ *  C-ABI (same surface as include/rt_b200.h) — host-side state, no arithmetic of the path below here.
+ * ====================================================================================================== */
+struct RtContext
+{
+    Shader sh;                        // uniforms live here; buffers point into the vectors below
+    std::vector<RtTriangle> triangles;
+    std::vector<RtNode> nodes;
+    std::vector<RtModel> models;
+    std::vector<RtSphere> spheres;
+    std::vector<float> frame, accum;
+    int width = 0, height = 0;
+    int tileRank = 0, tileWorld = 1, bandRows = 1;
+    int threads = 0;
+    RtStats stats = {};
+    std::string err;
+};
+
+static std::string g_createErr;
+
+static int fail(RtContext* c, int code, const std::string& msg) { if (c) c->err = msg; else g_createErr = msg; return code; }
+
+extern "C" {
+
+int rtGetVersion(void) { return RT_B200_VERSION; }
+
+int rtCreate(RtContext** out, int /*device*/)
+{
+    if (!out) return fail(nullptr, RT_E_INVALID, "rtCreate: out is NULL");
+    *out = new RtContext();
+    const char* e = getenv("RT_ORACLE_THREADS");
+    (*out)->threads = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+    if ((*out)->threads < 1) (*out)->threads = 1;
+    return RT_OK;
+}
+
+int rtDestroy(RtContext* ctx) { delete ctx; return RT_OK; }
+
+const char* rtLastError(const RtContext* ctx) { return ctx ? ctx->err.c_str() : g_createErr.c_str(); }
+
+int rtSetBuffer(RtContext* c, const char* name, const void* data, int count, int stride)
+{
+    if (!c || !name || count < 0 || (count > 0 && !data)) return fail(c, RT_E_INVALID, "rtSetBuffer: bad argument");
+    std::string n(name);
+#define SETBUF(NAME, VEC, T) if (n == NAME) { if (stride != (int)sizeof(T)) return fail(c, RT_E_INVALID, std::string("rtSetBuffer: stride mismatch for ") + NAME); \
+        c->VEC.resize(count); if (count) memcpy(c->VEC.data(), data, (size_t)count * sizeof(T)); return RT_OK; }
+    SETBUF("Triangles", triangles, RtTriangle)
+    SETBUF("Nodes", nodes, RtNode)
+    SETBUF("ModelInfo", models, RtModel)
+    SETBUF("Spheres", spheres, RtSphere)
+#undef SETBUF
+    return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetBuffer: unknown buffer ") + name);
+}
+
+int rtSetInt(RtContext* c, const char* name, int v)
+{
+    if (!c || !name) return fail(c, RT_E_INVALID, "rtSetInt: bad argument");
+    std::string n(name);
+    if (n == "Frame") c->sh.Frame = v;
+    else if (n == "UseSky") c->sh.UseSky = v;
+    else if (n == "MaxBounceCount") c->sh.MaxBounceCount = v;
+    else if (n == "NumRaysPerPixel") c->sh.NumRaysPerPixel = v;
+    else if (n == "renderSeed") c->sh.renderSeed = v;
+    else if (n == "modelCount") c->sh.modelCount = v;
+    else if (n == "triangleCount" || n == "visMode") { /* declared but unused by the shader (:24,120) */ }
+    else return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetInt: unknown uniform ") + name);
+    return RT_OK;
+}
+
+int rtSetInts(RtContext* c, const char* name, const int* v, int n)
+{
+    if (!c || !name || !v) return fail(c, RT_E_INVALID, "rtSetInts: bad argument");
+    if (std::string(name) == "Resolution")
+    {
+        if (n != 2) return fail(c, RT_E_INVALID, "rtSetInts: Resolution takes 2 values");
+        c->sh.Resolution[0] = (uint)v[0]; c->sh.Resolution[1] = (uint)v[1];
+        return RT_OK;
+    }
+    return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetInts: unknown uniform ") + name);
+}
+
+int rtSetFloat(RtContext* c, const char* name, float v)
+{
+    if (!c || !name) return fail(c, RT_E_INVALID, "rtSetFloat: bad argument");
+    std::string n(name);
+    if (n == "DefocusStrength") c->sh.DefocusStrength = v;
+    else if (n == "DivergeStrength") c->sh.DivergeStrength = v;
+    else if (n == "SunFocus") c->sh.SunFocus = v;
+    else if (n == "SunIntensity") c->sh.SunIntensity = v;
+    else if (n == "debugVisScale") { }
+    else return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetFloat: unknown uniform ") + name);
+    return RT_OK;
+}
+
+int rtSetVector(RtContext* c, const char* name, const float v[4])
+{
+    if (!c || !name || !v) return fail(c, RT_E_INVALID, "rtSetVector: bad argument");
+    std::string n(name);
+    if (n == "ViewParams") c->sh.ViewParams = mk3(v);
+    else if (n == "SunColour") c->sh.SunColour = mk3(v);
+    else if (n == "dirToSun") c->sh.dirToSun = mk3(v);
+    else if (n == "debugParams") { }
+    else return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetVector: unknown uniform ") + name);
+    return RT_OK;
+}
+
+int rtSetMatrix(RtContext* c, const char* name, const float v[16])
+{
+    if (!c || !name || !v) return fail(c, RT_E_INVALID, "rtSetMatrix: bad argument");
+    if (std::string(name) == "CamLocalToWorldMatrix") { memcpy(c->sh.CamLocalToWorldMatrix.m, v, 64); return RT_OK; }
+    return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetMatrix: unknown uniform ") + name);
+}
+
+int rtSetBool(RtContext* c, const char* name, int v)
+{
+    if (!c || !name) return fail(c, RT_E_INVALID, "rtSetBool: bad argument");
+    if (std::string(name) == "accumulate") { c->sh.accumulate = v != 0; return RT_OK; }
+    return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetBool: unknown uniform ") + name);
+}
+
+int rtResize(RtContext* c, int w, int h)
+{
+    if (!c || w <= 0 || h <= 0) return fail(c, RT_E_INVALID, "rtResize: bad size");
+    if (w != c->width || h != c->height)
+    {
+        c->width = w; c->height = h;
+        c->frame.assign((size_t)w * h * 4, 0.0f);
+        c->accum.assign((size_t)w * h * 4, 0.0f);
+    }
+    c->sh.Resolution[0] = (uint)w; c->sh.Resolution[1] = (uint)h;
+    return RT_OK;
+}
+
+int rtSetTile(RtContext* c, int rank, int world, int bandRows)
+{
+    if (!c || world < 1 || rank < 0 || rank >= world || bandRows < 1) return fail(c, RT_E_INVALID, "rtSetTile: bad argument");
+    c->tileRank = rank; c->tileWorld = world; c->bandRows = bandRows;
+    return RT_OK;
+}
+
+static void bind_buffers(RtContext* c, Shader& s)
+{
+    s.Triangles = c->triangles.data(); s.Nodes = c->nodes.data(); s.ModelInfo = c->models.data();
+    s.Spheres = c->spheres.data();
+    s.sphereCount = (int)c->spheres.size();     // the Spheres buffer length is its count (extension)
+}
+
+int rtDispatch(RtContext* c, int kernelIndex, int gx, int gy, int gz)
+{
+    if (!c || gx < 0 || gy < 0 || gz < 0) return fail(c, RT_E_INVALID, "rtDispatch: bad argument");
+    if (c->width == 0) return fail(c, RT_E_STATE, "rtDispatch: rtResize has not been called");
+    uint W = c->sh.Resolution[0], H = c->sh.Resolution[1];
+    if ((int)W != c->width || (int)H != c->height) return fail(c, RT_E_STATE, "rtDispatch: Resolution does not match the textures");
+    uint limX = (uint)gx * 8u < W ? (uint)gx * 8u : W, limY = (uint)gy * 8u < H ? (uint)gy * 8u : H;
+    if (gz == 0) limX = limY = 0;
+
+    if (kernelIndex == RT_KERNEL_RESET_ACCUMULATED)                    // RayCompute.compute:26-32
+    {
+        for (uint y = 0; y < limY; y++)
+            memset(&c->accum[((size_t)y * W) * 4], 0, (size_t)limX * 16);
+        return RT_OK;
+    }
+    if (kernelIndex != RT_KERNEL_RAYTRACE) return fail(c, RT_E_INVALID, "rtDispatch: kernelIndex must be 0 or 1");
+    if (c->sh.modelCount > (int)c->models.size()) return fail(c, RT_E_STATE, "rtDispatch: modelCount exceeds ModelInfo length");
+
+    auto t0 = std::chrono::steady_clock::now();
+    std::atomic<uint> nextRow(0);
+    int nt = c->threads;
+    std::vector<Shader> shaders(nt, c->sh);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; t++)
+    {
+        pool.emplace_back([&, t]() {
+            Shader& s = shaders[t];
+            bind_buffers(c, s);
+            for (;;)
+            {
+                uint y = nextRow.fetch_add(1);
+                if (y >= limY) break;
+                if ((int)((y / (uint)c->bandRows) % (uint)c->tileWorld) != c->tileRank) continue;
+                for (uint x = 0; x < limX; x++) s.Kernel_RayTrace(x, y, c->frame.data(), c->accum.data());
+            }
+        });
+    }
+    for (auto& th : pool) th.join();
+    for (auto& s : shaders) { c->stats.rays += s.nRays; c->stats.boxTests += s.nBox; c->stats.triTests += s.nTri; c->stats.sphereTests += s.nSphere; }
+    c->stats.dispatches++;
+    c->stats.kernelMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return RT_OK;
+}
+
+int rtReadback(RtContext* c, const char* tex, float* dst, size_t bytes)
+{
+    if (!c || !tex || !dst) return fail(c, RT_E_INVALID, "rtReadback: bad argument");
+    std::string n(tex);
+    const std::vector<float>* src = n == "FrameRender" ? &c->frame : n == "AccumulatedRender" ? &c->accum : nullptr;
+    if (!src) return fail(c, RT_E_UNKNOWN_NAME, std::string("rtReadback: unknown texture ") + tex);
+    if (bytes != src->size() * 4) return fail(c, RT_E_INVALID, "rtReadback: bytes must be W*H*16");
+    memcpy(dst, src->data(), bytes);
+    return RT_OK;
+}
+
+int rtSynchronize(RtContext* c) { return c ? RT_OK : RT_E_INVALID; }
+int rtSetStream(RtContext* c, void*) { return c ? RT_OK : RT_E_INVALID; }
+int rtPackTile(RtContext* c) { return fail(c, RT_E_STATE, "oracle: no device tile staging"); }
+int rtUnpackTiles(RtContext* c) { return fail(c, RT_E_STATE, "oracle: no device tile staging"); }
+int rtGetDevicePointer(RtContext* c, const char*, void**, size_t*) { return fail(c, RT_E_STATE, "oracle: no device memory"); }
+
+int rtSetOption(RtContext* c, const char* name, int value)
+{
+    if (!c || !name) return fail(c, RT_E_INVALID, "rtSetOption: bad argument");
+    std::string n(name);
+    if (n == "threads") { c->threads = value < 1 ? 1 : value; return RT_OK; }
+    if (n == "kernel" || n == "countStats" || n == "smemNodes") return RT_OK;   // accepted, meaningless on the CPU
+    return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetOption: unknown option ") + name);
+}
+
+int rtGetStats(RtContext* c, RtStats* out) { if (!c || !out) return RT_E_INVALID; *out = c->stats; return RT_OK; }
+int rtResetStats(RtContext* c) { if (!c) return RT_E_INVALID; c->stats = RtStats(); return RT_OK; }
+
+/* ---- oracle-only helpers for tests -------------------------------------------------------------------- */
+
+/* Trace only the listed pixels (xy = n pairs of global pixel coordinates) with the context's current
+ * uniforms and buffers; out = n float4 (the FrameRender value of each pixel).  Exact, because pixels are
+ * independent and seeded from their global index (RayCommon.hlsl:550-552).  Multi-threaded. */
+int orRenderPixels(RtContext* c, const int* xy, int n, float* out)
+{
+    if (!c || !xy || !out || n < 0) return fail(c, RT_E_INVALID, "orRenderPixels: bad argument");
+    auto t0 = std::chrono::steady_clock::now();
+    std::atomic<int> next(0);
+    int nt = c->threads;
+    std::vector<Shader> shaders(nt, c->sh);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; t++)
+    {
+        pool.emplace_back([&, t]() {
+            Shader& s = shaders[t];
+            bind_buffers(c, s);
+            const uint* R = s.Resolution;
+            for (;;)
+            {
+                int i0 = next.fetch_add(16);
+                if (i0 >= n) break;
+                for (int i = i0; i < n && i < i0 + 16; i++)
+                {
+                    uint x = (uint)xy[2 * i], y = (uint)xy[2 * i + 1];
+                    float2 uv = mk2((float)x / ((float)R[0] - 1.0f), (float)y / ((float)R[1] - 1.0f));   // RayCompute.compute:15
+                    float3 col = s.RayTrace(uv, R);
+                    out[4 * i + 0] = col.x; out[4 * i + 1] = col.y; out[4 * i + 2] = col.z; out[4 * i + 3] = 1.0f;
+                }
+            }
+        });
+    }
+    for (auto& th : pool) th.join();
+    for (auto& s : shaders) { c->stats.rays += s.nRays; c->stats.boxTests += s.nBox; c->stats.triTests += s.nTri; c->stats.sphereTests += s.nSphere; }
+    c->stats.kernelMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return RT_OK;
+}
+
+/* PCG known-answer access: advances *state once, returns NextRandom's result; *value = RandomValue. */
+unsigned orNextRandom(unsigned* state, float* value)
+{
+    uint s = *state;
+    uint r = Shader::NextRandom(s);
+    *state = s;
+    if (value) *value = (float)r / 4294967296.0f;
+    return r;
+}
+
+/* Pinned transcendental routines, for accuracy tests: fn 0 log, 1 exp, 2 sin, 3 cos, 4 pow(x, y[i]). */
+void orMath(int fn, const float* x, const float* y, float* out, int n)
+{
+    for (int i = 0; i < n; i++)
+    {
+        switch (fn)
+        {
+        case 0: out[i] = orc::log(x[i]); break;
+        case 1: out[i] = orc::exp(x[i]); break;
+        case 2: out[i] = orc::sin(x[i]); break;
+        case 3: out[i] = orc::cos(x[i]); break;
+        case 4: out[i] = orc::pow(x[i], y[i]); break;
+        default: out[i] = 0.0f;
+        }
+    }
+}
+
+/* Single-primitive probes for analytic tests. */
+float orRayBoundingBoxDst(const float pos[3], const float dir[3], const float bmin[3], const float bmax[3])
+{
+    Shader::Ray r; r.pos = mk3(pos); r.dir = mk3(dir); r.invDir = 1.0f / r.dir;
+    return Shader::RayBoundingBoxDst(r, mk3(bmin), mk3(bmax));
+}
+int orRayTriangle(const float pos[3], const float dir[3], const RtTriangle* tri, int cull, float* dst, float normal[3])
+{
+    Shader::Ray r; r.pos = mk3(pos); r.dir = mk3(dir); r.invDir = 1.0f / r.dir;
+    Shader::TriangleHitInfo h = Shader::RayTriangle(r, *tri, cull != 0);
+    *dst = h.dst; normal[0] = h.normal.x; normal[1] = h.normal.y; normal[2] = h.normal.z;
+    return (h.didHit ? 1 : 0) | (h.isBackface ? 2 : 0);
+}
+int orRaySphere(const float pos[3], const float dir[3], const float centre[3], float radius, float* dst, float normal[3])
+{
+    Shader::ModelHitInfo h = Shader::RaySphere(mk3(pos), mk3(dir), mk3(centre), radius);
+    *dst = h.dst; normal[0] = h.normal.x; normal[1] = h.normal.y; normal[2] = h.normal.z;
+    return (h.didHit ? 1 : 0) | (h.isBackface ? 2 : 0);
+}
+
+} // extern "C"

@@ -1,0 +1,503 @@
+// rt_api.cu — the C-ABI of librt_b200.so (include/rt_b200.h): context, named uniforms, structured
+// buffers, render targets, dispatch, readback, multi-GPU tile staging.  Host-side state only; all
+// arithmetic of the path lives in rt_device.cuh / rt_kernel_*.cuh.
+//
+// The interface mirrors the ComputeShader calls RayComputeManager makes (each entry point
+// cites its reference counterpart in the header).  There is deliberately no CPU path: every entry point
+// that needs the GPU fails with RT_E_NO_DEVICE / RT_E_CUDA when CUDA is unavailable.
+#include "../../include/rt_b200.h"
+#include "rt_kernel_mega.cuh"
+#include "rt_kernel_wave.cuh"
+#include "rt_repack.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace rtd;
+
+namespace {
+
+template <class T> struct DevBuf
+{
+    T* p = nullptr; size_t count = 0, cap = 0;
+    cudaError_t ensure(size_t n)
+    {
+        if (n == count && p) return cudaSuccess;             // unchanged size re-uses the allocation (CH:86-92)
+        if (n > cap || n == 0) { if (p) cudaFree(p); p = nullptr; cap = 0; if (n) { cudaError_t e = cudaMalloc(&p, n * sizeof(T)); if (e != cudaSuccess) { count = 0; return e; } cap = n; } }
+        count = n; return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; count = cap = 0; }
+};
+
+struct EventPair { cudaEvent_t a, b; };
+
+} // namespace
+
+struct RtContext
+{
+    int device = 0;
+    cudaStream_t ownStream = nullptr, stream = nullptr;
+    int numSMs = 0;
+    std::string err;
+
+    // uniforms (host copy)
+    DevParams P;
+
+    // reference-layout buffers
+    DevBuf<RtNode> nodes; DevBuf<RtTriangle> tris; DevBuf<RtModel> models; DevBuf<RtSphere> spheres;
+    std::vector<RtNode> hNodes; std::vector<RtModel> hModels; std::vector<RtSphere> hSpheres;   // host mirrors for the repack
+    // repacked buffers
+    RepackState repack;
+    bool sceneDirty = true, modelsDirty = true, spheresDirty = true;
+
+    // render targets
+    DevBuf<float4> frame, accum, tileSend, tileRecv;
+    int width = 0, height = 0;
+    int tileRank = 0, tileWorld = 1, bandRows = 1;
+
+    // options
+    int optKernel = 1, optCountStats = 0, optSmemPairs = -1;   // -1 = automatic
+
+    // counters / timing
+    unsigned long long* dCounters = nullptr;   // 4
+    unsigned int* dWork = nullptr;
+    std::vector<EventPair> pending, freeEvents;
+    RtStats stats;
+};
+
+static std::string g_createErr = "";
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return failCuda(c, e_, #call); } while (0)
+
+static int fail(RtContext* c, int code, const std::string& msg) { if (c) c->err = msg; else g_createErr = msg; return code; }
+static int failCuda(RtContext* c, cudaError_t e, const char* what)
+{
+    return fail(c, RT_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+static int drainEvents(RtContext* c)
+{
+    for (auto& ev : c->pending)
+    {
+        CK(cudaEventSynchronize(ev.b));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, ev.a, ev.b));
+        c->stats.kernelMs += ms;
+        c->freeEvents.push_back(ev);
+    }
+    c->pending.clear();
+    return RT_OK;
+}
+
+extern "C" {
+
+int rtGetVersion(void) { return RT_B200_VERSION; }
+
+int rtCreate(RtContext** out, int device)
+{
+    if (!out) return fail(nullptr, RT_E_INVALID, "rtCreate: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, RT_E_NO_DEVICE, std::string("rtCreate: no CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") + "); librt_b200 has no CPU path");
+    if (device < 0 || device >= n) return fail(nullptr, RT_E_INVALID, "rtCreate: device ordinal out of range");
+    RtContext* c = new RtContext();
+    memset(&c->P, 0, sizeof(c->P));
+    memset(&c->stats, 0, sizeof(c->stats));
+    c->device = device;
+    c->P.tileWorld = 1; c->P.bandRows = 1;
+    const float ident[16] = {1,0,0,0, 0,1,0,0, 0,0,1,0, 0,0,0,1};
+    memcpy(c->P.cam, ident, sizeof(ident));
+    auto bail = [&](cudaError_t err, const char* what) { std::string m = std::string(what) + ": " + cudaGetErrorString(err); delete c; return fail(nullptr, RT_E_CUDA, m); };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    if (prop.major < 10) { delete c; return fail(nullptr, RT_E_NO_DEVICE, "rtCreate: device is not sm_100-class; this library carries sm_100a code only"); }
+    c->numSMs = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    c->stream = c->ownStream;
+    if ((e = cudaMalloc(&c->dCounters, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&c->dWork, 64)) != cudaSuccess) return bail(e, "cudaMalloc");
+    cudaMemset(c->dCounters, 0, 4 * sizeof(unsigned long long));
+    cudaMemset(c->dWork, 0, 64);
+    if ((e = wave_configure()) != cudaSuccess) return bail(e, "cudaFuncSetAttribute");
+    *out = c;
+    return RT_OK;
+}
+
+int rtDestroy(RtContext* c)
+{
+    if (!c) return RT_E_INVALID;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->nodes.release(); c->tris.release(); c->models.release(); c->spheres.release();
+    c->frame.release(); c->accum.release(); c->tileSend.release(); c->tileRecv.release();
+    c->repack.release();
+    for (auto& ev : c->pending) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    for (auto& ev : c->freeEvents) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    if (c->dCounters) cudaFree(c->dCounters);
+    if (c->dWork) cudaFree(c->dWork);
+    if (c->ownStream) cudaStreamDestroy(c->ownStream);
+    delete c;
+    return RT_OK;
+}
+
+const char* rtLastError(const RtContext* c) { return c ? c->err.c_str() : g_createErr.c_str(); }
+
+int rtSetStream(RtContext* c, void* s)
+{
+    if (!c) return RT_E_INVALID;
+    c->stream = s ? (cudaStream_t)s : c->ownStream;
+    return RT_OK;
+}
+
+int rtSetBuffer(RtContext* c, const char* name, const void* data, int count, int stride)
+{
+    if (!c || !name || count < 0 || (count > 0 && !data)) return fail(c, RT_E_INVALID, "rtSetBuffer: bad argument");
+    CK(cudaSetDevice(c->device));
+    const std::string n(name);
+    if (n == "Triangles")
+    {
+        if (stride != (int)sizeof(RtTriangle)) return fail(c, RT_E_INVALID, "rtSetBuffer: Triangles stride must be 72");
+        CK(c->tris.ensure(count));
+        if (count) CK(cudaMemcpyAsync(c->tris.p, data, (size_t)count * sizeof(RtTriangle), cudaMemcpyHostToDevice, c->stream));
+        c->sceneDirty = true;
+        return RT_OK;
+    }
+    if (n == "Nodes")
+    {
+        if (stride != (int)sizeof(RtNode)) return fail(c, RT_E_INVALID, "rtSetBuffer: Nodes stride must be 32");
+        CK(c->nodes.ensure(count));
+        c->hNodes.assign((const RtNode*)data, (const RtNode*)data + count);
+        if (count) CK(cudaMemcpyAsync(c->nodes.p, c->hNodes.data(), (size_t)count * sizeof(RtNode), cudaMemcpyHostToDevice, c->stream));
+        c->sceneDirty = true;
+        return RT_OK;
+    }
+    if (n == "ModelInfo")
+    {
+        if (stride != (int)sizeof(RtModel)) return fail(c, RT_E_INVALID, "rtSetBuffer: ModelInfo stride must be 224");
+        // the BVH repack depends only on the (nodeOffset, triOffset) pairs; matrices / materials change every frame (RCM:192-204)
+        bool sameTopology = (size_t)count == c->hModels.size();
+        const RtModel* m = (const RtModel*)data;
+        for (int i = 0; sameTopology && i < count; i++)
+            sameTopology = m[i].nodeOffset == c->hModels[i].nodeOffset && m[i].triOffset == c->hModels[i].triOffset;
+        if (!sameTopology) c->sceneDirty = true;
+        CK(c->models.ensure(count));
+        c->hModels.assign(m, m + count);
+        if (count) CK(cudaMemcpyAsync(c->models.p, c->hModels.data(), (size_t)count * sizeof(RtModel), cudaMemcpyHostToDevice, c->stream));
+        c->modelsDirty = true;
+        return RT_OK;
+    }
+    if (n == "Spheres")
+    {
+        if (stride != (int)sizeof(RtSphere)) return fail(c, RT_E_INVALID, "rtSetBuffer: Spheres stride must be 104");
+        CK(c->spheres.ensure(count));
+        c->hSpheres.assign((const RtSphere*)data, (const RtSphere*)data + count);
+        if (count) CK(cudaMemcpyAsync(c->spheres.p, c->hSpheres.data(), (size_t)count * sizeof(RtSphere), cudaMemcpyHostToDevice, c->stream));
+        c->spheresDirty = true;
+        return RT_OK;
+    }
+    return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetBuffer: unknown buffer ") + name);
+}
+
+int rtSetInt(RtContext* c, const char* name, int v)
+{
+    if (!c || !name) return fail(c, RT_E_INVALID, "rtSetInt: bad argument");
+    const std::string n(name);
+    if (n == "Frame") c->P.Frame = v;
+    else if (n == "UseSky") c->P.UseSky = v;
+    else if (n == "MaxBounceCount") c->P.MaxBounceCount = v;
+    else if (n == "NumRaysPerPixel") c->P.NumRaysPerPixel = v;
+    else if (n == "renderSeed") c->P.renderSeed = v;
+    else if (n == "modelCount") c->P.modelCount = v;
+    else if (n == "triangleCount" || n == "visMode") { /* declared but never read by the shader (HL:24,120) */ }
+    else return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetInt: unknown uniform ") + name);
+    return RT_OK;
+}
+
+int rtSetInts(RtContext* c, const char* name, const int* v, int n)
+{
+    if (!c || !name || !v) return fail(c, RT_E_INVALID, "rtSetInts: bad argument");
+    if (std::string(name) == "Resolution")
+    {
+        if (n != 2 || v[0] <= 0 || v[1] <= 0) return fail(c, RT_E_INVALID, "rtSetInts: Resolution takes 2 positive values");
+        c->P.W = (unsigned)v[0]; c->P.H = (unsigned)v[1];
+        return RT_OK;
+    }
+    return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetInts: unknown uniform ") + name);
+}
+
+int rtSetFloat(RtContext* c, const char* name, float v)
+{
+    if (!c || !name) return fail(c, RT_E_INVALID, "rtSetFloat: bad argument");
+    const std::string n(name);
+    if (n == "DefocusStrength") c->P.DefocusStrength = v;
+    else if (n == "DivergeStrength") c->P.DivergeStrength = v;
+    else if (n == "SunFocus") c->P.SunFocus = v;
+    else if (n == "SunIntensity") c->P.SunIntensity = v;
+    else if (n == "debugVisScale") { }
+    else return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetFloat: unknown uniform ") + name);
+    return RT_OK;
+}
+
+int rtSetVector(RtContext* c, const char* name, const float v[4])
+{
+    if (!c || !name || !v) return fail(c, RT_E_INVALID, "rtSetVector: bad argument");
+    const std::string n(name);
+    if (n == "ViewParams") memcpy(c->P.ViewParams, v, 12);
+    else if (n == "SunColour") memcpy(c->P.SunColour, v, 12);
+    else if (n == "dirToSun") memcpy(c->P.dirToSun, v, 12);
+    else if (n == "debugParams") { }
+    else return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetVector: unknown uniform ") + name);
+    return RT_OK;
+}
+
+int rtSetMatrix(RtContext* c, const char* name, const float v[16])
+{
+    if (!c || !name || !v) return fail(c, RT_E_INVALID, "rtSetMatrix: bad argument");
+    if (std::string(name) == "CamLocalToWorldMatrix") { memcpy(c->P.cam, v, 64); return RT_OK; }
+    return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetMatrix: unknown uniform ") + name);
+}
+
+int rtSetBool(RtContext* c, const char* name, int v)
+{
+    if (!c || !name) return fail(c, RT_E_INVALID, "rtSetBool: bad argument");
+    if (std::string(name) == "accumulate") { c->P.accumulate = v != 0; return RT_OK; }
+    return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetBool: unknown uniform ") + name);
+}
+
+int rtResize(RtContext* c, int w, int h)
+{
+    if (!c || w <= 0 || h <= 0) return fail(c, RT_E_INVALID, "rtResize: bad size");
+    CK(cudaSetDevice(c->device));
+    if (w != c->width || h != c->height)
+    {
+        const size_t n = (size_t)w * h;
+        CK(c->frame.ensure(n)); CK(c->accum.ensure(n));
+        CK(cudaMemsetAsync(c->frame.p, 0, n * 16, c->stream));
+        CK(cudaMemsetAsync(c->accum.p, 0, n * 16, c->stream));
+        c->width = w; c->height = h;
+        c->tileSend.release(); c->tileRecv.release();
+    }
+    c->P.W = (unsigned)w; c->P.H = (unsigned)h;
+    return RT_OK;
+}
+
+int rtSetTile(RtContext* c, int rank, int world, int bandRows)
+{
+    if (!c || world < 1 || rank < 0 || rank >= world || bandRows < 1) return fail(c, RT_E_INVALID, "rtSetTile: bad argument");
+    if (rank != c->tileRank || world != c->tileWorld || bandRows != c->bandRows) { c->tileSend.release(); c->tileRecv.release(); }
+    c->tileRank = rank; c->tileWorld = world; c->bandRows = bandRows;
+    return RT_OK;
+}
+
+int rtSetOption(RtContext* c, const char* name, int value)
+{
+    if (!c || !name) return fail(c, RT_E_INVALID, "rtSetOption: bad argument");
+    const std::string n(name);
+    if (n == "kernel") { if (value < 0 || value > 1) return fail(c, RT_E_INVALID, "rtSetOption: kernel must be 0 or 1"); c->optKernel = value; }
+    else if (n == "countStats") c->optCountStats = value != 0;
+    else if (n == "smemNodes") { c->optSmemPairs = value; c->sceneDirty = true; }
+    else return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetOption: unknown option ") + name);
+    return RT_OK;
+}
+
+static int prepareScene(RtContext* c)
+{
+    if (c->P.modelCount < 0 || (size_t)c->P.modelCount > c->models.count) return fail(c, RT_E_STATE, "rtDispatch: modelCount exceeds the ModelInfo buffer");
+    if (c->P.modelCount > 0 && (c->nodes.count == 0 || c->tris.count == 0)) return fail(c, RT_E_STATE, "rtDispatch: models without Nodes / Triangles buffers");
+    for (int i = 0; i < c->P.modelCount; i++)
+    {
+        const RtModel& m = c->hModels[i];
+        if (m.nodeOffset < 0 || (size_t)m.nodeOffset >= c->nodes.count || m.triOffset < 0 || (size_t)m.triOffset > c->tris.count)
+            return fail(c, RT_E_STATE, "rtDispatch: model nodeOffset / triOffset out of range");
+    }
+    if (c->sceneDirty)
+    {
+        std::string msg;
+        cudaError_t e = c->repack.buildScene(c->hNodes, c->hModels, c->P.modelCount, c->tris.p, c->tris.count, c->optSmemPairs, c->stream, msg);
+        if (e != cudaSuccess) return failCuda(c, e, "repack scene");
+        if (!msg.empty()) return fail(c, RT_E_STATE, "rtDispatch: " + msg);
+        c->sceneDirty = false; c->modelsDirty = true;
+    }
+    if (c->modelsDirty)
+    {
+        cudaError_t e = c->repack.buildModels(c->hModels, c->P.modelCount, c->stream);
+        if (e != cudaSuccess) return failCuda(c, e, "repack models");
+        c->modelsDirty = false;
+    }
+    if (c->spheresDirty)
+    {
+        cudaError_t e = c->repack.buildSpheres(c->hSpheres, c->stream);
+        if (e != cudaSuccess) return failCuda(c, e, "repack spheres");
+        c->spheresDirty = false;
+    }
+    return RT_OK;
+}
+
+int rtDispatch(RtContext* c, int kernelIndex, int gx, int gy, int gz)
+{
+    if (!c || gx < 0 || gy < 0 || gz < 0) return fail(c, RT_E_INVALID, "rtDispatch: bad argument");
+    if (c->width == 0) return fail(c, RT_E_STATE, "rtDispatch: rtResize has not been called");
+    if ((int)c->P.W != c->width || (int)c->P.H != c->height) return fail(c, RT_E_STATE, "rtDispatch: Resolution does not match the render textures");
+    CK(cudaSetDevice(c->device));
+    const unsigned W = c->P.W, H = c->P.H;
+    unsigned limX = (unsigned long long)gx * 8ull < W ? (unsigned)gx * 8u : W;
+    unsigned limY = (unsigned long long)gy * 8ull < H ? (unsigned)gy * 8u : H;
+    if (gz == 0) limX = limY = 0;
+
+    if (kernelIndex == RT_KERNEL_RESET_ACCUMULATED)            // RC:26-32
+    {
+        if (limX == 0 || limY == 0) return RT_OK;
+        CK(cudaMemset2DAsync(c->accum.p, (size_t)W * 16, 0, (size_t)limX * 16, limY, c->stream));
+        return RT_OK;
+    }
+    if (kernelIndex != RT_KERNEL_RAYTRACE) return fail(c, RT_E_INVALID, "rtDispatch: kernelIndex must be 0 (RayTrace) or 1 (ResetAccumulated)");
+    if (limX == 0 || limY == 0) return RT_OK;
+    if (c->P.NumRaysPerPixel < 0 ) return fail(c, RT_E_STATE, "rtDispatch: NumRaysPerPixel is negative");
+
+    int rc = prepareScene(c);
+    if (rc != RT_OK) return rc;
+
+    DevParams P = c->P;
+    P.limX = limX; P.limY = limY;
+    P.tileRank = c->tileRank; P.tileWorld = c->tileWorld; P.bandRows = c->bandRows; P.countStats = c->optCountStats;
+    P.sphereCount = (int)c->spheres.count;
+    P.Nodes = c->nodes.p; P.Triangles = c->tris.p; P.ModelInfo = c->models.p; P.Spheres = c->spheres.p;
+    P.pairs = c->repack.pairs.p; P.triGeom = c->repack.triGeom.p; P.triNormals = c->repack.triNormals.p;
+    P.models = c->repack.models.p; P.spheres = c->repack.spheres.p; P.smemPairs = c->repack.smemPairs;
+    P.FrameRender = c->frame.p; P.AccumulatedRender = c->accum.p;
+    P.counters = c->dCounters; P.workCounter = c->dWork;
+
+    EventPair ev;
+    if (!c->freeEvents.empty()) { ev = c->freeEvents.back(); c->freeEvents.pop_back(); }
+    else { CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b)); }
+    if (c->pending.size() >= 512) { rc = drainEvents(c); if (rc != RT_OK) return rc; }
+
+    if (c->optKernel == 0)
+    {
+        CK(cudaEventRecord(ev.a, c->stream));
+        dim3 grid((limX + 7) / 8, (limY + 7) / 8, 1), block(8, 8, 1);
+        k_raytrace_mega<<<grid, block, 0, c->stream>>>(P);
+        CK(cudaEventRecord(ev.b, c->stream));
+    }
+    else
+    {
+        cudaError_t e = wave_launch(P, c->numSMs, c->stream, ev.a, ev.b);
+        if (e != cudaSuccess) return failCuda(c, e, "wavefront launch");
+    }
+    CK(cudaGetLastError());
+    c->pending.push_back(ev);
+    c->stats.dispatches++;
+    return RT_OK;
+}
+
+int rtReadback(RtContext* c, const char* tex, float* dst, size_t bytes)
+{
+    if (!c || !tex || !dst) return fail(c, RT_E_INVALID, "rtReadback: bad argument");
+    const std::string n(tex);
+    const float4* src = n == "FrameRender" ? c->frame.p : n == "AccumulatedRender" ? c->accum.p : nullptr;
+    if (n != "FrameRender" && n != "AccumulatedRender") return fail(c, RT_E_UNKNOWN_NAME, std::string("rtReadback: unknown texture ") + tex);
+    if (!src) return fail(c, RT_E_STATE, "rtReadback: rtResize has not been called");
+    if (bytes != (size_t)c->width * c->height * 16) return fail(c, RT_E_INVALID, "rtReadback: bytes must equal W*H*16");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return RT_OK;
+}
+
+int rtSynchronize(RtContext* c)
+{
+    if (!c) return RT_E_INVALID;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return RT_OK;
+}
+
+// ---- multi-GPU tile staging -----------------------------------------------------------------------------------------------
+
+static size_t tileRows(const RtContext* c, int rank)
+{
+    size_t rows = 0;
+    for (int y0 = 0, b = 0; y0 < c->height; y0 += c->bandRows, b++)
+        if (b % c->tileWorld == rank) rows += (size_t)((c->height - y0) < c->bandRows ? (c->height - y0) : c->bandRows);
+    return rows;
+}
+
+static int ensureTileBuffers(RtContext* c)
+{
+    if (c->width == 0) return fail(c, RT_E_STATE, "tile staging: rtResize has not been called");
+    // every rank must contribute the same count to the all-gather: size by the largest share (rank 0's)
+    const size_t per = tileRows(c, 0) * (size_t)c->width * 2;    // frame + accumulated
+    CK(c->tileSend.ensure(per));
+    CK(c->tileRecv.ensure(per * c->tileWorld));
+    return RT_OK;
+}
+
+int rtPackTile(RtContext* c)
+{
+    if (!c) return RT_E_INVALID;
+    CK(cudaSetDevice(c->device));
+    int rc = ensureTileBuffers(c); if (rc != RT_OK) return rc;
+    launch_pack_tile(c->frame.p, c->accum.p, c->tileSend.p, c->width, c->height, c->tileRank, c->tileWorld, c->bandRows,
+                     (int)tileRows(c, 0), c->stream);
+    CK(cudaGetLastError());
+    return RT_OK;
+}
+
+int rtUnpackTiles(RtContext* c)
+{
+    if (!c) return RT_E_INVALID;
+    CK(cudaSetDevice(c->device));
+    int rc = ensureTileBuffers(c); if (rc != RT_OK) return rc;
+    launch_unpack_tiles(c->tileRecv.p, c->frame.p, c->accum.p, c->width, c->height, c->tileWorld, c->bandRows,
+                        (int)tileRows(c, 0), c->stream);
+    CK(cudaGetLastError());
+    return RT_OK;
+}
+
+int rtGetDevicePointer(RtContext* c, const char* name, void** devPtr, size_t* bytes)
+{
+    if (!c || !name || !devPtr || !bytes) return fail(c, RT_E_INVALID, "rtGetDevicePointer: bad argument");
+    const std::string n(name);
+    CK(cudaSetDevice(c->device));
+    if (n == "FrameRender") { *devPtr = c->frame.p; *bytes = c->frame.count * 16; }
+    else if (n == "AccumulatedRender") { *devPtr = c->accum.p; *bytes = c->accum.count * 16; }
+    else if (n == "TileSend" || n == "TileRecv")
+    {
+        int rc = ensureTileBuffers(c); if (rc != RT_OK) return rc;
+        if (n == "TileSend") { *devPtr = c->tileSend.p; *bytes = c->tileSend.count * 16; }
+        else { *devPtr = c->tileRecv.p; *bytes = c->tileRecv.count * 16; }
+    }
+    else return fail(c, RT_E_UNKNOWN_NAME, std::string("rtGetDevicePointer: unknown object ") + name);
+    if (!*devPtr) return fail(c, RT_E_STATE, "rtGetDevicePointer: object not allocated yet (call rtResize)");
+    return RT_OK;
+}
+
+int rtGetStats(RtContext* c, RtStats* out)
+{
+    if (!c || !out) return fail(c, RT_E_INVALID, "rtGetStats: bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    int rc = drainEvents(c); if (rc != RT_OK) return rc;
+    unsigned long long h[4];
+    CK(cudaMemcpy(h, c->dCounters, sizeof(h), cudaMemcpyDeviceToHost));
+    c->stats.rays = h[0]; c->stats.boxTests = h[1]; c->stats.triTests = h[2]; c->stats.sphereTests = h[3];
+    *out = c->stats;
+    return RT_OK;
+}
+
+int rtResetStats(RtContext* c)
+{
+    if (!c) return RT_E_INVALID;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    int rc = drainEvents(c); if (rc != RT_OK) return rc;
+    CK(cudaMemset(c->dCounters, 0, 4 * sizeof(unsigned long long)));
+    memset(&c->stats, 0, sizeof(c->stats));
+    return RT_OK;
+}
+
+} // extern "C"

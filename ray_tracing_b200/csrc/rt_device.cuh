@@ -1,0 +1,378 @@
+// rt_device.cuh — device functions of the path-tracing hot path, shared by every kernel variant.
+//
+// What is computed follows the reference shader (paths relative to the reference repo:
+//   HL = Assets/Scripts/Tracer/RayCommon.hlsl, RC = Assets/Scripts/Tracer/RayCompute.compute);
+// how it is organised (parameter block, material pointers instead of 88-byte copies, deferred
+// normal evaluation, repacked node/triangle streams, ...) is this implementation's own.
+#pragma once
+#include "rt_devmath.cuh"
+#include "../../include/rt_types.h"
+
+namespace rtd {
+
+// ---- repacked device-side scene records (built at upload time by rt_repack.cu) ---------------------------
+
+// Two sibling BVH nodes in one 64-byte, 64-byte-aligned record (children are allocated adjacently by the
+// reference builder, BVH.cs:161-162).  Records are numbered breadth-first per mesh so that the top of
+// every tree is one contiguous range (staged in shared memory by a TMA bulk copy).
+//   start: leaf  -> first triangle, global index into triGeom (triOffset already added)
+//          inner -> global index of the pair record holding its two children
+//   count: > 0 <=> leaf (HL:246)
+struct __align__(64) NodePair
+{
+    float aMinX, aMinY, aMinZ, aMaxX, aMaxY, aMaxZ; int aStart, aCount;
+    float bMinX, bMinY, bMinZ, bMaxX, bMaxY, bMaxZ; int bStart, bCount;
+};
+
+// Triangle geometry as the intersection test consumes it: vertex A, the two edges and the face vector
+// cross(AB, AC) — each the single IEEE operation sequence of HL:190-192, evaluated once at upload
+// instead of once per test (same bits).  48 bytes = 3 × float4.
+struct __align__(16) TriGeom
+{
+    float ax, ay, az, abx;
+    float aby, abz, acx, acy;
+    float acz, nx, ny, nz;
+};
+
+// Vertex normals, fetched only for the winning triangle of a traversal.  48 bytes = 3 × float4.
+struct __align__(16) TriNormals
+{
+    float nax, nay, naz, nbx;
+    float nby, nbz, ncx, ncy;
+    float ncz, pad0, pad1, pad2;
+};
+
+// Per-model record: rows 0..2 of both matrices (all four columns kept, see mul_point/mul_dir), the root
+// of its BVH and where its material lives.  128 bytes.
+struct __align__(16) DevModel
+{
+    float w2l[12];      // row-major rows 0..2 of worldToLocalMatrix
+    float l2w[12];      // row-major rows 0..2 of localToWorldMatrix
+    int   rootStart;    // root node's start (pair index or first triangle), same encoding as NodePair
+    int   rootCount;    // root node's triangleCount
+    int   cullBackface; // material.flag != GLASS (HL:355)
+    int   matIndex;     // index into ModelInfo (material is read from the 224-byte record)
+    int   pad[4];
+};
+
+// Sphere with r*r precomputed (the exact product of HL:299).  32 bytes.
+struct __align__(16) DevSphere
+{
+    float cx, cy, cz, radius;
+    float r2; int pad0, pad1, pad2;
+};
+
+// ---- kernel parameter block (uniform names as in HL:5-21, RC:7-8) ---------------------------------------------
+
+struct DevParams
+{
+    int   MaxBounceCount, NumRaysPerPixel, Frame, renderSeed;
+    int   UseSky, modelCount, sphereCount, accumulate;
+    float DefocusStrength, DivergeStrength, SunFocus, SunIntensity;
+    float ViewParams[3]; float pad0;
+    float SunColour[3];  float pad1;
+    float dirToSun[3];   float pad2;
+    float cam[16];                          // CamLocalToWorldMatrix, column-major
+    unsigned int W, H;                      // Resolution
+    unsigned int limX, limY;                // pixels covered by the dispatched 8x8 groups
+    int   tileRank, tileWorld, bandRows, countStats;
+
+    // reference-layout buffers (what the host uploaded)
+    const RtNode*     Nodes;
+    const RtTriangle* Triangles;
+    const RtModel*    ModelInfo;
+    const RtSphere*   Spheres;
+    // repacked buffers
+    const NodePair*   pairs;
+    const TriGeom*    triGeom;
+    const TriNormals* triNormals;
+    const DevModel*   models;
+    const DevSphere*  spheres;
+    int   smemPairs;                        // number of leading pair records staged in shared memory
+    int   pad3;
+
+    float4* FrameRender;
+    float4* AccumulatedRender;
+    unsigned long long* counters;           // [0] rays [1] boxTests [2] triTests [3] sphereTests
+    unsigned int* workCounter;              // persistent kernel: next job
+};
+
+struct Counters { unsigned int rays, box, tri, sph; };
+
+// ---- RNG (HL:127-164) ---------------------------------------------------------------------------------------------
+
+RT_DI uint32_t NextRandom(uint32_t& state)
+{
+    state = state * 747796405u + 2891336453u;
+    uint32_t result = ((state >> ((state >> 28) + 4u)) ^ state) * 277803737u;
+    result = (result >> 22) ^ result;
+    return result;
+}
+// HL:137 divides by the float literal 4294967295.0 == 2^32 in FP32: an exact scaling
+RT_DI float RandomValue(uint32_t& state) { return __uint2float_rn(NextRandom(state)) * 2.3283064365386963e-10f; }
+
+RT_DI float RandomValueNormalDistribution(uint32_t& state)
+{
+    const float theta = 6.2831852f * RandomValue(state);             // 2 * 3.1415926 (HL:144)
+    const float rho = sqrtf(-2.0f * log_rt(RandomValue(state)));
+    return rho * cos_rt(theta);
+}
+RT_DI f3 RandomDirection(uint32_t& state)
+{
+    const float x = RandomValueNormalDistribution(state);
+    const float y = RandomValueNormalDistribution(state);
+    const float z = RandomValueNormalDistribution(state);
+    return normalize3(make_f3(x, y, z));
+}
+RT_DI f2 RandomPointInCircle(uint32_t& state)
+{
+    const float angle = (RandomValue(state) * 2.0f) * 3.1415f;       // PI = 3.1415 (HL:2,161)
+    float s, c; sincos_rt(angle, s, c);
+    const float rad = sqrtf(RandomValue(state));
+    return make_f2(c * rad, s * rad);
+}
+
+// ---- environment (HL:167-183) -----------------------------------------------------------------------------------
+
+RT_DI f3 GetEnvironmentLight(const DevParams& P, f3 dir)
+{
+    if (P.UseSky == 0) return splat3(0.0f);
+    const f3 GroundColour = make_f3(0.35f, 0.3f, 0.35f);
+    const f3 SkyColourHorizon = make_f3(1.0f, 1.0f, 1.0f);
+    const f3 SkyColourZenith = make_f3(0.08f, 0.37f, 0.73f);
+    const float skyGradientT = pow_rt(smoothstep1(0.0f, 0.4f, dir.y), 0.35f);
+    const float groundToSkyT = smoothstep1(-0.01f, 0.0f, dir.y);
+    const f3 skyGradient = lerp3(SkyColourHorizon, SkyColourZenith, skyGradientT);
+    const float s = 1000.0f / P.SunFocus;
+    const float sun = pow_rt(fmaxf(0.0f, dot3(dir, load3(P.dirToSun))), s) * P.SunIntensity;
+    return lerp3(GroundColour, skyGradient, groundToSkyT) + (sun * load3(P.SunColour)) * (groundToSkyT >= 1.0f ? 1.0f : 0.0f);
+}
+
+// ---- matrix · vector, all four products kept and summed left to right (HL:351-352,367,547,556) ------------
+
+RT_DI f3 mul_cm(const float* m, f3 v, float w)      // column-major 4x4, rows 0..2
+{
+    return make_f3(((m[0] * v.x + m[4] * v.y) + m[8]  * v.z) + m[12] * w,
+                   ((m[1] * v.x + m[5] * v.y) + m[9]  * v.z) + m[13] * w,
+                   ((m[2] * v.x + m[6] * v.y) + m[10] * v.z) + m[14] * w);
+}
+RT_DI f3 mul_rm(const float* r, f3 v, float w)      // row-major rows 0..2 (DevModel)
+{
+    return make_f3(((r[0] * v.x + r[1] * v.y) + r[2]  * v.z) + r[3]  * w,
+                   ((r[4] * v.x + r[5] * v.y) + r[6]  * v.z) + r[7]  * w,
+                   ((r[8] * v.x + r[9] * v.y) + r[10] * v.z) + r[11] * w);
+}
+
+// ---- primitive tests ---------------------------------------------------------------------------------------------------
+
+// HL:219-231
+RT_DI float RayBoundingBoxDst(f3 pos, f3 invDir, f3 boxMin, f3 boxMax)
+{
+    const f3 tMin = (boxMin - pos) * invDir;
+    const f3 tMax = (boxMax - pos) * invDir;
+    const float tNear = fmaxf(fmaxf(fminf(tMin.x, tMax.x), fminf(tMin.y, tMax.y)), fminf(tMin.z, tMax.z));
+    const float tFar  = fminf(fminf(fmaxf(tMin.x, tMax.x), fmaxf(tMin.y, tMax.y)), fmaxf(tMin.z, tMax.z));
+    const bool hit = tFar >= tNear && tFar > 0.0f;
+    return hit ? (tNear > 0.0f ? tNear : 0.0f) : inf32();
+}
+
+// HL:188-207 without the normal (evaluated later for the winner only): returns didHit, writes dst,u,v,det
+RT_DI bool RayTriangleCore(f3 pos, f3 dir, f3 A, f3 edgeAB, f3 edgeAC, f3 triFaceVector, bool cullBackface,
+                           float& dst, float& u, float& v, float& determinant)
+{
+    const f3 vertRayOffset = pos - A;
+    const f3 rayOffsetPerp = cross3(vertRayOffset, dir);
+    determinant = -dot3(dir, triFaceVector);
+    const float invDet = 1.0f / determinant;
+    dst = dot3(vertRayOffset, triFaceVector) * invDet;
+    u = dot3(edgeAC, rayOffsetPerp) * invDet;
+    v = -dot3(edgeAB, rayOffsetPerp) * invDet;
+    const float w = (1.0f - u) - v;
+    const bool keep = cullBackface ? determinant >= 1E-8f : fabsf(determinant) >= 1E-8f;
+    return keep && dst > 0.0f && u >= 0.0f && v >= 0.0f && w >= 0.0f;
+}
+// HL:208-209
+RT_DI f3 TriangleSmoothNormal(f3 nA, f3 nB, f3 nC, float u, float v, float determinant)
+{
+    const float w = (1.0f - u) - v;
+    const f3 smoothNormal = normalize3((nA * w + nB * u) + nC * v);
+    return smoothNormal * sign1(determinant);
+}
+
+// HL:289-320 (sphere extension): returns didHit; dst / isInside valid on hit
+RT_DI bool RaySphereCore(f3 rayPos, f3 rayDir, f3 centre, float r2, float& dst, bool& isInside)
+{
+    const f3 offsetRayOrigin = rayPos - centre;
+    const float a = dot3(rayDir, rayDir);
+    const float b = 2.0f * dot3(offsetRayOrigin, rayDir);
+    const float c = dot3(offsetRayOrigin, offsetRayOrigin) - r2;
+    const float discriminant = b * b - (4.0f * a) * c;
+    if (discriminant >= 0.0f)
+    {
+        const float s = sqrtf(discriminant);
+        const float dstNear = fmaxf(0.0f, (-b - s) / (2.0f * a));
+        const float dstFar = (-b + s) / (2.0f * a);
+        if (dstFar >= 0.0f)
+        {
+            isInside = dstNear == 0.0f;
+            dst = isInside ? dstFar : dstNear;
+            return true;
+        }
+    }
+    return false;
+}
+
+// ---- hit record -----------------------------------------------------------------------------------------------------------
+
+struct Hit
+{
+    float dst;                 // +inf = miss
+    bool  isBackface;
+    f3    normal;
+    f3    pos;
+    const RtMaterial* material;
+};
+
+// ---- shading (HL:383-466, 497-538) -----------------------------------------------------------------------------------
+
+RT_DI float CalculateReflectance(f3 inDir, f3 normal, float iorA, float iorB)
+{
+    const float refractRatio = iorA / iorB;
+    const float cosAngleIn = -dot3(inDir, normal);
+    const float sinSqrAngleOfRefraction = (refractRatio * refractRatio) * (1.0f - cosAngleIn * cosAngleIn);
+    if (sinSqrAngleOfRefraction >= 1.0f) return 1.0f;
+    const float cosAngleOfRefraction = sqrtf(1.0f - sinSqrAngleOfRefraction);
+    const float denominatorPerpendicular = iorA * cosAngleIn + iorB * cosAngleOfRefraction;
+    const float denominatorParallel = iorA * cosAngleIn + iorB * cosAngleOfRefraction;   // as in the reference (HL:392)
+    if (fminf(denominatorPerpendicular, denominatorParallel) < 1E-8f) return 1.0f;
+    float rPerpendicular = (iorA * cosAngleIn - iorB * cosAngleOfRefraction) / denominatorPerpendicular;
+    rPerpendicular *= rPerpendicular;
+    float rParallel = (iorB * cosAngleIn - iorA * cosAngleOfRefraction) / denominatorParallel;
+    rParallel *= rParallel;
+    return (rPerpendicular + rParallel) / 2.0f;
+}
+RT_DI f3 Refract(f3 inDir, f3 normal, float iorA, float iorB)
+{
+    const float refractRatio = iorA / iorB;
+    const float cosAngleIn = -dot3(inDir, normal);
+    const float sinSqrAngleOfRefraction = (refractRatio * refractRatio) * (1.0f - cosAngleIn * cosAngleIn);
+    if (sinSqrAngleOfRefraction > 1.0f) return splat3(0.0f);
+    return refractRatio * inDir + (refractRatio * cosAngleIn - sqrtf(1.0f - sinSqrAngleOfRefraction)) * normal;
+}
+RT_DI f3 Reflect(f3 inDir, f3 normal) { return inDir - (2.0f * dot3(inDir, normal)) * normal; }
+
+RT_DI f3 GetMaterialColour(const RtMaterial* mat, f3 pos, f3 normal, bool isSpecularBounce)
+{
+    f3 col = make_f3(mat->diffuseCol[0], mat->diffuseCol[1], mat->diffuseCol[2]);
+    if (mat->flag == RT_MATERIAL_CHECKERED)
+    {
+        f2 checkerPoint = make_f2(pos.x, pos.z);
+        if (fabsf(normal.x) > fabsf(normal.y)) checkerPoint = make_f2(pos.z, pos.y);
+        if (fabsf(normal.z) > fmaxf(fabsf(normal.x), fabsf(normal.y))) checkerPoint = make_f2(pos.x, pos.y);
+        checkerPoint.x = checkerPoint.x * 1.5f; checkerPoint.y = checkerPoint.y * 1.5f;
+        const float fx = floorf(checkerPoint.x), fy = floorf(checkerPoint.y);
+        const float cx = fx - 2.0f * floorf(fx / 2.0f);
+        const float cy = fy - 2.0f * floorf(fy / 2.0f);
+        if (!(cx == cy)) col = make_f3(mat->emissionCol[0], mat->emissionCol[1], mat->emissionCol[2]);
+    }
+    return lerp3(col, make_f3(mat->specularCol[0], mat->specularCol[1], mat->specularCol[2]), isSpecularBounce ? 1.0f : 0.0f);
+}
+
+struct PathState
+{
+    f3 pos, dir, transmittance, totalLight;
+};
+
+// One iteration of the bounce loop after the intersection (HL:488-538).
+// Returns true when the path continues with another segment.
+RT_DI bool ShadeSegment(const DevParams& P, const Hit& hit, PathState& ray, uint32_t& rngState)
+{
+    const float epsilon = 0.001f;
+    if (!(hit.dst < inf32()))
+    {
+        if (P.UseSky) ray.totalLight = ray.totalLight + ray.transmittance * GetEnvironmentLight(P, ray.dir);
+        return false;
+    }
+    const RtMaterial* material = hit.material;
+    if (material->flag == RT_MATERIAL_GLASS)
+    {
+        if (hit.isBackface)
+        {
+            const f3 absorb = ((-hit.dst) * make_f3(material->absorption[0], material->absorption[1], material->absorption[2])) * material->absorptionStrength;
+            ray.transmittance = ray.transmittance * make_f3(exp_rt(absorb.x), exp_rt(absorb.y), exp_rt(absorb.z));
+        }
+        const float iorCurrent = hit.isBackface ? material->ior : 1.0f;
+        const float iorNext = hit.isBackface ? 1.0f : material->ior;
+        f3 reflectDir = Reflect(ray.dir, hit.normal);
+        f3 refractDir = Refract(ray.dir, hit.normal, iorCurrent, iorNext);
+        const float reflectWeight = CalculateReflectance(ray.dir, hit.normal, iorCurrent, iorNext);
+
+        const f3 diffuseDir = normalize3(hit.normal + RandomDirection(rngState));
+        reflectDir = normalize3(lerp3(diffuseDir, reflectDir, material->specularProbability));
+        refractDir = normalize3(lerp3(-diffuseDir, refractDir, material->smoothness));
+
+        const bool followReflection = RandomValue(rngState) <= reflectWeight;
+        ray.dir = followReflection ? reflectDir : refractDir;
+        ray.pos = hit.pos + (epsilon * hit.normal) * sign1(dot3(hit.normal, ray.dir));
+    }
+    else
+    {
+        const bool isSpecularBounce = material->specularProbability >= RandomValue(rngState);
+        ray.pos = hit.pos + (hit.normal * epsilon);
+        const f3 diffuseDir = normalize3(hit.normal + RandomDirection(rngState));
+        const f3 specularDir = reflect3(ray.dir, hit.normal);
+        ray.dir = normalize3(lerp3(diffuseDir, specularDir, material->smoothness * (isSpecularBounce ? 1.0f : 0.0f)));
+
+        const f3 emittedLight = make_f3(material->emissionCol[0], material->emissionCol[1], material->emissionCol[2]) * material->emissionStrength;
+        ray.totalLight = ray.totalLight + emittedLight * ray.transmittance;
+        ray.transmittance = ray.transmittance * GetMaterialColour(material, hit.pos, hit.normal, isSpecularBounce);
+    }
+    const float p = fmaxf(ray.transmittance.x, fmaxf(ray.transmittance.y, ray.transmittance.z));
+    if (RandomValue(rngState) >= p) return false;
+    ray.transmittance = ray.transmittance * (1.0f / p);
+    return true;
+}
+
+// ---- camera (HL:545-576) --------------------------------------------------------------------------------------------------
+
+struct PixelSetup
+{
+    f3 camOrigin, focusPoint, camRight, camUp;
+    uint32_t rngState;
+};
+
+// Per-pixel constants and the RNG seed for thread id (x, y)  (RC:15, HL:547-558)
+RT_DI PixelSetup SetupPixel(const DevParams& P, unsigned int idx, unsigned int idy)
+{
+    PixelSetup s;
+    const float uvx = __uint2float_rn(idx) / (__uint2float_rn(P.W) - 1.0f);
+    const float uvy = __uint2float_rn(idy) / (__uint2float_rn(P.H) - 1.0f);
+    s.camOrigin = mul_cm(P.cam, make_f3(0.0f, 0.0f, 0.0f), 1.0f);
+    const uint32_t pixelCoordX = __float2uint_rz(uvx * __uint2float_rn(P.W));
+    const uint32_t pixelCoordY = __float2uint_rz(uvy * __uint2float_rn(P.H));
+    const uint32_t pixelIndex = pixelCoordY * P.W + pixelCoordX;
+    s.rngState = pixelIndex + (uint32_t)P.Frame * 719393u + (uint32_t)P.renderSeed;
+    const f3 focusPointLocal = make_f3(uvx - 0.5f, uvy - 0.5f, 1.0f) * load3(P.ViewParams);
+    s.focusPoint = mul_cm(P.cam, focusPointLocal, 1.0f);
+    s.camRight = make_f3(P.cam[0], P.cam[1], P.cam[2]);
+    s.camUp = make_f3(P.cam[4], P.cam[5], P.cam[6]);
+    return s;
+}
+
+// One camera sample (HL:567-576): consumes four draws, returns the path's initial state
+RT_DI void GenerateCameraRay(const DevParams& P, const PixelSetup& s, uint32_t& rngState, PathState& ray)
+{
+    const float numPixelsX = __uint2float_rn(P.W);
+    const f2 c0 = RandomPointInCircle(rngState);
+    const f2 defocusJitter = make_f2((c0.x * P.DefocusStrength) / numPixelsX, (c0.y * P.DefocusStrength) / numPixelsX);
+    const f3 rayOrigin = (s.camOrigin + s.camRight * defocusJitter.x) + s.camUp * defocusJitter.y;
+    const f2 c1 = RandomPointInCircle(rngState);
+    const f2 jitter = make_f2((c1.x * P.DivergeStrength) / numPixelsX, (c1.y * P.DivergeStrength) / numPixelsX);
+    const f3 jitteredFocusPoint = (s.focusPoint + s.camRight * jitter.x) + s.camUp * jitter.y;
+    ray.pos = rayOrigin;
+    ray.dir = normalize3(jitteredFocusPoint - rayOrigin);
+    ray.transmittance = splat3(1.0f);
+    ray.totalLight = splat3(0.0f);
+}
+
+} // namespace rtd

@@ -1,0 +1,374 @@
+// rt_kernel_wave.cuh — kernel variant 1: persistent-thread wavefront path tracer for sm_100a.
+//
+// Shape (this implementation's own; the arithmetic per path is the reference's, see rt_device.cuh):
+//   * persistent CTAs (a multiple of the SM count) pull pixel jobs from one global counter.  A lane that
+//     finishes its pixel is refilled in place: the lanes that need work are found with a warp ballot, ONE
+//     atomicAdd per warp reserves a contiguous job range, and the lanes take consecutive jobs by popcount
+//     rank (warp-ballot compaction of the free slots).  Jobs are ordered in 8x4-pixel tiles so a freshly
+//     filled warp traces a coherent 32-pixel block.
+//   * a pixel's samples stay on one lane, in order, because the reference threads ONE rng state through all
+//     NumRaysPerPixel samples of a pixel (HL:552,563-579) and sums them in order (HL:578): this keeps
+//     results bit-identical while every lane always has a live path segment to intersect (no idle lanes
+//     after early path termination, which is what the megakernel wastes).
+//   * every loop iteration is one wavefront step for the warp: [refill] -> [generate] -> [intersect] ->
+//     [shade]; all live lanes run the intersection phase together.
+//   * the top of every BVH (the first `smemPairs` breadth-first NodePair records, contiguous by
+//     construction) is staged into shared memory once per CTA by a TMA bulk copy (cp.async.bulk +
+//     mbarrier complete_tx); deeper records and triangles are read with 128-bit vector loads from the
+//     repacked 64-byte / 48-byte aligned streams.  Spheres are staged in shared memory too.
+//   * traversal visits exactly the nodes and triangles the reference visits, in the same order, with the
+//     same push-time-only culling (HL:243-283) — so closest hits, tie winners and the box/triangle test
+//     counts equal the oracle's.  What is removed is the re-read of a popped node (the stack carries the
+//     node's (start,count)) and the push/pop round trip of the near child.
+#pragma once
+#include "rt_device.cuh"
+
+namespace rtd {
+
+constexpr int WAVE_THREADS = 128;
+constexpr int WAVE_MAX_SMEM_SPHERES = 256;
+constexpr int WAVE_STACK = 64;
+
+struct WaveSmemHeader
+{
+    unsigned long long mbar;
+    unsigned int pad[14];
+};
+
+RT_DI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+RT_DI void mbar_init(uint32_t mbar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory"); }
+RT_DI void mbar_expect_tx(uint32_t mbar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory"); }
+RT_DI void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+RT_DI bool mbar_try_wait(uint32_t mbar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+struct NodeRef { int start, count; };
+
+// Fetch one 64-byte pair record: from the shared-memory copy of the tree tops, or from HBM/L2.
+RT_DI void LoadPair(const DevParams& P, const float4* __restrict__ smemPairs, int idx, float4& q0, float4& q1, float4& q2, float4& q3)
+{
+    if (idx < P.smemPairs)
+    {
+        const float4* p = smemPairs + (size_t)idx * 4;
+        q0 = p[0]; q1 = p[1]; q2 = p[2]; q3 = p[3];
+    }
+    else
+    {
+        const float4* p = reinterpret_cast<const float4*>(P.pairs + idx);
+        q0 = __ldg(p); q1 = __ldg(p + 1); q2 = __ldg(p + 2); q3 = __ldg(p + 3);
+    }
+}
+
+// HL:234-287 on the repacked streams.  Same visiting order and culling as the reference.
+template <bool STATS>
+RT_DI void TraverseMesh(const DevParams& P, const float4* __restrict__ smemPairs, f3 pos, f3 dir, f3 invDir, float rayLength,
+                        NodeRef root, bool cullBackface,
+                        float& bestDst, int& bestTri, float& bestU, float& bestV, float& bestDet, Counters& cnt)
+{
+    bestDst = rayLength; bestTri = -1;
+    NodeRef stack[WAVE_STACK];
+    int stackCount = 0;
+    NodeRef cur = root;
+    for (;;)
+    {
+        if (cur.count > 0)
+        {
+            const float4* g = reinterpret_cast<const float4*>(P.triGeom + cur.start);
+            for (int i = 0; i < cur.count; i++, g += 3)
+            {
+                const float4 g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2);
+                float dst, u, v, det;
+                const bool didHit = RayTriangleCore(pos, dir, make_f3(g0.x, g0.y, g0.z), make_f3(g0.w, g1.x, g1.y), make_f3(g1.z, g1.w, g2.x),
+                                                    make_f3(g2.y, g2.z, g2.w), cullBackface, dst, u, v, det);
+                if (STATS) cnt.tri++;
+                if (didHit && dst < bestDst) { bestDst = dst; bestTri = cur.start + i; bestU = u; bestV = v; bestDet = det; }
+            }
+            if (stackCount == 0) return;
+            cur = stack[--stackCount];
+        }
+        else
+        {
+            float4 q0, q1, q2, q3;
+            LoadPair(P, smemPairs, cur.start, q0, q1, q2, q3);
+            const float dstA = RayBoundingBoxDst(pos, invDir, make_f3(q0.x, q0.y, q0.z), make_f3(q0.w, q1.x, q1.y));
+            const float dstB = RayBoundingBoxDst(pos, invDir, make_f3(q2.x, q2.y, q2.z), make_f3(q2.w, q3.x, q3.y));
+            if (STATS) cnt.box += 2;
+            NodeRef a, b;
+            a.start = __float_as_int(q1.z); a.count = __float_as_int(q1.w);
+            b.start = __float_as_int(q3.z); b.count = __float_as_int(q3.w);
+            const bool isNearestA = dstA <= dstB;
+            const float dstNear = isNearestA ? dstA : dstB;
+            const float dstFar = isNearestA ? dstB : dstA;
+            const NodeRef nearRef = isNearestA ? a : b;
+            const NodeRef farRef = isNearestA ? b : a;
+            // reference: push far, push near, pop (= near).  Equivalent: push far, continue with near.
+            if (dstFar < bestDst && stackCount < WAVE_STACK) stack[stackCount++] = farRef;
+            if (dstNear < bestDst) cur = nearRef;
+            else { if (stackCount == 0) return; cur = stack[--stackCount]; }
+        }
+    }
+}
+
+// HL:335-374 (+ sphere extension) on the repacked streams
+template <bool STATS>
+RT_DI Hit Intersect(const DevParams& P, const float4* __restrict__ smemPairs, const DevSphere* __restrict__ smemSpheres,
+                    f3 rayPos, f3 rayDir, Counters& cnt)
+{
+    Hit result;
+    result.dst = inf32(); result.isBackface = false; result.normal = splat3(0.0f); result.pos = splat3(0.0f); result.material = nullptr;
+    cnt.rays++;
+
+    int bestSphere = -1; bool bestInside = false;
+    for (int i = 0; i < P.sphereCount; i++)
+    {
+        float cx, cy, cz, r2;
+        if (i < WAVE_MAX_SMEM_SPHERES) { const DevSphere s = smemSpheres[i]; cx = s.cx; cy = s.cy; cz = s.cz; r2 = s.r2; }
+        else { const float4 s0 = __ldg(reinterpret_cast<const float4*>(P.spheres + i)); cx = s0.x; cy = s0.y; cz = s0.z; r2 = __ldg(&P.spheres[i].r2); }
+        float dst; bool inside;
+        if (STATS) cnt.sph++;
+        if (RaySphereCore(rayPos, rayDir, make_f3(cx, cy, cz), r2, dst, inside) && dst < result.dst)
+        {
+            result.dst = dst; bestSphere = i; bestInside = inside;
+        }
+    }
+    if (bestSphere >= 0)
+    {
+        // HL:319-320 for the winner only (position / normal of a sphere hit depend on nothing but the winner)
+        f3 centre;
+        if (bestSphere < WAVE_MAX_SMEM_SPHERES) { const DevSphere s = smemSpheres[bestSphere]; centre = make_f3(s.cx, s.cy, s.cz); }
+        else centre = make_f3(P.spheres[bestSphere].cx, P.spheres[bestSphere].cy, P.spheres[bestSphere].cz);
+        result.isBackface = bestInside;
+        result.pos = rayPos + rayDir * result.dst;
+        result.normal = normalize3(result.pos - centre) * (bestInside ? -1.0f : 1.0f);
+        result.material = &P.Spheres[bestSphere].material;
+    }
+
+    for (int i = 0; i < P.modelCount; i++)
+    {
+        const DevModel* m = P.models + i;
+        const float4* mr = reinterpret_cast<const float4*>(m);
+        float w2l[12];
+        {
+            const float4 r0 = __ldg(mr), r1 = __ldg(mr + 1), r2 = __ldg(mr + 2);
+            w2l[0] = r0.x; w2l[1] = r0.y; w2l[2] = r0.z; w2l[3] = r0.w;
+            w2l[4] = r1.x; w2l[5] = r1.y; w2l[6] = r1.z; w2l[7] = r1.w;
+            w2l[8] = r2.x; w2l[9] = r2.y; w2l[10] = r2.z; w2l[11] = r2.w;
+        }
+        const int4 meta = __ldg(reinterpret_cast<const int4*>(mr + 6));     // rootStart, rootCount, cullBackface, matIndex
+        const f3 localPos = mul_rm(w2l, rayPos, 1.0f);
+        const f3 localDir = mul_rm(w2l, rayDir, 0.0f);
+        const f3 invDir = rcp3(localDir);
+        NodeRef root; root.start = meta.x; root.count = meta.y;
+        float dst, u, v, det; int tri;
+        TraverseMesh<STATS>(P, smemPairs, localPos, localDir, invDir, result.dst, root, meta.z != 0, dst, tri, u, v, det, cnt);
+        if (dst < result.dst)
+        {
+            const float4* nq = reinterpret_cast<const float4*>(P.triNormals + tri);
+            const float4 n0 = __ldg(nq), n1 = __ldg(nq + 1), n2 = __ldg(nq + 2);
+            const f3 n = TriangleSmoothNormal(make_f3(n0.x, n0.y, n0.z), make_f3(n0.w, n1.x, n1.y), make_f3(n1.z, n1.w, n2.x), u, v, det);
+            float l2w[12];
+            {
+                const float4 r0 = __ldg(mr + 3), r1 = __ldg(mr + 4), r2 = __ldg(mr + 5);
+                l2w[0] = r0.x; l2w[1] = r0.y; l2w[2] = r0.z; l2w[3] = r0.w;
+                l2w[4] = r1.x; l2w[5] = r1.y; l2w[6] = r1.z; l2w[7] = r1.w;
+                l2w[8] = r2.x; l2w[9] = r2.y; l2w[10] = r2.z; l2w[11] = r2.w;
+            }
+            result.isBackface = det < 0.0f;
+            result.dst = dst;
+            result.normal = normalize3(mul_rm(l2w, n, 0.0f));
+            result.pos = rayPos + rayDir * dst;
+            result.material = &P.ModelInfo[meta.w].material;
+        }
+    }
+    return result;
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(WAVE_THREADS) k_raytrace_wave(const __grid_constant__ DevParams P, const unsigned int totalJobs,
+                                                               const unsigned int tilesX, const unsigned int ownedRows)
+{
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    WaveSmemHeader* hdr = reinterpret_cast<WaveSmemHeader*>(smemRaw);
+    float4* smemPairs = reinterpret_cast<float4*>(smemRaw + sizeof(WaveSmemHeader));
+    DevSphere* smemSpheres = reinterpret_cast<DevSphere*>(smemRaw + sizeof(WaveSmemHeader) + (size_t)P.smemPairs * sizeof(NodePair));
+
+    // ---- stage the tree tops (TMA bulk copy) and the spheres ------------------------------------------------------------
+    const uint32_t mbar = smem_u32(&hdr->mbar);
+    if (threadIdx.x == 0)
+    {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (P.smemPairs > 0 && threadIdx.x == 0)
+    {
+        const uint32_t bytes = (uint32_t)P.smemPairs * (uint32_t)sizeof(NodePair);
+        mbar_expect_tx(mbar, bytes);
+        // chunks of <= 32 KB; all complete on the same mbarrier phase
+        uint32_t off = 0;
+        while (off < bytes)
+        {
+            const uint32_t n = (bytes - off) < 32768u ? (bytes - off) : 32768u;
+            tma_bulk_g2s(smem_u32(smemPairs) + off, reinterpret_cast<const unsigned char*>(P.pairs) + off, n, mbar);
+            off += n;
+        }
+    }
+    {
+        const int nS = P.sphereCount < WAVE_MAX_SMEM_SPHERES ? P.sphereCount : WAVE_MAX_SMEM_SPHERES;
+        for (int i = threadIdx.x; i < nS; i += WAVE_THREADS) smemSpheres[i] = P.spheres[i];
+    }
+    if (P.smemPairs > 0) { while (!mbar_try_wait(mbar, 0)) { } }
+    __syncthreads();
+
+    // ---- persistent wavefront loop ------------------------------------------------------------------------------------------
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int laneMaskLt = (1u << lane) - 1u;
+    Counters cnt; cnt.rays = cnt.box = cnt.tri = cnt.sph = 0;
+
+    bool exhausted = false;          // no more jobs for this lane
+    bool havePixel = false;
+    bool pathActive = false;
+    PixelSetup px; px.camOrigin = px.focusPoint = px.camRight = px.camUp = splat3(0.0f); px.rngState = 0;
+    uint32_t rngState = 0;
+    f3 totalIncomingLight = splat3(0.0f);
+    int sample = 0, bounce = 0;
+    size_t pixelOffset = 0;
+    PathState ray; ray.pos = ray.dir = ray.transmittance = ray.totalLight = splat3(0.0f);
+
+    for (;;)
+    {
+        // [refill] lanes without a pixel take the next jobs (ballot + one atomic per warp)
+        const bool need = !havePixel && !exhausted;
+        const unsigned int needMask = __ballot_sync(0xffffffffu, need);
+        if (needMask)
+        {
+            unsigned int base = 0;
+            const int leader = __ffs(needMask) - 1;
+            if ((int)lane == leader) base = atomicAdd(P.workCounter, (unsigned int)__popc(needMask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (need)
+            {
+                const unsigned int job = base + (unsigned int)__popc(needMask & laneMaskLt);
+                if (job >= totalJobs) exhausted = true;
+                else
+                {
+                    const unsigned int tile = job >> 5, l = job & 31u;
+                    const unsigned int x = (tile % tilesX) * 8u + (l & 7u);
+                    const unsigned int r = (tile / tilesX) * 4u + (l >> 3);
+                    if (x < P.limX && r < ownedRows)
+                    {
+                        const unsigned int y = ((r / (unsigned int)P.bandRows) * (unsigned int)P.tileWorld + (unsigned int)P.tileRank) * (unsigned int)P.bandRows
+                                             + (r % (unsigned int)P.bandRows);
+                        px = SetupPixel(P, x, y);
+                        rngState = px.rngState;
+                        totalIncomingLight = splat3(0.0f);
+                        sample = 0;
+                        pixelOffset = (size_t)y * P.W + x;
+                        havePixel = true; pathActive = false;
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, havePixel) == 0u)
+        {
+            if (__ballot_sync(0xffffffffu, !exhausted) == 0u) break;
+            continue;
+        }
+
+        // [generate] start the pixel's next sample
+        if (havePixel && !pathActive && sample < P.NumRaysPerPixel)
+        {
+            GenerateCameraRay(P, px, rngState, ray);
+            bounce = 0;
+            pathActive = true;
+        }
+
+        // [intersect] + [shade]
+        if (pathActive)
+        {
+            const Hit hit = Intersect<STATS>(P, smemPairs, smemSpheres, ray.pos, ray.dir, cnt);
+            const bool cont = ShadeSegment(P, hit, ray, rngState);
+            bounce++;
+            if (!cont || bounce > P.MaxBounceCount)
+            {
+                totalIncomingLight = totalIncomingLight + ray.totalLight;        // HL:578
+                sample++;
+                pathActive = false;
+            }
+        }
+
+        // [write] pixel finished (RC:18-23)
+        if (havePixel && !pathActive && sample >= P.NumRaysPerPixel)
+        {
+            const f3 pixelCol = totalIncomingLight / __int2float_rn(P.NumRaysPerPixel);
+            P.FrameRender[pixelOffset] = make_float4(pixelCol.x, pixelCol.y, pixelCol.z, 1.0f);
+            if (P.accumulate)
+            {
+                float4 a = P.AccumulatedRender[pixelOffset];
+                a.x += pixelCol.x; a.y += pixelCol.y; a.z += pixelCol.z; a.w += 1.0f;
+                P.AccumulatedRender[pixelOffset] = a;
+            }
+            havePixel = false;
+        }
+    }
+
+    // ---- counters ---------------------------------------------------------------------------------------------------------------
+    unsigned int r = __reduce_add_sync(0xffffffffu, cnt.rays);
+    if (lane == 0) atomicAdd(P.counters + 0, (unsigned long long)r);
+    if (STATS)
+    {
+        const unsigned int b = __reduce_add_sync(0xffffffffu, cnt.box), t = __reduce_add_sync(0xffffffffu, cnt.tri), s = __reduce_add_sync(0xffffffffu, cnt.sph);
+        if (lane == 0) { atomicAdd(P.counters + 1, (unsigned long long)b); atomicAdd(P.counters + 2, (unsigned long long)t); atomicAdd(P.counters + 3, (unsigned long long)s); }
+    }
+}
+
+inline cudaError_t wave_configure()
+{
+    cudaError_t e = cudaFuncSetAttribute(k_raytrace_wave<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_raytrace_wave<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+}
+
+inline cudaError_t wave_launch(const DevParams& P, int numSMs, cudaStream_t stream, cudaEvent_t evA, cudaEvent_t evB)
+{
+    // rows of this rank's bands inside the dispatched region
+    unsigned int ownedRows = 0;
+    for (unsigned int y0 = 0, b = 0; y0 < P.limY; y0 += (unsigned int)P.bandRows, b++)
+        if ((int)(b % (unsigned int)P.tileWorld) == P.tileRank) ownedRows += (P.limY - y0) < (unsigned int)P.bandRows ? (P.limY - y0) : (unsigned int)P.bandRows;
+    const unsigned int tilesX = (P.limX + 7u) / 8u;
+    const unsigned int tileRows = (ownedRows + 3u) / 4u;
+    const unsigned long long jobs64 = (unsigned long long)tilesX * tileRows * 32ull;
+    if (jobs64 >= 0xffff0000ull) return cudaErrorInvalidValue;
+    const unsigned int totalJobs = (unsigned int)jobs64;
+
+    const size_t smemBytes = sizeof(WaveSmemHeader) + (size_t)P.smemPairs * sizeof(NodePair) + (size_t)WAVE_MAX_SMEM_SPHERES * sizeof(DevSphere);
+    cudaError_t e;
+    int ctasPerSM = 0;
+    if (P.countStats) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, k_raytrace_wave<true>, WAVE_THREADS, smemBytes);
+    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, k_raytrace_wave<false>, WAVE_THREADS, smemBytes);
+    if (e != cudaSuccess) return e;
+    if (ctasPerSM < 1) return cudaErrorInvalidConfiguration;
+    unsigned int grid = (unsigned int)(numSMs * ctasPerSM);                  // persistent: a multiple of the SM count
+    const unsigned int warpsNeeded = (totalJobs + 31u) / 32u;
+    const unsigned int ctasNeeded = (warpsNeeded + (WAVE_THREADS / 32) - 1) / (WAVE_THREADS / 32);
+    if (grid > ctasNeeded) grid = ctasNeeded ? ctasNeeded : 1;
+
+    if ((e = cudaMemsetAsync(P.workCounter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(evA, stream)) != cudaSuccess) return e;
+    if (P.countStats) k_raytrace_wave<true><<<grid, WAVE_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows);
+    else k_raytrace_wave<false><<<grid, WAVE_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    return cudaEventRecord(evB, stream);
+}
+
+} // namespace rtd

@@ -1,0 +1,244 @@
+// rt_repack.cuh — upload-time repack of the reference-layout buffers into the streams the wavefront
+// kernel reads (records defined in rt_device.cuh), plus the multi-GPU tile pack / unpack kernels.
+//
+//  Nodes (32 B, depth-first order of the reference builder, BVH.cs:89-181)
+//      -> NodePair (64 B, 64-B aligned): the two children of one inner node, numbered breadth-first per
+//         mesh; the first `hot` pairs of every mesh are gathered at the front of the array so the top of
+//         every tree is ONE contiguous range that a single TMA bulk copy stages into shared memory.
+//         Child order (A = first child, B = second) and therefore the traversal order are unchanged.
+//  Triangles (72 B) -> TriGeom (48 B: A, AB, AC, cross(AB,AC)) + TriNormals (48 B), same triangle order.
+//  ModelInfo (224 B) -> DevModel (128 B): matrix rows, BVH root, cull flag, material index.
+//  Spheres (104 B)   -> DevSphere (32 B): centre, radius, r*r.
+#pragma once
+#include "rt_device.cuh"
+#include <algorithm>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace rtd {
+
+__global__ void k_repack_tris(const RtTriangle* __restrict__ in, TriGeom* __restrict__ geom, TriNormals* __restrict__ nrm, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RtTriangle t = in[i];
+    const f3 A = load3(t.posA), B = load3(t.posB), C = load3(t.posC);
+    const f3 edgeAB = B - A, edgeAC = C - A;            // HL:190-191
+    const f3 N = cross3(edgeAB, edgeAC);                // HL:192
+    TriGeom g;
+    g.ax = A.x; g.ay = A.y; g.az = A.z; g.abx = edgeAB.x; g.aby = edgeAB.y; g.abz = edgeAB.z;
+    g.acx = edgeAC.x; g.acy = edgeAC.y; g.acz = edgeAC.z; g.nx = N.x; g.ny = N.y; g.nz = N.z;
+    geom[i] = g;
+    TriNormals q;
+    q.nax = t.normA[0]; q.nay = t.normA[1]; q.naz = t.normA[2];
+    q.nbx = t.normB[0]; q.nby = t.normB[1]; q.nbz = t.normB[2];
+    q.ncx = t.normC[0]; q.ncy = t.normC[1]; q.ncz = t.normC[2];
+    q.pad0 = q.pad1 = q.pad2 = 0.0f;
+    nrm[i] = q;
+}
+
+template <class T> struct RBuf
+{
+    T* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t n) { if (n <= cap && p) return cudaSuccess; if (p) cudaFree(p); p = nullptr; cap = 0; if (!n) return cudaSuccess; cudaError_t e = cudaMalloc(&p, n * sizeof(T)); if (e == cudaSuccess) cap = n; return e; }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct MeshRoot { int rootStart, rootCount; };
+
+struct RepackState
+{
+    RBuf<NodePair> pairs; RBuf<TriGeom> triGeom; RBuf<TriNormals> triNormals; RBuf<DevModel> models; RBuf<DevSphere> spheres;
+    std::map<std::pair<int,int>, MeshRoot> roots;     // (nodeOffset, triOffset) -> encoded root
+    int smemPairs = 0;
+    size_t totalPairs = 0;
+
+    void release() { pairs.release(); triGeom.release(); triNormals.release(); models.release(); spheres.release(); roots.clear(); }
+
+    // Breadth-first renumbering of every distinct mesh referenced by the first modelCount models.
+    cudaError_t buildScene(const std::vector<RtNode>& nodes, const std::vector<RtModel>& mdl, int modelCount,
+                           const RtTriangle* dTris, size_t triCount, int smemOpt, cudaStream_t stream, std::string& msg)
+    {
+        roots.clear(); smemPairs = 0; totalPairs = 0;
+        struct Mesh { int nodeOffset, triOffset; std::vector<int> order; /* global node index of first child, in BFS pair order */ size_t hot = 0, hotBase = 0, coldBase = 0; };
+        std::vector<Mesh> meshes;
+        for (int i = 0; i < modelCount; i++)
+        {
+            const std::pair<int,int> key(mdl[i].nodeOffset, mdl[i].triOffset);
+            if (roots.count(key)) continue;
+            roots[key] = MeshRoot{0, 0};
+            Mesh m; m.nodeOffset = key.first; m.triOffset = key.second;
+            const RtNode& root = nodes[m.nodeOffset];
+            if (root.triangleCount <= 0)
+            {
+                // BFS over inner nodes; order[k] = global index of the first child of the k-th inner node met
+                std::vector<int> queue; queue.push_back(m.nodeOffset);
+                for (size_t q = 0; q < queue.size(); q++)
+                {
+                    const RtNode& nd = nodes[queue[q]];
+                    const long long a = (long long)m.nodeOffset + nd.startIndex;
+                    if (a < 0 || a + 1 >= (long long)nodes.size()) { msg = "BVH child index out of range"; return cudaSuccess; }
+                    if (queue.size() > nodes.size()) { msg = "BVH has a cycle"; return cudaSuccess; }
+                    m.order.push_back((int)a);
+                    if (nodes[a].triangleCount <= 0) queue.push_back((int)a);
+                    if (nodes[a + 1].triangleCount <= 0) queue.push_back((int)a + 1);
+                }
+            }
+            meshes.push_back(std::move(m));
+        }
+        for (auto& m : meshes) totalPairs += m.order.size();
+
+        // shared-memory budget (pairs) split over the meshes by water-filling, smallest mesh first
+        size_t budget = smemOpt < 0 ? 1024 : (size_t)smemOpt;
+        if (budget > 3072) budget = 3072;                                   // 192 KB of the 227 KB a CTA may own
+        {
+            std::vector<size_t> idx(meshes.size());
+            for (size_t i = 0; i < idx.size(); i++) idx[i] = i;
+            std::sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return meshes[a].order.size() < meshes[b].order.size(); });
+            size_t left = budget;
+            for (size_t k = 0; k < idx.size(); k++)
+            {
+                const size_t share = left / (idx.size() - k);
+                Mesh& m = meshes[idx[k]];
+                m.hot = std::min(share, m.order.size());
+                left -= m.hot;
+            }
+        }
+        size_t hotTotal = 0; for (auto& m : meshes) { m.hotBase = hotTotal; hotTotal += m.hot; }
+        size_t coldTotal = hotTotal; for (auto& m : meshes) { m.coldBase = coldTotal; coldTotal += m.order.size() - m.hot; }
+        smemPairs = (int)hotTotal;
+
+        std::vector<NodePair> out(totalPairs);
+        for (auto& m : meshes)
+        {
+            auto globalPair = [&](size_t local) { return (int)(local < m.hot ? m.hotBase + local : m.coldBase + (local - m.hot)); };
+            // second pass in the same BFS order: the k-th inner node met owns pair k; its inner children get the next free ids
+            size_t nextChildPair = 1;       // pair 0 belongs to the root
+            const RtNode& root = nodes[m.nodeOffset];
+            MeshRoot r;
+            if (root.triangleCount > 0) { r.rootStart = m.triOffset + root.startIndex; r.rootCount = root.triangleCount; }
+            else { r.rootStart = globalPair(0); r.rootCount = 0; }
+            roots[std::make_pair(m.nodeOffset, m.triOffset)] = r;
+            for (size_t k = 0; k < m.order.size(); k++)
+            {
+                const RtNode& A = nodes[m.order[k]];
+                const RtNode& B = nodes[m.order[k] + 1];
+                NodePair p;
+                p.aMinX = A.boundsMin[0]; p.aMinY = A.boundsMin[1]; p.aMinZ = A.boundsMin[2];
+                p.aMaxX = A.boundsMax[0]; p.aMaxY = A.boundsMax[1]; p.aMaxZ = A.boundsMax[2];
+                p.bMinX = B.boundsMin[0]; p.bMinY = B.boundsMin[1]; p.bMinZ = B.boundsMin[2];
+                p.bMaxX = B.boundsMax[0]; p.bMaxY = B.boundsMax[1]; p.bMaxZ = B.boundsMax[2];
+                if (A.triangleCount > 0) { p.aStart = m.triOffset + A.startIndex; p.aCount = A.triangleCount; if (p.aStart < 0 || (size_t)p.aStart + p.aCount > triCount) { msg = "BVH leaf triangle range out of bounds"; return cudaSuccess; } }
+                else { p.aStart = globalPair(nextChildPair++); p.aCount = 0; }
+                if (B.triangleCount > 0) { p.bStart = m.triOffset + B.startIndex; p.bCount = B.triangleCount; if (p.bStart < 0 || (size_t)p.bStart + p.bCount > triCount) { msg = "BVH leaf triangle range out of bounds"; return cudaSuccess; } }
+                else { p.bStart = globalPair(nextChildPair++); p.bCount = 0; }
+                out[globalPair(k)] = p;
+            }
+            if (root.triangleCount > 0 && ((size_t)r.rootStart + r.rootCount > triCount)) { msg = "BVH root triangle range out of bounds"; return cudaSuccess; }
+        }
+        cudaError_t e;
+        if ((e = pairs.ensure(std::max<size_t>(totalPairs, 1))) != cudaSuccess) return e;
+        if (totalPairs && (e = cudaMemcpyAsync(pairs.p, out.data(), totalPairs * sizeof(NodePair), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;      // `out` is a local
+        if ((e = triGeom.ensure(std::max<size_t>(triCount, 1))) != cudaSuccess) return e;
+        if ((e = triNormals.ensure(std::max<size_t>(triCount, 1))) != cudaSuccess) return e;
+        if (triCount)
+        {
+            k_repack_tris<<<(unsigned)((triCount + 255) / 256), 256, 0, stream>>>(dTris, triGeom.p, triNormals.p, triCount);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+
+    cudaError_t buildModels(const std::vector<RtModel>& mdl, int modelCount, cudaStream_t stream)
+    {
+        std::vector<DevModel> out(std::max(modelCount, 1));
+        for (int i = 0; i < modelCount; i++)
+        {
+            DevModel d; memset(&d, 0, sizeof(d));
+            for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++)
+            {
+                d.w2l[r * 4 + c] = mdl[i].worldToLocal[c * 4 + r];
+                d.l2w[r * 4 + c] = mdl[i].localToWorld[c * 4 + r];
+            }
+            const MeshRoot& r = roots[std::make_pair(mdl[i].nodeOffset, mdl[i].triOffset)];
+            d.rootStart = r.rootStart; d.rootCount = r.rootCount;
+            d.cullBackface = mdl[i].material.flag != RT_MATERIAL_GLASS;       // HL:355
+            d.matIndex = i;
+            out[i] = d;
+        }
+        cudaError_t e;
+        if ((e = models.ensure(out.size())) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(models.p, out.data(), out.size() * sizeof(DevModel), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+        return cudaStreamSynchronize(stream);
+    }
+
+    cudaError_t buildSpheres(const std::vector<RtSphere>& sp, cudaStream_t stream)
+    {
+        std::vector<DevSphere> out(std::max<size_t>(sp.size(), 1));
+        for (size_t i = 0; i < sp.size(); i++)
+        {
+            DevSphere d; memset(&d, 0, sizeof(d));
+            d.cx = sp[i].centre[0]; d.cy = sp[i].centre[1]; d.cz = sp[i].centre[2]; d.radius = sp[i].radius;
+            // r*r is one IEEE multiply (HL:299).  Host code is built without FMA contraction, so this is that product.
+            volatile float r = sp[i].radius; d.r2 = r * r;
+            out[i] = d;
+        }
+        cudaError_t e;
+        if ((e = spheres.ensure(out.size())) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(spheres.p, out.data(), out.size() * sizeof(DevSphere), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+        return cudaStreamSynchronize(stream);
+    }
+};
+
+// ---- multi-GPU tile staging --------------------------------------------------------------------------------------------
+// TileSend layout: [rowsPerRank rows of FrameRender | rowsPerRank rows of AccumulatedRender], rows in ascending
+// global y of the bands this rank owns (band b belongs to rank b % world); ranks owning fewer rows pad.
+
+__device__ __forceinline__ int owned_row_to_y(int r, int rank, int world, int bandRows)
+{
+    return ((r / bandRows) * world + rank) * bandRows + (r % bandRows);
+}
+
+__global__ void k_pack_tile(const float4* __restrict__ frame, const float4* __restrict__ accum, float4* __restrict__ send,
+                            int W, int H, int rank, int world, int bandRows, int rowsPerRank)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (x >= W) return;
+    const int y = owned_row_to_y(r, rank, world, bandRows);
+    const size_t dst = (size_t)r * W + x;
+    const size_t half = (size_t)rowsPerRank * W;
+    if (y < H) { send[dst] = frame[(size_t)y * W + x]; send[half + dst] = accum[(size_t)y * W + x]; }
+    else { send[dst] = make_float4(0, 0, 0, 0); send[half + dst] = make_float4(0, 0, 0, 0); }
+}
+
+__global__ void k_unpack_tiles(const float4* __restrict__ recv, float4* __restrict__ frame, float4* __restrict__ accum,
+                               int W, int H, int world, int bandRows, int rowsPerRank)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    const int rank = blockIdx.z;
+    if (x >= W) return;
+    const int y = owned_row_to_y(r, rank, world, bandRows);
+    if (y >= H) return;
+    const size_t half = (size_t)rowsPerRank * W;
+    const float4* src = recv + (size_t)rank * 2 * half;
+    frame[(size_t)y * W + x] = src[(size_t)r * W + x];
+    accum[(size_t)y * W + x] = src[half + (size_t)r * W + x];
+}
+
+inline void launch_pack_tile(const float4* frame, const float4* accum, float4* send, int W, int H, int rank, int world, int bandRows, int rowsPerRank, cudaStream_t s)
+{
+    dim3 grid((W + 255) / 256, rowsPerRank, 1);
+    k_pack_tile<<<grid, 256, 0, s>>>(frame, accum, send, W, H, rank, world, bandRows, rowsPerRank);
+}
+inline void launch_unpack_tiles(const float4* recv, float4* frame, float4* accum, int W, int H, int world, int bandRows, int rowsPerRank, cudaStream_t s)
+{
+    dim3 grid((W + 255) / 256, rowsPerRank, world);
+    k_unpack_tiles<<<grid, 256, 0, s>>>(recv, frame, accum, W, H, world, bandRows, rowsPerRank);
+}
+
+} // namespace rtd

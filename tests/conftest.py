@@ -1,0 +1,72 @@
+"""Shared fixtures.  Markers: `gpu` = needs a B200 (run by the driver with `-m gpu` on the GPU box)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+ORACLE_LIB = os.path.join(REPO, "oracle", "liboracle.so")
+CUDA_LIB = os.path.join(REPO, "ray_tracing_b200", "librt_b200.so")
+GOLDEN = os.path.join(REPO, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Make sure the native libraries exist (they travel pre-built to the GPU box; here we build on demand)."""
+    from ray_tracing_b200 import build
+    if not (os.path.exists(ORACLE_LIB) and os.path.exists(build.LIB_HOST)):
+        build.build_host()
+        build.build_oracle()
+    if not os.path.exists(CUDA_LIB):
+        build.build_cuda()
+
+
+@pytest.fixture(scope="session")
+def oracle_path():
+    return ORACLE_LIB
+
+
+@pytest.fixture(scope="session")
+def cuda_path():
+    return CUDA_LIB
+
+
+def render(backend, scene, frames=1, width=None, height=None, options=None, want_stats=False, tile=None):
+    """Drive `frames` RenderFrame() calls of the host manager against a backend library; returns (frame, accumulated[, stats])."""
+    import ray_tracing_b200 as rt
+    from ray_tracing_b200 import scenes
+    mgr = rt.RayComputeManager(backend)
+    scenes.apply(scene, mgr, width, height)
+    ctx = mgr.context
+    for k, v in (options or {}).items():
+        ctx.set_option(k, v)
+    if tile:
+        ctx.set_tile(*tile)
+    mgr.OnEnable()
+    ctx.reset_stats()
+    for _ in range(frames):
+        mgr.RenderFrame()
+    out = (mgr.raytraceFrameTex, mgr.accumulatedResult)
+    if want_stats:
+        out = out + (ctx.stats(),)
+    mgr.OnDestroy()
+    return out
+
+
+def assert_bit_equal(a: np.ndarray, b: np.ndarray, what=""):
+    """Bitwise comparison (NaN payloads included) with a readable report."""
+    ai, bi = a.view(np.uint32), b.view(np.uint32)
+    if np.array_equal(ai, bi):
+        return
+    bad = np.argwhere(ai != bi)
+    diff = np.abs(a.astype(np.float64) - b.astype(np.float64))
+    raise AssertionError(f"{what}: {len(bad)} of {ai.size} values differ bitwise; max |Δ| = {np.nanmax(diff):.3e}; first at {bad[0].tolist()} "
+                         f"({a[tuple(bad[0])]!r} vs {b[tuple(bad[0])]!r})")
