@@ -149,6 +149,8 @@ const char* rtLastError(const RtContext* c) { return c ? c->err.c_str() : g_crea
 int rtSetStream(RtContext* c, void* s)
 {
     if (!c) return RT_E_INVALID;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));           // work already queued finishes before the switch
     c->stream = s ? (cudaStream_t)s : c->ownStream;
     return RT_OK;
 }
@@ -356,7 +358,8 @@ int rtDispatch(RtContext* c, int kernelIndex, int gx, int gy, int gz)
     }
     if (kernelIndex != RT_KERNEL_RAYTRACE) return fail(c, RT_E_INVALID, "rtDispatch: kernelIndex must be 0 (RayTrace) or 1 (ResetAccumulated)");
     if (limX == 0 || limY == 0) return RT_OK;
-    if (c->P.NumRaysPerPixel < 0 ) return fail(c, RT_E_STATE, "rtDispatch: NumRaysPerPixel is negative");
+    if (c->P.NumRaysPerPixel < 0) return fail(c, RT_E_STATE, "rtDispatch: NumRaysPerPixel is negative");
+    if (c->P.MaxBounceCount < 0) return fail(c, RT_E_STATE, "rtDispatch: MaxBounceCount is negative (the reference clamps it to [0, 32], RCM:15)");
 
     int rc = prepareScene(c);
     if (rc != RT_OK) return rc;

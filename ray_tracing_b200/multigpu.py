@@ -1,0 +1,92 @@
+"""Row-band tiling of one frame over several GPUs.
+
+The image is cut into bands of `band_rows` rows; band b belongs to rank b % world.  Every rank holds the whole
+scene, traces only its bands (pixels keep their GLOBAL index, so seeds and therefore results equal the 1-GPU
+run), and after each frame ONE all-gather over NCCL/NVLink hands every rank the finished tiles of all ranks;
+a local scatter puts them back at their global position.
+
+`TiledRenderer` is the device path (C-ABI rtPackTile -> torch.distributed all_gather_into_tensor on views of
+the context's own device buffers -> rtUnpackTiles).  The host-side helpers (owned_rows, pack_rows,
+unpack_rows) state the same layout in numpy; the world_size-2 gloo test uses them with CPU tensors.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def owned_rows(height: int, rank: int, world: int, band_rows: int) -> np.ndarray:
+    """Global y of every row rank owns, ascending (band b -> rank b % world)."""
+    y = np.arange(height)
+    return y[(y // band_rows) % world == rank]
+
+
+def rows_per_rank(height: int, world: int, band_rows: int) -> int:
+    """Rows in the all-gather contribution of every rank = the largest share (rank 0's); others pad."""
+    return int(owned_rows(height, 0, world, band_rows).size)
+
+
+def pack_rows(frame: np.ndarray, accum: np.ndarray, rank: int, world: int, band_rows: int) -> np.ndarray:
+    """[frame bands | accumulated bands] of one rank, padded to rows_per_rank — the TileSend layout."""
+    h, w = frame.shape[:2]
+    n = rows_per_rank(h, world, band_rows)
+    out = np.zeros((2, n, w, 4), dtype=np.float32)
+    ys = owned_rows(h, rank, world, band_rows)
+    out[0, :ys.size] = frame[ys]
+    out[1, :ys.size] = accum[ys]
+    return out
+
+
+def unpack_rows(gathered: np.ndarray, height: int, world: int, band_rows: int):
+    """Inverse of pack_rows over the rank-major all-gather result (world, 2, rows_per_rank, W, 4)."""
+    w = gathered.shape[3]
+    frame = np.zeros((height, w, 4), dtype=np.float32)
+    accum = np.zeros((height, w, 4), dtype=np.float32)
+    for r in range(world):
+        ys = owned_rows(height, r, world, band_rows)
+        frame[ys] = gathered[r, 0, :ys.size]
+        accum[ys] = gathered[r, 1, :ys.size]
+    return frame, accum
+
+
+class _DevView:
+    """Minimal __cuda_array_interface__ holder so torch can view a raw device pointer without copying."""
+
+    def __init__(self, ptr: int, nfloats: int):
+        self.__cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+
+
+class TiledRenderer:
+    """One rank of a row-tiled render: manager + per-frame all-gather of finished tiles (NCCL)."""
+
+    def __init__(self, mgr, rank: int, world: int, band_rows: int = 8, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.mgr, self.rank, self.world, self.band_rows = mgr, rank, world, band_rows
+        self.ctx = mgr.context
+        self.ctx.set_tile(rank, world, band_rows)
+        self.device = device
+        self._send = self._recv = None
+        # one torch stream carries everything: trace -> pack -> all-gather -> unpack are ordered on it
+        self.stream = torch.cuda.Stream(device=device)
+        self.ctx.set_stream(self.stream.cuda_stream)
+
+    def _views(self):
+        if self._send is None:
+            torch = self.torch
+            ps, ns = self.ctx.device_pointer("TileSend")
+            pr, nr = self.ctx.device_pointer("TileRecv")
+            self._send = torch.as_tensor(_DevView(ps, ns // 4), device=self.device)
+            self._recv = torch.as_tensor(_DevView(pr, nr // 4), device=self.device)
+        return self._send, self._recv
+
+    def render_frame(self):
+        """RenderFrame on this rank's bands, then the single all-gather of the frame's tiles."""
+        with self.torch.cuda.stream(self.stream):
+            self.mgr.RenderFrame()
+            if self.world == 1:
+                return
+            send, recv = self._views()
+            self.ctx.pack_tile()
+            self.dist.all_gather_into_tensor(recv, send)
+            self.ctx.unpack_tiles()

@@ -1,0 +1,213 @@
+"""CPU tests of the oracle (the CPU restatement of RayCommon.hlsl): pinned by the integer RNG known answers,
+analytic primitive checks, accuracy of the pinned transcendental routines, and the committed Cornell fixture.
+"""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ORACLE_LIB, assert_bit_equal, render
+from ray_tracing_b200 import scenes
+from ray_tracing_b200.capi import TRIANGLE_DTYPE
+
+
+@pytest.fixture(scope="module")
+def L():
+    lib = C.CDLL(ORACLE_LIB)
+    lib.orNextRandom.restype = C.c_uint
+    lib.orRayBoundingBoxDst.restype = C.c_float
+    return lib
+
+
+def f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+# ---- RNG: RayCommon.hlsl:127-138 ------------------------------------------------------------------------------------
+
+def test_pcg_known_answers(L):
+    kat = json.load(open(os.path.join(GOLDEN, "pcg_kat.json")))
+    assert len(kat) >= 4
+    for case in kat:
+        s = C.c_uint(case["seed"])
+        for d in case["draws"]:
+            v = C.c_float()
+            r = L.orNextRandom(C.byref(s), C.byref(v))
+            assert s.value == d["state"] and r == d["result"]
+            assert np.float32(v.value).view(np.uint32) == d["value_bits"]
+
+
+def test_pcg_survey_table(L):
+    # SURVEY.md Appendix A, hand-derived from RayCommon.hlsl:127-137 (seed 731738 = pixel 0, Frame 1, renderSeed 12345)
+    table = {0: [(2891336453, 129708002), (1192405134, 582399676), (568162667, 1006035121)],
+             731738: [(2218726055, 3682287243), (3587709976, 541555797), (2028031997, 2363192455)],
+             4294967295: [(2143540048, 3861530882), (1285874325, 1233271289), (1463271774, 3660874854)]}
+    for seed, rows in table.items():
+        s = C.c_uint(seed)
+        for st, res in rows:
+            assert L.orNextRandom(C.byref(s), None) == res and s.value == st
+
+
+def test_random_value_is_inclusive_unit_interval(L):
+    # quirk Q4: value = float(r) * 2^-32 reaches exactly 1.0 for r >= 2^32 - 128
+    assert np.float32(np.float32(4294967295) / np.float32(4294967296.0)) == np.float32(1.0)
+
+
+# ---- pinned transcendental routines ------------------------------------------------------------------------------------
+
+def _math(L, fn, x, y=None):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.ascontiguousarray(x if y is None else y, dtype=np.float32)
+    out = np.empty_like(x)
+    L.orMath(fn, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), len(x))
+    return out
+
+
+def _ulp_err(a, ref):
+    sp = np.spacing(np.abs(ref.astype(np.float32))).astype(np.float64)
+    return np.abs(a.astype(np.float64) - ref) / sp
+
+
+def test_log_exp_accuracy(L):
+    rng = np.random.default_rng(0)
+    x = (rng.integers(1, 2 ** 32, 400000).astype(np.float32) / np.float32(2 ** 32))      # RandomValue's range
+    assert _ulp_err(_math(L, 0, x), np.log(x.astype(np.float64))).max() < 1.0
+    x = np.exp(rng.uniform(-80, 80, 200000)).astype(np.float32)
+    assert _ulp_err(_math(L, 0, x), np.log(x.astype(np.float64))).max() < 1.0
+    x = rng.uniform(-85, 85, 200000).astype(np.float32)
+    assert _ulp_err(_math(L, 1, x), np.exp(x.astype(np.float64))).max() < 1.0
+
+
+def test_sin_cos_accuracy(L):
+    rng = np.random.default_rng(1)
+    x = rng.uniform(0, 6.2832, 400000).astype(np.float32)                                # the path's range: [0, 2π]
+    assert np.abs(_math(L, 2, x) - np.sin(x.astype(np.float64))).max() < 1.5e-7
+    assert np.abs(_math(L, 3, x) - np.cos(x.astype(np.float64))).max() < 1.5e-7
+    x = rng.uniform(-1000, 1000, 200000).astype(np.float32)
+    assert np.abs(_math(L, 2, x) - np.sin(x.astype(np.float64))).max() < 2e-7
+    assert np.abs(_math(L, 3, x) - np.cos(x.astype(np.float64))).max() < 2e-7
+
+
+def test_math_special_values(L):
+    lg = _math(L, 0, [0.0, -1.0, np.inf, 1.0])
+    assert lg[0] == -np.inf and np.isnan(lg[1]) and lg[2] == np.inf and lg[3] == 0.0      # log(0) = -inf feeds Box–Muller (Q4)
+    ex = _math(L, 1, [-np.inf, np.inf, 0.0, -200.0])
+    assert ex[0] == 0.0 and ex[1] == np.inf and ex[2] == 1.0 and ex[3] == 0.0
+    pw = _math(L, 4, [0.0, 1.0, 4.0, 0.0], [0.35, 0.35, 0.5, 2.0])
+    assert pw[0] == 0.0 and pw[1] == 1.0 and abs(pw[2] - 2.0) < 1e-6 and pw[3] == 0.0
+
+
+# ---- primitives --------------------------------------------------------------------------------------------------------------
+
+def test_ray_box(L):
+    bmin, bmax = f3((-1, -1, -1)), f3((1, 1, 1))
+    assert L.orRayBoundingBoxDst(f3((0, 0, -5)), f3((0, 0, 1)), bmin, bmax) == 4.0          # entry distance
+    assert L.orRayBoundingBoxDst(f3((0, 0, 0)), f3((0, 0, 1)), bmin, bmax) == 0.0           # inside -> 0 (RayCommon.hlsl:229)
+    assert L.orRayBoundingBoxDst(f3((0, 0, 5)), f3((0, 0, 1)), bmin, bmax) == np.inf        # behind
+    assert L.orRayBoundingBoxDst(f3((3, 0, -5)), f3((0, 0, 1)), bmin, bmax) == np.inf       # miss, dir component 0 -> inf slabs
+
+
+def _tri(a, b, c, n=(0, 0, -1)):
+    t = np.zeros((), dtype=TRIANGLE_DTYPE)
+    t["posA"], t["posB"], t["posC"] = a, b, c
+    t["normA"] = t["normB"] = t["normC"] = n
+    return t
+
+
+def test_ray_triangle(L):
+    L.orRayTriangle.restype = C.c_int
+    # front face <=> dot(dir, cross(B-A, C-A)) < 0   (RayCommon.hlsl:192-195,206)
+    t = _tri((-1, -1, 0), (-1, 1, 0), (1, -1, 0))
+    dst, n = C.c_float(), (C.c_float * 3)()
+    r = L.orRayTriangle(f3((-0.5, -0.5, -3)), f3((0, 0, 1)), t.ctypes.data_as(C.c_void_p), 1, C.byref(dst), n)
+    assert r == 1 and dst.value == 3.0 and list(n) == [0.0, 0.0, -1.0]
+    # from behind: culled when cullBackface, hit + backface + flipped normal otherwise
+    r = L.orRayTriangle(f3((-0.5, -0.5, 3)), f3((0, 0, -1)), t.ctypes.data_as(C.c_void_p), 1, C.byref(dst), n)
+    assert (r & 1) == 0
+    r = L.orRayTriangle(f3((-0.5, -0.5, 3)), f3((0, 0, -1)), t.ctypes.data_as(C.c_void_p), 0, C.byref(dst), n)
+    assert r == 3 and dst.value == 3.0 and list(n) == [0.0, 0.0, 1.0]
+    # outside the triangle, and a hit behind the origin
+    assert (L.orRayTriangle(f3((0.9, 0.9, -3)), f3((0, 0, 1)), t.ctypes.data_as(C.c_void_p), 0, C.byref(dst), n) & 1) == 0
+    assert (L.orRayTriangle(f3((-0.5, -0.5, 3)), f3((0, 0, 1)), t.ctypes.data_as(C.c_void_p), 0, C.byref(dst), n) & 1) == 0
+
+
+def test_ray_sphere(L):
+    L.orRaySphere.restype = C.c_int
+    dst, n = C.c_float(), (C.c_float * 3)()
+    r = L.orRaySphere(f3((0, 0, -5)), f3((0, 0, 1)), f3((0, 0, 0)), C.c_float(1.0), C.byref(dst), n)
+    assert r == 1 and dst.value == 4.0 and list(n) == [0.0, 0.0, -1.0]
+    r = L.orRaySphere(f3((0, 0, 0)), f3((0, 0, 1)), f3((0, 0, 0)), C.c_float(1.0), C.byref(dst), n)     # inside: far hit, backface, inward normal
+    assert r == 3 and dst.value == 1.0 and list(n) == [0.0, 0.0, -1.0]
+    assert (L.orRaySphere(f3((0, 0, 5)), f3((0, 0, 1)), f3((0, 0, 0)), C.c_float(1.0), C.byref(dst), n) & 1) == 0
+    assert (L.orRaySphere(f3((2, 0, -5)), f3((0, 0, 1)), f3((0, 0, 0)), C.c_float(1.0), C.byref(dst), n) & 1) == 0
+
+
+# ---- whole-path checks ----------------------------------------------------------------------------------------------------------
+
+def test_cornell_golden_fixture():
+    fix = json.load(open(os.path.join(GOLDEN, "cornell_c1.json")))
+    sc = scenes.cornell_spheres(256, 256, 4, 1)
+    frame, accum, st = render(ORACLE_LIB, sc, frames=2, want_stats=True)
+    assert st["rays"] == fix["rays"] and st["sphereTests"] == fix["sphereTests"]
+    for p in fix["probes"]:
+        assert [int(v) for v in accum[p["y"], p["x"]].view(np.uint32)] == p["accum_bits"]
+    assert hashlib.sha256(accum.tobytes()).hexdigest() == fix["accum_sha256"]
+    assert hashlib.sha256(frame.tobytes()).hexdigest() == fix["frame_sha256"]
+    assert np.all(accum[..., 3] == 2.0)                         # quirk Q9: alpha of the SUM buffer = frame count
+
+
+def _furnace(emission_strength, diffuse, spp, bounces):
+    s = np.zeros(1, dtype=scenes.SPHERE_DTYPE)
+    s["centre"] = (0, 0, 0)
+    s["radius"] = 10.0
+    s["material"][0] = scenes.material(diffuse=diffuse, emission=(1, 1, 1), emissionStrength=emission_strength, specularProbability=0.0)
+    return scenes.Scene(name="furnace", width=32, height=32, spheres=s, settings=dict(maxBounceCount=bounces, numRaysPerPixel=spp))
+
+
+def test_furnace_black_emitter_is_exact():
+    # camera inside one emissive sphere with zero albedo: every path is  emission * 1  then dies in the roulette
+    frame, accum = render(ORACLE_LIB, _furnace(2.5, (0, 0, 0), 4, 8))
+    assert np.all(frame[..., :3] == np.float32(2.5)) and np.all(frame[..., 3] == 1.0)
+
+
+def test_furnace_grey_converges_to_geometric_series():
+    # L = e + a L  ->  e / (1 - a); the roulette keeps the estimator unbiased up to the bounce cut-off (a^33 ~ 1e-10)
+    frame, _ = render(ORACLE_LIB, _furnace(1.0, (0.5, 0.5, 0.5), 256, 32))
+    assert abs(frame[..., :3].mean() - 2.0) < 0.02
+
+
+def test_accumulate_flag_and_partial_dispatch(oracle_path):
+    import ray_tracing_b200 as rt
+    sc = scenes.cornell_spheres(40, 24, 2, 1)
+    mgr = rt.RayComputeManager(oracle_path)
+    scenes.apply(sc, mgr)
+    mgr.OnEnable()
+    mgr.RenderFrame()
+    a1 = mgr.accumulatedResult
+    mgr.accumulate = False
+    mgr.RenderFrame()
+    assert_bit_equal(mgr.accumulatedResult, a1, "accumulate=false must leave the SUM buffer untouched")
+    assert mgr.numAccumulatedFrames == 2                       # RayComputeManager.cs:94: only counted when accumulating
+    # a dispatch of 2x1 groups touches only 16x8 pixels (threads outside were never launched)
+    ctx = mgr.context
+    ctx.dispatch(1, (40 + 7) // 8, (24 + 7) // 8, 1)            # ResetAccumulated over the whole image
+    ctx.set_bool("accumulate", True)
+    ctx.dispatch(0, 2, 1, 1)
+    acc = mgr.accumulatedResult
+    assert np.all(acc[:8, :16, 3] == 1.0) and np.all(acc[8:, :, 3] == 0.0) and np.all(acc[:, 16:, 3] == 0.0)
+
+
+def test_seed_depends_on_frame_and_render_seed(oracle_path):
+    sc = scenes.cornell_spheres(32, 32, 3, 2)
+    f1, _ = render(oracle_path, sc, frames=1)
+    f2, _ = render(oracle_path, sc, frames=2)                   # FrameRender of frame 2
+    assert not np.array_equal(f1, f2)
+    sc.settings["renderSeed"] = 999
+    f3_, _ = render(oracle_path, sc, frames=1)
+    assert not np.array_equal(f1, f3_)
+    sc.settings["renderSeed"] = 12345
+    f4, _ = render(oracle_path, sc, frames=1)
+    assert_bit_equal(f1, f4, "same seed, same frame")
