@@ -179,6 +179,10 @@ def run_gpu(args, w):
     ctx, stream = tiled.ctx, tiled.stream
     if args.kernel is not None:
         ctx.set_option("kernel", args.kernel)
+    if args.pool_slots is not None:
+        ctx.set_option("poolSlots", args.pool_slots)
+    if args.smem_nodes is not None:
+        ctx.set_option("smemNodes", args.smem_nodes)
     mgr.OnEnable()
     model_count = len(sc.models)
 
@@ -281,7 +285,9 @@ def run_gpu(args, w):
             "config": {"workload": w["desc"], "rays_per_frame": rays // args.steps, "spp_per_frame": w["spp"],
                        "tiling": f"row bands of {args.band_rows} rows round-robin over {world} GPU(s), one all-gather per frame" if world > 1 else "single GPU",
                        "l2": "flushed between steps (256 MiB write inside the timed region)",
-                       "kernel": "k_raytrace_wave (persistent wavefront)" if args.kernel in (None, 1) else "k_raytrace_mega"},
+                       "kernel": {None: "k_raytrace_pool (persistent wavefront, per-warp path pools)", 2: "k_raytrace_pool (persistent wavefront, per-warp path pools)",
+                                  1: "k_raytrace_wave (persistent threads)", 0: "k_raytrace_mega (reference-shaped)"}[args.kernel],
+                       "pool_slots": args.pool_slots, "smem_nodes": args.smem_nodes},
             "ms_per_frame": round(ms_total / args.steps, 4),
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": W * H * 16,
@@ -311,7 +317,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cornell64", choices=sorted(WORKLOADS))
     ap.add_argument("--band-rows", type=int, default=8)
-    ap.add_argument("--kernel", type=int, default=None, help="0 = megakernel, 1 = persistent wavefront (default)")
+    ap.add_argument("--kernel", type=int, default=None, help="0 = megakernel, 1 = persistent threads, 2 = pooled wavefront (default)")
+    ap.add_argument("--pool-slots", type=int, default=None, help="paths per warp pool of kernel 2 (64, 96, 128)")
+    ap.add_argument("--smem-nodes", type=int, default=None, help="node pairs staged in shared memory (-1 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

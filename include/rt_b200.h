@@ -117,9 +117,11 @@ int rtUnpackTiles(RtContext* ctx);
 int rtGetDevicePointer(RtContext* ctx, const char* name, void** devPtr, size_t* bytes);
 
 /* Tuning / instrumentation switches.  name ∈
- *   "kernel"      0 = reference-shaped per-pixel megakernel, 1 = persistent-thread wavefront (default)
+ *   "kernel"      0 = reference-shaped per-pixel megakernel, 1 = persistent threads (one path per lane),
+ *                 2 = persistent-thread wavefront with per-warp path pools, sorting and ray compaction (default)
  *   "countStats"  1 = also count box / triangle tests (HL:254,271) — slower, off by default
- *   "smemNodes"   number of top-of-tree node pairs staged in shared memory by TMA bulk copy (0 = off)
+ *   "smemNodes"   number of top-of-tree node pairs staged in shared memory by TMA bulk copy (0 = off, -1 = auto)
+ *   "poolSlots"   paths per warp pool of kernel 2: 64, 96 or 128
  * Unknown names return RT_E_UNKNOWN_NAME. */
 int rtSetOption(RtContext* ctx, const char* name, int value);
 

@@ -8,6 +8,7 @@
 #include "../../include/rt_b200.h"
 #include "rt_kernel_mega.cuh"
 #include "rt_kernel_wave.cuh"
+#include "rt_kernel_pool.cuh"
 #include "rt_repack.cuh"
 
 #include <cstdio>
@@ -58,7 +59,7 @@ struct RtContext
     int tileRank = 0, tileWorld = 1, bandRows = 1;
 
     // options
-    int optKernel = 1, optCountStats = 0, optSmemPairs = -1;   // -1 = automatic
+    int optKernel = 2, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64;   // smemPairs -1 = automatic
 
     // counters / timing
     unsigned long long* dCounters = nullptr;   // 4
@@ -123,6 +124,7 @@ int rtCreate(RtContext** out, int device)
     cudaMemset(c->dCounters, 0, 4 * sizeof(unsigned long long));
     cudaMemset(c->dWork, 0, 64);
     if ((e = wave_configure()) != cudaSuccess) return bail(e, "cudaFuncSetAttribute");
+    if ((e = pool_configure()) != cudaSuccess) return bail(e, "cudaFuncSetAttribute");
     *out = c;
     return RT_OK;
 }
@@ -299,9 +301,10 @@ int rtSetOption(RtContext* c, const char* name, int value)
 {
     if (!c || !name) return fail(c, RT_E_INVALID, "rtSetOption: bad argument");
     const std::string n(name);
-    if (n == "kernel") { if (value < 0 || value > 1) return fail(c, RT_E_INVALID, "rtSetOption: kernel must be 0 or 1"); c->optKernel = value; }
+    if (n == "kernel") { if (value < 0 || value > 2) return fail(c, RT_E_INVALID, "rtSetOption: kernel must be 0, 1 or 2"); c->optKernel = value; }
     else if (n == "countStats") c->optCountStats = value != 0;
-    else if (n == "smemNodes") { c->optSmemPairs = value; c->sceneDirty = true; }
+    else if (n == "smemNodes") c->optSmemPairs = value;
+    else if (n == "poolSlots") { if (value != 64 && value != 96 && value != 128) return fail(c, RT_E_INVALID, "rtSetOption: poolSlots must be 64, 96 or 128"); c->optPoolSlots = value; }
     else return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetOption: unknown option ") + name);
     return RT_OK;
 }
@@ -316,10 +319,15 @@ static int prepareScene(RtContext* c)
         if (m.nodeOffset < 0 || (size_t)m.nodeOffset >= c->nodes.count || m.triOffset < 0 || (size_t)m.triOffset > c->tris.count)
             return fail(c, RT_E_STATE, "rtDispatch: model nodeOffset / triOffset out of range");
     }
+    // shared-memory budget for the tree tops: what the selected kernel can afford next to its own shared state
+    int budget = c->optSmemPairs < 0 ? 1024 : c->optSmemPairs;
+    if (c->optKernel == 2) { const int mx = pool_max_smem_pairs(c->optPoolSlots, (int)c->spheres.count); if (budget > mx) budget = mx; }
+    else if (c->optKernel == 0) budget = 0;
+    if (budget != c->repack.budgetUsed) c->sceneDirty = true;
     if (c->sceneDirty)
     {
         std::string msg;
-        cudaError_t e = c->repack.buildScene(c->hNodes, c->hModels, c->P.modelCount, c->tris.p, c->tris.count, c->optSmemPairs, c->stream, msg);
+        cudaError_t e = c->repack.buildScene(c->hNodes, c->hModels, c->P.modelCount, c->tris.p, c->tris.count, budget, c->stream, msg);
         if (e != cudaSuccess) return failCuda(c, e, "repack scene");
         if (!msg.empty()) return fail(c, RT_E_STATE, "rtDispatch: " + msg);
         c->sceneDirty = false; c->modelsDirty = true;
@@ -359,6 +367,7 @@ int rtDispatch(RtContext* c, int kernelIndex, int gx, int gy, int gz)
     if (kernelIndex != RT_KERNEL_RAYTRACE) return fail(c, RT_E_INVALID, "rtDispatch: kernelIndex must be 0 (RayTrace) or 1 (ResetAccumulated)");
     if (limX == 0 || limY == 0) return RT_OK;
     if (c->P.NumRaysPerPixel < 0) return fail(c, RT_E_STATE, "rtDispatch: NumRaysPerPixel is negative");
+    if (c->P.MaxBounceCount > 200 || W > 65535u || H > 65535u) return fail(c, RT_E_STATE, "rtDispatch: MaxBounceCount > 200 or a resolution above 65535 is not supported");
     if (c->P.MaxBounceCount < 0) return fail(c, RT_E_STATE, "rtDispatch: MaxBounceCount is negative (the reference clamps it to [0, 32], RCM:15)");
 
     int rc = prepareScene(c);
@@ -379,17 +388,24 @@ int rtDispatch(RtContext* c, int kernelIndex, int gx, int gy, int gz)
     else { CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b)); }
     if (c->pending.size() >= 512) { rc = drainEvents(c); if (rc != RT_OK) return rc; }
 
-    if (c->optKernel == 0)
+    int kernel = c->optKernel;
+    if (c->P.NumRaysPerPixel == 0) kernel = 0;       // 0 samples: the per-pixel kernel reproduces the reference's 0/0 directly
+    if (kernel == 0)
     {
         CK(cudaEventRecord(ev.a, c->stream));
         dim3 grid((limX + 7) / 8, (limY + 7) / 8, 1), block(8, 8, 1);
         k_raytrace_mega<<<grid, block, 0, c->stream>>>(P);
         CK(cudaEventRecord(ev.b, c->stream));
     }
-    else
+    else if (kernel == 1)
     {
         cudaError_t e = wave_launch(P, c->numSMs, c->stream, ev.a, ev.b);
         if (e != cudaSuccess) return failCuda(c, e, "wavefront launch");
+    }
+    else
+    {
+        cudaError_t e = pool_launch(P, c->optPoolSlots, c->numSMs, c->stream, ev.a, ev.b);
+        if (e != cudaSuccess) return failCuda(c, e, "pool wavefront launch");
     }
     CK(cudaGetLastError());
     c->pending.push_back(ev);

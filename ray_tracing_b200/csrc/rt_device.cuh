@@ -199,7 +199,10 @@ RT_DI f3 TriangleSmoothNormal(f3 nA, f3 nB, f3 nC, float u, float v, float deter
     return smoothNormal * sign1(determinant);
 }
 
-// HL:289-320 (sphere extension): returns didHit; dst / isInside valid on hit
+// HL:289-320 (sphere extension): returns didHit; dst / isInside valid on hit.
+// Same values as the reference's expressions; the two divisions are only evaluated when their result is used:
+//   dstFar >= 0  <=>  (-b + s) >= 0  whenever 2a > 0 (an IEEE quotient has the sign of its numerator, and -0 >= 0 holds
+//   for both), so a sphere behind the ray is rejected without dividing; dstFar itself is needed only from inside.
 RT_DI bool RaySphereCore(f3 rayPos, f3 rayDir, f3 centre, float r2, float& dst, bool& isInside)
 {
     const f3 offsetRayOrigin = rayPos - centre;
@@ -210,12 +213,14 @@ RT_DI bool RaySphereCore(f3 rayPos, f3 rayDir, f3 centre, float r2, float& dst, 
     if (discriminant >= 0.0f)
     {
         const float s = sqrtf(discriminant);
-        const float dstNear = fmaxf(0.0f, (-b - s) / (2.0f * a));
-        const float dstFar = (-b + s) / (2.0f * a);
-        if (dstFar >= 0.0f)
+        const float den = 2.0f * a;
+        const float numFar = -b + s;
+        const bool farOk = den > 0.0f ? (numFar >= 0.0f) : ((numFar / den) >= 0.0f);
+        if (farOk)
         {
+            const float dstNear = fmaxf(0.0f, (-b - s) / den);
             isInside = dstNear == 0.0f;
-            dst = isInside ? dstFar : dstNear;
+            dst = isInside ? (numFar / den) : dstNear;
             return true;
         }
     }
@@ -285,6 +290,12 @@ struct PathState
 
 // One iteration of the bounce loop after the intersection (HL:488-538).
 // Returns true when the path continues with another segment.
+//
+// Both material branches consume seven draws before the roulette draw, in a different order (Appendix A of SURVEY.md):
+//   glass     : RandomDirection (draws 1-6), reflect-vs-refract test (draw 7)
+//   otherwise : specular test (draw 1), RandomDirection (draws 2-7)
+// The seven values are drawn once and the Box-Muller / normalize work of RandomDirection — the most expensive part of
+// shading — is evaluated once on the selected six, instead of once per divergent branch.  Same values, same order.
 RT_DI bool ShadeSegment(const DevParams& P, const Hit& hit, PathState& ray, uint32_t& rngState)
 {
     const float epsilon = 0.001f;
@@ -294,7 +305,21 @@ RT_DI bool ShadeSegment(const DevParams& P, const Hit& hit, PathState& ray, uint
         return false;
     }
     const RtMaterial* material = hit.material;
-    if (material->flag == RT_MATERIAL_GLASS)
+    const bool isGlass = material->flag == RT_MATERIAL_GLASS;
+
+    const float v1 = RandomValue(rngState), v2 = RandomValue(rngState), v3 = RandomValue(rngState), v4 = RandomValue(rngState);
+    const float v5 = RandomValue(rngState), v6 = RandomValue(rngState), v7 = RandomValue(rngState);
+    // RandomDirection (HL:141-157): component k uses (theta draw, rho draw) = consecutive pairs
+    const float tx = isGlass ? v1 : v2, rx = isGlass ? v2 : v3;
+    const float ty = isGlass ? v3 : v4, ry = isGlass ? v4 : v5;
+    const float tz = isGlass ? v5 : v6, rz = isGlass ? v6 : v7;
+    const float nx = sqrtf(-2.0f * log_rt(rx)) * cos_rt(6.2831852f * tx);
+    const float ny = sqrtf(-2.0f * log_rt(ry)) * cos_rt(6.2831852f * ty);
+    const float nz = sqrtf(-2.0f * log_rt(rz)) * cos_rt(6.2831852f * tz);
+    const f3 randomDirection = normalize3(make_f3(nx, ny, nz));
+    const f3 diffuseDir = normalize3(hit.normal + randomDirection);
+
+    if (isGlass)
     {
         if (hit.isBackface)
         {
@@ -307,19 +332,17 @@ RT_DI bool ShadeSegment(const DevParams& P, const Hit& hit, PathState& ray, uint
         f3 refractDir = Refract(ray.dir, hit.normal, iorCurrent, iorNext);
         const float reflectWeight = CalculateReflectance(ray.dir, hit.normal, iorCurrent, iorNext);
 
-        const f3 diffuseDir = normalize3(hit.normal + RandomDirection(rngState));
         reflectDir = normalize3(lerp3(diffuseDir, reflectDir, material->specularProbability));
         refractDir = normalize3(lerp3(-diffuseDir, refractDir, material->smoothness));
 
-        const bool followReflection = RandomValue(rngState) <= reflectWeight;
+        const bool followReflection = v7 <= reflectWeight;
         ray.dir = followReflection ? reflectDir : refractDir;
         ray.pos = hit.pos + (epsilon * hit.normal) * sign1(dot3(hit.normal, ray.dir));
     }
     else
     {
-        const bool isSpecularBounce = material->specularProbability >= RandomValue(rngState);
+        const bool isSpecularBounce = material->specularProbability >= v1;
         ray.pos = hit.pos + (hit.normal * epsilon);
-        const f3 diffuseDir = normalize3(hit.normal + RandomDirection(rngState));
         const f3 specularDir = reflect3(ray.dir, hit.normal);
         ray.dir = normalize3(lerp3(diffuseDir, specularDir, material->smoothness * (isSpecularBounce ? 1.0f : 0.0f)));
 

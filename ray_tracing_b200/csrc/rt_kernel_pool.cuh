@@ -1,0 +1,492 @@
+// rt_kernel_pool.cuh — kernel variant 2: persistent-thread WAVEFRONT path tracer with per-warp path pools.
+//
+// Why: in variant 1 a lane owns one path, so during BVH traversal the warp waits for its longest ray — ncu showed
+// 6 of 32 lanes active in the node loop on the mesh scene (profiles/).  Here every warp owns a pool of M paths
+// (M = 2..4 x 32) that lives in shared memory, and alternates two phases, each of which keeps the lanes full:
+//
+//   SHADE phase   the paths that came back from tracing are SORTED by what their hit needs (miss / opaque / glass)
+//                 with ballot+popcount compaction into an index list, then shaded 32 at a time — each batch runs one
+//                 material branch.  Finished pixels are written out; their slots are refilled from the global pixel
+//                 queue (ballot compaction of free slots, ONE atomicAdd per warp per refill); camera rays for new
+//                 samples are generated in compacted batches.
+//   TRACE phase   the warp's M rays are consumed through a warp-local queue: a lane that finishes its ray stores the
+//                 hit record and immediately takes the next ray (ballot-ranked pop from a warp-uniform counter, no
+//                 atomics), so lanes only idle at the tail of the phase instead of after every ray.
+//
+// A pool slot is a PIXEL: its NumRaysPerPixel samples run one after the other on the slot, threading the pixel's
+// single rng state and summing in order (HL:552,563-579) — the reference's per-pixel arithmetic order is untouched,
+// and traversal visits the reference's nodes and triangles in the reference's order (HL:243-283), so the output is
+// bit-identical to the oracle's and the box / triangle test counts are too.
+//
+// Tree tops are staged once per CTA into shared memory by TMA bulk copies (cp.async.bulk + mbarrier), spheres too;
+// deeper NodePair / TriGeom records are fetched with 128-bit loads from the repacked aligned streams.
+#pragma once
+#include "rt_kernel_wave.cuh"
+
+namespace rtd {
+
+constexpr int POOL_WARPS = 16;                 // warps per CTA (one persistent CTA per SM)
+constexpr int POOL_THREADS = POOL_WARPS * 32;
+constexpr int POOL_WORDS = 24;                 // 32-bit words of state per path slot
+
+// slot state (low 4 bits of the info word)
+enum : unsigned { PS_EMPTY = 0, PS_GEN = 1, PS_RAY = 2, PS_HIT_MISS = 3, PS_HIT_OPAQUE = 4, PS_HIT_GLASS = 5, PS_DONE = 6 };
+
+// word index of each field inside a pool (field-major: word f of slot e is pool[f * M + e], conflict-free for lane = e)
+enum : int { F_XY = 0, F_RNG, F_INFO, F_POS, F_DIR = F_POS + 3, F_TRN = F_DIR + 3, F_LGT = F_TRN + 3, F_SUM = F_LGT + 3,
+             F_HDST = F_SUM + 3, F_HPRIM, F_HU, F_HV, F_HDET, F_HMODEL };
+static_assert(F_HMODEL == POOL_WORDS - 1, "pool layout");
+
+RT_DI unsigned info_pack(unsigned sample, unsigned bounce, unsigned state) { return (sample << 12) | (bounce << 4) | state; }
+RT_DI unsigned info_state(unsigned i) { return i & 15u; }
+RT_DI unsigned info_bounce(unsigned i) { return (i >> 4) & 255u; }
+RT_DI unsigned info_sample(unsigned i) { return i >> 12; }
+
+template <int M> struct PoolView
+{
+    float* w;                                   // POOL_WORDS * M words
+    unsigned char* order;                       // M slot indices
+    RT_DI float& f(int field, int e) const { return w[field * M + e]; }
+    RT_DI unsigned& u(int field, int e) const { return reinterpret_cast<unsigned*>(w)[field * M + e]; }
+    RT_DI int& i(int field, int e) const { return reinterpret_cast<int*>(w)[field * M + e]; }
+    RT_DI f3 get3(int field, int e) const { return make_f3(w[field * M + e], w[(field + 1) * M + e], w[(field + 2) * M + e]); }
+    RT_DI void set3(int field, int e, f3 v) const { w[field * M + e] = v.x; w[(field + 1) * M + e] = v.y; w[(field + 2) * M + e] = v.z; }
+};
+
+// Build in `order` the list of slots whose state is in [lo, hi], grouped by state (ascending); returns the count.
+template <int M> RT_DI int CompactByState(const PoolView<M>& pool, unsigned lane, unsigned lo, unsigned hi)
+{
+    const unsigned ltMask = (1u << lane) - 1u;
+    int base = 0;
+    for (unsigned st = lo; st <= hi; st++)
+    {
+#pragma unroll
+        for (int c = 0; c < M / 32; c++)
+        {
+            const int e = c * 32 + (int)lane;
+            const bool has = info_state(pool.u(F_INFO, e)) == st;
+            const unsigned m = __ballot_sync(0xffffffffu, has);
+            if (has) pool.order[base + __popc(m & ltMask)] = (unsigned char)e;
+            base += __popc(m);
+        }
+    }
+    __syncwarp();
+    return base;
+}
+
+template <bool STATS, int M>
+__global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_constant__ DevParams P, const unsigned int totalJobs,
+                                                                  const unsigned int tilesX, const unsigned int ownedRows)
+{
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    WaveSmemHeader* hdr = reinterpret_cast<WaveSmemHeader*>(smemRaw);
+    float4* smemPairs = reinterpret_cast<float4*>(smemRaw + sizeof(WaveSmemHeader));
+    DevSphere* smemSpheres = reinterpret_cast<DevSphere*>(smemRaw + sizeof(WaveSmemHeader) + (size_t)P.smemPairs * sizeof(NodePair));
+    const int nSmemSpheres = P.sphereCount < WAVE_MAX_SMEM_SPHERES ? P.sphereCount : WAVE_MAX_SMEM_SPHERES;
+    unsigned char* poolBase = reinterpret_cast<unsigned char*>(smemSpheres + nSmemSpheres);
+    constexpr int POOL_BYTES = POOL_WORDS * M * 4 + M;          // M is a multiple of 32, so every pool stays 16-byte aligned
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned warp = threadIdx.x >> 5;
+    const unsigned ltMask = (1u << lane) - 1u;
+    PoolView<M> pool;
+    pool.w = reinterpret_cast<float*>(poolBase + (size_t)warp * POOL_BYTES);
+    pool.order = reinterpret_cast<unsigned char*>(pool.w + POOL_WORDS * M);
+
+    // ---- stage the tree tops (TMA bulk copy) and the spheres; initialise the pool -------------------------------------
+    const uint32_t mbar = smem_u32(&hdr->mbar);
+    if (threadIdx.x == 0)
+    {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (P.smemPairs > 0 && threadIdx.x == 0)
+    {
+        const uint32_t bytes = (uint32_t)P.smemPairs * (uint32_t)sizeof(NodePair);
+        mbar_expect_tx(mbar, bytes);
+        uint32_t off = 0;
+        while (off < bytes)
+        {
+            const uint32_t n = (bytes - off) < 32768u ? (bytes - off) : 32768u;
+            tma_bulk_g2s(smem_u32(smemPairs) + off, reinterpret_cast<const unsigned char*>(P.pairs) + off, n, mbar);
+            off += n;
+        }
+    }
+    for (int i = threadIdx.x; i < nSmemSpheres; i += POOL_THREADS) smemSpheres[i] = P.spheres[i];
+#pragma unroll
+    for (int c = 0; c < M / 32; c++) pool.u(F_INFO, c * 32 + (int)lane) = info_pack(0, 0, PS_EMPTY);
+    if (P.smemPairs > 0) { while (!mbar_try_wait(mbar, 0)) { } }
+    __syncthreads();
+
+    Counters cnt; cnt.rays = cnt.box = cnt.tri = cnt.sph = 0;
+    bool exhausted = false;                     // warp-uniform: the global pixel queue is empty
+
+    for (;;)
+    {
+        // ================================================= SHADE phase =================================================
+        // (1) shade the slots that came back from tracing, sorted by hit kind
+        {
+            const int n = CompactByState<M>(pool, lane, PS_HIT_MISS, PS_HIT_GLASS);
+            for (int i0 = 0; i0 < n; i0 += 32)
+            {
+                const int i = i0 + (int)lane;
+                if (i < n)
+                {
+                    const int e = pool.order[i];
+                    const unsigned info = pool.u(F_INFO, e);
+                    PathState ray;
+                    ray.pos = pool.get3(F_POS, e); ray.dir = pool.get3(F_DIR, e);
+                    ray.transmittance = pool.get3(F_TRN, e); ray.totalLight = pool.get3(F_LGT, e);
+                    uint32_t rngState = pool.u(F_RNG, e);
+
+                    // rebuild the hit (HL:319-320 / HL:208-209,365-369) from the compact record
+                    Hit hit;
+                    hit.dst = pool.f(F_HDST, e); hit.isBackface = false; hit.material = nullptr;
+                    hit.normal = splat3(0.0f); hit.pos = splat3(0.0f);
+                    if (info_state(info) != PS_HIT_MISS)
+                    {
+                        const int prim = pool.i(F_HPRIM, e);
+                        hit.pos = ray.pos + ray.dir * hit.dst;
+                        if (prim < 0)
+                        {
+                            const int s = -prim - 1;
+                            const bool inside = pool.f(F_HDET, e) < 0.0f;
+                            f3 centre;
+                            if (s < WAVE_MAX_SMEM_SPHERES) { const DevSphere sp = smemSpheres[s]; centre = make_f3(sp.cx, sp.cy, sp.cz); }
+                            else centre = make_f3(P.spheres[s].cx, P.spheres[s].cy, P.spheres[s].cz);
+                            hit.isBackface = inside;
+                            hit.normal = normalize3(hit.pos - centre) * (inside ? -1.0f : 1.0f);
+                            hit.material = &P.Spheres[s].material;
+                        }
+                        else
+                        {
+                            const int model = pool.i(F_HMODEL, e);
+                            const float det = pool.f(F_HDET, e);
+                            const float4* nq = reinterpret_cast<const float4*>(P.triNormals + prim);
+                            const float4 n0 = __ldg(nq), n1 = __ldg(nq + 1), n2 = __ldg(nq + 2);
+                            const f3 n = TriangleSmoothNormal(make_f3(n0.x, n0.y, n0.z), make_f3(n0.w, n1.x, n1.y), make_f3(n1.z, n1.w, n2.x),
+                                                              pool.f(F_HU, e), pool.f(F_HV, e), det);
+                            const float4* mr = reinterpret_cast<const float4*>(P.models + model) + 3;
+                            const float4 r0 = __ldg(mr), r1 = __ldg(mr + 1), r2 = __ldg(mr + 2);
+                            const float l2w[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+                            hit.isBackface = det < 0.0f;
+                            hit.normal = normalize3(mul_rm(l2w, n, 0.0f));
+                            hit.material = &P.ModelInfo[model].material;
+                        }
+                    }
+                    const bool cont = ShadeSegment(P, hit, ray, rngState);
+                    unsigned sample = info_sample(info), bounce = info_bounce(info) + 1u;
+                    unsigned state = PS_RAY;
+                    pool.u(F_RNG, e) = rngState;
+                    if (!cont || (int)bounce > P.MaxBounceCount)
+                    {
+                        const f3 sum = pool.get3(F_SUM, e) + ray.totalLight;              // HL:578
+                        sample++;
+                        if ((int)sample >= P.NumRaysPerPixel)
+                        {
+                            // pixel finished (RC:18-23)
+                            const unsigned xy = pool.u(F_XY, e);
+                            const size_t o = (size_t)(xy >> 16) * P.W + (xy & 0xffffu);
+                            const f3 pixelCol = sum / __int2float_rn(P.NumRaysPerPixel);
+                            P.FrameRender[o] = make_float4(pixelCol.x, pixelCol.y, pixelCol.z, 1.0f);
+                            if (P.accumulate)
+                            {
+                                float4 a = P.AccumulatedRender[o];
+                                a.x += pixelCol.x; a.y += pixelCol.y; a.z += pixelCol.z; a.w += 1.0f;
+                                P.AccumulatedRender[o] = a;
+                            }
+                            state = PS_EMPTY;
+                        }
+                        else { pool.set3(F_SUM, e, sum); state = PS_GEN; }
+                        bounce = 0;
+                    }
+                    else
+                    {
+                        pool.set3(F_POS, e, ray.pos); pool.set3(F_DIR, e, ray.dir);
+                        pool.set3(F_TRN, e, ray.transmittance); pool.set3(F_LGT, e, ray.totalLight);
+                    }
+                    pool.u(F_INFO, e) = info_pack(sample, bounce, state);
+                }
+            }
+            __syncwarp();
+        }
+
+        // (2) refill free slots from the global pixel queue (ballot compaction, one atomic per warp per pass)
+        while (!exhausted)
+        {
+            bool anyEmpty = false;
+#pragma unroll
+            for (int c = 0; c < M / 32; c++)
+            {
+                const int e = c * 32 + (int)lane;
+                const bool need = info_state(pool.u(F_INFO, e)) == PS_EMPTY;
+                const unsigned needMask = __ballot_sync(0xffffffffu, need);
+                if (needMask == 0u || exhausted) continue;
+                unsigned base = 0;
+                const int leader = __ffs(needMask) - 1;
+                if ((int)lane == leader) base = atomicAdd(P.workCounter, (unsigned)__popc(needMask));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (need)
+                {
+                    const unsigned job = base + (unsigned)__popc(needMask & ltMask);
+                    if (job < totalJobs)
+                    {
+                        const unsigned tile = job >> 5, l = job & 31u;
+                        const unsigned x = (tile % tilesX) * 8u + (l & 7u);
+                        const unsigned r = (tile / tilesX) * 4u + (l >> 3);
+                        if (x < P.limX && r < ownedRows)
+                        {
+                            const unsigned y = ((r / (unsigned)P.bandRows) * (unsigned)P.tileWorld + (unsigned)P.tileRank) * (unsigned)P.bandRows
+                                             + (r % (unsigned)P.bandRows);
+                            pool.u(F_XY, e) = (y << 16) | x;
+                            pool.u(F_RNG, e) = SetupPixel(P, x, y).rngState;
+                            pool.set3(F_SUM, e, splat3(0.0f));
+                            pool.u(F_INFO, e) = info_pack(0, 0, PS_GEN);
+                        }
+                    }
+                }
+                if (base + (unsigned)__popc(needMask) >= totalJobs) exhausted = true;        // warp-uniform
+                else if (__ballot_sync(0xffffffffu, info_state(pool.u(F_INFO, e)) == PS_EMPTY)) anyEmpty = true;   // padding jobs: try again
+            }
+            if (!anyEmpty) break;
+        }
+        if (exhausted)
+        {
+#pragma unroll
+            for (int c = 0; c < M / 32; c++)
+            {
+                const int e = c * 32 + (int)lane;
+                if (info_state(pool.u(F_INFO, e)) == PS_EMPTY) pool.u(F_INFO, e) = info_pack(0, 0, PS_DONE);
+            }
+        }
+        __syncwarp();
+
+        // (3) camera rays for the slots that start a sample (HL:567-576), in compacted batches
+        {
+            const int n = CompactByState<M>(pool, lane, PS_GEN, PS_GEN);
+            for (int i0 = 0; i0 < n; i0 += 32)
+            {
+                const int i = i0 + (int)lane;
+                if (i < n)
+                {
+                    const int e = pool.order[i];
+                    const unsigned xy = pool.u(F_XY, e);
+                    const PixelSetup px = SetupPixel(P, xy & 0xffffu, xy >> 16);
+                    uint32_t rngState = pool.u(F_RNG, e);
+                    PathState ray;
+                    GenerateCameraRay(P, px, rngState, ray);
+                    pool.u(F_RNG, e) = rngState;
+                    pool.set3(F_POS, e, ray.pos); pool.set3(F_DIR, e, ray.dir);
+                    pool.set3(F_TRN, e, ray.transmittance); pool.set3(F_LGT, e, ray.totalLight);
+                    pool.u(F_INFO, e) = info_pack(info_sample(pool.u(F_INFO, e)), 0, PS_RAY);
+                }
+            }
+            __syncwarp();
+        }
+
+        // ================================================= TRACE phase =================================================
+        const int nRays = CompactByState<M>(pool, lane, PS_RAY, PS_RAY);
+        if (nRays == 0) break;                                       // every slot is DONE: this warp is finished
+        int next = 0;                                                // warp-uniform queue head
+        int myEntry = -1;                                            // slot this lane is tracing
+        // per-ray state
+        f3 rayPos = splat3(0.0f), rayDir = splat3(0.0f), lpos = splat3(0.0f), ldir = splat3(0.0f), linv = splat3(0.0f);
+        float resDst = inf32(), resU = 0.0f, resV = 0.0f, resDet = 0.0f; int resPrim = 0, resModel = 0; unsigned resKind = PS_HIT_MISS;
+        float bestDst = 0.0f, bestU = 0.0f, bestV = 0.0f, bestDet = 0.0f; int bestTri = -1;
+        int model = 0; bool cull = true;
+        NodeRef cur; cur.start = 0; cur.count = 0;
+        int leafK = 0;
+        NodeRef stack[WAVE_STACK];
+        int stackCount = 0;
+        enum { T_IDLE = 0, T_INNER = 1, T_LEAF = 2, T_NEXT = 3 };
+        int mode = T_IDLE;
+
+        for (;;)
+        {
+            // ---- fetch: idle lanes pop the next rays of the warp queue (ballot rank, no atomics) ----
+            {
+                const bool need = mode == T_IDLE;
+                const unsigned needMask = __ballot_sync(0xffffffffu, need);
+                if (needMask != 0u && next < nRays)
+                {
+                    const int idx = next + __popc(needMask & ltMask);
+                    next += __popc(needMask);
+                    if (need && idx < nRays)
+                    {
+                        myEntry = pool.order[idx];
+                        rayPos = pool.get3(F_POS, myEntry); rayDir = pool.get3(F_DIR, myEntry);
+                        cnt.rays++;
+                        resDst = inf32(); resPrim = 0; resModel = 0; resKind = PS_HIT_MISS; resU = resV = resDet = 0.0f;
+                        // spheres first (extension; where the reference's commented call sits, HL:341)
+                        for (int s = 0; s < P.sphereCount; s++)
+                        {
+                            float cx, cy, cz, r2; int flag;
+                            if (s < WAVE_MAX_SMEM_SPHERES) { const DevSphere sp = smemSpheres[s]; cx = sp.cx; cy = sp.cy; cz = sp.cz; r2 = sp.r2; flag = sp.pad0; }
+                            else { const float4 s0 = __ldg(reinterpret_cast<const float4*>(P.spheres + s)); cx = s0.x; cy = s0.y; cz = s0.z;
+                                   r2 = __ldg(&P.spheres[s].r2); flag = __ldg(&P.spheres[s].pad0); }
+                            float dst; bool inside;
+                            if (STATS) cnt.sph++;
+                            if (RaySphereCore(rayPos, rayDir, make_f3(cx, cy, cz), r2, dst, inside) && dst < resDst)
+                            {
+                                resDst = dst; resPrim = -(s + 1); resDet = inside ? -1.0f : 1.0f;
+                                resKind = flag == RT_MATERIAL_GLASS ? PS_HIT_GLASS : PS_HIT_OPAQUE;
+                            }
+                        }
+                        model = -1; mode = T_NEXT;
+                    }
+                }
+                if (__ballot_sync(0xffffffffu, mode != T_IDLE) == 0u) break;
+            }
+
+            // ---- advance to the next model / finish the ray ----
+            if (mode == T_NEXT)
+            {
+                if (model >= 0 && bestDst < resDst)                  // HL:362-370 (normal / position are rebuilt when shading)
+                {
+                    resDst = bestDst; resPrim = bestTri; resU = bestU; resV = bestV; resDet = bestDet; resModel = model;
+                    resKind = cull ? PS_HIT_OPAQUE : PS_HIT_GLASS;   // cull == (flag != GLASS)
+                }
+                model++;
+                if (model < P.modelCount)
+                {
+                    const float4* mr = reinterpret_cast<const float4*>(P.models + model);
+                    const float4 r0 = __ldg(mr), r1 = __ldg(mr + 1), r2 = __ldg(mr + 2);
+                    const float w2l[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+                    const int4 meta = __ldg(reinterpret_cast<const int4*>(mr + 6));
+                    lpos = mul_rm(w2l, rayPos, 1.0f);
+                    ldir = mul_rm(w2l, rayDir, 0.0f);
+                    linv = rcp3(ldir);
+                    cull = meta.z != 0;
+                    bestDst = resDst; bestTri = -1;                  // result.dst is the ray length shared across models (HL:359)
+                    cur.start = meta.x; cur.count = meta.y; leafK = 0; stackCount = 0;
+                    mode = cur.count > 0 ? T_LEAF : T_INNER;
+                }
+                else
+                {
+                    pool.f(F_HDST, myEntry) = resDst; pool.i(F_HPRIM, myEntry) = resPrim;
+                    pool.f(F_HU, myEntry) = resU; pool.f(F_HV, myEntry) = resV; pool.f(F_HDET, myEntry) = resDet; pool.i(F_HMODEL, myEntry) = resModel;
+                    const unsigned info = pool.u(F_INFO, myEntry);
+                    pool.u(F_INFO, myEntry) = (info & ~15u) | resKind;
+                    mode = T_IDLE; myEntry = -1;
+                }
+            }
+
+            // ---- inner nodes: HL:262-282 ----
+            while (mode == T_INNER)
+            {
+                float4 q0, q1, q2, q3;
+                LoadPair(P, smemPairs, cur.start, q0, q1, q2, q3);
+                const float dstA = RayBoundingBoxDst(lpos, linv, make_f3(q0.x, q0.y, q0.z), make_f3(q0.w, q1.x, q1.y));
+                const float dstB = RayBoundingBoxDst(lpos, linv, make_f3(q2.x, q2.y, q2.z), make_f3(q2.w, q3.x, q3.y));
+                if (STATS) cnt.box += 2;
+                NodeRef a, b;
+                a.start = __float_as_int(q1.z); a.count = __float_as_int(q1.w);
+                b.start = __float_as_int(q3.z); b.count = __float_as_int(q3.w);
+                const bool isNearestA = dstA <= dstB;
+                const float dstNear = isNearestA ? dstA : dstB;
+                const float dstFar = isNearestA ? dstB : dstA;
+                const NodeRef nearRef = isNearestA ? a : b;
+                const NodeRef farRef = isNearestA ? b : a;
+                if (dstFar < bestDst && stackCount < WAVE_STACK) stack[stackCount++] = farRef;
+                if (dstNear < bestDst) cur = nearRef;
+                else if (stackCount > 0) cur = stack[--stackCount];
+                else { mode = T_NEXT; break; }
+                if (cur.count > 0) { mode = T_LEAF; leafK = 0; }
+            }
+
+            // ---- leaf triangles: HL:248-260 ----
+            while (mode == T_LEAF)
+            {
+                const float4* g = reinterpret_cast<const float4*>(P.triGeom + cur.start + leafK);
+                const float4 g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2);
+                float dst, u, v, det;
+                const bool didHit = RayTriangleCore(lpos, ldir, make_f3(g0.x, g0.y, g0.z), make_f3(g0.w, g1.x, g1.y), make_f3(g1.z, g1.w, g2.x),
+                                                    make_f3(g2.y, g2.z, g2.w), cull, dst, u, v, det);
+                if (STATS) cnt.tri++;
+                if (didHit && dst < bestDst) { bestDst = dst; bestTri = cur.start + leafK; bestU = u; bestV = v; bestDet = det; }
+                leafK++;
+                if (leafK >= cur.count)
+                {
+                    if (stackCount > 0) { cur = stack[--stackCount]; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
+                    else mode = T_NEXT;
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- counters ---------------------------------------------------------------------------------------------------------------
+    const unsigned int r = __reduce_add_sync(0xffffffffu, cnt.rays);
+    if (lane == 0) atomicAdd(P.counters + 0, (unsigned long long)r);
+    if (STATS)
+    {
+        const unsigned int b = __reduce_add_sync(0xffffffffu, cnt.box), t = __reduce_add_sync(0xffffffffu, cnt.tri), s = __reduce_add_sync(0xffffffffu, cnt.sph);
+        if (lane == 0) { atomicAdd(P.counters + 1, (unsigned long long)b); atomicAdd(P.counters + 2, (unsigned long long)t); atomicAdd(P.counters + 3, (unsigned long long)s); }
+    }
+}
+
+template <int M> inline size_t pool_smem_bytes(const DevParams& P)
+{
+    const int nS = P.sphereCount < WAVE_MAX_SMEM_SPHERES ? P.sphereCount : WAVE_MAX_SMEM_SPHERES;
+    return sizeof(WaveSmemHeader) + (size_t)P.smemPairs * sizeof(NodePair) + (size_t)nS * sizeof(DevSphere) + (size_t)POOL_WARPS * (POOL_WORDS * M * 4 + M);
+}
+
+template <int M> inline cudaError_t pool_configure_one()
+{
+    cudaError_t e = cudaFuncSetAttribute(k_raytrace_pool<false, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_raytrace_pool<true, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+inline cudaError_t pool_configure()
+{
+    cudaError_t e;
+    if ((e = pool_configure_one<64>()) != cudaSuccess) return e;
+    if ((e = pool_configure_one<96>()) != cudaSuccess) return e;
+    return pool_configure_one<128>();
+}
+
+// shared-memory bytes the pools leave for the tree-top cache (in NodePair records)
+inline int pool_max_smem_pairs(int M, int sphereCount)
+{
+    const int nS = sphereCount < WAVE_MAX_SMEM_SPHERES ? sphereCount : WAVE_MAX_SMEM_SPHERES;
+    const long long left = 227LL * 1024 - (long long)sizeof(WaveSmemHeader) - (long long)nS * (long long)sizeof(DevSphere)
+                         - (long long)POOL_WARPS * (POOL_WORDS * M * 4 + M) - 1024;
+    return left <= 0 ? 0 : (int)(left / (long long)sizeof(NodePair));
+}
+
+template <int M> inline cudaError_t pool_launch_m(const DevParams& P, int numSMs, cudaStream_t stream, cudaEvent_t evA, cudaEvent_t evB,
+                                                  unsigned totalJobs, unsigned tilesX, unsigned ownedRows)
+{
+    const size_t smemBytes = pool_smem_bytes<M>(P);
+    if (smemBytes > 227 * 1024) return cudaErrorInvalidConfiguration;
+    unsigned grid = (unsigned)numSMs;                                   // one persistent CTA per SM
+    const unsigned slots = POOL_WARPS * M;
+    const unsigned ctasNeeded = (totalJobs + slots - 1) / slots;
+    if (grid > ctasNeeded) grid = ctasNeeded ? ctasNeeded : 1;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(P.workCounter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(evA, stream)) != cudaSuccess) return e;
+    if (P.countStats) k_raytrace_pool<true, M><<<grid, POOL_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows);
+    else k_raytrace_pool<false, M><<<grid, POOL_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    return cudaEventRecord(evB, stream);
+}
+
+inline cudaError_t pool_launch(const DevParams& P, int M, int numSMs, cudaStream_t stream, cudaEvent_t evA, cudaEvent_t evB)
+{
+    unsigned int ownedRows = 0;
+    for (unsigned int y0 = 0, b = 0; y0 < P.limY; y0 += (unsigned int)P.bandRows, b++)
+        if ((int)(b % (unsigned int)P.tileWorld) == P.tileRank) ownedRows += (P.limY - y0) < (unsigned int)P.bandRows ? (P.limY - y0) : (unsigned int)P.bandRows;
+    const unsigned int tilesX = (P.limX + 7u) / 8u;
+    const unsigned int tileRows = (ownedRows + 3u) / 4u;
+    const unsigned long long jobs64 = (unsigned long long)tilesX * tileRows * 32ull;
+    if (jobs64 >= 0xffff0000ull) return cudaErrorInvalidValue;
+    const unsigned int totalJobs = (unsigned int)jobs64;
+    if (M == 64) return pool_launch_m<64>(P, numSMs, stream, evA, evB, totalJobs, tilesX, ownedRows);
+    if (M == 96) return pool_launch_m<96>(P, numSMs, stream, evA, evB, totalJobs, tilesX, ownedRows);
+    if (M == 128) return pool_launch_m<128>(P, numSMs, stream, evA, evB, totalJobs, tilesX, ownedRows);
+    return cudaErrorInvalidValue;
+}
+
+} // namespace rtd

@@ -53,6 +53,7 @@ struct RepackState
     RBuf<NodePair> pairs; RBuf<TriGeom> triGeom; RBuf<TriNormals> triNormals; RBuf<DevModel> models; RBuf<DevSphere> spheres;
     std::map<std::pair<int,int>, MeshRoot> roots;     // (nodeOffset, triOffset) -> encoded root
     int smemPairs = 0;
+    int budgetUsed = -1;
     size_t totalPairs = 0;
 
     void release() { pairs.release(); triGeom.release(); triNormals.release(); models.release(); spheres.release(); roots.clear(); }
@@ -91,8 +92,9 @@ struct RepackState
         for (auto& m : meshes) totalPairs += m.order.size();
 
         // shared-memory budget (pairs) split over the meshes by water-filling, smallest mesh first
-        size_t budget = smemOpt < 0 ? 1024 : (size_t)smemOpt;
+        size_t budget = smemOpt < 0 ? 0 : (size_t)smemOpt;
         if (budget > 3072) budget = 3072;                                   // 192 KB of the 227 KB a CTA may own
+        budgetUsed = (int)budget;
         {
             std::vector<size_t> idx(meshes.size());
             for (size_t i = 0; i < idx.size(); i++) idx[i] = i;
@@ -184,6 +186,7 @@ struct RepackState
             d.cx = sp[i].centre[0]; d.cy = sp[i].centre[1]; d.cz = sp[i].centre[2]; d.radius = sp[i].radius;
             // r*r is one IEEE multiply (HL:299).  Host code is built without FMA contraction, so this is that product.
             volatile float r = sp[i].radius; d.r2 = r * r;
+            d.pad0 = sp[i].material.flag;                       // material flag, for sorting hits by kind without touching HBM
             out[i] = d;
         }
         cudaError_t e;

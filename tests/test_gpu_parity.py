@@ -17,7 +17,7 @@ from ray_tracing_b200 import capi, scenes
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [0, 1]        # 0 = reference-shaped megakernel, 1 = persistent wavefront kernel (the product default)
+KERNELS = [0, 1, 2]     # 0 = reference-shaped megakernel, 1 = persistent threads, 2 = pooled wavefront (the product default)
 
 
 def _same_counters(a, b, keys=("rays", "boxTests", "triTests", "sphereTests")):
@@ -80,9 +80,20 @@ def test_shared_memory_staging_does_not_change_results():
     """TMA-staged tree tops: 0, a few, many pairs in shared memory — identical output."""
     sc = scenes.knot_room(96, 54, max_bounces=4, rays_per_pixel=2, nu=200, nv=12)
     ref, _ = render(CUDA_LIB, sc, options={"kernel": 1, "smemNodes": 0})
-    for n in (1, 7, 64, 1024, 3000):
-        img, _ = render(CUDA_LIB, sc, options={"kernel": 1, "smemNodes": n})
-        assert_bit_equal(img, ref, f"smemNodes={n}")
+    for kernel in (1, 2):
+        for n in (0, 1, 7, 64, 1024, 3000):
+            img, _ = render(CUDA_LIB, sc, options={"kernel": kernel, "smemNodes": n})
+            assert_bit_equal(img, ref, f"kernel={kernel} smemNodes={n}")
+
+
+@pytest.mark.parametrize("slots", [64, 96, 128])
+def test_pool_sizes_do_not_change_results(slots):
+    """Paths per warp pool of the wavefront kernel: scheduling only, identical output and counters."""
+    sc = scenes.knot_room(128, 72, max_bounces=6, rays_per_pixel=3, nu=150, nv=10, glass=True)
+    fo, ao, so = render(ORACLE_LIB, sc, frames=1, want_stats=True)
+    fg, ag, sg = render(CUDA_LIB, sc, frames=1, options={"kernel": 2, "poolSlots": slots, "countStats": 1}, want_stats=True)
+    assert_bit_equal(fg, fo, f"poolSlots={slots}")
+    _same_counters(sg, so)
 
 
 def test_bvh_quality_modes_on_gpu():
@@ -91,8 +102,9 @@ def test_bvh_quality_modes_on_gpu():
         sc = scenes.knot_room(64, 36, max_bounces=3, rays_per_pixel=1, nu=60, nv=8)
         sc.settings["bvhQuality"] = q
         fo, _ = render(ORACLE_LIB, sc)
-        fg, _ = render(CUDA_LIB, sc, options={"kernel": 1})
-        assert_bit_equal(fg, fo, f"bvhQuality={q}")
+        for kernel in (1, 2):
+            fg, _ = render(CUDA_LIB, sc, options={"kernel": kernel})
+            assert_bit_equal(fg, fo, f"bvhQuality={q} kernel={kernel}")
 
 
 def test_config2_size_sparse_pixels_against_oracle():
@@ -118,11 +130,13 @@ def test_full_size_properties():
     """Size-independent properties at config-2 size: determinism, megakernel == wavefront kernel, alpha = frame count,
     FrameRender alpha = 1, accumulated = sum of frames."""
     sc = scenes.cornell_spheres(1920, 1080, 8, 2)
-    f1, a1 = render(CUDA_LIB, sc, frames=2, options={"kernel": 1})
-    f1b, a1b = render(CUDA_LIB, sc, frames=2, options={"kernel": 1})
+    f1, a1 = render(CUDA_LIB, sc, frames=2, options={"kernel": 2})
+    f1b, a1b = render(CUDA_LIB, sc, frames=2, options={"kernel": 2})
     assert_bit_equal(a1, a1b, "two runs of the wavefront kernel")
     f0, a0 = render(CUDA_LIB, sc, frames=2, options={"kernel": 0})
     assert_bit_equal(a1, a0, "wavefront vs megakernel")
+    fp, ap = render(CUDA_LIB, sc, frames=2, options={"kernel": 1})
+    assert_bit_equal(a1, ap, "wavefront vs persistent-threads kernel")
     assert np.all(a1[..., 3] == 2.0) and np.all(f1[..., 3] == 1.0)
     first, _ = render(CUDA_LIB, sc, frames=1)
     assert_bit_equal(a1[..., :3], first[..., :3] + f1[..., :3], "SUM buffer = frame 1 + frame 2 (RayCompute.compute:22)")
