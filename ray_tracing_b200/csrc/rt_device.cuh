@@ -124,7 +124,8 @@ RT_DI f3 RandomDirection(uint32_t& state)
     const float z = RandomValueNormalDistribution(state);
     return normalize3(make_f3(x, y, z));
 }
-RT_DI f2 RandomPointInCircle(uint32_t& state)
+// (not inlined: two call sites per camera sample; keeping one copy shrinks the kernels' instruction footprint)
+__device__ __noinline__ f2 RandomPointInCircle(uint32_t& state)
 {
     const float angle = (RandomValue(state) * 2.0f) * 3.1415f;       // PI = 3.1415 (HL:2,161)
     float s, c; sincos_rt(angle, s, c);
@@ -134,7 +135,8 @@ RT_DI f2 RandomPointInCircle(uint32_t& state)
 
 // ---- environment (HL:167-183) -----------------------------------------------------------------------------------
 
-RT_DI f3 GetEnvironmentLight(const DevParams& P, f3 dir)
+// (not inlined: two pow() bodies that only sky scenes execute, on miss)
+__device__ __noinline__ f3 GetEnvironmentLight(const DevParams& P, f3 dir)
 {
     if (P.UseSky == 0) return splat3(0.0f);
     const f3 GroundColour = make_f3(0.35f, 0.3f, 0.35f);
@@ -283,6 +285,9 @@ RT_DI f3 GetMaterialColour(const RtMaterial* mat, f3 pos, f3 normal, bool isSpec
     return lerp3(col, make_f3(mat->specularCol[0], mat->specularCol[1], mat->specularCol[2]), isSpecularBounce ? 1.0f : 0.0f);
 }
 
+// exp of three components (not inlined: glass back-face hits only)
+__device__ __noinline__ f3 exp3_rt(f3 a) { return make_f3(exp_rt(a.x), exp_rt(a.y), exp_rt(a.z)); }
+
 struct PathState
 {
     f3 pos, dir, transmittance, totalLight;
@@ -313,9 +318,16 @@ RT_DI bool ShadeSegment(const DevParams& P, const Hit& hit, PathState& ray, uint
     const float tx = isGlass ? v1 : v2, rx = isGlass ? v2 : v3;
     const float ty = isGlass ? v3 : v4, ry = isGlass ? v4 : v5;
     const float tz = isGlass ? v5 : v6, rz = isGlass ? v6 : v7;
-    const float nx = sqrtf(-2.0f * log_rt(rx)) * cos_rt(6.2831852f * tx);
-    const float ny = sqrtf(-2.0f * log_rt(ry)) * cos_rt(6.2831852f * ty);
-    const float nz = sqrtf(-2.0f * log_rt(rz)) * cos_rt(6.2831852f * tz);
+    // one copy of the log / sqrt / cos body, run three times (instruction-cache footprint; the values are the same)
+    float nx = 0.0f, ny = 0.0f, nz = 0.0f;
+#pragma unroll 1
+    for (int k = 0; k < 3; k++)
+    {
+        const float t = k == 0 ? tx : (k == 1 ? ty : tz);
+        const float r = k == 0 ? rx : (k == 1 ? ry : rz);
+        const float val = sqrtf(-2.0f * log_rt(r)) * cos_rt(6.2831852f * t);
+        if (k == 0) nx = val; else if (k == 1) ny = val; else nz = val;
+    }
     const f3 randomDirection = normalize3(make_f3(nx, ny, nz));
     const f3 diffuseDir = normalize3(hit.normal + randomDirection);
 
@@ -324,7 +336,7 @@ RT_DI bool ShadeSegment(const DevParams& P, const Hit& hit, PathState& ray, uint
         if (hit.isBackface)
         {
             const f3 absorb = ((-hit.dst) * make_f3(material->absorption[0], material->absorption[1], material->absorption[2])) * material->absorptionStrength;
-            ray.transmittance = ray.transmittance * make_f3(exp_rt(absorb.x), exp_rt(absorb.y), exp_rt(absorb.z));
+            ray.transmittance = ray.transmittance * exp3_rt(absorb);
         }
         const float iorCurrent = hit.isBackface ? material->ior : 1.0f;
         const float iorNext = hit.isBackface ? 1.0f : material->ior;

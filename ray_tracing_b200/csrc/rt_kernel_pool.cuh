@@ -339,77 +339,91 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                 if (__ballot_sync(0xffffffffu, mode != T_IDLE) == 0u) break;
             }
 
-            // ---- advance to the next model / finish the ray ----
-            if (mode == T_NEXT)
+            // ---- vote: run the step kind most lanes are waiting for (ties: finish/advance first, then inner nodes) ----
+            // Lanes are independent state machines (inner node / leaf triangle / next model); executing every kind each
+            // iteration would run each at a fraction of the warp.  One kind per iteration keeps the executed block dense,
+            // the others catch up when their kind becomes the majority.  The per-ray visiting order is unchanged.
+            const int nInner = __popc(__ballot_sync(0xffffffffu, mode == T_INNER));
+            const int nLeaf = __popc(__ballot_sync(0xffffffffu, mode == T_LEAF));
+            const int nNext = __popc(__ballot_sync(0xffffffffu, mode == T_NEXT));
+
+            if (nNext >= nInner && nNext >= nLeaf)
             {
-                if (model >= 0 && bestDst < resDst)                  // HL:362-370 (normal / position are rebuilt when shading)
+                // ---- advance to the next model / finish the ray ----
+                if (mode == T_NEXT)
                 {
-                    resDst = bestDst; resPrim = bestTri; resU = bestU; resV = bestV; resDet = bestDet; resModel = model;
-                    resKind = cull ? PS_HIT_OPAQUE : PS_HIT_GLASS;   // cull == (flag != GLASS)
-                }
-                model++;
-                if (model < P.modelCount)
-                {
-                    const float4* mr = reinterpret_cast<const float4*>(P.models + model);
-                    const float4 r0 = __ldg(mr), r1 = __ldg(mr + 1), r2 = __ldg(mr + 2);
-                    const float w2l[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
-                    const int4 meta = __ldg(reinterpret_cast<const int4*>(mr + 6));
-                    lpos = mul_rm(w2l, rayPos, 1.0f);
-                    ldir = mul_rm(w2l, rayDir, 0.0f);
-                    linv = rcp3(ldir);
-                    cull = meta.z != 0;
-                    bestDst = resDst; bestTri = -1;                  // result.dst is the ray length shared across models (HL:359)
-                    cur.start = meta.x; cur.count = meta.y; leafK = 0; stackCount = 0;
-                    mode = cur.count > 0 ? T_LEAF : T_INNER;
-                }
-                else
-                {
-                    pool.f(F_HDST, myEntry) = resDst; pool.i(F_HPRIM, myEntry) = resPrim;
-                    pool.f(F_HU, myEntry) = resU; pool.f(F_HV, myEntry) = resV; pool.f(F_HDET, myEntry) = resDet; pool.i(F_HMODEL, myEntry) = resModel;
-                    const unsigned info = pool.u(F_INFO, myEntry);
-                    pool.u(F_INFO, myEntry) = (info & ~15u) | resKind;
-                    mode = T_IDLE; myEntry = -1;
+                    if (model >= 0 && bestDst < resDst)              // HL:362-370 (normal / position are rebuilt when shading)
+                    {
+                        resDst = bestDst; resPrim = bestTri; resU = bestU; resV = bestV; resDet = bestDet; resModel = model;
+                        resKind = cull ? PS_HIT_OPAQUE : PS_HIT_GLASS;   // cull == (flag != GLASS)
+                    }
+                    model++;
+                    if (model < P.modelCount)
+                    {
+                        const float4* mr = reinterpret_cast<const float4*>(P.models + model);
+                        const float4 r0 = __ldg(mr), r1 = __ldg(mr + 1), r2 = __ldg(mr + 2);
+                        const float w2l[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+                        const int4 meta = __ldg(reinterpret_cast<const int4*>(mr + 6));
+                        lpos = mul_rm(w2l, rayPos, 1.0f);
+                        ldir = mul_rm(w2l, rayDir, 0.0f);
+                        linv = rcp3(ldir);
+                        cull = meta.z != 0;
+                        bestDst = resDst; bestTri = -1;              // result.dst is the ray length shared across models (HL:359)
+                        cur.start = meta.x; cur.count = meta.y; leafK = 0; stackCount = 0;
+                        mode = cur.count > 0 ? T_LEAF : T_INNER;
+                    }
+                    else
+                    {
+                        pool.f(F_HDST, myEntry) = resDst; pool.i(F_HPRIM, myEntry) = resPrim;
+                        pool.f(F_HU, myEntry) = resU; pool.f(F_HV, myEntry) = resV; pool.f(F_HDET, myEntry) = resDet; pool.i(F_HMODEL, myEntry) = resModel;
+                        const unsigned info = pool.u(F_INFO, myEntry);
+                        pool.u(F_INFO, myEntry) = (info & ~15u) | resKind;
+                        mode = T_IDLE; myEntry = -1;
+                    }
                 }
             }
-
-            // ---- inner nodes: HL:262-282 ----
-            while (mode == T_INNER)
+            else if (nInner >= nLeaf)
             {
-                float4 q0, q1, q2, q3;
-                LoadPair(P, smemPairs, cur.start, q0, q1, q2, q3);
-                const float dstA = RayBoundingBoxDst(lpos, linv, make_f3(q0.x, q0.y, q0.z), make_f3(q0.w, q1.x, q1.y));
-                const float dstB = RayBoundingBoxDst(lpos, linv, make_f3(q2.x, q2.y, q2.z), make_f3(q2.w, q3.x, q3.y));
-                if (STATS) cnt.box += 2;
-                NodeRef a, b;
-                a.start = __float_as_int(q1.z); a.count = __float_as_int(q1.w);
-                b.start = __float_as_int(q3.z); b.count = __float_as_int(q3.w);
-                const bool isNearestA = dstA <= dstB;
-                const float dstNear = isNearestA ? dstA : dstB;
-                const float dstFar = isNearestA ? dstB : dstA;
-                const NodeRef nearRef = isNearestA ? a : b;
-                const NodeRef farRef = isNearestA ? b : a;
-                if (dstFar < bestDst && stackCount < WAVE_STACK) stack[stackCount++] = farRef;
-                if (dstNear < bestDst) cur = nearRef;
-                else if (stackCount > 0) cur = stack[--stackCount];
-                else { mode = T_NEXT; break; }
-                if (cur.count > 0) { mode = T_LEAF; leafK = 0; }
-            }
-
-            // ---- leaf triangles: HL:248-260 ----
-            while (mode == T_LEAF)
-            {
-                const float4* g = reinterpret_cast<const float4*>(P.triGeom + cur.start + leafK);
-                const float4 g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2);
-                float dst, u, v, det;
-                const bool didHit = RayTriangleCore(lpos, ldir, make_f3(g0.x, g0.y, g0.z), make_f3(g0.w, g1.x, g1.y), make_f3(g1.z, g1.w, g2.x),
-                                                    make_f3(g2.y, g2.z, g2.w), cull, dst, u, v, det);
-                if (STATS) cnt.tri++;
-                if (didHit && dst < bestDst) { bestDst = dst; bestTri = cur.start + leafK; bestU = u; bestV = v; bestDet = det; }
-                leafK++;
-                if (leafK >= cur.count)
+                // ---- one inner node: HL:262-282 ----
+                if (mode == T_INNER)
                 {
-                    if (stackCount > 0) { cur = stack[--stackCount]; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
+                    float4 q0, q1, q2, q3;
+                    LoadPair(P, smemPairs, cur.start, q0, q1, q2, q3);
+                    const float dstA = RayBoundingBoxDst(lpos, linv, make_f3(q0.x, q0.y, q0.z), make_f3(q0.w, q1.x, q1.y));
+                    const float dstB = RayBoundingBoxDst(lpos, linv, make_f3(q2.x, q2.y, q2.z), make_f3(q2.w, q3.x, q3.y));
+                    if (STATS) cnt.box += 2;
+                    NodeRef a, b;
+                    a.start = __float_as_int(q1.z); a.count = __float_as_int(q1.w);
+                    b.start = __float_as_int(q3.z); b.count = __float_as_int(q3.w);
+                    const bool isNearestA = dstA <= dstB;
+                    const float dstNear = isNearestA ? dstA : dstB;
+                    const float dstFar = isNearestA ? dstB : dstA;
+                    const NodeRef nearRef = isNearestA ? a : b;
+                    const NodeRef farRef = isNearestA ? b : a;
+                    if (dstFar < bestDst && stackCount < WAVE_STACK) stack[stackCount++] = farRef;
+                    if (dstNear < bestDst) { cur = nearRef; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
+                    else if (stackCount > 0) { cur = stack[--stackCount]; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
                     else mode = T_NEXT;
+                }
+            }
+            else
+            {
+                // ---- one leaf triangle: HL:248-260 ----
+                if (mode == T_LEAF)
+                {
+                    const float4* g = reinterpret_cast<const float4*>(P.triGeom + cur.start + leafK);
+                    const float4 g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2);
+                    float dst, u, v, det;
+                    const bool didHit = RayTriangleCore(lpos, ldir, make_f3(g0.x, g0.y, g0.z), make_f3(g0.w, g1.x, g1.y), make_f3(g1.z, g1.w, g2.x),
+                                                        make_f3(g2.y, g2.z, g2.w), cull, dst, u, v, det);
+                    if (STATS) cnt.tri++;
+                    if (didHit && dst < bestDst) { bestDst = dst; bestTri = cur.start + leafK; bestU = u; bestV = v; bestDet = det; }
+                    leafK++;
+                    if (leafK >= cur.count)
+                    {
+                        if (stackCount > 0) { cur = stack[--stackCount]; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
+                        else mode = T_NEXT;
+                    }
                 }
             }
         }
