@@ -122,6 +122,7 @@ int rtGetDevicePointer(RtContext* ctx, const char* name, void** devPtr, size_t* 
  *   "countStats"  1 = also count box / triangle tests (HL:254,271) — slower, off by default
  *   "smemNodes"   number of top-of-tree node pairs staged in shared memory by TMA bulk copy (0 = off, -1 = auto)
  *   "poolSlots"   paths per warp pool of kernel 2: 64, 96 or 128
+ *   "tailLanes"   kernel 2 leaves its trace phase when the ray queue is empty and at most this many lanes still trace
  * Unknown names return RT_E_UNKNOWN_NAME. */
 int rtSetOption(RtContext* ctx, const char* name, int value);
 

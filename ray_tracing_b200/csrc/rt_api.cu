@@ -59,7 +59,7 @@ struct RtContext
     int tileRank = 0, tileWorld = 1, bandRows = 1;
 
     // options
-    int optKernel = 2, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64;   // smemPairs -1 = automatic
+    int optKernel = 2, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 8;   // smemPairs -1 = automatic
 
     // counters / timing
     unsigned long long* dCounters = nullptr;   // 4
@@ -304,6 +304,7 @@ int rtSetOption(RtContext* c, const char* name, int value)
     if (n == "kernel") { if (value < 0 || value > 2) return fail(c, RT_E_INVALID, "rtSetOption: kernel must be 0, 1 or 2"); c->optKernel = value; }
     else if (n == "countStats") c->optCountStats = value != 0;
     else if (n == "smemNodes") c->optSmemPairs = value;
+    else if (n == "tailLanes") { if (value < 0 || value > 31) return fail(c, RT_E_INVALID, "rtSetOption: tailLanes must be in [0, 31]"); c->optTailLanes = value; }
     else if (n == "poolSlots") { if (value != 64 && value != 96 && value != 128) return fail(c, RT_E_INVALID, "rtSetOption: poolSlots must be 64, 96 or 128"); c->optPoolSlots = value; }
     else return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetOption: unknown option ") + name);
     return RT_OK;
@@ -379,7 +380,7 @@ int rtDispatch(RtContext* c, int kernelIndex, int gx, int gy, int gz)
     P.sphereCount = (int)c->spheres.count;
     P.Nodes = c->nodes.p; P.Triangles = c->tris.p; P.ModelInfo = c->models.p; P.Spheres = c->spheres.p;
     P.pairs = c->repack.pairs.p; P.triGeom = c->repack.triGeom.p; P.triNormals = c->repack.triNormals.p;
-    P.models = c->repack.models.p; P.spheres = c->repack.spheres.p; P.smemPairs = c->repack.smemPairs;
+    P.models = c->repack.models.p; P.spheres = c->repack.spheres.p; P.smemPairs = c->repack.smemPairs; P.tailLanes = c->optTailLanes;
     P.FrameRender = c->frame.p; P.AccumulatedRender = c->accum.p;
     P.counters = c->dCounters; P.workCounter = c->dWork;
 

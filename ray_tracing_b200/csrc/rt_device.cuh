@@ -89,7 +89,7 @@ struct DevParams
     const DevModel*   models;
     const DevSphere*  spheres;
     int   smemPairs;                        // number of leading pair records staged in shared memory
-    int   pad3;
+    int   tailLanes;                        // pooled kernel: leave the trace phase when this few lanes are still tracing
 
     float4* FrameRender;
     float4* AccumulatedRender;

@@ -30,7 +30,9 @@ constexpr int POOL_THREADS = POOL_WARPS * 32;
 constexpr int POOL_WORDS = 24;                 // 32-bit words of state per path slot
 
 // slot state (low 4 bits of the info word)
-enum : unsigned { PS_EMPTY = 0, PS_GEN = 1, PS_RAY = 2, PS_HIT_MISS = 3, PS_HIT_OPAQUE = 4, PS_HIT_GLASS = 5, PS_DONE = 6 };
+enum : unsigned { PS_EMPTY = 0, PS_GEN = 1, PS_RAY = 2, PS_HIT_MISS = 3, PS_HIT_OPAQUE = 4, PS_HIT_GLASS = 5, PS_DONE = 6,
+                  PS_FLIGHT = 7 /* a lane is tracing this slot's ray (possibly across phases) */ };
+
 
 // word index of each field inside a pool (field-major: word f of slot e is pool[f * M + e], conflict-free for lane = e)
 enum : int { F_XY = 0, F_RNG, F_INFO, F_POS, F_DIR = F_POS + 3, F_TRN = F_DIR + 3, F_LGT = F_TRN + 3, F_SUM = F_LGT + 3,
@@ -121,6 +123,20 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
 
     Counters cnt; cnt.rays = cnt.box = cnt.tri = cnt.sph = 0;
     bool exhausted = false;                     // warp-uniform: the global pixel queue is empty
+
+    // per-lane ray state of the trace phase.  It lives across phases: a lane whose ray is still in flight when the phase
+    // ends keeps it (slot state PS_FLIGHT) and continues in the next trace phase, so long rays never hold the warp back.
+    enum { T_IDLE = 0, T_INNER = 1, T_LEAF = 2, T_NEXT = 3 };
+    int mode = T_IDLE;
+    int myEntry = -1;                                                // slot this lane is tracing
+    f3 rayPos = splat3(0.0f), rayDir = splat3(0.0f), lpos = splat3(0.0f), ldir = splat3(0.0f), linv = splat3(0.0f);
+    float resDst = inf32(), resU = 0.0f, resV = 0.0f, resDet = 0.0f; int resPrim = 0, resModel = 0; unsigned resKind = PS_HIT_MISS;
+    float bestDst = 0.0f, bestU = 0.0f, bestV = 0.0f, bestDet = 0.0f; int bestTri = -1;
+    int model = 0; bool cull = true;
+    NodeRef cur; cur.start = 0; cur.count = 0;
+    int leafK = 0;
+    NodeRef stack[WAVE_STACK];
+    int stackCount = 0;
 
     for (;;)
     {
@@ -287,20 +303,9 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
 
         // ================================================= TRACE phase =================================================
         const int nRays = CompactByState<M>(pool, lane, PS_RAY, PS_RAY);
-        if (nRays == 0) break;                                       // every slot is DONE: this warp is finished
+        if (nRays == 0 && __ballot_sync(0xffffffffu, mode != T_IDLE) == 0u) break;   // every slot is DONE: this warp is finished
         int next = 0;                                                // warp-uniform queue head
-        int myEntry = -1;                                            // slot this lane is tracing
-        // per-ray state
-        f3 rayPos = splat3(0.0f), rayDir = splat3(0.0f), lpos = splat3(0.0f), ldir = splat3(0.0f), linv = splat3(0.0f);
-        float resDst = inf32(), resU = 0.0f, resV = 0.0f, resDet = 0.0f; int resPrim = 0, resModel = 0; unsigned resKind = PS_HIT_MISS;
-        float bestDst = 0.0f, bestU = 0.0f, bestV = 0.0f, bestDet = 0.0f; int bestTri = -1;
-        int model = 0; bool cull = true;
-        NodeRef cur; cur.start = 0; cur.count = 0;
-        int leafK = 0;
-        NodeRef stack[WAVE_STACK];
-        int stackCount = 0;
-        enum { T_IDLE = 0, T_INNER = 1, T_LEAF = 2, T_NEXT = 3 };
-        int mode = T_IDLE;
+        bool finishedAny = false;                                    // warp-uniform: some ray completed in this phase
 
         for (;;)
         {
@@ -315,6 +320,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                     if (need && idx < nRays)
                     {
                         myEntry = pool.order[idx];
+                        pool.u(F_INFO, myEntry) = (pool.u(F_INFO, myEntry) & ~15u) | PS_FLIGHT;
                         rayPos = pool.get3(F_POS, myEntry); rayDir = pool.get3(F_DIR, myEntry);
                         cnt.rays++;
                         resDst = inf32(); resPrim = 0; resModel = 0; resKind = PS_HIT_MISS; resU = resV = resDet = 0.0f;
@@ -336,7 +342,10 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                         model = -1; mode = T_NEXT;
                     }
                 }
-                if (__ballot_sync(0xffffffffu, mode != T_IDLE) == 0u) break;
+                const int nActive = __popc(__ballot_sync(0xffffffffu, mode != T_IDLE));
+                if (nActive == 0) break;
+                // queue drained and only a few long rays left: go shade what has finished, they continue next phase
+                if (next >= nRays && nActive <= P.tailLanes && finishedAny) break;
             }
 
             // ---- vote: run the step kind most lanes are waiting for (ties: finish/advance first, then inner nodes) ----
@@ -350,6 +359,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
             if (nNext >= nInner && nNext >= nLeaf)
             {
                 // ---- advance to the next model / finish the ray ----
+                bool fin = false;
                 if (mode == T_NEXT)
                 {
                     if (model >= 0 && bestDst < resDst)              // HL:362-370 (normal / position are rebuilt when shading)
@@ -378,9 +388,10 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                         pool.f(F_HU, myEntry) = resU; pool.f(F_HV, myEntry) = resV; pool.f(F_HDET, myEntry) = resDet; pool.i(F_HMODEL, myEntry) = resModel;
                         const unsigned info = pool.u(F_INFO, myEntry);
                         pool.u(F_INFO, myEntry) = (info & ~15u) | resKind;
-                        mode = T_IDLE; myEntry = -1;
+                        mode = T_IDLE; myEntry = -1; fin = true;
                     }
                 }
+                if (__any_sync(0xffffffffu, fin)) finishedAny = true;
             }
             else if (nInner >= nLeaf)
             {
