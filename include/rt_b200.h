@@ -118,7 +118,8 @@ int rtGetDevicePointer(RtContext* ctx, const char* name, void** devPtr, size_t* 
 
 /* Tuning / instrumentation switches.  name ∈
  *   "kernel"      0 = reference-shaped per-pixel megakernel, 1 = persistent threads (one path per lane),
- *                 2 = persistent-thread wavefront with per-warp path pools, sorting and ray compaction (default)
+ *                 2 = persistent-thread wavefront with per-warp path pools, sorting and ray compaction,
+ *                 -1 = automatic (default): 2 when the scene has meshes, 1 for sphere-only scenes
  *   "countStats"  1 = also count box / triangle tests (HL:254,271) — slower, off by default
  *   "smemNodes"   number of top-of-tree node pairs staged in shared memory by TMA bulk copy (0 = off, -1 = auto)
  *   "poolSlots"   paths per warp pool of kernel 2: 64, 96 or 128

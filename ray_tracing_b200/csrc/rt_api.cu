@@ -59,7 +59,7 @@ struct RtContext
     int tileRank = 0, tileWorld = 1, bandRows = 1;
 
     // options
-    int optKernel = 2, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 8;   // smemPairs -1 = automatic
+    int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16;   // kernel -1 = automatic   // smemPairs -1 = automatic
 
     // counters / timing
     unsigned long long* dCounters = nullptr;   // 4
@@ -301,13 +301,21 @@ int rtSetOption(RtContext* c, const char* name, int value)
 {
     if (!c || !name) return fail(c, RT_E_INVALID, "rtSetOption: bad argument");
     const std::string n(name);
-    if (n == "kernel") { if (value < 0 || value > 2) return fail(c, RT_E_INVALID, "rtSetOption: kernel must be 0, 1 or 2"); c->optKernel = value; }
+    if (n == "kernel") { if (value < -1 || value > 2) return fail(c, RT_E_INVALID, "rtSetOption: kernel must be -1 (auto), 0, 1 or 2"); c->optKernel = value; }
     else if (n == "countStats") c->optCountStats = value != 0;
     else if (n == "smemNodes") c->optSmemPairs = value;
     else if (n == "tailLanes") { if (value < 0 || value > 31) return fail(c, RT_E_INVALID, "rtSetOption: tailLanes must be in [0, 31]"); c->optTailLanes = value; }
     else if (n == "poolSlots") { if (value != 64 && value != 96 && value != 128) return fail(c, RT_E_INVALID, "rtSetOption: poolSlots must be 64, 96 or 128"); c->optPoolSlots = value; }
     else return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetOption: unknown option ") + name);
     return RT_OK;
+}
+
+// Automatic choice (measured, profiles/): with meshes the pooled wavefront kernel wins (BVH traversal needs the ray queue);
+// for sphere-only scenes every ray costs the same and one path per lane avoids the pool's shared-memory round trips.
+static int effectiveKernel(const RtContext* c)
+{
+    if (c->optKernel >= 0) return c->optKernel;
+    return c->P.modelCount > 0 ? 2 : 1;
 }
 
 static int prepareScene(RtContext* c)
@@ -322,8 +330,9 @@ static int prepareScene(RtContext* c)
     }
     // shared-memory budget for the tree tops: what the selected kernel can afford next to its own shared state
     int budget = c->optSmemPairs < 0 ? 1024 : c->optSmemPairs;
-    if (c->optKernel == 2) { const int mx = pool_max_smem_pairs(c->optPoolSlots, (int)c->spheres.count); if (budget > mx) budget = mx; }
-    else if (c->optKernel == 0) budget = 0;
+    const int kernelSel = effectiveKernel(c);
+    if (kernelSel == 2) { const int mx = pool_max_smem_pairs(c->optPoolSlots, (int)c->spheres.count); if (budget > mx) budget = mx; }
+    else if (kernelSel == 0) budget = 0;
     if (budget != c->repack.budgetUsed) c->sceneDirty = true;
     if (c->sceneDirty)
     {
@@ -389,7 +398,7 @@ int rtDispatch(RtContext* c, int kernelIndex, int gx, int gy, int gz)
     else { CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b)); }
     if (c->pending.size() >= 512) { rc = drainEvents(c); if (rc != RT_OK) return rc; }
 
-    int kernel = c->optKernel;
+    int kernel = effectiveKernel(c);
     if (c->P.NumRaysPerPixel == 0) kernel = 0;       // 0 samples: the per-pixel kernel reproduces the reference's 0/0 directly
     if (kernel == 0)
     {
