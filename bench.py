@@ -39,6 +39,11 @@ WORKLOADS = {
                       desc="9-sphere Cornell box, 1920x1080, 8 bounces, 64 spp per frame (BASELINE.json configs[1])"),
     "knot64": dict(kind="knot", width=1920, height=1080, bounces=8, spp=16,
                    desc="87,132-triangle knot in a Cornell room (3 models, BVH), 1920x1080, 8 bounces, 16 spp per frame (configs[2] shape)"),
+    "cluster4k": dict(kind="cluster", width=3840, height=2160, bounces=12, spp=4,
+                      desc="871,212-triangle glass knot cluster (one mesh, one deep BVH) in a room, 3840x2160, 12 bounces, 4 spp per frame (configs[3] shape)"),
+    "soup4k": dict(kind="soup", width=4096, height=4096, bounces=16, spp=2,
+                   desc="1,000,000 random triangles in 3 models + 16 spheres, sky on, 4096x4096, 16 bounces, 2 spp per frame (configs[4] shape; "
+                        "the 10k-sphere buffer waits for the exact sphere accelerator)"),
 }
 METRIC = "Mrays/s at 1920x1080, 8 bounces (ray = one CalculateRayCollision call)"
 FALLBACK_HBM_GBS = 6650.0
@@ -48,6 +53,10 @@ def make_scene(w):
     from ray_tracing_b200 import scenes
     if w["kind"] == "cornell":
         return scenes.cornell_spheres(w["width"], w["height"], w["bounces"], w["spp"])
+    if w["kind"] == "cluster":
+        return scenes.knot_cluster(w["width"], w["height"], w["bounces"], w["spp"])
+    if w["kind"] == "soup":
+        return scenes.random_soup(w["width"], w["height"], w["bounces"], w["spp"], triangles=1_000_000, spheres=16)
     return scenes.knot_room(w["width"], w["height"], w["bounces"], w["spp"])
 
 
@@ -173,7 +182,7 @@ def run_gpu(args, w):
 
     sc = make_scene(w)
     W, H = w["width"], w["height"]
-    mgr = rt.RayComputeManager(b.LIB_CUDA, device=local)           # raises without the CUDA library / a GPU
+    mgr = rt.RayComputeManager(args.lib or b.LIB_CUDA, device=local)   # raises without the CUDA library / a GPU
     scenes.apply(sc, mgr)
     tiled = multigpu.TiledRenderer(mgr, rank, world, band_rows=args.band_rows, device=dev)   # also puts the context on a torch stream
     ctx, stream = tiled.ctx, tiled.stream
@@ -287,8 +296,9 @@ def run_gpu(args, w):
             "config": {"workload": w["desc"], "rays_per_frame": rays // args.steps, "spp_per_frame": w["spp"],
                        "tiling": f"row bands of {args.band_rows} rows round-robin over {world} GPU(s), one all-gather per frame" if world > 1 else "single GPU",
                        "l2": "flushed between steps (256 MiB write inside the timed region)",
-                       "kernel": {None: "k_raytrace_pool (persistent wavefront, per-warp path pools)", 2: "k_raytrace_pool (persistent wavefront, per-warp path pools)",
-                                  1: "k_raytrace_wave (persistent threads)", 0: "k_raytrace_mega (reference-shaped)"}[args.kernel],
+                       "kernel": {2: "k_raytrace_pool (persistent wavefront, per-warp path pools)",
+                                  1: "k_raytrace_wave (persistent threads, one path per lane)", 0: "k_raytrace_mega (reference-shaped)"}[
+                                      args.kernel if args.kernel is not None else (2 if model_count > 0 else 1)],
                        "pool_slots": args.pool_slots, "smem_nodes": args.smem_nodes},
             "ms_per_frame": round(ms_total / args.steps, 4),
             "clocks": clocks,
@@ -323,6 +333,7 @@ def main():
     ap.add_argument("--pool-slots", type=int, default=None, help="paths per warp pool of kernel 2 (64, 96, 128)")
     ap.add_argument("--tail-lanes", type=int, default=None, help="kernel 2: leave the trace phase when this few lanes still trace")
     ap.add_argument("--smem-nodes", type=int, default=None, help="node pairs staged in shared memory (-1 = auto)")
+    ap.add_argument("--lib", default=None, help="alternative build of librt_b200.so (A/B experiments)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -65,13 +65,15 @@ def nvcc_path() -> str:
     return p
 
 
-def build_cuda(force: bool = False, verbose_ptxas: bool = False) -> str:
+def build_cuda(force: bool = False, verbose_ptxas: bool = False, defines: tuple = (), out: str = "") -> str:
+    """Builds librt_b200.so; `defines` / `out` build an experimental variant next to it (A/B measurements)."""
     srcs = _glob(CSRC, (".cu", ".cuh")) + _glob(INCLUDE, (".h",))
-    if force or _newer(LIB_CUDA, srcs):
-        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose_ptxas else []) + \
-              ["-I", INCLUDE, "-o", LIB_CUDA, os.path.join(CSRC, "rt_api.cu")]
+    target = out or LIB_CUDA
+    if force or _newer(target, srcs):
+        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose_ptxas else []) + [f"-D{d}" for d in defines] + \
+              ["-I", INCLUDE, "-o", target, os.path.join(CSRC, "rt_api.cu")]
         _run(cmd)
-    return LIB_CUDA
+    return target
 
 
 def build_host(force: bool = False) -> str:

@@ -217,12 +217,14 @@ RT_DI bool RaySphereCore(f3 rayPos, f3 rayDir, f3 centre, float r2, float& dst, 
         const float s = sqrtf(discriminant);
         const float den = 2.0f * a;
         const float numFar = -b + s;
-        const bool farOk = den > 0.0f ? (numFar >= 0.0f) : ((numFar / den) >= 0.0f);
+        // finite positive denominator (always, for a normalised direction): the sign test replaces the division
+        const bool farOk = (den > 0.0f && den < inf32()) ? (numFar >= 0.0f) : (div_cold(numFar, den) >= 0.0f);
         if (farOk)
         {
             const float dstNear = fmaxf(0.0f, (-b - s) / den);
             isInside = dstNear == 0.0f;
-            dst = isInside ? (numFar / den) : dstNear;
+            dst = dstNear;
+            if (isInside) dst = div_cold(numFar, den);      // only from inside a sphere (glass interiors)
             return true;
         }
     }
@@ -320,7 +322,11 @@ RT_DI bool ShadeSegment(const DevParams& P, const Hit& hit, PathState& ray, uint
     const float tz = isGlass ? v5 : v6, rz = isGlass ? v6 : v7;
     // one copy of the log / sqrt / cos body, run three times (instruction-cache footprint; the values are the same)
     float nx = 0.0f, ny = 0.0f, nz = 0.0f;
+#ifndef RT_RANDDIR_INLINE
 #pragma unroll 1
+#else
+#pragma unroll
+#endif
     for (int k = 0; k < 3; k++)
     {
         const float t = k == 0 ? tx : (k == 1 ? ty : tz);

@@ -37,7 +37,13 @@ RT_DI f3 rcp3(f3 a) { return make_f3(1.0f / a.x, 1.0f / a.y, 1.0f / a.z); }
 
 RT_DI float dot3(f3 a, f3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 RT_DI f3 cross3(f3 a, f3 b) { return make_f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+#ifdef RT_NOINLINE_NORMALIZE
+__device__ __noinline__ f3 normalize3(f3 v) { float inv = 1.0f / sqrtf(dot3(v, v)); return v * inv; }
+#else
 RT_DI f3 normalize3(f3 v) { float inv = 1.0f / sqrtf(dot3(v, v)); return v * inv; }
+#endif
+// IEEE quotient behind a call: for divisions on rarely taken paths, so the compiler cannot speculate them
+__device__ __noinline__ float div_cold(float a, float b) { return a / b; }
 RT_DI f3 lerp3(f3 a, f3 b, float t) { return a + t * (b - a); }
 RT_DI f3 reflect3(f3 i, f3 n) { return i - (2.0f * dot3(n, i)) * n; }
 RT_DI float sign1(float a) { return (a > 0.0f ? 1.0f : 0.0f) - (a < 0.0f ? 1.0f : 0.0f); }

@@ -193,8 +193,11 @@ RT_DI Hit Intersect(const DevParams& P, const float4* __restrict__ smemPairs, co
     return result;
 }
 
+#ifndef RT_WAVE_MINBLOCKS
+#define RT_WAVE_MINBLOCKS 1
+#endif
 template <bool STATS>
-__global__ void __launch_bounds__(WAVE_THREADS) k_raytrace_wave(const __grid_constant__ DevParams P, const unsigned int totalJobs,
+__global__ void __launch_bounds__(WAVE_THREADS, RT_WAVE_MINBLOCKS) k_raytrace_wave(const __grid_constant__ DevParams P, const unsigned int totalJobs,
                                                                const unsigned int tilesX, const unsigned int ownedRows)
 {
     extern __shared__ __align__(128) unsigned char smemRaw[];

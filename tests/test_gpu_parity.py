@@ -126,6 +126,38 @@ def test_config2_size_sparse_pixels_against_oracle():
     assert_bit_equal(fg[xy[:, 1], xy[:, 0]], out, "sparse pixels of the 1080p frame")
 
 
+def _sparse_oracle(sc, n, seed):
+    """Oracle values of n seeded random pixels of the scene's first frame (Frame = 1)."""
+    rng = np.random.RandomState(seed)
+    xy = np.stack([rng.randint(0, sc.width, n), rng.randint(0, sc.height, n)], axis=1).astype(np.int32)
+    mgr = rt.RayComputeManager(ORACLE_LIB)
+    scenes.apply(sc, mgr)
+    mgr.OnEnable()
+    L = C.CDLL(ORACLE_LIB)
+    out = np.empty((n, 4), dtype=np.float32)
+    assert L.orRenderPixels(C.c_void_p(mgr.context.handle.value), xy.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p)) == 0
+    return xy, out
+
+
+def test_config4_shape_deep_bvh_sparse_pixels():
+    """BASELINE config 4 shape: ~871k triangles merged into ONE mesh (1.7M-node BVH), glass, 12 bounces.  The GPU renders
+    the frame at reduced resolution; 2048 seeded pixels are checked bitwise against the oracle."""
+    sc = scenes.knot_cluster(960, 540, max_bounces=12, rays_per_pixel=1)
+    assert sc.triangle_count > 870000
+    fg, _ = render(CUDA_LIB, sc, frames=1)
+    xy, out = _sparse_oracle(sc, 2048, 21)
+    assert_bit_equal(fg[xy[:, 1], xy[:, 0]], out, "sparse pixels, 871k-triangle scene")
+
+
+def test_config5_shape_million_triangles_sparse_pixels():
+    """BASELINE config 5 shape: 1,000,000 random triangles in three models (opaque / glass / emissive) + spheres, sky on,
+    16 bounces; 2048 seeded pixels bitwise against the oracle."""
+    sc = scenes.random_soup(768, 768, max_bounces=16, rays_per_pixel=1, triangles=1_000_000, spheres=16)
+    fg, _ = render(CUDA_LIB, sc, frames=1)
+    xy, out = _sparse_oracle(sc, 2048, 22)
+    assert_bit_equal(fg[xy[:, 1], xy[:, 0]], out, "sparse pixels, 1M-triangle scene")
+
+
 def test_full_size_properties():
     """Size-independent properties at config-2 size: determinism, megakernel == wavefront kernel, alpha = frame count,
     FrameRender alpha = 1, accumulated = sum of frames."""
