@@ -217,14 +217,14 @@ RT_DI bool RaySphereCore(f3 rayPos, f3 rayDir, f3 centre, float r2, float& dst, 
         const float s = sqrtf(discriminant);
         const float den = 2.0f * a;
         const float numFar = -b + s;
-        // finite positive denominator (always, for a normalised direction): the sign test replaces the division
-        const bool farOk = (den > 0.0f && den < inf32()) ? (numFar >= 0.0f) : (div_cold(numFar, den) >= 0.0f);
+        // dstFar >= 0  <=>  numFar >= 0 for a positive denominator (an IEEE quotient has the sign of its numerator, -0 >= 0
+        // holds for both, inf/inf cannot occur for a finite den): spheres behind the ray are rejected without dividing
+        const bool farOk = (den > 0.0f && den < inf32()) ? (numFar >= 0.0f) : ((numFar / den) >= 0.0f);
         if (farOk)
         {
             const float dstNear = fmaxf(0.0f, (-b - s) / den);
             isInside = dstNear == 0.0f;
-            dst = dstNear;
-            if (isInside) dst = div_cold(numFar, den);      // only from inside a sphere (glass interiors)
+            dst = isInside ? (numFar / den) : dstNear;
             return true;
         }
     }
@@ -320,9 +320,9 @@ RT_DI bool ShadeSegment(const DevParams& P, const Hit& hit, PathState& ray, uint
     const float tx = isGlass ? v1 : v2, rx = isGlass ? v2 : v3;
     const float ty = isGlass ? v3 : v4, ry = isGlass ? v4 : v5;
     const float tz = isGlass ? v5 : v6, rz = isGlass ? v6 : v7;
-    // one copy of the log / sqrt / cos body, run three times (instruction-cache footprint; the values are the same)
+    // three independent log / sqrt / cos chains (measured: the unrolled form beats a rolled loop, ILP > instruction footprint)
     float nx = 0.0f, ny = 0.0f, nz = 0.0f;
-#ifndef RT_RANDDIR_INLINE
+#ifdef RT_RANDDIR_LOOP
 #pragma unroll 1
 #else
 #pragma unroll

@@ -25,7 +25,10 @@
 
 namespace rtd {
 
-constexpr int POOL_WARPS = 16;                 // warps per CTA (one persistent CTA per SM)
+#ifndef RT_POOL_WARPS
+#define RT_POOL_WARPS 24      // measured (profiles/r01_sweeps.log): 16 -> 24 warps per SM: knot 33.8 -> 31.7 ms, 871k-triangle scene 109.8 -> 93.4 ms
+#endif
+constexpr int POOL_WARPS = RT_POOL_WARPS;      // warps per CTA (one persistent CTA per SM)
 constexpr int POOL_THREADS = POOL_WARPS * 32;
 constexpr int POOL_WORDS = 24;                 // 32-bit words of state per path slot
 
