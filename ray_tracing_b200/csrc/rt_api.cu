@@ -59,7 +59,7 @@ struct RtContext
     int tileRank = 0, tileWorld = 1, bandRows = 1;
 
     // options
-    int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16;   // kernel -1 = automatic   // smemPairs -1 = automatic
+    int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16, optSortRays = 1;   // kernel -1 = automatic   // smemPairs -1 = automatic
 
     // counters / timing
     unsigned long long* dCounters = nullptr;   // 4
@@ -304,6 +304,7 @@ int rtSetOption(RtContext* c, const char* name, int value)
     if (n == "kernel") { if (value < -1 || value > 2) return fail(c, RT_E_INVALID, "rtSetOption: kernel must be -1 (auto), 0, 1 or 2"); c->optKernel = value; }
     else if (n == "countStats") c->optCountStats = value != 0;
     else if (n == "smemNodes") c->optSmemPairs = value;
+    else if (n == "sortRays") c->optSortRays = value != 0;
     else if (n == "tailLanes") { if (value < 0 || value > 31) return fail(c, RT_E_INVALID, "rtSetOption: tailLanes must be in [0, 31]"); c->optTailLanes = value; }
     else if (n == "poolSlots") { if (value != 64 && value != 96 && value != 128) return fail(c, RT_E_INVALID, "rtSetOption: poolSlots must be 64, 96 or 128"); c->optPoolSlots = value; }
     else return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetOption: unknown option ") + name);
@@ -329,7 +330,8 @@ static int prepareScene(RtContext* c)
             return fail(c, RT_E_STATE, "rtDispatch: model nodeOffset / triOffset out of range");
     }
     // shared-memory budget for the tree tops: what the selected kernel can afford next to its own shared state
-    int budget = c->optSmemPairs < 0 ? 1024 : c->optSmemPairs;
+    // automatic = 0: measured (profiles/r01_sweeps.log), staging tree tops never beat leaving that shared memory to L1
+    int budget = c->optSmemPairs < 0 ? 0 : c->optSmemPairs;
     const int kernelSel = effectiveKernel(c);
     if (kernelSel == 2) { const int mx = pool_max_smem_pairs(c->optPoolSlots, (int)c->spheres.count); if (budget > mx) budget = mx; }
     else if (kernelSel == 0) budget = 0;
@@ -389,7 +391,7 @@ int rtDispatch(RtContext* c, int kernelIndex, int gx, int gy, int gz)
     P.sphereCount = (int)c->spheres.count;
     P.Nodes = c->nodes.p; P.Triangles = c->tris.p; P.ModelInfo = c->models.p; P.Spheres = c->spheres.p;
     P.pairs = c->repack.pairs.p; P.triGeom = c->repack.triGeom.p; P.triNormals = c->repack.triNormals.p;
-    P.models = c->repack.models.p; P.spheres = c->repack.spheres.p; P.smemPairs = c->repack.smemPairs; P.tailLanes = c->optTailLanes;
+    P.models = c->repack.models.p; P.spheres = c->repack.spheres.p; P.smemPairs = c->repack.smemPairs; P.tailLanes = c->optTailLanes; P.sortRays = c->optSortRays;
     P.FrameRender = c->frame.p; P.AccumulatedRender = c->accum.p;
     P.counters = c->dCounters; P.workCounter = c->dWork;
 

@@ -90,6 +90,8 @@ struct DevParams
     const DevSphere*  spheres;
     int   smemPairs;                        // number of leading pair records staged in shared memory
     int   tailLanes;                        // pooled kernel: leave the trace phase when this few lanes are still tracing
+    int   sortRays;                         // pooled kernel: group the ray queue by direction octant
+    int   pad4;
 
     float4* FrameRender;
     float4* AccumulatedRender;

@@ -79,6 +79,37 @@ template <int M> RT_DI int CompactByState(const PoolView<M>& pool, unsigned lane
     return base;
 }
 
+// Ray queue of the trace phase, grouped by the octant of the ray direction (sign bits): rays that pop together tend to
+// order the children of a node the same way and touch the same nodes.  Active-path sorting; the order in which rays are
+// traced does not enter any result.
+template <int M> RT_DI int CompactRaysByOctant(const PoolView<M>& pool, unsigned lane)
+{
+    const unsigned ltMask = (1u << lane) - 1u;
+    unsigned key[M / 32];
+#pragma unroll
+    for (int c = 0; c < M / 32; c++)
+    {
+        const int e = c * 32 + (int)lane;
+        const bool isRay = info_state(pool.u(F_INFO, e)) == PS_RAY;
+        const unsigned oct = (pool.u(F_DIR, e) >> 31) | ((pool.u(F_DIR + 1, e) >> 31) << 1) | ((pool.u(F_DIR + 2, e) >> 31) << 2);
+        key[c] = isRay ? oct : 8u;
+    }
+    int base = 0;
+    for (unsigned o = 0; o < 8u; o++)
+    {
+#pragma unroll
+        for (int c = 0; c < M / 32; c++)
+        {
+            const bool has = key[c] == o;
+            const unsigned m = __ballot_sync(0xffffffffu, has);
+            if (has) pool.order[base + __popc(m & ltMask)] = (unsigned char)(c * 32 + (int)lane);
+            base += __popc(m);
+        }
+    }
+    __syncwarp();
+    return base;
+}
+
 template <bool STATS, int M>
 __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_constant__ DevParams P, const unsigned int totalJobs,
                                                                   const unsigned int tilesX, const unsigned int ownedRows)
@@ -305,60 +336,58 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
         }
 
         // ================================================= TRACE phase =================================================
-        const int nRays = CompactByState<M>(pool, lane, PS_RAY, PS_RAY);
+        const int nRays = P.sortRays ? CompactRaysByOctant<M>(pool, lane) : CompactByState<M>(pool, lane, PS_RAY, PS_RAY);
         if (nRays == 0 && __ballot_sync(0xffffffffu, mode != T_IDLE) == 0u) break;   // every slot is DONE: this warp is finished
         int next = 0;                                                // warp-uniform queue head
         bool finishedAny = false;                                    // warp-uniform: some ray completed in this phase
 
         for (;;)
         {
+            // ---- census: how many lanes wait in each mode (one warp reduction on byte-packed counters) ----
+            const unsigned census = __reduce_add_sync(0xffffffffu, 1u << (8 * mode));
+            const int nIdle = (int)(census & 255u), nInner = (int)((census >> 8) & 255u), nLeaf = (int)((census >> 16) & 255u), nNext = (int)(census >> 24);
+
             // ---- fetch: idle lanes pop the next rays of the warp queue (ballot rank, no atomics) ----
+            if (nIdle != 0 && next < nRays)
             {
                 const bool need = mode == T_IDLE;
                 const unsigned needMask = __ballot_sync(0xffffffffu, need);
-                if (needMask != 0u && next < nRays)
+                const int idx = next + __popc(needMask & ltMask);
+                next += nIdle;
+                if (need && idx < nRays)
                 {
-                    const int idx = next + __popc(needMask & ltMask);
-                    next += __popc(needMask);
-                    if (need && idx < nRays)
+                    myEntry = pool.order[idx];
+                    pool.u(F_INFO, myEntry) = (pool.u(F_INFO, myEntry) & ~15u) | PS_FLIGHT;
+                    rayPos = pool.get3(F_POS, myEntry); rayDir = pool.get3(F_DIR, myEntry);
+                    cnt.rays++;
+                    resDst = inf32(); resPrim = 0; resModel = 0; resKind = PS_HIT_MISS; resU = resV = resDet = 0.0f;
+                    // spheres first (extension; where the reference's commented call sits, HL:341)
+                    for (int s = 0; s < P.sphereCount; s++)
                     {
-                        myEntry = pool.order[idx];
-                        pool.u(F_INFO, myEntry) = (pool.u(F_INFO, myEntry) & ~15u) | PS_FLIGHT;
-                        rayPos = pool.get3(F_POS, myEntry); rayDir = pool.get3(F_DIR, myEntry);
-                        cnt.rays++;
-                        resDst = inf32(); resPrim = 0; resModel = 0; resKind = PS_HIT_MISS; resU = resV = resDet = 0.0f;
-                        // spheres first (extension; where the reference's commented call sits, HL:341)
-                        for (int s = 0; s < P.sphereCount; s++)
+                        float cx, cy, cz, r2; int flag;
+                        if (s < WAVE_MAX_SMEM_SPHERES) { const DevSphere sp = smemSpheres[s]; cx = sp.cx; cy = sp.cy; cz = sp.cz; r2 = sp.r2; flag = sp.pad0; }
+                        else { const float4 s0 = __ldg(reinterpret_cast<const float4*>(P.spheres + s)); cx = s0.x; cy = s0.y; cz = s0.z;
+                               r2 = __ldg(&P.spheres[s].r2); flag = __ldg(&P.spheres[s].pad0); }
+                        float dst; bool inside;
+                        if (STATS) cnt.sph++;
+                        if (RaySphereCore(rayPos, rayDir, make_f3(cx, cy, cz), r2, dst, inside) && dst < resDst)
                         {
-                            float cx, cy, cz, r2; int flag;
-                            if (s < WAVE_MAX_SMEM_SPHERES) { const DevSphere sp = smemSpheres[s]; cx = sp.cx; cy = sp.cy; cz = sp.cz; r2 = sp.r2; flag = sp.pad0; }
-                            else { const float4 s0 = __ldg(reinterpret_cast<const float4*>(P.spheres + s)); cx = s0.x; cy = s0.y; cz = s0.z;
-                                   r2 = __ldg(&P.spheres[s].r2); flag = __ldg(&P.spheres[s].pad0); }
-                            float dst; bool inside;
-                            if (STATS) cnt.sph++;
-                            if (RaySphereCore(rayPos, rayDir, make_f3(cx, cy, cz), r2, dst, inside) && dst < resDst)
-                            {
-                                resDst = dst; resPrim = -(s + 1); resDet = inside ? -1.0f : 1.0f;
-                                resKind = flag == RT_MATERIAL_GLASS ? PS_HIT_GLASS : PS_HIT_OPAQUE;
-                            }
+                            resDst = dst; resPrim = -(s + 1); resDet = inside ? -1.0f : 1.0f;
+                            resKind = flag == RT_MATERIAL_GLASS ? PS_HIT_GLASS : PS_HIT_OPAQUE;
                         }
-                        model = -1; mode = T_NEXT;
                     }
+                    model = -1; mode = T_NEXT;
                 }
-                const int nActive = __popc(__ballot_sync(0xffffffffu, mode != T_IDLE));
-                if (nActive == 0) break;
-                // queue drained and only a few long rays left: go shade what has finished, they continue next phase
-                if (next >= nRays && nActive <= P.tailLanes && finishedAny) break;
+                continue;                                            // recount: the fetched lanes now wait in T_NEXT
             }
+            if (nIdle == 32) break;
+            // queue drained and only a few long rays left: go shade what has finished, they continue next phase
+            if (next >= nRays && (32 - nIdle) <= P.tailLanes && finishedAny) break;
 
             // ---- vote: run the step kind most lanes are waiting for (ties: finish/advance first, then inner nodes) ----
             // Lanes are independent state machines (inner node / leaf triangle / next model); executing every kind each
             // iteration would run each at a fraction of the warp.  One kind per iteration keeps the executed block dense,
             // the others catch up when their kind becomes the majority.  The per-ray visiting order is unchanged.
-            const int nInner = __popc(__ballot_sync(0xffffffffu, mode == T_INNER));
-            const int nLeaf = __popc(__ballot_sync(0xffffffffu, mode == T_LEAF));
-            const int nNext = __popc(__ballot_sync(0xffffffffu, mode == T_NEXT));
-
             if (nNext >= nInner && nNext >= nLeaf)
             {
                 // ---- advance to the next model / finish the ray ----
