@@ -59,7 +59,7 @@ struct RtContext
     int tileRank = 0, tileWorld = 1, bandRows = 1;
 
     // options
-    int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16, optSortRays = 1;   // kernel -1 = automatic   // smemPairs -1 = automatic
+    int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16, optSortRays = 0;   // kernel -1 = automatic   // smemPairs -1 = automatic
 
     // counters / timing
     unsigned long long* dCounters = nullptr;   // 4
@@ -306,7 +306,7 @@ int rtSetOption(RtContext* c, const char* name, int value)
     else if (n == "smemNodes") c->optSmemPairs = value;
     else if (n == "sortRays") c->optSortRays = value != 0;
     else if (n == "tailLanes") { if (value < 0 || value > 31) return fail(c, RT_E_INVALID, "rtSetOption: tailLanes must be in [0, 31]"); c->optTailLanes = value; }
-    else if (n == "poolSlots") { if (value != 64 && value != 96 && value != 128) return fail(c, RT_E_INVALID, "rtSetOption: poolSlots must be 64, 96 or 128"); c->optPoolSlots = value; }
+    else if (n == "poolSlots") { if (value != 32 && value != 64 && value != 96) return fail(c, RT_E_INVALID, "rtSetOption: poolSlots must be 32, 64 or 96"); c->optPoolSlots = value; }
     else return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetOption: unknown option ") + name);
     return RT_OK;
 }

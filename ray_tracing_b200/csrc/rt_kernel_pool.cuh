@@ -2,7 +2,7 @@
 //
 // Why: in variant 1 a lane owns one path, so during BVH traversal the warp waits for its longest ray — ncu showed
 // 6 of 32 lanes active in the node loop on the mesh scene (profiles/).  Here every warp owns a pool of M paths
-// (M = 2..4 x 32) that lives in shared memory, and alternates two phases, each of which keeps the lanes full:
+// (M = 1..3 x 32) that lives in shared memory, and alternates two phases, each of which keeps the lanes full:
 //
 //   SHADE phase   the paths that came back from tracing are SORTED by what their hit needs (miss / opaque / glass)
 //                 with ballot+popcount compaction into an index list, then shaded 32 at a time — each batch runs one
@@ -498,9 +498,9 @@ template <int M> inline cudaError_t pool_configure_one()
 inline cudaError_t pool_configure()
 {
     cudaError_t e;
+    if ((e = pool_configure_one<32>()) != cudaSuccess) return e;
     if ((e = pool_configure_one<64>()) != cudaSuccess) return e;
-    if ((e = pool_configure_one<96>()) != cudaSuccess) return e;
-    return pool_configure_one<128>();
+    return pool_configure_one<96>();
 }
 
 // shared-memory bytes the pools leave for the tree-top cache (in NodePair records)
@@ -540,9 +540,9 @@ inline cudaError_t pool_launch(const DevParams& P, int M, int numSMs, cudaStream
     const unsigned long long jobs64 = (unsigned long long)tilesX * tileRows * 32ull;
     if (jobs64 >= 0xffff0000ull) return cudaErrorInvalidValue;
     const unsigned int totalJobs = (unsigned int)jobs64;
+    if (M == 32) return pool_launch_m<32>(P, numSMs, stream, evA, evB, totalJobs, tilesX, ownedRows);
     if (M == 64) return pool_launch_m<64>(P, numSMs, stream, evA, evB, totalJobs, tilesX, ownedRows);
     if (M == 96) return pool_launch_m<96>(P, numSMs, stream, evA, evB, totalJobs, tilesX, ownedRows);
-    if (M == 128) return pool_launch_m<128>(P, numSMs, stream, evA, evB, totalJobs, tilesX, ownedRows);
     return cudaErrorInvalidValue;
 }
 

@@ -86,14 +86,16 @@ def test_shared_memory_staging_does_not_change_results():
             assert_bit_equal(img, ref, f"kernel={kernel} smemNodes={n}")
 
 
-@pytest.mark.parametrize("slots", [64, 96, 128])
+@pytest.mark.parametrize("slots", [32, 64, 96])
 def test_pool_sizes_do_not_change_results(slots):
     """Paths per warp pool of the wavefront kernel: scheduling only, identical output and counters."""
     sc = scenes.knot_room(128, 72, max_bounces=6, rays_per_pixel=3, nu=150, nv=10, glass=True)
     fo, ao, so = render(ORACLE_LIB, sc, frames=1, want_stats=True)
-    fg, ag, sg = render(CUDA_LIB, sc, frames=1, options={"kernel": 2, "poolSlots": slots, "countStats": 1}, want_stats=True)
-    assert_bit_equal(fg, fo, f"poolSlots={slots}")
-    _same_counters(sg, so)
+    for sort_rays in (0, 1):
+        fg, ag, sg = render(CUDA_LIB, sc, frames=1, options={"kernel": 2, "poolSlots": slots, "countStats": 1, "sortRays": sort_rays, "tailLanes": 4 + 9 * sort_rays},
+                            want_stats=True)
+        assert_bit_equal(fg, fo, f"poolSlots={slots} sortRays={sort_rays}")
+        _same_counters(sg, so)
 
 
 def test_bvh_quality_modes_on_gpu():
