@@ -4,8 +4,11 @@ N=$1; TAG=${2:-mg}
 OUT=gpurun_out; mkdir -p $OUT
 nvidia-smi -L | tee $OUT/gpus_$TAG.txt
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 tools/multigpu_check.py 2>&1 | grep -v "^W\|^\*\*\*" | tail -6 | tee $OUT/multigpu_check_$TAG.log
-for wl in cornell64 knot64; do
+for wl in ${WORKLOADS:-cornell64 knot64}; do
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus $N --steps 5 --warmup 3 --workload $wl 2>&1 | grep '^{' | tail -1 | tee $OUT/bench_${wl}_n${N}_$TAG.log
 done
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu 2>&1 | tail -1 | tee $OUT/bench_cornell64_n1_$TAG.log
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --workload knot64 2>&1 | tail -1 | tee $OUT/bench_knot64_n1_$TAG.log
+if [ "${SKIP_N1:-0}" = "0" ]; then
+for wl in ${WORKLOADS:-cornell64 knot64}; do
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --workload $wl 2>&1 | tail -1 | tee $OUT/bench_${wl}_n1_$TAG.log
+done
+fi
