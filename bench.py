@@ -133,7 +133,7 @@ class ClockSampler(threading.Thread):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.samples.append([x.strip() for x in line.split(",")])
@@ -150,6 +150,17 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+
+
+def ncu_traffic(workload, kernel_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture of this
+    workload (profiles/ncu_traffic.json, written from `ncu --set full` reports by tools/ncu_traffic.py); None if not captured."""
+    p = os.path.join(REPO, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p)).get(workload, {})
+        return d.get(kernel_name.split(" ")[0])
+    except Exception:
+        return None
 
 
 def measured_hbm_peak():
@@ -226,12 +237,12 @@ def run_gpu(args, w):
 
     # ---- device-resident timing ------------------------------------------------------------------------------------
     frame_no = 1
+    sampler = ClockSampler(local); sampler.start()                   # samples cover warm-up + timed region (clocks under load)
     for _ in range(args.warmup):
         step_resident(frame_no); frame_no += 1
     barrier()
     ctx.reset_stats()
     first_timed = frame_no
-    sampler = ClockSampler(local); sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     with torch.cuda.stream(stream):
@@ -241,7 +252,6 @@ def run_gpu(args, w):
     with torch.cuda.stream(stream):
         e1.record(stream)
     barrier()
-    clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
     st = ctx.stats()
     rays_local, kernel_ms = st["rays"], st["kernelMs"]
@@ -269,6 +279,7 @@ def run_gpu(args, w):
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_rays_local = ctx.stats()["rays"]
+    clocks = sampler.stop()
 
     # ---- reduce over ranks --------------------------------------------------------------------------------------------------
     if world > 1:
@@ -290,6 +301,9 @@ def run_gpu(args, w):
         alg = algorithmic_bytes({"boxTests": cst["boxTests"], "triTests": cst["triTests"], "rays": cst["rays"], "sphereTests": cst["sphereTests"]},
                                 model_count, W, H // world if world > 1 else H, args.steps)
         achieved = alg / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+        kernel_label = {2: "k_raytrace_pool (persistent wavefront, per-warp path pools)",
+                        1: "k_raytrace_wave (persistent threads, one path per lane)", 0: "k_raytrace_mega (reference-shaped)"}[
+                            args.kernel if args.kernel is not None else (2 if model_count > 0 else 1)]
         h2d = 224 * model_count + 104 * len(sc.spheres) + 4 * 40
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -298,9 +312,7 @@ def run_gpu(args, w):
             "config": {"workload": w["desc"], "rays_per_frame": rays // args.steps, "spp_per_frame": w["spp"],
                        "tiling": f"row bands of {args.band_rows} rows round-robin over {world} GPU(s), one all-gather per frame" if world > 1 else "single GPU",
                        "l2": "flushed between steps (256 MiB write inside the timed region)",
-                       "kernel": {2: "k_raytrace_pool (persistent wavefront, per-warp path pools)",
-                                  1: "k_raytrace_wave (persistent threads, one path per lane)", 0: "k_raytrace_mega (reference-shaped)"}[
-                                      args.kernel if args.kernel is not None else (2 if model_count > 0 else 1)],
+                       "kernel": kernel_label,
                        "pool_slots": args.pool_slots, "smem_nodes": args.smem_nodes},
             "ms_per_frame": round(ms_total / args.steps, 4),
             "clocks": clocks,
@@ -308,11 +320,11 @@ def run_gpu(args, w):
                     "ms_per_step": round(1e3 * e2e_s / args.steps, 4)},
             "gpu_launches": args.steps * (1 + (2 if world > 1 else 0)),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": ncu_traffic(args.workload, kernel_label) if world == 1 else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg // args.steps, "kernel_ms_per_launch": round(kernel_ms / args.steps, 4),
                          "counts_per_launch": {"rays": cst["rays"] // args.steps, "boxTests": cst["boxTests"] // args.steps,
                                                "triTests": cst["triTests"] // args.steps, "sphereTests": cst["sphereTests"] // args.steps},
-                         "note": "algorithmic bytes per SURVEY.md 8(d); the 9 spheres live in shared memory, so DRAM traffic is far below this"},
+                         "note": "algorithmic bytes per SURVEY.md 8(d) from the reference's own test counters; sphere-only scenes keep their spheres in shared memory, so their DRAM traffic is far below this and frac can exceed 1"},
         }
         if world == 1 and not args.no_cpu:
             v, ms, cores, sample = cpu_sample(w, 1, 0)
