@@ -195,7 +195,7 @@ def run_gpu(args, w):
     W, H = w["width"], w["height"]
     mgr = rt.RayComputeManager(args.lib or b.LIB_CUDA, device=local)   # raises without the CUDA library / a GPU
     scenes.apply(sc, mgr)
-    tiled = multigpu.TiledRenderer(mgr, rank, world, band_rows=args.band_rows, device=dev)   # also puts the context on a torch stream
+    tiled = multigpu.TiledRenderer(mgr, rank, world, band_rows=args.band_rows, device=dev, fused=args.exchange == "fused")   # also puts the context on a torch stream
     ctx, stream = tiled.ctx, tiled.stream
     if args.kernel is not None:
         ctx.set_option("kernel", args.kernel)
@@ -208,6 +208,10 @@ def run_gpu(args, w):
     if args.tail_lanes is not None:
         ctx.set_option("tailLanes", args.tail_lanes)
     mgr.OnEnable()
+    if tiled.fused:
+        with torch.cuda.stream(stream):
+            tiled._connect_peers()
+            dist.barrier()
     model_count = len(sc.models)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
@@ -222,8 +226,13 @@ def run_gpu(args, w):
     def step_resident(frame_no):
         with torch.cuda.stream(stream):
             ctx.set_int("Frame", frame_no)
-            ctx.dispatch_full(0)
-            if world > 1:
+            if tiled.fused:
+                tiled.frame_fence()
+                ctx.dispatch_full(0)
+                tiled.frame_fence()
+            else:
+                ctx.dispatch_full(0)
+            if world > 1 and not tiled.fused:
                 send, recv = tiled._views()
                 ctx.pack_tile()
                 dist.all_gather_into_tensor(recv, send)
@@ -310,7 +319,9 @@ def run_gpu(args, w):
             "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["desc"], "rays_per_frame": rays // args.steps, "spp_per_frame": w["spp"],
-                       "tiling": f"row bands of {args.band_rows} rows round-robin over {world} GPU(s), one all-gather per frame" if world > 1 else "single GPU",
+                       "tiling": (f"row bands of {args.band_rows} rows round-robin over {world} GPU(s), " +
+                                  ("finished pixels stored into the peers' images by the trace kernel (CUDA-IPC over NVLink), 4-byte all-reduce as frame fence"
+                                   if tiled.fused else "one NCCL all-gather of finished tiles per frame")) if world > 1 else "single GPU",
                        "l2": "flushed between steps (256 MiB write inside the timed region)",
                        "kernel": kernel_label,
                        "pool_slots": args.pool_slots, "smem_nodes": args.smem_nodes},
@@ -318,7 +329,7 @@ def run_gpu(args, w):
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": W * H * 16,
                     "ms_per_step": round(1e3 * e2e_s / args.steps, 4)},
-            "gpu_launches": args.steps * (1 + (2 if world > 1 else 0)),
+            "gpu_launches": args.steps * (1 + (2 if (world > 1 and not tiled.fused) else 0)),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": ncu_traffic(args.workload, kernel_label) if world == 1 else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg // args.steps, "kernel_ms_per_launch": round(kernel_ms / args.steps, 4),
@@ -343,6 +354,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cornell64", choices=sorted(WORKLOADS))
     ap.add_argument("--band-rows", type=int, default=8)
+    ap.add_argument("--exchange", default="allgather", choices=["allgather", "fused"],
+                    help="N > 1: one NCCL all-gather of finished tiles per frame, or pixels stored into the peers' images by the trace kernel (CUDA-IPC over NVLink)")
     ap.add_argument("--kernel", type=int, default=None, help="0 = megakernel, 1 = persistent threads, 2 = pooled wavefront (default)")
     ap.add_argument("--pool-slots", type=int, default=None, help="paths per warp pool of kernel 2 (32, 64, 96)")
     ap.add_argument("--sort-rays", type=int, default=None, help="kernel 2: group the ray queue by direction octant (1/0)")

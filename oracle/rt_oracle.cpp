@@ -785,6 +785,9 @@ int rtPackTile(RtContext* c) { return fail(c, RT_E_STATE, "oracle: no device til
 int rtUnpackTiles(RtContext* c) { return fail(c, RT_E_STATE, "oracle: no device tile staging"); }
 int rtGetDevicePointer(RtContext* c, const char*, void**, size_t*) { return fail(c, RT_E_STATE, "oracle: no device memory"); }
 
+int rtGetIpcHandles(RtContext* c, void*, size_t) { return fail(c, RT_E_STATE, "oracle: no device memory"); }
+int rtSetPeers(RtContext* c, int, const void*, size_t) { return fail(c, RT_E_STATE, "oracle: no device memory"); }
+
 int rtSetOption(RtContext* c, const char* name, int value)
 {
     if (!c || !name) return fail(c, RT_E_INVALID, "rtSetOption: bad argument");

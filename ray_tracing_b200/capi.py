@@ -80,6 +80,8 @@ class RtLib:
             "rtUnpackTiles": ([vp], ci),
             "rtGetDevicePointer": ([vp, cp, C.POINTER(vp), C.POINTER(C.c_size_t)], ci),
             "rtSetOption": ([vp, cp, ci], ci),
+            "rtGetIpcHandles": ([vp, vp, C.c_size_t], ci),
+            "rtSetPeers": ([vp, ci, vp, C.c_size_t], ci),
             "rtGetStats": ([vp, C.POINTER(RtStats)], ci),
             "rtResetStats": ([vp], ci),
         }
@@ -197,6 +199,16 @@ class RtContext:
         p, n = C.c_void_p(), C.c_size_t()
         self._ck(self._L.rtGetDevicePointer(self._h, name.encode(), C.byref(p), C.byref(n)))
         return int(p.value), int(n.value)
+
+    def ipc_handles(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._ck(self._L.rtGetIpcHandles(self._h, buf, 128))
+        return buf.raw
+
+    def set_peers(self, handles: list):
+        """handles: one 128-byte blob (ipc_handles()) per peer rank."""
+        blob = b"".join(handles)
+        self._ck(self._L.rtSetPeers(self._h, len(handles), blob if handles else None, len(blob)))
 
     def set_option(self, name: str, v: int):
         self._ck(self._L.rtSetOption(self._h, name.encode(), int(v)))

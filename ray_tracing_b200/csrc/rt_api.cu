@@ -58,6 +58,10 @@ struct RtContext
     int width = 0, height = 0;
     int tileRank = 0, tileWorld = 1, bandRows = 1;
 
+    // peers (fused tile exchange): IPC-mapped images of the other ranks
+    std::vector<void*> peerBase;               // opened IPC mappings (to close)
+    float4* peerFrame[RT_MAX_PEERS]; float4* peerAccum[RT_MAX_PEERS]; int nPeers = 0;
+
     // options
     int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16, optSortRays = 0;   // kernel -1 = automatic   // smemPairs -1 = automatic
 
@@ -89,6 +93,12 @@ static int drainEvents(RtContext* c)
     }
     c->pending.clear();
     return RT_OK;
+}
+
+static void closePeers(RtContext* c)
+{
+    for (void* p : c->peerBase) cudaIpcCloseMemHandle(p);
+    c->peerBase.clear(); c->nPeers = 0;
 }
 
 extern "C" {
@@ -137,6 +147,7 @@ int rtDestroy(RtContext* c)
     c->nodes.release(); c->tris.release(); c->models.release(); c->spheres.release();
     c->frame.release(); c->accum.release(); c->tileSend.release(); c->tileRecv.release();
     c->repack.release();
+    closePeers(c);
     for (auto& ev : c->pending) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (auto& ev : c->freeEvents) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     if (c->dCounters) cudaFree(c->dCounters);
@@ -284,6 +295,7 @@ int rtResize(RtContext* c, int w, int h)
         CK(cudaMemsetAsync(c->accum.p, 0, n * 16, c->stream));
         c->width = w; c->height = h;
         c->tileSend.release(); c->tileRecv.release();
+        closePeers(c);                                      // peer mappings refer to images of the old size
     }
     c->P.W = (unsigned)w; c->P.H = (unsigned)h;
     return RT_OK;
@@ -394,6 +406,8 @@ int rtDispatch(RtContext* c, int kernelIndex, int gx, int gy, int gz)
     P.models = c->repack.models.p; P.spheres = c->repack.spheres.p; P.smemPairs = c->repack.smemPairs; P.tailLanes = c->optTailLanes; P.sortRays = c->optSortRays;
     P.FrameRender = c->frame.p; P.AccumulatedRender = c->accum.p;
     P.counters = c->dCounters; P.workCounter = c->dWork;
+    P.nPeers = c->nPeers;
+    for (int k = 0; k < c->nPeers; k++) { P.peerFrame[k] = c->peerFrame[k]; P.peerAccum[k] = c->peerAccum[k]; }
 
     EventPair ev;
     if (!c->freeEvents.empty()) { ev = c->freeEvents.back(); c->freeEvents.pop_back(); }
@@ -504,6 +518,39 @@ int rtGetDevicePointer(RtContext* c, const char* name, void** devPtr, size_t* by
     }
     else return fail(c, RT_E_UNKNOWN_NAME, std::string("rtGetDevicePointer: unknown object ") + name);
     if (!*devPtr) return fail(c, RT_E_STATE, "rtGetDevicePointer: object not allocated yet (call rtResize)");
+    return RT_OK;
+}
+
+int rtGetIpcHandles(RtContext* c, void* handles, size_t bytes)
+{
+    if (!c || !handles || bytes != 2 * sizeof(cudaIpcMemHandle_t)) return fail(c, RT_E_INVALID, "rtGetIpcHandles: handles must hold 2 x 64 bytes");
+    if (!c->frame.p || !c->accum.p) return fail(c, RT_E_STATE, "rtGetIpcHandles: rtResize has not been called");
+    CK(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h[2];
+    CK(cudaIpcGetMemHandle(&h[0], c->frame.p));
+    CK(cudaIpcGetMemHandle(&h[1], c->accum.p));
+    memcpy(handles, h, sizeof(h));
+    return RT_OK;
+}
+
+int rtSetPeers(RtContext* c, int nPeers, const void* handles, size_t bytes)
+{
+    if (!c || nPeers < 0 || nPeers > RT_MAX_PEERS) return fail(c, RT_E_INVALID, "rtSetPeers: at most 7 peers");
+    if (nPeers > 0 && (!handles || bytes != (size_t)nPeers * 2 * sizeof(cudaIpcMemHandle_t))) return fail(c, RT_E_INVALID, "rtSetPeers: handles must hold nPeers x 2 x 64 bytes");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    closePeers(c);
+    const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)handles;
+    for (int k = 0; k < nPeers; k++)
+    {
+        void *pf = nullptr, *pa = nullptr;
+        CK(cudaIpcOpenMemHandle(&pf, h[2 * k], cudaIpcMemLazyEnablePeerAccess));
+        c->peerBase.push_back(pf);
+        CK(cudaIpcOpenMemHandle(&pa, h[2 * k + 1], cudaIpcMemLazyEnablePeerAccess));
+        c->peerBase.push_back(pa);
+        c->peerFrame[k] = (float4*)pf; c->peerAccum[k] = (float4*)pa;
+    }
+    c->nPeers = nPeers;
     return RT_OK;
 }
 

@@ -64,6 +64,8 @@ struct __align__(16) DevSphere
 
 // ---- kernel parameter block (uniform names as in HL:5-21, RC:7-8) ---------------------------------------------
 
+constexpr int RT_MAX_PEERS = 7;
+
 struct DevParams
 {
     int   MaxBounceCount, NumRaysPerPixel, Frame, renderSeed;
@@ -95,11 +97,36 @@ struct DevParams
 
     float4* FrameRender;
     float4* AccumulatedRender;
+    // fused tile exchange: the same images on the other GPUs of the job (CUDA-IPC mapped peer memory over NVLink);
+    // a finished pixel is stored straight into every peer's images by the kernel that produced it
+    float4* peerFrame[RT_MAX_PEERS];
+    float4* peerAccum[RT_MAX_PEERS];
+    int   nPeers, pad5;
     unsigned long long* counters;           // [0] rays [1] boxTests [2] triTests [3] sphereTests
     unsigned int* workCounter;              // persistent kernel: next job
 };
 
 struct Counters { unsigned int rays, box, tri, sph; };
+
+// RC:18-23: write the pixel of this frame and accumulate; with peers, also store both values into every peer GPU's copy
+// (the all-gather of finished tiles fused into the producing kernel: 32 bytes per pixel per peer over NVLink).
+__device__ __forceinline__ void WritePixel(const DevParams& P, size_t o, float r, float g, float b)
+{
+    const float4 f = make_float4(r, g, b, 1.0f);
+    P.FrameRender[o] = f;
+    float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (P.accumulate)
+    {
+        a = P.AccumulatedRender[o];
+        a.x += r; a.y += g; a.z += b; a.w += 1.0f;
+        P.AccumulatedRender[o] = a;
+    }
+    for (int k = 0; k < P.nPeers; k++)
+    {
+        P.peerFrame[k][o] = f;
+        if (P.accumulate) P.peerAccum[k][o] = a;
+    }
+}
 
 // ---- RNG (HL:127-164) ---------------------------------------------------------------------------------------------
 

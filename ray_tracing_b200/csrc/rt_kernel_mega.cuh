@@ -147,13 +147,7 @@ __global__ void __launch_bounds__(64) k_raytrace_mega(const __grid_constant__ De
     const f3 pixelCol = totalIncomingLight / __int2float_rn(P.NumRaysPerPixel);
 
     const size_t o = (size_t)idy * P.W + idx;
-    P.FrameRender[o] = make_float4(pixelCol.x, pixelCol.y, pixelCol.z, 1.0f);
-    if (P.accumulate)
-    {
-        float4 a = P.AccumulatedRender[o];
-        a.x += pixelCol.x; a.y += pixelCol.y; a.z += pixelCol.z; a.w += 1.0f;
-        P.AccumulatedRender[o] = a;
-    }
+    WritePixel(P, o, pixelCol.x, pixelCol.y, pixelCol.z);
     FlushCounters(P, cnt);
 }
 

@@ -239,13 +239,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                             const unsigned xy = pool.u(F_XY, e);
                             const size_t o = (size_t)(xy >> 16) * P.W + (xy & 0xffffu);
                             const f3 pixelCol = sum / __int2float_rn(P.NumRaysPerPixel);
-                            P.FrameRender[o] = make_float4(pixelCol.x, pixelCol.y, pixelCol.z, 1.0f);
-                            if (P.accumulate)
-                            {
-                                float4 a = P.AccumulatedRender[o];
-                                a.x += pixelCol.x; a.y += pixelCol.y; a.z += pixelCol.z; a.w += 1.0f;
-                                P.AccumulatedRender[o] = a;
-                            }
+                            WritePixel(P, o, pixelCol.x, pixelCol.y, pixelCol.z);
                             state = PS_EMPTY;
                         }
                         else { pool.set3(F_SUM, e, sum); state = PS_GEN; }

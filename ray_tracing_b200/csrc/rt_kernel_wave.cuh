@@ -314,13 +314,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, RT_WAVE_MINBLOCKS) k_raytrace_wa
         if (havePixel && !pathActive && sample >= P.NumRaysPerPixel)
         {
             const f3 pixelCol = totalIncomingLight / __int2float_rn(P.NumRaysPerPixel);
-            P.FrameRender[pixelOffset] = make_float4(pixelCol.x, pixelCol.y, pixelCol.z, 1.0f);
-            if (P.accumulate)
-            {
-                float4 a = P.AccumulatedRender[pixelOffset];
-                a.x += pixelCol.x; a.y += pixelCol.y; a.z += pixelCol.z; a.w += 1.0f;
-                P.AccumulatedRender[pixelOffset] = a;
-            }
+            WritePixel(P, pixelOffset, pixelCol.x, pixelCol.y, pixelCol.z);
             havePixel = false;
         }
     }

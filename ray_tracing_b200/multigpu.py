@@ -58,7 +58,7 @@ class _DevView:
 class TiledRenderer:
     """One rank of a row-tiled render: manager + per-frame all-gather of finished tiles (NCCL)."""
 
-    def __init__(self, mgr, rank: int, world: int, band_rows: int = 8, device=None):
+    def __init__(self, mgr, rank: int, world: int, band_rows: int = 8, device=None, fused: bool = False):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -70,6 +70,23 @@ class TiledRenderer:
         # one torch stream carries everything: trace -> pack -> all-gather -> unpack are ordered on it
         self.stream = torch.cuda.Stream(device=device)
         self.ctx.set_stream(self.stream.cuda_stream)
+        # fused = the trace kernel stores finished pixels straight into the peers' images (CUDA-IPC over NVLink);
+        # the per-frame collective shrinks to a 4-byte all-reduce used as a stream-ordered barrier
+        self.fused = bool(fused) and world > 1
+        self._peers_ready = False
+        self._token = torch.zeros(1, dtype=torch.int32, device=device) if self.fused else None
+
+    def frame_fence(self):
+        """4-byte all-reduce on the renderer's stream = stream-ordered barrier across ranks."""
+        self.dist.all_reduce(self._token)
+
+    def _connect_peers(self):
+        """Exchange IPC handles of the two images (after the manager has created them) and map the peers'."""
+        mine = self.ctx.ipc_handles()
+        gathered = [None] * self.world
+        self.dist.all_gather_object(gathered, mine)
+        self.ctx.set_peers([h for r, h in enumerate(gathered) if r != self.rank])
+        self._peers_ready = True
 
     def _views(self):
         if self._send is None:
@@ -83,6 +100,14 @@ class TiledRenderer:
     def render_frame(self):
         """RenderFrame on this rank's bands, then the single all-gather of the frame's tiles."""
         with self.torch.cuda.stream(self.stream):
+            if self.fused:
+                if not self._peers_ready:
+                    self._connect_peers()
+                    self.dist.barrier()
+                self.frame_fence()                                  # every rank has consumed the previous frame
+                self.mgr.RenderFrame()                              # pixels land in every rank's images as they finish
+                self.frame_fence()                                  # every rank's kernel is done: the images are complete
+                return
             self.mgr.RenderFrame()
             if self.world == 1:
                 return

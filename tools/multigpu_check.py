@@ -12,13 +12,17 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 ok = True
-for name, sc in (("cornell", scenes.cornell_spheres(400, 300, 5, 3)), ("knot", scenes.knot_room(320, 180, 5, 2, nu=200, nv=12))):
+cases = [(n, s, f) for f in (False, True) for n, s in (("cornell", scenes.cornell_spheres(400, 300, 5, 3)), ("knot", scenes.knot_room(320, 180, 5, 2, nu=200, nv=12)))]
+for name, sc, fused in cases:
+    name = name + ("/fused-p2p" if fused else "/all-gather")
     mgr = rt.RayComputeManager(b.LIB_CUDA, device=local)
     scenes.apply(sc, mgr)
-    tiled = multigpu.TiledRenderer(mgr, rank, world, band_rows=8, device=dev)
+    tiled = multigpu.TiledRenderer(mgr, rank, world, band_rows=8, device=dev, fused=fused)
     mgr.OnEnable()
     for _ in range(3):
         tiled.render_frame()
+    if fused:
+        tiled.frame_fence()
     torch.cuda.synchronize()
     frame, accum = mgr.raytraceFrameTex, mgr.accumulatedResult
     if rank == 0:
@@ -32,5 +36,6 @@ for name, sc in (("cornell", scenes.cornell_spheres(400, 300, 5, 3)), ("knot", s
         print(f"multigpu_check {name}: world={world} bitwise_equal_to_single_gpu={same}", flush=True)
         ok = ok and same
     dist.barrier()
+    mgr.OnDestroy()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
