@@ -146,6 +146,8 @@ typedef struct RtStats {
     uint64_t sphereTests;   /* RaySphere calls (extension), only when "countStats" = 1                     */
     uint64_t dispatches;    /* RAYTRACE dispatches since the last reset                                    */
     double   kernelMs;      /* CUDA-event time of the RAYTRACE kernels since the last reset (sum)          */
+    uint64_t sphereBoxTests;/* box tests of the sphere accelerator (Spheres buffers above 64 entries), "countStats" = 1;
+                               with the accelerator, sphereTests counts the sphere tests actually made               */
 } RtStats;
 
 /* Synchronises, then reports the counters accumulated since the last rtResetStats. */

@@ -38,7 +38,7 @@ BUFFER_DTYPES = {"Triangles": TRIANGLE_DTYPE, "Nodes": NODE_DTYPE, "ModelInfo": 
 
 class RtStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("boxTests", C.c_uint64), ("triTests", C.c_uint64), ("sphereTests", C.c_uint64),
-                ("dispatches", C.c_uint64), ("kernelMs", C.c_double)]
+                ("dispatches", C.c_uint64), ("kernelMs", C.c_double), ("sphereBoxTests", C.c_uint64)]
 
 
 class RtError(RuntimeError):

@@ -11,6 +11,7 @@
 #include "rt_kernel_pool.cuh"
 #include "rt_repack.cuh"
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -66,7 +67,7 @@ struct RtContext
     int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16, optSortRays = 0;   // kernel -1 = automatic   // smemPairs -1 = automatic
 
     // counters / timing
-    unsigned long long* dCounters = nullptr;   // 4
+    unsigned long long* dCounters = nullptr;   // 5
     unsigned int* dWork = nullptr;
     std::vector<EventPair> pending, freeEvents;
     RtStats stats;
@@ -129,9 +130,9 @@ int rtCreate(RtContext** out, int device)
     c->numSMs = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     c->stream = c->ownStream;
-    if ((e = cudaMalloc(&c->dCounters, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&c->dCounters, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&c->dWork, 64)) != cudaSuccess) return bail(e, "cudaMalloc");
-    cudaMemset(c->dCounters, 0, 4 * sizeof(unsigned long long));
+    cudaMemset(c->dCounters, 0, 8 * sizeof(unsigned long long));
     cudaMemset(c->dWork, 0, 64);
     if ((e = wave_configure()) != cudaSuccess) return bail(e, "cudaFuncSetAttribute");
     if ((e = pool_configure()) != cudaSuccess) return bail(e, "cudaFuncSetAttribute");
@@ -362,11 +363,36 @@ static int prepareScene(RtContext* c)
         if (e != cudaSuccess) return failCuda(c, e, "repack models");
         c->modelsDirty = false;
     }
-    if (c->spheresDirty)
     {
-        cudaError_t e = c->repack.buildSpheres(c->hSpheres, c->stream);
-        if (e != cudaSuccess) return failCuda(c, e, "repack spheres");
-        c->spheresDirty = false;
+        // box containing every possible ray origin: the camera (with its defocus disc) and all geometry; it sizes the padding
+        // of the sphere accelerator, which is rebuilt when the box outgrows the one it was built for
+        float lo[3], hi[3];
+        const float jitter = fabsf(c->P.DefocusStrength) / (float)(c->P.W ? c->P.W : 1u) *
+                             (fabsf(c->P.cam[0]) + fabsf(c->P.cam[1]) + fabsf(c->P.cam[2]) + fabsf(c->P.cam[4]) + fabsf(c->P.cam[5]) + fabsf(c->P.cam[6]));
+        for (int a = 0; a < 3; a++) { lo[a] = c->P.cam[12 + a] - jitter; hi[a] = c->P.cam[12 + a] + jitter; }
+        for (const RtSphere& s : c->hSpheres) for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], s.centre[a] - fabsf(s.radius)); hi[a] = fmaxf(hi[a], s.centre[a] + fabsf(s.radius)); }
+        for (int i = 0; i < c->P.modelCount; i++)
+        {
+            const RtModel& m = c->hModels[i];
+            const RtNode& root = c->hNodes[m.nodeOffset];
+            for (int k = 0; k < 8; k++)
+            {
+                const float v[3] = {k & 1 ? root.boundsMax[0] : root.boundsMin[0], k & 2 ? root.boundsMax[1] : root.boundsMin[1], k & 4 ? root.boundsMax[2] : root.boundsMin[2]};
+                for (int a = 0; a < 3; a++)
+                {
+                    const float w = m.localToWorld[a] * v[0] + m.localToWorld[4 + a] * v[1] + m.localToWorld[8 + a] * v[2] + m.localToWorld[12 + a];
+                    lo[a] = fminf(lo[a], w); hi[a] = fmaxf(hi[a], w);
+                }
+            }
+        }
+        if (!c->spheresDirty && c->repack.sphBvh && !c->repack.sphereBoundCovers(lo, hi)) c->spheresDirty = true;
+        if (c->spheresDirty)
+        {
+            for (int a = 0; a < 3; a++) { const float ext = 0.25f * (hi[a] - lo[a]) + 0.01f; lo[a] -= ext; hi[a] += ext; }
+            cudaError_t e = c->repack.buildSpheres(c->hSpheres, lo, hi, c->stream);
+            if (e != cudaSuccess) return failCuda(c, e, "repack spheres");
+            c->spheresDirty = false;
+        }
     }
     return RT_OK;
 }
@@ -403,7 +429,9 @@ int rtDispatch(RtContext* c, int kernelIndex, int gx, int gy, int gz)
     P.sphereCount = (int)c->spheres.count;
     P.Nodes = c->nodes.p; P.Triangles = c->tris.p; P.ModelInfo = c->models.p; P.Spheres = c->spheres.p;
     P.pairs = c->repack.pairs.p; P.triGeom = c->repack.triGeom.p; P.triNormals = c->repack.triNormals.p;
-    P.models = c->repack.models.p; P.spheres = c->repack.spheres.p; P.smemPairs = c->repack.smemPairs; P.tailLanes = c->optTailLanes; P.sortRays = c->optSortRays;
+    P.models = c->repack.models.p; P.spheres = c->repack.spheres.p;
+    P.sphPairs = c->repack.sphPairs.p; P.sphLeaves = c->repack.sphLeaves.p; P.sphBvh = c->repack.sphBvh;
+    P.sphRootStart = c->repack.sphRootStart; P.sphRootCount = c->repack.sphRootCount; P.smemPairs = c->repack.smemPairs; P.tailLanes = c->optTailLanes; P.sortRays = c->optSortRays;
     P.FrameRender = c->frame.p; P.AccumulatedRender = c->accum.p;
     P.counters = c->dCounters; P.workCounter = c->dWork;
     P.nPeers = c->nPeers;
@@ -560,9 +588,9 @@ int rtGetStats(RtContext* c, RtStats* out)
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     int rc = drainEvents(c); if (rc != RT_OK) return rc;
-    unsigned long long h[4];
+    unsigned long long h[5];
     CK(cudaMemcpy(h, c->dCounters, sizeof(h), cudaMemcpyDeviceToHost));
-    c->stats.rays = h[0]; c->stats.boxTests = h[1]; c->stats.triTests = h[2]; c->stats.sphereTests = h[3];
+    c->stats.rays = h[0]; c->stats.boxTests = h[1]; c->stats.triTests = h[2]; c->stats.sphereTests = h[3]; c->stats.sphereBoxTests = h[4];
     *out = c->stats;
     return RT_OK;
 }
@@ -573,7 +601,7 @@ int rtResetStats(RtContext* c)
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     int rc = drainEvents(c); if (rc != RT_OK) return rc;
-    CK(cudaMemset(c->dCounters, 0, 4 * sizeof(unsigned long long)));
+    CK(cudaMemset(c->dCounters, 0, 8 * sizeof(unsigned long long)));
     memset(&c->stats, 0, sizeof(c->stats));
     return RT_OK;
 }

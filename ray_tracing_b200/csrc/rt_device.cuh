@@ -90,6 +90,11 @@ struct DevParams
     const TriNormals* triNormals;
     const DevModel*   models;
     const DevSphere*  spheres;
+    // sphere accelerator (only when the Spheres buffer is large): pair records over padded sphere boxes + the spheres in
+    // leaf order (pad1 = index in the Spheres buffer)
+    const NodePair*   sphPairs;
+    const DevSphere*  sphLeaves;
+    int   sphBvh, sphRootStart, sphRootCount, pad6;
     int   smemPairs;                        // number of leading pair records staged in shared memory
     int   tailLanes;                        // pooled kernel: leave the trace phase when this few lanes are still tracing
     int   sortRays;                         // pooled kernel: group the ray queue by direction octant
@@ -102,11 +107,11 @@ struct DevParams
     float4* peerFrame[RT_MAX_PEERS];
     float4* peerAccum[RT_MAX_PEERS];
     int   nPeers, pad5;
-    unsigned long long* counters;           // [0] rays [1] boxTests [2] triTests [3] sphereTests
+    unsigned long long* counters;           // [0] rays [1] boxTests [2] triTests [3] sphereTests [4] sphere-accelerator box tests
     unsigned int* workCounter;              // persistent kernel: next job
 };
 
-struct Counters { unsigned int rays, box, tri, sph; };
+struct Counters { unsigned int rays, box, tri, sph, sbox; };
 
 // RC:18-23: write the pixel of this frame and accumulate; with peers, also store both values into every peer GPU's copy
 // (the all-gather of finished tiles fused into the producing kernel: 32 bytes per pixel per peer over NVLink).
@@ -270,6 +275,62 @@ RT_DI bool RaySphereCore(f3 rayPos, f3 rayDir, f3 centre, float r2, float& dst, 
 #endif
     }
     return false;
+}
+
+// Closest sphere of a LARGE Spheres buffer through a BVH over padded sphere boxes, with the reference's semantics: the
+// result is the sphere a front-to-back linear scan with strict `<` would keep (HL:341 extended to a buffer) — the smallest
+// dst, and among equal dst the smallest buffer index.  Every sphere that is tested is tested with RaySphereCore, so dst is
+// the reference's value; the tree only decides which spheres can be skipped, and it is conservative:
+//   * boxes are padded (rt_repack.cuh) by more than the reference's own rounding error can move a computed hit point, so
+//     a computed hit point always lies inside its sphere's box;
+//   * a box is skipped only if its entry distance, reduced by a relative 2^-18 and an absolute 1e-6, still exceeds the best
+//     dst so far (strictly), so equal-distance candidates with a smaller index are never lost.
+RT_DI void TraverseSpheres(const DevParams& P, f3 rayPos, f3 rayDir, float& bestDst, int& bestIndex, bool& bestInside, int& bestFlag,
+                           Counters& cnt, bool countStats)
+{
+    const f3 invDir = rcp3(rayDir);
+    int2 stack[48];
+    int stackCount = 0;
+    int2 cur = make_int2(P.sphRootStart, P.sphRootCount);
+    for (;;)
+    {
+        if (cur.y > 0)
+        {
+            for (int i = 0; i < cur.y; i++)
+            {
+                const float4* q = reinterpret_cast<const float4*>(P.sphLeaves + cur.x + i);
+                const float4 s0 = __ldg(q);
+                const float4 s1 = __ldg(q + 1);
+                float dst; bool inside;
+                if (countStats) cnt.sph++;
+                if (RaySphereCore(rayPos, rayDir, make_f3(s0.x, s0.y, s0.z), s1.x, dst, inside))
+                {
+                    const int orig = __float_as_int(s1.z);
+                    if (dst < bestDst || (dst == bestDst && orig < bestIndex))
+                    {
+                        bestDst = dst; bestIndex = orig; bestInside = inside; bestFlag = __float_as_int(s1.y);
+                    }
+                }
+            }
+            if (stackCount == 0) return;
+            cur = stack[--stackCount];
+        }
+        else
+        {
+            const float4* p = reinterpret_cast<const float4*>(P.sphPairs + cur.x);
+            const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+            const float dA = RayBoundingBoxDst(rayPos, invDir, make_f3(q0.x, q0.y, q0.z), make_f3(q0.w, q1.x, q1.y));
+            const float dB = RayBoundingBoxDst(rayPos, invDir, make_f3(q2.x, q2.y, q2.z), make_f3(q2.w, q3.x, q3.y));
+            if (countStats) cnt.sbox += 2;
+            const bool nearA = dA <= dB;
+            const float dNear = nearA ? dA : dB, dFar = nearA ? dB : dA;
+            const int2 a = make_int2(__float_as_int(q1.z), __float_as_int(q1.w)), b = make_int2(__float_as_int(q3.z), __float_as_int(q3.w));
+            const int2 nearRef = nearA ? a : b, farRef = nearA ? b : a;
+            if (dFar < inf32() && (dFar * 0.99999619f - 1e-6f) <= bestDst && stackCount < 48) stack[stackCount++] = farRef;
+            if (dNear < inf32() && (dNear * 0.99999619f - 1e-6f) <= bestDst) cur = nearRef;
+            else { if (stackCount == 0) return; cur = stack[--stackCount]; }
+        }
+    }
 }
 
 // ---- hit record -----------------------------------------------------------------------------------------------------------

@@ -62,6 +62,20 @@ RT_DI Hit CalculateRayCollision_ref(const DevParams& P, f3 rayPos, f3 rayDir, Co
     result.dst = inf32(); result.isBackface = false; result.normal = splat3(0.0f); result.pos = splat3(0.0f); result.material = nullptr;
     cnt.rays++;
 
+    if (P.sphBvh)
+    {
+        int idx = 0x7fffffff, flag = 0; bool inside = false;
+        TraverseSpheres(P, rayPos, rayDir, result.dst, idx, inside, flag, cnt, true);
+        if (idx != 0x7fffffff)
+        {
+            const RtSphere* sp = P.Spheres + idx;
+            result.isBackface = inside;
+            result.pos = rayPos + rayDir * result.dst;
+            result.normal = normalize3(result.pos - load3(sp->centre)) * (inside ? -1.0f : 1.0f);
+            result.material = &sp->material;
+        }
+    }
+    else
     for (int i = 0; i < P.sphereCount; i++)
     {
         const RtSphere* sp = P.Spheres + i;
@@ -103,10 +117,10 @@ RT_DI Hit CalculateRayCollision_ref(const DevParams& P, f3 rayPos, f3 rayDir, Co
 RT_DI void FlushCounters(const DevParams& P, const Counters& cnt)
 {
     // warp-aggregate, then one atomic per warp per counter
-    unsigned int r = cnt.rays, b = cnt.box, t = cnt.tri, s = cnt.sph;
+    unsigned int r = cnt.rays, b = cnt.box, t = cnt.tri, s = cnt.sph, sb = cnt.sbox;
     const unsigned int m = __activemask();
     r = __reduce_add_sync(m, r);
-    if (P.countStats) { b = __reduce_add_sync(m, b); t = __reduce_add_sync(m, t); s = __reduce_add_sync(m, s); }
+    if (P.countStats) { b = __reduce_add_sync(m, b); t = __reduce_add_sync(m, t); s = __reduce_add_sync(m, s); sb = __reduce_add_sync(m, sb); }
     const int lane = (threadIdx.x + threadIdx.y * blockDim.x) & 31;
     if (lane == (__ffs(m) - 1))
     {
@@ -116,6 +130,7 @@ RT_DI void FlushCounters(const DevParams& P, const Counters& cnt)
             atomicAdd(P.counters + 1, (unsigned long long)b);
             atomicAdd(P.counters + 2, (unsigned long long)t);
             atomicAdd(P.counters + 3, (unsigned long long)s);
+            atomicAdd(P.counters + 4, (unsigned long long)sb);
         }
     }
 }
@@ -128,7 +143,7 @@ __global__ void __launch_bounds__(64) k_raytrace_mega(const __grid_constant__ De
     if (idx >= P.limX || idy >= P.limY) return;
     if ((int)((idy / (unsigned int)P.bandRows) % (unsigned int)P.tileWorld) != P.tileRank) return;
 
-    Counters cnt; cnt.rays = cnt.box = cnt.tri = cnt.sph = 0;
+    Counters cnt; cnt.rays = cnt.box = cnt.tri = cnt.sph = cnt.sbox = 0;
     const PixelSetup px = SetupPixel(P, idx, idy);
     uint32_t rngState = px.rngState;
     f3 totalIncomingLight = splat3(0.0f);

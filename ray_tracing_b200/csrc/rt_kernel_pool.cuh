@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
     if (P.smemPairs > 0) { while (!mbar_try_wait(mbar, 0)) { } }
     __syncthreads();
 
-    Counters cnt; cnt.rays = cnt.box = cnt.tri = cnt.sph = 0;
+    Counters cnt; cnt.rays = cnt.box = cnt.tri = cnt.sph = cnt.sbox = 0;
     bool exhausted = false;                     // warp-uniform: the global pixel queue is empty
 
     // per-lane ray state of the trace phase.  It lives across phases: a lane whose ray is still in flight when the phase
@@ -356,6 +356,17 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                     cnt.rays++;
                     resDst = inf32(); resPrim = 0; resModel = 0; resKind = PS_HIT_MISS; resU = resV = resDet = 0.0f;
                     // spheres first (extension; where the reference's commented call sits, HL:341)
+                    if (P.sphBvh)
+                    {
+                        int idx = 0x7fffffff, flag = 0; bool inside = false;
+                        TraverseSpheres(P, rayPos, rayDir, resDst, idx, inside, flag, cnt, STATS);
+                        if (idx != 0x7fffffff)
+                        {
+                            resPrim = -(idx + 1); resDet = inside ? -1.0f : 1.0f;
+                            resKind = flag == RT_MATERIAL_GLASS ? PS_HIT_GLASS : PS_HIT_OPAQUE;
+                        }
+                    }
+                    else
                     for (int s = 0; s < P.sphereCount; s++)
                     {
                         float cx, cy, cz, r2; int flag;
@@ -437,7 +448,15 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                     const float dstFar = isNearestA ? dstB : dstA;
                     const NodeRef nearRef = isNearestA ? a : b;
                     const NodeRef farRef = isNearestA ? b : a;
-                    if (dstFar < bestDst && stackCount < WAVE_STACK) stack[stackCount++] = farRef;
+                    if (dstFar < bestDst && stackCount < WAVE_STACK)
+                    {
+                        stack[stackCount++] = farRef;
+#ifdef RT_PREFETCH_FAR
+                        // the far child is visited after the whole near subtree: start moving its record towards L1 now
+                        const void* pf = farRef.count > 0 ? (const void*)(P.triGeom + farRef.start) : (const void*)(P.pairs + farRef.start);
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(pf));
+#endif
+                    }
                     if (dstNear < bestDst) { cur = nearRef; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
                     else if (stackCount > 0) { cur = stack[--stackCount]; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
                     else mode = T_NEXT;
@@ -472,8 +491,8 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
     if (lane == 0) atomicAdd(P.counters + 0, (unsigned long long)r);
     if (STATS)
     {
-        const unsigned int b = __reduce_add_sync(0xffffffffu, cnt.box), t = __reduce_add_sync(0xffffffffu, cnt.tri), s = __reduce_add_sync(0xffffffffu, cnt.sph);
-        if (lane == 0) { atomicAdd(P.counters + 1, (unsigned long long)b); atomicAdd(P.counters + 2, (unsigned long long)t); atomicAdd(P.counters + 3, (unsigned long long)s); }
+        const unsigned int b = __reduce_add_sync(0xffffffffu, cnt.box), t = __reduce_add_sync(0xffffffffu, cnt.tri), s = __reduce_add_sync(0xffffffffu, cnt.sph), sb = __reduce_add_sync(0xffffffffu, cnt.sbox);
+        if (lane == 0) { atomicAdd(P.counters + 1, (unsigned long long)b); atomicAdd(P.counters + 2, (unsigned long long)t); atomicAdd(P.counters + 3, (unsigned long long)s); atomicAdd(P.counters + 4, (unsigned long long)sb); }
     }
 }
 

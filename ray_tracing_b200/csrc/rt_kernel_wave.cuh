@@ -129,6 +129,13 @@ RT_DI Hit Intersect(const DevParams& P, const float4* __restrict__ smemPairs, co
     cnt.rays++;
 
     int bestSphere = -1; bool bestInside = false;
+    if (P.sphBvh)
+    {
+        int idx = 0x7fffffff, flag = 0;
+        TraverseSpheres(P, rayPos, rayDir, result.dst, idx, bestInside, flag, cnt, STATS);
+        if (idx != 0x7fffffff) bestSphere = idx;
+    }
+    else
     for (int i = 0; i < P.sphereCount; i++)
     {
         float cx, cy, cz, r2;
@@ -236,7 +243,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, RT_WAVE_MINBLOCKS) k_raytrace_wa
     // ---- persistent wavefront loop ------------------------------------------------------------------------------------------
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int laneMaskLt = (1u << lane) - 1u;
-    Counters cnt; cnt.rays = cnt.box = cnt.tri = cnt.sph = 0;
+    Counters cnt; cnt.rays = cnt.box = cnt.tri = cnt.sph = cnt.sbox = 0;
 
     bool exhausted = false;          // no more jobs for this lane
     bool havePixel = false;
@@ -324,8 +331,8 @@ __global__ void __launch_bounds__(WAVE_THREADS, RT_WAVE_MINBLOCKS) k_raytrace_wa
     if (lane == 0) atomicAdd(P.counters + 0, (unsigned long long)r);
     if (STATS)
     {
-        const unsigned int b = __reduce_add_sync(0xffffffffu, cnt.box), t = __reduce_add_sync(0xffffffffu, cnt.tri), s = __reduce_add_sync(0xffffffffu, cnt.sph);
-        if (lane == 0) { atomicAdd(P.counters + 1, (unsigned long long)b); atomicAdd(P.counters + 2, (unsigned long long)t); atomicAdd(P.counters + 3, (unsigned long long)s); }
+        const unsigned int b = __reduce_add_sync(0xffffffffu, cnt.box), t = __reduce_add_sync(0xffffffffu, cnt.tri), s = __reduce_add_sync(0xffffffffu, cnt.sph), sb = __reduce_add_sync(0xffffffffu, cnt.sbox);
+        if (lane == 0) { atomicAdd(P.counters + 1, (unsigned long long)b); atomicAdd(P.counters + 2, (unsigned long long)t); atomicAdd(P.counters + 3, (unsigned long long)s); atomicAdd(P.counters + 4, (unsigned long long)sb); }
     }
 }
 

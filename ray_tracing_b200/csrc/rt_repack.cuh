@@ -12,6 +12,7 @@
 #pragma once
 #include "rt_device.cuh"
 #include <algorithm>
+#include <cmath>
 #include <map>
 #include <string>
 #include <utility>
@@ -56,7 +57,7 @@ struct RepackState
     int budgetUsed = -1;
     size_t totalPairs = 0;
 
-    void release() { pairs.release(); triGeom.release(); triNormals.release(); models.release(); spheres.release(); roots.clear(); }
+    void release() { pairs.release(); triGeom.release(); triNormals.release(); models.release(); spheres.release(); sphPairs.release(); sphLeaves.release(); roots.clear(); }
 
     // Breadth-first renumbering of every distinct mesh referenced by the first modelCount models.
     cudaError_t buildScene(const std::vector<RtNode>& nodes, const std::vector<RtModel>& mdl, int modelCount,
@@ -177,7 +178,20 @@ struct RepackState
         return cudaStreamSynchronize(stream);
     }
 
-    cudaError_t buildSpheres(const std::vector<RtSphere>& sp, cudaStream_t stream)
+    // ---- spheres ------------------------------------------------------------------------------------------------------------
+    RBuf<NodePair> sphPairs; RBuf<DevSphere> sphLeaves;
+    int sphBvh = 0, sphRootStart = 0, sphRootCount = 0;
+    float sphBoundLo[3] = {0, 0, 0}, sphBoundHi[3] = {0, 0, 0};     // region of ray origins the current padding is valid for
+    static constexpr size_t SPHERE_BVH_THRESHOLD = 64;               // below this a linear scan is cheaper
+
+    bool sphereBoundCovers(const float lo[3], const float hi[3]) const
+    {
+        for (int a = 0; a < 3; a++) if (lo[a] < sphBoundLo[a] || hi[a] > sphBoundHi[a]) return false;
+        return true;
+    }
+
+    // originLo / originHi: a box containing every possible ray origin (camera, all geometry); only used for the BVH padding.
+    cudaError_t buildSpheres(const std::vector<RtSphere>& sp, const float originLo[3], const float originHi[3], cudaStream_t stream)
     {
         std::vector<DevSphere> out(std::max<size_t>(sp.size(), 1));
         for (size_t i = 0; i < sp.size(); i++)
@@ -187,12 +201,100 @@ struct RepackState
             // r*r is one IEEE multiply (HL:299).  Host code is built without FMA contraction, so this is that product.
             volatile float r = sp[i].radius; d.r2 = r * r;
             d.pad0 = sp[i].material.flag;                       // material flag, for sorting hits by kind without touching HBM
+            d.pad1 = (int)i;
             out[i] = d;
         }
         cudaError_t e;
         if ((e = spheres.ensure(out.size())) != cudaSuccess) return e;
         if ((e = cudaMemcpyAsync(spheres.p, out.data(), out.size() * sizeof(DevSphere), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
-        return cudaStreamSynchronize(stream);
+        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+        sphBvh = 0;
+        if (sp.size() <= SPHERE_BVH_THRESHOLD) return cudaSuccess;
+
+        // ---- BVH over padded sphere boxes (see TraverseSpheres in rt_device.cuh for the exactness argument) ----
+        // padding of sphere i: the reference's discriminant carries an absolute error of at most ~2e-6 (D^2 + r^2) (D = distance
+        // from the ray origin to the centre), which moves a computed hit point at most 2.5e-7 (D^2 + r^2) / r off the sphere;
+        // pad by 16 * 2^-23 * (Dmax^2 + r^2) / r (7.6x that bound) plus 1e-5 of the scene size for the slab test itself.
+        for (int a = 0; a < 3; a++) { sphBoundLo[a] = originLo[a]; sphBoundHi[a] = originHi[a]; }
+        const size_t n = sp.size();
+        std::vector<float> lo(3 * n), hi(3 * n), cen(3 * n);
+        double sceneSize = 0;
+        for (int a = 0; a < 3; a++) sceneSize = std::max(sceneSize, (double)originHi[a] - originLo[a]);
+        for (size_t i = 0; i < n; i++)
+        {
+            double dmax2 = 0;
+            for (int a = 0; a < 3; a++)
+            {
+                const double c = sp[i].centre[a];
+                const double far = std::max(std::fabs(c - originLo[a]), std::fabs(c - originHi[a]));
+                dmax2 += far * far;
+            }
+            const double r = std::fabs((double)sp[i].radius);
+            const double pad = 16.0 * 1.1920929e-7 * (dmax2 + r * r) / std::max(r, 1e-30) + 1e-5 * sceneSize + 1e-6;
+            for (int a = 0; a < 3; a++)
+            {
+                lo[3 * i + a] = (float)(sp[i].centre[a] - r - pad); hi[3 * i + a] = (float)(sp[i].centre[a] + r + pad);
+                lo[3 * i + a] = std::nextafterf(lo[3 * i + a], -INFINITY); hi[3 * i + a] = std::nextafterf(hi[3 * i + a], INFINITY);
+                cen[3 * i + a] = sp[i].centre[a];
+            }
+        }
+        // median split on the widest centroid axis, leaves of <= 4 spheres; pairs emitted parent-before-children
+        std::vector<int> order(n);
+        for (size_t i = 0; i < n; i++) order[i] = (int)i;
+        std::vector<NodePair> pairsOut; pairsOut.reserve(n);
+        struct Ref { int start, count; float lo[3], hi[3]; };
+        auto boundsOf = [&](int start, int count, float blo[3], float bhi[3]) {
+            for (int a = 0; a < 3; a++) { blo[a] = INFINITY; bhi[a] = -INFINITY; }
+            for (int k = start; k < start + count; k++) for (int a = 0; a < 3; a++) { blo[a] = std::min(blo[a], lo[3 * order[k] + a]); bhi[a] = std::max(bhi[a], hi[3 * order[k] + a]); }
+        };
+        struct Work { int pairIndex, side, start, count; };
+        std::vector<Work> work;
+        auto splitRange = [&](int start, int count) -> int {
+            float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (int k = start; k < start + count; k++) for (int a = 0; a < 3; a++) { clo[a] = std::min(clo[a], cen[3 * order[k] + a]); chi[a] = std::max(chi[a], cen[3 * order[k] + a]); }
+            int axis = 0; for (int a = 1; a < 3; a++) if (chi[a] - clo[a] > chi[axis] - clo[axis]) axis = a;
+            const int mid = start + count / 2;
+            std::nth_element(order.begin() + start, order.begin() + mid, order.begin() + start + count,
+                             [&](int x, int y) { return cen[3 * x + axis] < cen[3 * y + axis] || (cen[3 * x + axis] == cen[3 * y + axis] && x < y); });
+            return mid;
+        };
+        // root
+        const int LEAF = 4;
+        if ((int)n <= LEAF) { sphRootStart = 0; sphRootCount = (int)n; }
+        else
+        {
+            sphRootStart = 0; sphRootCount = 0;
+            pairsOut.push_back(NodePair());
+            work.push_back(Work{0, -1, 0, (int)n});
+            for (size_t w = 0; w < work.size(); w++)
+            {
+                const Work cur = work[w];
+                const int mid = splitRange(cur.start, cur.count);
+                const int cs[2] = {cur.start, mid}, cc[2] = {mid - cur.start, cur.start + cur.count - mid};
+                NodePair& p = pairsOut[cur.pairIndex];
+                for (int side = 0; side < 2; side++)
+                {
+                    float blo[3], bhi[3];
+                    boundsOf(cs[side], cc[side], blo, bhi);
+                    int st, ct;
+                    if (cc[side] <= LEAF) { st = cs[side]; ct = cc[side]; }
+                    else { st = (int)pairsOut.size(); ct = 0; pairsOut.push_back(NodePair()); work.push_back(Work{st, side, cs[side], cc[side]}); }
+                    NodePair& q = pairsOut[cur.pairIndex];       // (push_back may have moved the vector)
+                    if (side == 0) { q.aMinX = blo[0]; q.aMinY = blo[1]; q.aMinZ = blo[2]; q.aMaxX = bhi[0]; q.aMaxY = bhi[1]; q.aMaxZ = bhi[2]; q.aStart = st; q.aCount = ct; }
+                    else           { q.bMinX = blo[0]; q.bMinY = blo[1]; q.bMinZ = blo[2]; q.bMaxX = bhi[0]; q.bMaxY = bhi[1]; q.bMaxZ = bhi[2]; q.bStart = st; q.bCount = ct; }
+                }
+                (void)p;
+            }
+        }
+        std::vector<DevSphere> leaves(n);
+        for (size_t k = 0; k < n; k++) leaves[k] = out[order[k]];
+        if ((e = sphPairs.ensure(std::max<size_t>(pairsOut.size(), 1))) != cudaSuccess) return e;
+        if ((e = sphLeaves.ensure(n)) != cudaSuccess) return e;
+        if (!pairsOut.empty() && (e = cudaMemcpyAsync(sphPairs.p, pairsOut.data(), pairsOut.size() * sizeof(NodePair), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(sphLeaves.p, leaves.data(), n * sizeof(DevSphere), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+        sphBvh = 1;
+        return cudaSuccess;
     }
 };
 

@@ -73,7 +73,41 @@ def test_soup_with_spheres_sky_defocus_bitwise(kernel):
     fo, ao, so = render(ORACLE_LIB, sc, frames=1, want_stats=True)
     fg, ag, sg = render(CUDA_LIB, sc, frames=1, options={"kernel": kernel, "countStats": 1}, want_stats=True)
     assert_bit_equal(fg, fo, "FrameRender")
-    _same_counters(sg, so)
+    # 300 spheres go through the sphere accelerator: same pixels, same mesh traversal, fewer sphere tests than the linear scan
+    _same_counters(sg, so, keys=("rays", "boxTests", "triTests"))
+    assert 0 < sg["sphereTests"] < so["sphereTests"] and sg["sphereBoxTests"] > 0
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_sphere_accelerator_keeps_first_index_on_ties(kernel):
+    """Large Spheres buffers are searched through a BVH over padded boxes; the winner must be the sphere a linear scan
+    with strict `<` keeps: exact duplicates (equal dst) resolve to the LOWEST buffer index, whatever the tree order."""
+    rng = np.random.RandomState(3)
+    n = 400
+    sph = np.zeros(n, dtype=scenes.SPHERE_DTYPE)
+    sph["centre"] = rng.uniform(-4, 4, (n, 3)).astype(np.float32) + np.float32([0, 0, 9])
+    sph["radius"] = rng.uniform(0.15, 0.6, n).astype(np.float32)
+    for i in range(n):
+        sph["material"][i] = scenes.material(diffuse=tuple(rng.uniform(0.1, 1, 3)), emission=tuple(rng.uniform(0, 1, 3)), emissionStrength=1.0,
+                                             specularProbability=0.0)
+    # duplicates: sphere 7 copied to 250 and 399, sphere 300 copied to 11 — different materials, identical geometry
+    for src, dst in ((7, 250), (7, 399), (300, 11)):
+        sph["centre"][dst] = sph["centre"][src]; sph["radius"][dst] = sph["radius"][src]
+    sc = scenes.Scene(name="dups", width=160, height=120, spheres=sph, settings=dict(maxBounceCount=3, numRaysPerPixel=2))
+    fo, _ = render(ORACLE_LIB, sc)
+    fg, _ = render(CUDA_LIB, sc, options={"kernel": kernel})
+    assert_bit_equal(fg, fo, "duplicate spheres")
+
+
+def test_config5_ten_thousand_spheres_bitwise():
+    """BASELINE config 5's Sphere buffer: 10,000 spheres (+ 20k triangles, sky).  Oracle = linear scan of all 10,000 per ray;
+    GPU = sphere accelerator.  Bit-identical frames."""
+    sc = scenes.random_soup(96, 96, max_bounces=8, rays_per_pixel=2, triangles=20000, spheres=10000)
+    fo, _, so = render(ORACLE_LIB, sc, frames=1, want_stats=True)
+    fg, _, sg = render(CUDA_LIB, sc, frames=1, options={"countStats": 1}, want_stats=True)
+    assert_bit_equal(fg, fo, "10k spheres")
+    _same_counters(sg, so, keys=("rays", "boxTests", "triTests"))
+    assert so["sphereTests"] == so["rays"] * 10000 and sg["sphereTests"] < so["sphereTests"] // 100
 
 
 def test_shared_memory_staging_does_not_change_results():
@@ -154,7 +188,7 @@ def test_config4_shape_deep_bvh_sparse_pixels():
 def test_config5_shape_million_triangles_sparse_pixels():
     """BASELINE config 5 shape: 1,000,000 random triangles in three models (opaque / glass / emissive) + spheres, sky on,
     16 bounces; 2048 seeded pixels bitwise against the oracle."""
-    sc = scenes.random_soup(768, 768, max_bounces=16, rays_per_pixel=1, triangles=1_000_000, spheres=16)
+    sc = scenes.random_soup(768, 768, max_bounces=16, rays_per_pixel=1, triangles=1_000_000, spheres=10_000)
     fg, _ = render(CUDA_LIB, sc, frames=1)
     xy, out = _sparse_oracle(sc, 2048, 22)
     assert_bit_equal(fg[xy[:, 1], xy[:, 0]], out, "sparse pixels, 1M-triangle scene")
