@@ -86,6 +86,10 @@ class RtLib:
             "rtResetStats": ([vp], ci),
         }
         for name, (args, res) in sig.items():
+            if not hasattr(L, name):
+                if name in ("rtGetIpcHandles", "rtSetPeers"):      # absent from older experimental builds used in A/B runs
+                    continue
+                raise AttributeError(f"{self.path} does not export {name}")
             fn = getattr(L, name)
             fn.argtypes, fn.restype = args, res
 

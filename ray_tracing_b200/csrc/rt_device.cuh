@@ -115,6 +115,8 @@ struct Counters { unsigned int rays, box, tri, sph, sbox; };
 
 // RC:18-23: write the pixel of this frame and accumulate; with peers, also store both values into every peer GPU's copy
 // (the all-gather of finished tiles fused into the producing kernel: 32 bytes per pixel per peer over NVLink).
+// EXT = the launch has peers (or another extension) — the common single-GPU instantiation carries no trace of them.
+template <bool EXT>
 __device__ __forceinline__ void WritePixel(const DevParams& P, size_t o, float r, float g, float b)
 {
     const float4 f = make_float4(r, g, b, 1.0f);
@@ -126,10 +128,13 @@ __device__ __forceinline__ void WritePixel(const DevParams& P, size_t o, float r
         a.x += r; a.y += g; a.z += b; a.w += 1.0f;
         P.AccumulatedRender[o] = a;
     }
-    for (int k = 0; k < P.nPeers; k++)
+    if (EXT)
     {
-        P.peerFrame[k][o] = f;
-        if (P.accumulate) P.peerAccum[k][o] = a;
+        for (int k = 0; k < P.nPeers; k++)
+        {
+            P.peerFrame[k][o] = f;
+            if (P.accumulate) P.peerAccum[k][o] = a;
+        }
     }
 }
 
@@ -285,7 +290,7 @@ RT_DI bool RaySphereCore(f3 rayPos, f3 rayDir, f3 centre, float r2, float& dst, 
 //     a computed hit point always lies inside its sphere's box;
 //   * a box is skipped only if its entry distance, reduced by a relative 2^-18 and an absolute 1e-6, still exceeds the best
 //     dst so far (strictly), so equal-distance candidates with a smaller index are never lost.
-RT_DI void TraverseSpheres(const DevParams& P, f3 rayPos, f3 rayDir, float& bestDst, int& bestIndex, bool& bestInside, int& bestFlag,
+__device__ __noinline__ void TraverseSpheres(const DevParams& P, f3 rayPos, f3 rayDir, float& bestDst, int& bestIndex, bool& bestInside, int& bestFlag,
                            Counters& cnt, bool countStats)
 {
     const f3 invDir = rcp3(rayDir);

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(64) k_raytrace_mega(const __grid_constant__ De
     const f3 pixelCol = totalIncomingLight / __int2float_rn(P.NumRaysPerPixel);
 
     const size_t o = (size_t)idy * P.W + idx;
-    WritePixel(P, o, pixelCol.x, pixelCol.y, pixelCol.z);
+    WritePixel<true>(P, o, pixelCol.x, pixelCol.y, pixelCol.z);
     FlushCounters(P, cnt);
 }
 

@@ -110,7 +110,7 @@ template <int M> RT_DI int CompactRaysByOctant(const PoolView<M>& pool, unsigned
     return base;
 }
 
-template <bool STATS, int M>
+template <bool STATS, bool EXT, int M>
 __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_constant__ DevParams P, const unsigned int totalJobs,
                                                                   const unsigned int tilesX, const unsigned int ownedRows)
 {
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                             const unsigned xy = pool.u(F_XY, e);
                             const size_t o = (size_t)(xy >> 16) * P.W + (xy & 0xffffu);
                             const f3 pixelCol = sum / __int2float_rn(P.NumRaysPerPixel);
-                            WritePixel(P, o, pixelCol.x, pixelCol.y, pixelCol.z);
+                            WritePixel<EXT>(P, o, pixelCol.x, pixelCol.y, pixelCol.z);
                             state = PS_EMPTY;
                         }
                         else { pool.set3(F_SUM, e, sum); state = PS_GEN; }
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                     cnt.rays++;
                     resDst = inf32(); resPrim = 0; resModel = 0; resKind = PS_HIT_MISS; resU = resV = resDet = 0.0f;
                     // spheres first (extension; where the reference's commented call sits, HL:341)
-                    if (P.sphBvh)
+                    if (EXT && P.sphBvh)
                     {
                         int idx = 0x7fffffff, flag = 0; bool inside = false;
                         TraverseSpheres(P, rayPos, rayDir, resDst, idx, inside, flag, cnt, STATS);
@@ -448,15 +448,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                     const float dstFar = isNearestA ? dstB : dstA;
                     const NodeRef nearRef = isNearestA ? a : b;
                     const NodeRef farRef = isNearestA ? b : a;
-                    if (dstFar < bestDst && stackCount < WAVE_STACK)
-                    {
-                        stack[stackCount++] = farRef;
-#ifdef RT_PREFETCH_FAR
-                        // the far child is visited after the whole near subtree: start moving its record towards L1 now
-                        const void* pf = farRef.count > 0 ? (const void*)(P.triGeom + farRef.start) : (const void*)(P.pairs + farRef.start);
-                        asm volatile("prefetch.global.L1 [%0];" :: "l"(pf));
-#endif
-                    }
+                    if (dstFar < bestDst && stackCount < WAVE_STACK) stack[stackCount++] = farRef;   // (prefetching the far record here was measured: -2 %)
                     if (dstNear < bestDst) { cur = nearRef; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
                     else if (stackCount > 0) { cur = stack[--stackCount]; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
                     else mode = T_NEXT;
@@ -504,9 +496,11 @@ template <int M> inline size_t pool_smem_bytes(const DevParams& P)
 
 template <int M> inline cudaError_t pool_configure_one()
 {
-    cudaError_t e = cudaFuncSetAttribute(k_raytrace_pool<false, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_raytrace_pool<true, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_raytrace_pool<false, false, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_raytrace_pool<true, false, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_raytrace_pool<false, true, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_raytrace_pool<true, true, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 inline cudaError_t pool_configure()
 {
@@ -537,8 +531,11 @@ template <int M> inline cudaError_t pool_launch_m(const DevParams& P, int numSMs
     cudaError_t e;
     if ((e = cudaMemsetAsync(P.workCounter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(evA, stream)) != cudaSuccess) return e;
-    if (P.countStats) k_raytrace_pool<true, M><<<grid, POOL_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows);
-    else k_raytrace_pool<false, M><<<grid, POOL_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows);
+    const bool ext = P.nPeers > 0 || P.sphBvh != 0;          // extensions compiled into their own instantiation
+    if (P.countStats) { if (ext) k_raytrace_pool<true, true, M><<<grid, POOL_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows);
+                        else k_raytrace_pool<true, false, M><<<grid, POOL_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows); }
+    else { if (ext) k_raytrace_pool<false, true, M><<<grid, POOL_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows);
+           else k_raytrace_pool<false, false, M><<<grid, POOL_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows); }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     return cudaEventRecord(evB, stream);
 }

@@ -120,7 +120,7 @@ RT_DI void TraverseMesh(const DevParams& P, const float4* __restrict__ smemPairs
 }
 
 // HL:335-374 (+ sphere extension) on the repacked streams
-template <bool STATS>
+template <bool STATS, bool EXT>
 RT_DI Hit Intersect(const DevParams& P, const float4* __restrict__ smemPairs, const DevSphere* __restrict__ smemSpheres,
                     f3 rayPos, f3 rayDir, Counters& cnt)
 {
@@ -129,7 +129,7 @@ RT_DI Hit Intersect(const DevParams& P, const float4* __restrict__ smemPairs, co
     cnt.rays++;
 
     int bestSphere = -1; bool bestInside = false;
-    if (P.sphBvh)
+    if (EXT && P.sphBvh)
     {
         int idx = 0x7fffffff, flag = 0;
         TraverseSpheres(P, rayPos, rayDir, result.dst, idx, bestInside, flag, cnt, STATS);
@@ -203,7 +203,7 @@ RT_DI Hit Intersect(const DevParams& P, const float4* __restrict__ smemPairs, co
 #ifndef RT_WAVE_MINBLOCKS
 #define RT_WAVE_MINBLOCKS 6      // <= 85 registers: 24 warps per SM (measured: 31.0 ms vs 37.1 ms at 16 warps on config 2)
 #endif
-template <bool STATS>
+template <bool STATS, bool EXT>
 __global__ void __launch_bounds__(WAVE_THREADS, RT_WAVE_MINBLOCKS) k_raytrace_wave(const __grid_constant__ DevParams P, const unsigned int totalJobs,
                                                                const unsigned int tilesX, const unsigned int ownedRows)
 {
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, RT_WAVE_MINBLOCKS) k_raytrace_wa
         // [intersect] + [shade]
         if (pathActive)
         {
-            const Hit hit = Intersect<STATS>(P, smemPairs, smemSpheres, ray.pos, ray.dir, cnt);
+            const Hit hit = Intersect<STATS, EXT>(P, smemPairs, smemSpheres, ray.pos, ray.dir, cnt);
             const bool cont = ShadeSegment(P, hit, ray, rngState);
             bounce++;
             if (!cont || bounce > P.MaxBounceCount)
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, RT_WAVE_MINBLOCKS) k_raytrace_wa
         if (havePixel && !pathActive && sample >= P.NumRaysPerPixel)
         {
             const f3 pixelCol = totalIncomingLight / __int2float_rn(P.NumRaysPerPixel);
-            WritePixel(P, pixelOffset, pixelCol.x, pixelCol.y, pixelCol.z);
+            WritePixel<EXT>(P, pixelOffset, pixelCol.x, pixelCol.y, pixelCol.z);
             havePixel = false;
         }
     }
@@ -336,11 +336,35 @@ __global__ void __launch_bounds__(WAVE_THREADS, RT_WAVE_MINBLOCKS) k_raytrace_wa
     }
 }
 
+template <bool S, bool X> inline cudaError_t wave_configure_one()
+{
+    return cudaFuncSetAttribute(k_raytrace_wave<S, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+}
 inline cudaError_t wave_configure()
 {
-    cudaError_t e = cudaFuncSetAttribute(k_raytrace_wave<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    cudaError_t e;
+    if ((e = wave_configure_one<false, false>()) != cudaSuccess) return e;
+    if ((e = wave_configure_one<true, false>()) != cudaSuccess) return e;
+    if ((e = wave_configure_one<false, true>()) != cudaSuccess) return e;
+    return wave_configure_one<true, true>();
+}
+
+template <bool S, bool X> inline cudaError_t wave_launch_one(const DevParams& P, int numSMs, size_t smemBytes, unsigned totalJobs, unsigned tilesX, unsigned ownedRows,
+                                                             cudaStream_t stream, cudaEvent_t evA, cudaEvent_t evB)
+{
+    int ctasPerSM = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, k_raytrace_wave<S, X>, WAVE_THREADS, smemBytes);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_raytrace_wave<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    if (ctasPerSM < 1) return cudaErrorInvalidConfiguration;
+    unsigned int grid = (unsigned int)(numSMs * ctasPerSM);                  // persistent: a multiple of the SM count
+    const unsigned int warpsNeeded = (totalJobs + 31u) / 32u;
+    const unsigned int ctasNeeded = (warpsNeeded + (WAVE_THREADS / 32) - 1) / (WAVE_THREADS / 32);
+    if (grid > ctasNeeded) grid = ctasNeeded ? ctasNeeded : 1;
+    if ((e = cudaMemsetAsync(P.workCounter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(evA, stream)) != cudaSuccess) return e;
+    k_raytrace_wave<S, X><<<grid, WAVE_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    return cudaEventRecord(evB, stream);
 }
 
 inline cudaError_t wave_launch(const DevParams& P, int numSMs, cudaStream_t stream, cudaEvent_t evA, cudaEvent_t evB)
@@ -356,23 +380,11 @@ inline cudaError_t wave_launch(const DevParams& P, int numSMs, cudaStream_t stre
     const unsigned int totalJobs = (unsigned int)jobs64;
 
     const size_t smemBytes = sizeof(WaveSmemHeader) + (size_t)P.smemPairs * sizeof(NodePair) + (size_t)WAVE_MAX_SMEM_SPHERES * sizeof(DevSphere);
-    cudaError_t e;
-    int ctasPerSM = 0;
-    if (P.countStats) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, k_raytrace_wave<true>, WAVE_THREADS, smemBytes);
-    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, k_raytrace_wave<false>, WAVE_THREADS, smemBytes);
-    if (e != cudaSuccess) return e;
-    if (ctasPerSM < 1) return cudaErrorInvalidConfiguration;
-    unsigned int grid = (unsigned int)(numSMs * ctasPerSM);                  // persistent: a multiple of the SM count
-    const unsigned int warpsNeeded = (totalJobs + 31u) / 32u;
-    const unsigned int ctasNeeded = (warpsNeeded + (WAVE_THREADS / 32) - 1) / (WAVE_THREADS / 32);
-    if (grid > ctasNeeded) grid = ctasNeeded ? ctasNeeded : 1;
-
-    if ((e = cudaMemsetAsync(P.workCounter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
-    if ((e = cudaEventRecord(evA, stream)) != cudaSuccess) return e;
-    if (P.countStats) k_raytrace_wave<true><<<grid, WAVE_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows);
-    else k_raytrace_wave<false><<<grid, WAVE_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    return cudaEventRecord(evB, stream);
+    const bool ext = P.nPeers > 0 || P.sphBvh != 0;          // extensions compiled into their own instantiation
+    if (P.countStats) return ext ? wave_launch_one<true, true>(P, numSMs, smemBytes, totalJobs, tilesX, ownedRows, stream, evA, evB)
+                                 : wave_launch_one<true, false>(P, numSMs, smemBytes, totalJobs, tilesX, ownedRows, stream, evA, evB);
+    return ext ? wave_launch_one<false, true>(P, numSMs, smemBytes, totalJobs, tilesX, ownedRows, stream, evA, evB)
+               : wave_launch_one<false, false>(P, numSMs, smemBytes, totalJobs, tilesX, ownedRows, stream, evA, evB);
 }
 
 } // namespace rtd
