@@ -356,17 +356,9 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                     cnt.rays++;
                     resDst = inf32(); resPrim = 0; resModel = 0; resKind = PS_HIT_MISS; resU = resV = resDet = 0.0f;
                     // spheres first (extension; where the reference's commented call sits, HL:341)
-                    if (EXT && P.sphBvh)
-                    {
-                        int idx = 0x7fffffff, flag = 0; bool inside = false;
-                        TraverseSpheres(P, rayPos, rayDir, resDst, idx, inside, flag, cnt, STATS);
-                        if (idx != 0x7fffffff)
-                        {
-                            resPrim = -(idx + 1); resDet = inside ? -1.0f : 1.0f;
-                            resKind = flag == RT_MATERIAL_GLASS ? PS_HIT_GLASS : PS_HIT_OPAQUE;
-                        }
-                    }
-                    else
+                    // A large Spheres buffer is searched through its accelerator by the same state machine as the meshes
+                    // ("model -1": inner nodes = padded sphere boxes, leaves = spheres), see the T_NEXT / T_INNER / T_LEAF blocks.
+                    if (!(EXT && P.sphBvh))
                     for (int s = 0; s < P.sphereCount; s++)
                     {
                         float cx, cy, cz, r2; int flag;
@@ -381,7 +373,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                             resKind = flag == RT_MATERIAL_GLASS ? PS_HIT_GLASS : PS_HIT_OPAQUE;
                         }
                     }
-                    model = -1; mode = T_NEXT;
+                    model = (EXT && P.sphBvh) ? -2 : -1; mode = T_NEXT;
                 }
                 continue;                                            // recount: the fetched lanes now wait in T_NEXT
             }
@@ -404,8 +396,21 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                         resDst = bestDst; resPrim = bestTri; resU = bestU; resV = bestV; resDet = bestDet; resModel = model;
                         resKind = cull ? PS_HIT_OPAQUE : PS_HIT_GLASS;   // cull == (flag != GLASS)
                     }
+                    if (EXT && model == -1 && bestTri != 0x7fffffff)     // sphere phase finished with a winner (bestTri = buffer index)
+                    {
+                        resDst = bestDst; resPrim = -(bestTri + 1); resDet = bestDet;
+                        resKind = __float_as_int(bestU) == RT_MATERIAL_GLASS ? PS_HIT_GLASS : PS_HIT_OPAQUE;
+                    }
                     model++;
-                    if (model < P.modelCount)
+                    if (EXT && model == -1)
+                    {
+                        // sphere phase: world-space ray against the accelerator of the Spheres buffer (semantics of TraverseSpheres)
+                        lpos = rayPos; ldir = rayDir; linv = rcp3(rayDir);
+                        bestDst = inf32(); bestTri = 0x7fffffff; bestDet = 1.0f; bestU = 0.0f;
+                        cur.start = P.sphRootStart; cur.count = P.sphRootCount; leafK = 0; stackCount = 0;
+                        mode = cur.count > 0 ? T_LEAF : T_INNER;
+                    }
+                    else if (model < P.modelCount)
                     {
                         const float4* mr = reinterpret_cast<const float4*>(P.models + model);
                         const float4 r0 = __ldg(mr), r1 = __ldg(mr + 1), r2 = __ldg(mr + 2);
@@ -435,11 +440,21 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                 // ---- one inner node: HL:262-282 ----
                 if (mode == T_INNER)
                 {
+                    const bool sph = EXT && model < 0;
                     float4 q0, q1, q2, q3;
-                    LoadPair(P, smemPairs, cur.start, q0, q1, q2, q3);
+                    if (sph)
+                    {
+                        const float4* p = reinterpret_cast<const float4*>(P.sphPairs + cur.start);
+                        q0 = __ldg(p); q1 = __ldg(p + 1); q2 = __ldg(p + 2); q3 = __ldg(p + 3);
+                        if (STATS) cnt.sbox += 2;
+                    }
+                    else
+                    {
+                        LoadPair(P, smemPairs, cur.start, q0, q1, q2, q3);
+                        if (STATS) cnt.box += 2;
+                    }
                     const float dstA = RayBoundingBoxDst(lpos, linv, make_f3(q0.x, q0.y, q0.z), make_f3(q0.w, q1.x, q1.y));
                     const float dstB = RayBoundingBoxDst(lpos, linv, make_f3(q2.x, q2.y, q2.z), make_f3(q2.w, q3.x, q3.y));
-                    if (STATS) cnt.box += 2;
                     NodeRef a, b;
                     a.start = __float_as_int(q1.z); a.count = __float_as_int(q1.w);
                     b.start = __float_as_int(q3.z); b.count = __float_as_int(q3.w);
@@ -448,8 +463,11 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                     const float dstFar = isNearestA ? dstB : dstA;
                     const NodeRef nearRef = isNearestA ? a : b;
                     const NodeRef farRef = isNearestA ? b : a;
-                    if (dstFar < bestDst && stackCount < WAVE_STACK) stack[stackCount++] = farRef;   // (prefetching the far record here was measured: -2 %)
-                    if (dstNear < bestDst) { cur = nearRef; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
+                    // meshes: the reference's push-time test dst < best (HL:280-281).  Sphere boxes: conservative slack, ties kept
+                    // (x*1 - 0 is x exactly, so the mesh comparison is unchanged; inf stays inf and never passes)
+                    const float cs = sph ? 0.99999619f : 1.0f, cb = sph ? 1e-6f : 0.0f;
+                    if ((dstFar * cs - cb) < bestDst && stackCount < WAVE_STACK) stack[stackCount++] = farRef;   // (prefetching the far record here was measured: -2 %)
+                    if ((dstNear * cs - cb) < bestDst) { cur = nearRef; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
                     else if (stackCount > 0) { cur = stack[--stackCount]; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
                     else mode = T_NEXT;
                 }
@@ -457,7 +475,26 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
             else
             {
                 // ---- one leaf triangle: HL:248-260 ----
-                if (mode == T_LEAF)
+                if (EXT && mode == T_LEAF && model < 0)
+                {
+                    // one sphere of the accelerator's leaf (reference test, first-index rule on equal dst)
+                    const float4* q = reinterpret_cast<const float4*>(P.sphLeaves + cur.start + leafK);
+                    const float4 s0 = __ldg(q), s1 = __ldg(q + 1);
+                    float dst; bool inside;
+                    if (STATS) cnt.sph++;
+                    if (RaySphereCore(lpos, ldir, make_f3(s0.x, s0.y, s0.z), s1.x, dst, inside))
+                    {
+                        const int orig = __float_as_int(s1.z);
+                        if (dst < bestDst || (dst == bestDst && orig < bestTri)) { bestDst = dst; bestTri = orig; bestDet = inside ? -1.0f : 1.0f; bestU = s1.y; }
+                    }
+                    leafK++;
+                    if (leafK >= cur.count)
+                    {
+                        if (stackCount > 0) { cur = stack[--stackCount]; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
+                        else mode = T_NEXT;
+                    }
+                }
+                else if (mode == T_LEAF)
                 {
                     const float4* g = reinterpret_cast<const float4*>(P.triGeom + cur.start + leafK);
                     const float4 g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2);
