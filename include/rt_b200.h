@@ -89,6 +89,13 @@ int rtDispatch(RtContext* ctx, int kernelIndex, int groupsX, int groupsY, int gr
  * bytes must equal W·H·16.  Synchronises. */
 int rtReadback(RtContext* ctx, const char* tex, float* dst, size_t bytes);
 
+/* Replaces: RayTraceDisplay.OnRenderImage -> Graphics.Blit(rt, destination, displayMat) with Display.shader
+ * (Assets/Scripts/Tracer/RayTraceDisplay.cs:9-23, Display.shader:42-47): col = tex / Frame, where tex is the accumulated
+ * image and Frame = numAccumulatedFrames when accumulating, else the frame image and Frame = 1.  The quotient is then
+ * encoded like Unity's linear-colour-space back buffer: clamp to [0,1], sRGB transfer function, 8 bits per channel.
+ * dst receives W*H RGBA8 pixels in [y][x] order (row 0 = bottom), bytes must equal W*H*4.  Synchronises. */
+int rtDisplay(RtContext* ctx, int useAccumulated, int Frame, uint8_t* dst, size_t bytes);
+
 /* Block until all work queued on this context has finished. */
 int rtSynchronize(RtContext* ctx);
 

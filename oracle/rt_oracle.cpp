@@ -779,6 +779,26 @@ int rtReadback(RtContext* c, const char* tex, float* dst, size_t bytes)
     return RT_OK;
 }
 
+// Display.shader:42-47 (col = tex / Frame) + sRGB 8-bit back buffer
+static unsigned DisplayEncode(float v)
+{
+    if (!(v > 0.0f)) return 0u;
+    if (v > 1.0f) v = 1.0f;
+    const float e = v <= 0.0031308f ? 12.92f * v : 1.055f * orc::pow(v, 0.41666666f) - 0.055f;
+    return (unsigned)(orc::min(orc::max(e, 0.0f), 1.0f) * 255.0f + 0.5f);
+}
+
+int rtDisplay(RtContext* c, int useAccumulated, int Frame, uint8_t* dst, size_t bytes)
+{
+    if (!c || !dst) return fail(c, RT_E_INVALID, "rtDisplay: bad argument");
+    const std::vector<float>& tex = useAccumulated ? c->accum : c->frame;
+    if (tex.empty()) return fail(c, RT_E_STATE, "rtDisplay: rtResize has not been called");
+    if (bytes != tex.size()) return fail(c, RT_E_INVALID, "rtDisplay: bytes must equal W*H*4");
+    const float frame = (float)Frame;
+    for (size_t i = 0; i < tex.size(); i++) dst[i] = (uint8_t)DisplayEncode(tex[i] / frame);
+    return RT_OK;
+}
+
 int rtSynchronize(RtContext* c) { return c ? RT_OK : RT_E_INVALID; }
 int rtSetStream(RtContext* c, void*) { return c ? RT_OK : RT_E_INVALID; }
 int rtPackTile(RtContext* c) { return fail(c, RT_E_STATE, "oracle: no device tile staging"); }

@@ -74,6 +74,7 @@ class RtLib:
             "rtDispatch": ([vp, ci, ci, ci, ci], ci),
             "rtReadback": ([vp, cp, vp, C.c_size_t], ci),
             "rtSynchronize": ([vp], ci),
+            "rtDisplay": ([vp, ci, ci, vp, C.c_size_t], ci),
             "rtSetStream": ([vp, vp], ci),
             "rtSetTile": ([vp, ci, ci, ci], ci),
             "rtPackTile": ([vp], ci),
@@ -182,6 +183,12 @@ class RtContext:
 
     def readback_into(self, tex: str, ptr: int, nbytes: int):
         self._ck(self._L.rtReadback(self._h, tex.encode(), C.c_void_p(ptr), nbytes))
+
+    def display(self, use_accumulated: bool, frame: int) -> np.ndarray:
+        """Display.shader: tex / Frame, encoded as the sRGB 8-bit back buffer.  Returns (H, W, 4) uint8, row 0 = bottom."""
+        out = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        self._ck(self._L.rtDisplay(self._h, 1 if use_accumulated else 0, int(frame), out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
 
     def synchronize(self):
         self._ck(self._L.rtSynchronize(self._h))

@@ -56,6 +56,7 @@ struct RtContext
 
     // render targets
     DevBuf<float4> frame, accum, tileSend, tileRecv;
+    DevBuf<uchar4> display;
     int width = 0, height = 0;
     int tileRank = 0, tileWorld = 1, bandRows = 1;
 
@@ -146,7 +147,7 @@ int rtDestroy(RtContext* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->nodes.release(); c->tris.release(); c->models.release(); c->spheres.release();
-    c->frame.release(); c->accum.release(); c->tileSend.release(); c->tileRecv.release();
+    c->frame.release(); c->accum.release(); c->tileSend.release(); c->tileRecv.release(); c->display.release();
     c->repack.release();
     closePeers(c);
     for (auto& ev : c->pending) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
@@ -477,6 +478,21 @@ int rtReadback(RtContext* c, const char* tex, float* dst, size_t bytes)
     if (bytes != (size_t)c->width * c->height * 16) return fail(c, RT_E_INVALID, "rtReadback: bytes must equal W*H*16");
     CK(cudaSetDevice(c->device));
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return RT_OK;
+}
+
+int rtDisplay(RtContext* c, int useAccumulated, int Frame, uint8_t* dst, size_t bytes)
+{
+    if (!c || !dst) return fail(c, RT_E_INVALID, "rtDisplay: bad argument");
+    if (!c->frame.p) return fail(c, RT_E_STATE, "rtDisplay: rtResize has not been called");
+    const size_t n = (size_t)c->width * c->height;
+    if (bytes != n * 4) return fail(c, RT_E_INVALID, "rtDisplay: bytes must equal W*H*4");
+    CK(cudaSetDevice(c->device));
+    CK(c->display.ensure(n));
+    k_display<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(useAccumulated ? c->accum.p : c->frame.p, c->display.p, n, (float)Frame);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dst, c->display.p, bytes, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return RT_OK;
 }

@@ -481,6 +481,16 @@ RT_DI bool ShadeSegment(const DevParams& P, const Hit& hit, PathState& ray, uint
     return true;
 }
 
+// ---- display (Display.shader:42-47 + sRGB back buffer) -------------------------------------------------------------------
+RT_DI unsigned int DisplayEncode(float v)
+{
+    // NaN -> 0; clamp; IEC 61966-2-1 transfer function with the pinned pow; round to nearest
+    if (!(v > 0.0f)) return 0u;
+    if (v > 1.0f) v = 1.0f;
+    const float e = v <= 0.0031308f ? 12.92f * v : 1.055f * pow_rt(v, 0.41666666f) - 0.055f;
+    return __float2uint_rz(fminf(fmaxf(e, 0.0f), 1.0f) * 255.0f + 0.5f);
+}
+
 // ---- camera (HL:545-576) --------------------------------------------------------------------------------------------------
 
 struct PixelSetup

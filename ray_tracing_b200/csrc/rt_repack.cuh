@@ -335,6 +335,15 @@ __global__ void k_unpack_tiles(const float4* __restrict__ recv, float4* __restri
     accum[(size_t)y * W + x] = src[half + (size_t)r * W + x];
 }
 
+__global__ void k_display(const float4* __restrict__ tex, uchar4* __restrict__ out, size_t n, float frame)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 t = tex[i];
+    out[i] = make_uchar4((unsigned char)DisplayEncode(t.x / frame), (unsigned char)DisplayEncode(t.y / frame),
+                         (unsigned char)DisplayEncode(t.z / frame), (unsigned char)DisplayEncode(t.w / frame));
+}
+
 inline void launch_pack_tile(const float4* frame, const float4* accum, float4* send, int W, int H, int rank, int world, int bandRows, int rowsPerRank, cudaStream_t s)
 {
     dim3 grid((W + 255) / 256, rowsPerRank, 1);

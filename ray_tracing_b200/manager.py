@@ -34,6 +34,9 @@ def host_lib() -> C.CDLL:
         L.rthBuildBVH.argtypes = [vp, ci, vp, ci, vp, ci, vp, vp, ci, vp]
         L.rthBuildBVH.restype = ci
         L.rthLastError.restype = cp
+        L.rthObjLoad.argtypes = [cp, ci, C.POINTER(ci), C.POINTER(ci)]
+        L.rthObjCopy.argtypes = [vp, vp, vp]
+        L.rthObjLastError.restype = cp
         L.rcmCreate.argtypes = [cp, ci, C.POINTER(vp)]
         L.rcmDestroy.argtypes = [vp]
         L.rcmLastError.argtypes = [vp]
@@ -80,6 +83,20 @@ def build_bvh(vertices: np.ndarray, indices: np.ndarray, normals: np.ndarray, qu
     if rc < 0:
         raise ValueError("rthBuildBVH: " + L.rthLastError().decode())
     return tris[:ntri].copy(), nodes[:rc].copy(), dict(zip(STAT_NAMES, (int(s) for s in stats)))
+
+
+def load_obj(path: str, unity_handedness: bool = True):
+    """Wavefront OBJ -> (vertices (n,3) f32, indices (3t,) i32, normals (n,3) f32) as Unity's importer hands them to the
+    reference's manager (host/ObjLoader.cpp)."""
+    L = host_lib()
+    nv, ni = C.c_int(), C.c_int()
+    if L.rthObjLoad(path.encode(), 1 if unity_handedness else 0, C.byref(nv), C.byref(ni)) != 0:
+        raise ValueError("load_obj: " + L.rthObjLastError().decode())
+    v = np.empty((nv.value, 3), dtype=np.float32)
+    n = np.empty((nv.value, 3), dtype=np.float32)
+    idx = np.empty(ni.value, dtype=np.int32)
+    L.rthObjCopy(v.ctypes.data, n.ctypes.data, idx.ctypes.data)
+    return v, idx, n
 
 
 def column_major(m) -> np.ndarray:
