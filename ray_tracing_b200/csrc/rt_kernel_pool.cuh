@@ -25,6 +25,9 @@
 
 namespace rtd {
 
+#ifndef RT_INNER_REPEAT
+#define RT_INNER_REPEAT 2      // measured (profiles/r01_sweeps.log): 2 visits per census = +1.4 % .. +4.2 % on the mesh scenes, 3 = no better
+#endif
 #ifndef RT_POOL_WARPS
 #define RT_POOL_WARPS 24      // measured (profiles/r01_sweeps.log): 16 -> 24 warps per SM: knot 33.8 -> 31.7 ms, 871k-triangle scene 109.8 -> 93.4 ms
 #endif
@@ -437,7 +440,10 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
             }
             else if (nInner >= nLeaf)
             {
-                // ---- one inner node: HL:262-282 ----
+                // ---- inner nodes: HL:262-282 ----  (RT_INNER_REPEAT visits per census: most lanes stay in this mode after a
+                // visit, and the census / vote / loop control of an iteration costs about a third of a visit)
+#pragma unroll 1
+                for (int rep = 0; rep < RT_INNER_REPEAT; rep++)
                 if (mode == T_INNER)
                 {
                     const bool sph = EXT && model < 0;
