@@ -120,8 +120,9 @@ int rtPackTile(RtContext* ctx);
 int rtUnpackTiles(RtContext* ctx);
 
 /* Fused tile exchange (alternative to rtPackTile / all-gather / rtUnpackTiles): every rank exports CUDA-IPC handles of
- * its two images (rtGetIpcHandles: 2 x 64 bytes = cudaIpcMemHandle_t of FrameRender, AccumulatedRender), the host
- * exchanges them, and each rank maps the images of the other ranks (rtSetPeers: nPeers x 2 x 64 bytes, at most 7 peers).
+ * its two images (rtGetIpcHandles: 2 x 72 bytes = {cudaIpcMemHandle_t of the allocation, byte offset inside it} for
+ * FrameRender and AccumulatedRender), the host
+ * exchanges them, and each rank maps the images of the other ranks (rtSetPeers: nPeers x 2 x 72 bytes, at most 7 peers).
  * From then on the RayTrace kernel stores every finished pixel into its own images AND into every peer's, over NVLink,
  * as part of the kernel that produced it; the host only needs a stream-ordered barrier across ranks after the dispatch
  * before any rank reads its images.  rtResize with a new size and rtSetPeers(0) drop the mappings. */

@@ -212,12 +212,12 @@ class RtContext:
         return int(p.value), int(n.value)
 
     def ipc_handles(self) -> bytes:
-        buf = C.create_string_buffer(128)
-        self._ck(self._L.rtGetIpcHandles(self._h, buf, 128))
+        buf = C.create_string_buffer(144)
+        self._ck(self._L.rtGetIpcHandles(self._h, buf, 144))
         return buf.raw
 
     def set_peers(self, handles: list):
-        """handles: one 128-byte blob (ipc_handles()) per peer rank."""
+        """handles: one 144-byte blob (ipc_handles()) per peer rank."""
         blob = b"".join(handles)
         self._ck(self._L.rtSetPeers(self._h, len(handles), blob if handles else None, len(blob)))
 

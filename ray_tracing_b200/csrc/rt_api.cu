@@ -565,14 +565,40 @@ int rtGetDevicePointer(RtContext* c, const char* name, void** devPtr, size_t* by
     return RT_OK;
 }
 
+// One exported image: the IPC handle of the allocation that contains it + its byte offset inside that allocation
+// (cudaMalloc may sub-allocate small buffers from a larger block; the handle always names the whole block).
+struct RtIpcImage { cudaIpcMemHandle_t handle; unsigned long long offset; };
+static_assert(sizeof(RtIpcImage) == 72, "IPC blob layout");
+
+static cudaError_t allocationBase(const void* p, unsigned long long* offset)
+{
+    typedef int (*GetRangeFn)(unsigned long long*, size_t*, unsigned long long);
+    static GetRangeFn fn = nullptr;
+    if (!fn)
+    {
+        void* sym = nullptr; cudaDriverEntryPointQueryResult qr;
+        cudaError_t e = cudaGetDriverEntryPoint("cuMemGetAddressRange", &sym, cudaEnableDefault, &qr);
+        if (e != cudaSuccess) return e;
+        if (!sym) return cudaErrorNotSupported;
+        fn = (GetRangeFn)sym;
+    }
+    unsigned long long base = 0; size_t size = 0;
+    if (fn(&base, &size, (unsigned long long)(uintptr_t)p) != 0) return cudaErrorInvalidValue;
+    *offset = (unsigned long long)(uintptr_t)p - base;
+    return cudaSuccess;
+}
+
 int rtGetIpcHandles(RtContext* c, void* handles, size_t bytes)
 {
-    if (!c || !handles || bytes != 2 * sizeof(cudaIpcMemHandle_t)) return fail(c, RT_E_INVALID, "rtGetIpcHandles: handles must hold 2 x 64 bytes");
+    if (!c || !handles || bytes != 2 * sizeof(RtIpcImage)) return fail(c, RT_E_INVALID, "rtGetIpcHandles: handles must hold 2 x 72 bytes");
     if (!c->frame.p || !c->accum.p) return fail(c, RT_E_STATE, "rtGetIpcHandles: rtResize has not been called");
     CK(cudaSetDevice(c->device));
-    cudaIpcMemHandle_t h[2];
-    CK(cudaIpcGetMemHandle(&h[0], c->frame.p));
-    CK(cudaIpcGetMemHandle(&h[1], c->accum.p));
+    RtIpcImage h[2];
+    memset(h, 0, sizeof(h));
+    CK(cudaIpcGetMemHandle(&h[0].handle, c->frame.p));
+    CK(allocationBase(c->frame.p, &h[0].offset));
+    CK(cudaIpcGetMemHandle(&h[1].handle, c->accum.p));
+    CK(allocationBase(c->accum.p, &h[1].offset));
     memcpy(handles, h, sizeof(h));
     return RT_OK;
 }
@@ -580,19 +606,23 @@ int rtGetIpcHandles(RtContext* c, void* handles, size_t bytes)
 int rtSetPeers(RtContext* c, int nPeers, const void* handles, size_t bytes)
 {
     if (!c || nPeers < 0 || nPeers > RT_MAX_PEERS) return fail(c, RT_E_INVALID, "rtSetPeers: at most 7 peers");
-    if (nPeers > 0 && (!handles || bytes != (size_t)nPeers * 2 * sizeof(cudaIpcMemHandle_t))) return fail(c, RT_E_INVALID, "rtSetPeers: handles must hold nPeers x 2 x 64 bytes");
+    if (nPeers > 0 && (!handles || bytes != (size_t)nPeers * 2 * sizeof(RtIpcImage))) return fail(c, RT_E_INVALID, "rtSetPeers: handles must hold nPeers x 2 x 72 bytes");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     closePeers(c);
-    const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)handles;
+    const RtIpcImage* h = (const RtIpcImage*)handles;
     for (int k = 0; k < nPeers; k++)
     {
-        void *pf = nullptr, *pa = nullptr;
-        CK(cudaIpcOpenMemHandle(&pf, h[2 * k], cudaIpcMemLazyEnablePeerAccess));
-        c->peerBase.push_back(pf);
-        CK(cudaIpcOpenMemHandle(&pa, h[2 * k + 1], cudaIpcMemLazyEnablePeerAccess));
-        c->peerBase.push_back(pa);
-        c->peerFrame[k] = (float4*)pf; c->peerAccum[k] = (float4*)pa;
+        void* base[2] = {nullptr, nullptr};
+        for (int j = 0; j < 2; j++)
+        {
+            // both images of a peer may live in the same allocation: open every distinct handle once
+            if (j == 1 && memcmp(&h[2 * k].handle, &h[2 * k + 1].handle, sizeof(cudaIpcMemHandle_t)) == 0) { base[1] = base[0]; continue; }
+            CK(cudaIpcOpenMemHandle(&base[j], h[2 * k + j].handle, cudaIpcMemLazyEnablePeerAccess));
+            c->peerBase.push_back(base[j]);
+        }
+        c->peerFrame[k] = (float4*)((char*)base[0] + h[2 * k].offset);
+        c->peerAccum[k] = (float4*)((char*)base[1] + h[2 * k + 1].offset);
     }
     c->nPeers = nPeers;
     return RT_OK;
