@@ -141,6 +141,8 @@ int rtGetDevicePointer(RtContext* ctx, const char* name, void** devPtr, size_t* 
  *   "smemNodes"   number of top-of-tree node pairs staged in shared memory by TMA bulk copy (0 = off; -1 = automatic, which
  *                 is currently 0: measured, the staging never beat leaving that shared memory to L1)
  *   "poolSlots"   paths per warp pool of kernel 2: 32, 64 (default) or 96
+ *   "extInstantiation"  1 = launch the kernel instantiation that carries the extensions (peer stores, sphere accelerator)
+ *                 even when none is active — for testing that instantiation on one GPU
  *   "sortRays"    kernel 2: 1 = group each warp's ray queue by direction octant before tracing, 0 = slot order (default;
  *                 measured: the grouping changes throughput by -3 % .. +1.5 %)
  *   "tailLanes"   kernel 2 leaves its trace phase when the ray queue is empty and at most this many lanes still trace

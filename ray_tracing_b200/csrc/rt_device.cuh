@@ -106,7 +106,8 @@ struct DevParams
     // a finished pixel is stored straight into every peer's images by the kernel that produced it
     float4* peerFrame[RT_MAX_PEERS];
     float4* peerAccum[RT_MAX_PEERS];
-    int   nPeers, pad5;
+    int   nPeers;
+    int   forceExt;                         // testing: run the <EXT = true> instantiation although no extension is active
     unsigned long long* counters;           // [0] rays [1] boxTests [2] triTests [3] sphereTests [4] sphere-accelerator box tests
     unsigned int* workCounter;              // persistent kernel: next job
 };

@@ -399,13 +399,13 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                         resDst = bestDst; resPrim = bestTri; resU = bestU; resV = bestV; resDet = bestDet; resModel = model;
                         resKind = cull ? PS_HIT_OPAQUE : PS_HIT_GLASS;   // cull == (flag != GLASS)
                     }
-                    if (EXT && model == -1 && bestTri != 0x7fffffff)     // sphere phase finished with a winner (bestTri = buffer index)
+                    if (EXT && P.sphBvh && model == -1 && bestTri != 0x7fffffff)     // sphere phase finished with a winner (bestTri = buffer index)
                     {
                         resDst = bestDst; resPrim = -(bestTri + 1); resDet = bestDet;
                         resKind = __float_as_int(bestU) == RT_MATERIAL_GLASS ? PS_HIT_GLASS : PS_HIT_OPAQUE;
                     }
                     model++;
-                    if (EXT && model == -1)
+                    if (EXT && P.sphBvh && model == -1)
                     {
                         // sphere phase: world-space ray against the accelerator of the Spheres buffer (semantics of TraverseSpheres)
                         lpos = rayPos; ldir = rayDir; linv = rcp3(rayDir);
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                 for (int rep = 0; rep < RT_INNER_REPEAT; rep++)
                 if (mode == T_INNER)
                 {
-                    const bool sph = EXT && model < 0;
+                    const bool sph = EXT && P.sphBvh && model < 0;
                     float4 q0, q1, q2, q3;
                     if (sph)
                     {
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
             else
             {
                 // ---- one leaf triangle: HL:248-260 ----
-                if (EXT && mode == T_LEAF && model < 0)
+                if (EXT && P.sphBvh && mode == T_LEAF && model < 0)
                 {
                     // one sphere of the accelerator's leaf (reference test, first-index rule on equal dst)
                     const float4* q = reinterpret_cast<const float4*>(P.sphLeaves + cur.start + leafK);
@@ -574,7 +574,7 @@ template <int M> inline cudaError_t pool_launch_m(const DevParams& P, int numSMs
     cudaError_t e;
     if ((e = cudaMemsetAsync(P.workCounter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(evA, stream)) != cudaSuccess) return e;
-    const bool ext = P.nPeers > 0 || P.sphBvh != 0;          // extensions compiled into their own instantiation
+    const bool ext = P.nPeers > 0 || P.sphBvh != 0 || P.forceExt != 0;   // extensions compiled into their own instantiation
     if (P.countStats) { if (ext) k_raytrace_pool<true, true, M><<<grid, POOL_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows);
                         else k_raytrace_pool<true, false, M><<<grid, POOL_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows); }
     else { if (ext) k_raytrace_pool<false, true, M><<<grid, POOL_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows);

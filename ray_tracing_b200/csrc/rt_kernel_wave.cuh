@@ -380,7 +380,7 @@ inline cudaError_t wave_launch(const DevParams& P, int numSMs, cudaStream_t stre
     const unsigned int totalJobs = (unsigned int)jobs64;
 
     const size_t smemBytes = sizeof(WaveSmemHeader) + (size_t)P.smemPairs * sizeof(NodePair) + (size_t)WAVE_MAX_SMEM_SPHERES * sizeof(DevSphere);
-    const bool ext = P.nPeers > 0 || P.sphBvh != 0;          // extensions compiled into their own instantiation
+    const bool ext = P.nPeers > 0 || P.sphBvh != 0 || P.forceExt != 0;   // extensions compiled into their own instantiation
     if (P.countStats) return ext ? wave_launch_one<true, true>(P, numSMs, smemBytes, totalJobs, tilesX, ownedRows, stream, evA, evB)
                                  : wave_launch_one<true, false>(P, numSMs, smemBytes, totalJobs, tilesX, ownedRows, stream, evA, evB);
     return ext ? wave_launch_one<false, true>(P, numSMs, smemBytes, totalJobs, tilesX, ownedRows, stream, evA, evB)

@@ -110,6 +110,18 @@ def test_config5_ten_thousand_spheres_bitwise():
     assert so["sphereTests"] == so["rays"] * 10000 and sg["sphereTests"] < so["sphereTests"] // 100
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_extension_instantiation_alone_is_equivalent(kernel):
+    """The <EXT = true> kernel instantiation (used with peers and/or the sphere accelerator) must equal the plain one when no
+    extension is active — the case of a multi-GPU job with fused tile exchange on a scene without a large Spheres buffer."""
+    for sc in (scenes.knot_room(160, 90, max_bounces=5, rays_per_pixel=2, nu=120, nv=10),
+               scenes.random_soup(64, 64, max_bounces=5, rays_per_pixel=2, triangles=5000, spheres=20)):
+        fo, ao, so = render(ORACLE_LIB, sc, frames=2, want_stats=True)
+        fg, ag, sg = render(CUDA_LIB, sc, frames=2, options={"kernel": kernel, "extInstantiation": 1, "countStats": 1}, want_stats=True)
+        assert_bit_equal(ag, ao, f"{sc.name} EXT instantiation, kernel {kernel}")
+        _same_counters(sg, so)
+
+
 def test_shared_memory_staging_does_not_change_results():
     """TMA-staged tree tops: 0, a few, many pairs in shared memory — identical output."""
     sc = scenes.knot_room(96, 54, max_bounces=4, rays_per_pixel=2, nu=200, nv=12)
