@@ -68,6 +68,18 @@ def algorithmic_bytes(st, model_count, width, height, frames):
 # CPU arm: the oracle on the host cores (cpu_baseline leg and --impl reference)
 # ---------------------------------------------------------------------------------------------------------------------
 
+def effective_cores():
+    """Host threads this process can really use: the affinity mask, capped by a cgroup CPU quota if one is set."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_sample(w, steps, warmup, pixels=262144):
     """Times the oracle on a seeded sparse pixel sample of the workload (exact: pixels are independent and seeded from
     their global index).  Returns (Mrays/s, ms per step, cores, sample description)."""
@@ -83,6 +95,7 @@ def cpu_sample(w, steps, warmup, pixels=262144):
     xy = np.stack([rng.randint(0, w["width"], pixels), rng.randint(0, w["height"], pixels)], axis=1).astype(np.int32)
     out = np.empty((pixels, 4), dtype=np.float32)
     ctx = mgr.context
+    ctx.set_option("threads", effective_cores())
     handle = C.c_void_p(ctx.handle.value)
     times, rays = [], 0
     for i in range(warmup + steps):
@@ -95,7 +108,7 @@ def cpu_sample(w, steps, warmup, pixels=262144):
         if i >= warmup:
             times.append(dt)
             rays += ctx.stats()["rays"]
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     total = sum(times)
     sample = f"{pixels} seeded random pixels x {w['spp']} spp of the {w['width']}x{w['height']} frame per step, {cores} threads"
     return rays / total / 1e6, 1e3 * total / max(len(times), 1), cores, sample

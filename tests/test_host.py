@@ -244,3 +244,27 @@ def test_two_rank_tiles_equal_single_rank(tmp_path, oracle_path):
     frame, accum = render(oracle_path, scenes.cornell_spheres(40, 26, 3, 2), frames=2)
     assert_bit_equal(tiled[0], frame, "N=2 FrameRender vs N=1")
     assert_bit_equal(tiled[1], accum, "N=2 AccumulatedRender vs N=1")
+
+
+# ---- the C++ host stands on its own (no Python in the loop) ------------------------------------------------------------------
+
+def test_cpp_example_drives_the_abi_like_the_reference_manager(tmp_path, oracle_path):
+    """examples/render_cornell.cpp: a C++ program using host/RayComputeManager directly (scene, OnEnable, RenderFrame x N,
+    readback).  Run against the CPU oracle it must produce the image the Python-driven manager produces."""
+    exe = str(tmp_path / "render_cornell")
+    src = [os.path.join(REPO, "examples", "render_cornell.cpp"), os.path.join(REPO, "ray_tracing_b200", "host", "RayComputeManager.cpp"),
+           os.path.join(REPO, "ray_tracing_b200", "host", "BVH.cpp")]
+    cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O1", "-ffp-contract=off", "-I", os.path.join(REPO, "include"),
+           "-I", os.path.join(REPO, "ray_tracing_b200", "host")] + src + ["-ldl", "-pthread", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, oracle_path, "2"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr + r.stdout
+    m = re.search(r"numAccumulatedFrames=(\d+) alpha=([\d.]+) mean_rgb=([\d.eE+-]+)", r.stdout)
+    assert m and int(m.group(1)) == 3 and float(m.group(2)) == 2.0
+    _, accum = render(oracle_path, scenes.cornell_spheres(256, 256, 4, 1), frames=2)
+    assert abs(float(m.group(3)) - accum[..., :3].astype(np.float64).sum() / (3.0 * 256 * 256 * 2)) < 1e-6
+    # and it refuses to run without a GPU instead of falling back
+    if not os.path.exists("/dev/nvidiactl"):
+        r = subprocess.run([exe, CUDA_LIB, "1"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 2 and "no CPU path" in r.stderr
