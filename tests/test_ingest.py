@@ -110,3 +110,45 @@ def test_display_matches_oracle_on_gpu():
         outs.append(rt.RayTraceDisplay(mgr).OnRenderImage())       # not accumulating: the frame image with Frame = 1
         mgr.OnDestroy()
     assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[3])
+
+
+# ---- the reference's serialized scenes (Unity YAML) ---------------------------------------------------------------------------
+
+SCENES_DIR = "/root/reference/Assets/Scenes"
+
+
+def test_builtin_unity_meshes():
+    from ray_tracing_b200 import unity_scene
+    cube, quad = unity_scene.builtin_cube(), unity_scene.builtin_quad()
+    assert cube.triangle_count == 12 and cube.vertices.shape == (24, 3) and np.abs(cube.vertices).max() == 0.5
+    for t in range(12):                                            # outward-facing: cross(B-A, C-A) along the vertex normal and away from the centre
+        a, b, c = (cube.vertices[cube.indices[3 * t + k]] for k in range(3))
+        n = np.cross(b - a, c - a)
+        assert np.dot(n, cube.normals[cube.indices[3 * t]]) > 0 and np.dot(n, a + b + c) > 0
+    assert quad.triangle_count == 2 and np.allclose(quad.normals, [[0, 0, -1]] * 4)
+
+
+@pytest.mark.skipif(not os.path.isdir(SCENES_DIR), reason="reference scenes not mounted")
+def test_reference_scenes_load_with_the_serialized_settings(oracle_path):
+    from ray_tracing_b200 import unity_scene
+    expect = {
+        "Glass Dragon": dict(models=11, bounces=10, fov=54.5, cam=(0.0, 1.9, -5.67), diverge=1.5, defocus=0.0),
+        "Glass Balls": dict(models=17, bounces=10, fov=60.0, cam=(0.0, 1.99, -5.895), diverge=1.5, defocus=0.0),
+        "Sphere Refract": dict(models=10, bounces=32, fov=38.0, cam=(0.0, 1.28, -11.65), diverge=1.5, defocus=100.0),
+    }
+    for name, e in expect.items():
+        sc = unity_scene.load_unity_scene(os.path.join(SCENES_DIR, name + ".unity"), width=64, height=36)
+        assert len(sc.models) == e["models"] and sc.settings["maxBounceCount"] == e["bounces"] and sc.fov == e["fov"]
+        assert np.allclose(sc.cam_local_to_world[:3, 3], e["cam"], atol=1e-3)
+        assert sc.settings["divergeStrength"] == e["diverge"] and sc.settings["defocusStrength"] == e["defocus"]
+    assert sc.settings["focusDistance"] == pytest.approx(5.3)      # Sphere Refract: depth of field
+    # Glass Dragon: the dragon mesh is the shipped OBJ, glass, as serialized (Glass Dragon.unity:1988-2073)
+    sc = unity_scene.load_unity_scene(os.path.join(SCENES_DIR, "Glass Dragon.unity"), width=64, height=36)
+    dragon = [m for m in sc.models if sc.meshes[m.mesh].triangle_count == 87130]
+    assert len(dragon) == 1 and int(dragon[0].material["flag"]) == scenes.MAT_GLASS and float(dragon[0].material["ior"]) == 1.5
+    assert np.allclose(np.linalg.norm(dragon[0].local_to_world[:3, 0]), 4.98, atol=1e-2)
+    frame, _ = render(oracle_path, sc)
+    assert np.isfinite(frame).all() and (frame[..., :3].sum(-1) > 0).mean() > 0.02
+    # scenes that need binary .fbx meshes say so instead of rendering something else
+    with pytest.raises(NotImplementedError):
+        unity_scene.load_unity_scene(os.path.join(SCENES_DIR, "Text.unity"))
