@@ -147,8 +147,9 @@ def test_reference_scenes_load_with_the_serialized_settings(oracle_path):
     dragon = [m for m in sc.models if sc.meshes[m.mesh].triangle_count == 87130]
     assert len(dragon) == 1 and int(dragon[0].material["flag"]) == scenes.MAT_GLASS and float(dragon[0].material["ior"]) == 1.5
     assert np.allclose(np.linalg.norm(dragon[0].local_to_world[:3, 0]), 4.98, atol=1e-2)
+    sc.settings["numRaysPerPixel"] = 16
     frame, _ = render(oracle_path, sc)
-    assert np.isfinite(frame).all() and (frame[..., :3].sum(-1) > 0).mean() > 0.02
+    assert np.isfinite(frame).all() and (frame[..., :3].sum(-1) > 0).mean() > 0.1
     # scenes that need binary .fbx meshes say so instead of rendering something else
     with pytest.raises(NotImplementedError):
         unity_scene.load_unity_scene(os.path.join(SCENES_DIR, "Text.unity"))
