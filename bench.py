@@ -39,6 +39,11 @@ WORKLOADS = {
                       desc="9-sphere Cornell box, 1920x1080, 8 bounces, 64 spp per frame (BASELINE.json configs[1])"),
     "knot64": dict(kind="knot", width=1920, height=1080, bounces=8, spp=16,
                    desc="87,132-triangle knot in a Cornell room (3 models, BVH), 1920x1080, 8 bounces, 16 spp per frame (configs[2] shape)"),
+    # the reference's own usage: one sample per pixel per frame, many accumulated frames (all five shipped scenes)
+    "cornell1": dict(kind="cornell", width=1920, height=1080, bounces=8, spp=1,
+                     desc="9-sphere Cornell box, 1920x1080, 8 bounces, 1 spp per frame (the (R = 1, F = spp) split of configs[1])"),
+    "knot1": dict(kind="knot", width=1920, height=1080, bounces=8, spp=1,
+                  desc="87,132-triangle knot in a Cornell room (3 models, BVH), 1920x1080, 8 bounces, 1 spp per frame"),
     "cluster4k": dict(kind="cluster", width=3840, height=2160, bounces=12, spp=4,
                       desc="871,212-triangle glass knot cluster (one mesh, one deep BVH) in a room, 3840x2160, 12 bounces, 4 spp per frame (configs[3] shape)"),
     "soup4k": dict(kind="soup", width=4096, height=4096, bounces=16, spp=2,
