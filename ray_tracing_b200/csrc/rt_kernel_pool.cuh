@@ -11,15 +11,22 @@
 //                 samples are generated in compacted batches.
 //   TRACE phase   the warp's M rays are consumed through a warp-local queue: a lane that finishes its ray stores the
 //                 hit record and immediately takes the next ray (ballot-ranked pop from a warp-uniform counter, no
-//                 atomics), so lanes only idle at the tail of the phase instead of after every ray.
+//                 atomics).  Every lane is a small state machine (inner node / leaf primitive / next model); each
+//                 iteration one warp reduction counts the lanes per state and the warp executes the step kind most
+//                 lanes wait for (two inner-node visits per census).  When the queue is empty and at most `tailLanes`
+//                 lanes still trace, the phase ends and those rays stay in flight, in their lanes, across the next
+//                 shade phase (slot state PS_FLIGHT) — long rays never hold the warp back.
 //
 // A pool slot is a PIXEL: its NumRaysPerPixel samples run one after the other on the slot, threading the pixel's
 // single rng state and summing in order (HL:552,563-579) — the reference's per-pixel arithmetic order is untouched,
 // and traversal visits the reference's nodes and triangles in the reference's order (HL:243-283), so the output is
 // bit-identical to the oracle's and the box / triangle test counts are too.
 //
-// Tree tops are staged once per CTA into shared memory by TMA bulk copies (cp.async.bulk + mbarrier), spheres too;
-// deeper NodePair / TriGeom records are fetched with 128-bit loads from the repacked aligned streams.
+// NodePair / TriGeom records are fetched with 128-bit loads from the repacked aligned streams; small Spheres buffers are
+// staged in shared memory.  The first `smemPairs` pair records of every tree CAN be staged into shared memory once per CTA
+// by TMA bulk copies (cp.async.bulk + mbarrier) — implemented, parity-tested, and off by default because it measured
+// neutral-to-negative (L1 already holds the hot tree tops).  Large Spheres buffers go through the padded-box
+// accelerator as "model -1" of the same state machine (EXT instantiation).
 #pragma once
 #include "rt_kernel_wave.cuh"
 

@@ -1,4 +1,5 @@
-// rt_kernel_wave.cuh — kernel variant 1: persistent-thread wavefront path tracer for sm_100a.
+// rt_kernel_wave.cuh — kernel variant 1: persistent threads, one path per lane (the default for sphere-only scenes; the
+// pooled wavefront kernel, rt_kernel_pool.cuh, is the default when the scene has meshes).
 //
 // Shape (this implementation's own; the arithmetic per path is the reference's, see rt_device.cuh):
 //   * persistent CTAs (a multiple of the SM count) pull pixel jobs from one global counter.  A lane that
