@@ -286,6 +286,20 @@ def test_cuda_abi_error_behaviour():
     ctx.destroy()
 
 
+def test_nan_pixels_are_nan_on_both_sides():
+    """Quirk Q4 territory: whatever makes a pixel NaN in the reference arithmetic (log(0) in Box-Muller, ...) must make it NaN
+    on the GPU too.  Forced here with a NaN sun intensity and the sky on: every path that escapes to the sky picks up
+    NaN * 0 = NaN (RayCommon.hlsl:179-181), every other path stays finite."""
+    sc = scenes.random_soup(48, 48, max_bounces=3, rays_per_pixel=1, triangles=2000, spheres=8)
+    sc.settings["sunIntensity"] = float("nan")
+    fo, _ = render(ORACLE_LIB, sc)
+    assert 0.2 < np.isnan(fo[..., 0]).mean() < 1.0
+    for kernel in KERNELS:
+        fg, _ = render(CUDA_LIB, sc, options={"kernel": kernel})
+        assert np.array_equal(np.isnan(fg), np.isnan(fo)), f"kernel {kernel}"
+        assert_bit_equal(fg, fo, f"kernel {kernel}")
+
+
 def test_stated_tolerance_on_averaged_rgb():
     """BASELINE.json north_star: per-pixel RGB within 1e-4 of the reference at matched seed.  Stated on the
     per-frame-averaged RGB (SUM.rgb / SUM.a); NaN pixels (quirk Q4) must be NaN in both."""
