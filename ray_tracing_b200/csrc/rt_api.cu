@@ -361,7 +361,7 @@ static int prepareScene(RtContext* c)
     }
     if (c->modelsDirty)
     {
-        cudaError_t e = c->repack.buildModels(c->hModels, c->P.modelCount, c->stream);
+        cudaError_t e = c->repack.buildModels(c->hModels, c->hNodes, c->P.modelCount, c->stream);
         if (e != cudaSuccess) return failCuda(c, e, "repack models");
         c->modelsDirty = false;
     }

@@ -43,7 +43,7 @@ struct __align__(16) TriNormals
 };
 
 // Per-model record: rows 0..2 of both matrices (all four columns kept, see mul_point/mul_dir), the root
-// of its BVH and where its material lives.  128 bytes.
+// of its BVH, where its material lives, and a padded world-space box of the whole model.  144 bytes.
 struct __align__(16) DevModel
 {
     float w2l[12];      // row-major rows 0..2 of worldToLocalMatrix
@@ -52,8 +52,26 @@ struct __align__(16) DevModel
     int   rootCount;    // root node's triangleCount
     int   cullBackface; // material.flag != GLASS (HL:355)
     int   matIndex;     // index into ModelInfo (material is read from the 224-byte record)
-    int   pad[4];
+    // Padded world-space bounds of the model (image of its root box under localToWorld, grown by 1e-4 of its size and
+    // position).  A ray that misses this box, or enters it beyond the closest hit so far, cannot be changed by this model:
+    // the non-instrumented kernels skip the model without transforming the ray (the reference's per-model loop, HL:347-371,
+    // would traverse it and find nothing).  +-inf when the two matrices of the model are not inverses of each other.
+    float wmin[3], wmaxx;
+    float wmaxy, wmaxz; int pad[2];
 };
+static_assert(sizeof(DevModel) == 144, "DevModel layout");
+
+// true when model record `mr` cannot change the current result: its padded world box is missed or lies beyond bestDst
+RT_DI bool ModelOutOfReach(const float4* __restrict__ mr, f3 rayPos, f3 rayInv, float bestDst)
+{
+    const float4 b0 = __ldg(mr + 7), b1 = __ldg(mr + 8);
+    const f3 tMin = (make_f3(b0.x, b0.y, b0.z) - rayPos) * rayInv;
+    const f3 tMax = (make_f3(b0.w, b1.x, b1.y) - rayPos) * rayInv;
+    const float tNear = fmaxf(fmaxf(fminf(tMin.x, tMax.x), fminf(tMin.y, tMax.y)), fminf(tMin.z, tMax.z));
+    const float tFar  = fminf(fminf(fmaxf(tMin.x, tMax.x), fmaxf(tMin.y, tMax.y)), fmaxf(tMin.z, tMax.z));
+    const bool hit = tFar >= tNear && tFar > 0.0f;
+    return !hit || (tNear * 0.99999619f - 1e-6f) > bestDst;
+}
 
 // Sphere with r*r precomputed (the exact product of HL:299).  32 bytes.
 struct __align__(16) DevSphere

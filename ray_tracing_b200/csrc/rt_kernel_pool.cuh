@@ -412,6 +412,13 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                         resKind = __float_as_int(bestU) == RT_MATERIAL_GLASS ? PS_HIT_GLASS : PS_HIT_OPAQUE;
                     }
                     model++;
+                    // skip the models this ray cannot reach before its current best hit (not in the instrumented build, which
+                    // walks every model like the reference so that the test counts stay identical)
+                    if (!STATS && model >= 0)
+                    {
+                        const f3 rayInv = rcp3(rayDir);
+                        while (model < P.modelCount && ModelOutOfReach(reinterpret_cast<const float4*>(P.models + model), rayPos, rayInv, resDst)) model++;
+                    }
                     if (EXT && P.sphBvh && model == -1)
                     {
                         // sphere phase: world-space ray against the accelerator of the Spheres buffer (semantics of TraverseSpheres)

@@ -155,7 +155,7 @@ struct RepackState
         return cudaSuccess;
     }
 
-    cudaError_t buildModels(const std::vector<RtModel>& mdl, int modelCount, cudaStream_t stream)
+    cudaError_t buildModels(const std::vector<RtModel>& mdl, const std::vector<RtNode>& nodes, int modelCount, cudaStream_t stream)
     {
         std::vector<DevModel> out(std::max(modelCount, 1));
         for (int i = 0; i < modelCount; i++)
@@ -170,6 +170,38 @@ struct RepackState
             d.rootStart = r.rootStart; d.rootCount = r.rootCount;
             d.cullBackface = mdl[i].material.flag != RT_MATERIAL_GLASS;       // HL:355
             d.matIndex = i;
+            // padded world bounds: the 8 corners of the root box through localToWorld (double), valid only if the two
+            // matrices really are inverses (the ray test itself only uses worldToLocal)
+            {
+                const float* L = mdl[i].localToWorld; const float* W = mdl[i].worldToLocal;
+                bool consistent = true;
+                for (int r = 0; r < 3 && consistent; r++) for (int c = 0; c < 4; c++)
+                {
+                    double sum = 0;                                   // (W * L)(r, c), column-major 4x4, affine
+                    for (int k = 0; k < 4; k++) sum += (double)W[k * 4 + r] * (double)L[c * 4 + k];
+                    if (!(std::fabs(sum - (r == c ? 1.0 : 0.0)) < 1e-3)) { consistent = false; break; }
+                }
+                const RtNode& root = nodes[mdl[i].nodeOffset];
+                double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+                for (int k = 0; k < 8 && consistent; k++)
+                {
+                    const double v[3] = {k & 1 ? root.boundsMax[0] : root.boundsMin[0], k & 2 ? root.boundsMax[1] : root.boundsMin[1], k & 4 ? root.boundsMax[2] : root.boundsMin[2]};
+                    for (int a = 0; a < 3; a++)
+                    {
+                        const double w = (double)L[a] * v[0] + (double)L[4 + a] * v[1] + (double)L[8 + a] * v[2] + (double)L[12 + a];
+                        if (!(w == w) || std::fabs(w) > 1e30) consistent = false;
+                        lo[a] = std::min(lo[a], w); hi[a] = std::max(hi[a], w);
+                    }
+                }
+                float bmin[3], bmax[3];
+                for (int a = 0; a < 3; a++)
+                {
+                    if (!consistent) { bmin[a] = -INFINITY; bmax[a] = INFINITY; continue; }
+                    const double pad = 1e-4 * ((hi[a] - lo[a]) + std::fabs(lo[a]) + std::fabs(hi[a])) + 1e-5;
+                    bmin[a] = std::nextafterf((float)(lo[a] - pad), -INFINITY); bmax[a] = std::nextafterf((float)(hi[a] + pad), INFINITY);
+                }
+                d.wmin[0] = bmin[0]; d.wmin[1] = bmin[1]; d.wmin[2] = bmin[2]; d.wmaxx = bmax[0]; d.wmaxy = bmax[1]; d.wmaxz = bmax[2];
+            }
             out[i] = d;
         }
         cudaError_t e;

@@ -50,6 +50,9 @@ def test_mesh_scene_bitwise_with_traversal_counters(kernel):
     assert_bit_equal(ag, ao, "AccumulatedRender")
     _same_counters(sg, so)
     assert sg["boxTests"] > 0 and sg["triTests"] > 0
+    # the non-instrumented build skips models whose padded world box the ray cannot reach: same pixels
+    fn, an = render(CUDA_LIB, sc, frames=2, options={"kernel": kernel})
+    assert_bit_equal(an, ao, "AccumulatedRender without instrumentation (model skipping active)")
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
@@ -120,6 +123,26 @@ def test_extension_instantiation_alone_is_equivalent(kernel):
         fg, ag, sg = render(CUDA_LIB, sc, frames=2, options={"kernel": kernel, "extInstantiation": 1, "countStats": 1}, want_stats=True)
         assert_bit_equal(ag, ao, f"{sc.name} EXT instantiation, kernel {kernel}")
         _same_counters(sg, so)
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_many_instanced_models_with_world_bounds_skipping(kernel):
+    """Twelve models sharing two meshes (instancing through nodeOffset / triOffset), scattered, rotated, non-uniformly scaled,
+    some glass: most rays miss most models, which the non-instrumented kernels skip by their padded world boxes."""
+    rng = np.random.RandomState(9)
+    meshes = [scenes.knot_mesh(nu=60, nv=8), scenes.room_mesh()]
+    models = [scenes.ModelDesc(1, np.eye(4), np.eye(4), scenes.material(diffuse=(0.7, 0.7, 0.7), specularProbability=0.0))]
+    for i in range(11):
+        l2w, w2l = scenes.trs(position=(rng.uniform(-2, 2), rng.uniform(0.4, 3.4), rng.uniform(-1, 2)), euler_deg=tuple(rng.uniform(0, 360, 3)),
+                              scale=tuple(rng.uniform(0.08, 0.22, 3)))
+        mat = (scenes.material(flag=scenes.MAT_GLASS, ior=1.4, smoothness=0.9, specularProbability=0.9) if i % 3 == 0 else
+               scenes.material(diffuse=tuple(rng.uniform(0.2, 0.9, 3)), emission=(1, 1, 1), emissionStrength=float(i % 4 == 1) * 3.0, specularProbability=0.1))
+        models.append(scenes.ModelDesc(0, l2w, w2l, mat))
+    sc = scenes.Scene(name="instances", width=160, height=90, meshes=meshes, models=models, cam_local_to_world=scenes.trs(position=(0, 1.9, -5.67))[0],
+                      fov=54.5, settings=dict(maxBounceCount=6, numRaysPerPixel=2))
+    fo, ao = render(ORACLE_LIB, sc, frames=2)
+    fg, ag = render(CUDA_LIB, sc, frames=2, options={"kernel": kernel})
+    assert_bit_equal(ag, ao, "instanced models")
 
 
 def test_shared_memory_staging_does_not_change_results():
