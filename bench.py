@@ -44,6 +44,9 @@ WORKLOADS = {
                      desc="9-sphere Cornell box, 1920x1080, 8 bounces, 1 spp per frame (the (R = 1, F = spp) split of configs[1])"),
     "knot1": dict(kind="knot", width=1920, height=1080, bounces=8, spp=1,
                   desc="87,132-triangle knot in a Cornell room (3 models, BVH), 1920x1080, 8 bounces, 1 spp per frame"),
+    "instances16": dict(kind="instances", width=1920, height=1080, bounces=8, spp=16,
+                        desc="24 models sharing two meshes (a 7,680-triangle knot instanced 23 times, glass / opaque / emissive, + room), "
+                             "1920x1080, 8 bounces, 16 spp per frame (the many-Model shape of the reference's shipped scenes)"),
     "cluster4k": dict(kind="cluster", width=3840, height=2160, bounces=12, spp=4,
                       desc="871,212-triangle glass knot cluster (one mesh, one deep BVH) in a room, 3840x2160, 12 bounces, 4 spp per frame (configs[3] shape)"),
     "soup4k": dict(kind="soup", width=4096, height=4096, bounces=16, spp=2,
@@ -57,6 +60,8 @@ def make_scene(w):
     from ray_tracing_b200 import scenes
     if w["kind"] == "cornell":
         return scenes.cornell_spheres(w["width"], w["height"], w["bounces"], w["spp"])
+    if w["kind"] == "instances":
+        return scenes.instanced_knots(w["width"], w["height"], w["bounces"], w["spp"])
     if w["kind"] == "cluster":
         return scenes.knot_cluster(w["width"], w["height"], w["bounces"], w["spp"])
     if w["kind"] == "soup":
@@ -220,6 +225,8 @@ def run_gpu(args, w):
         ctx.set_option("poolSlots", args.pool_slots)
     if args.smem_nodes is not None:
         ctx.set_option("smemNodes", args.smem_nodes)
+    if args.model_skip is not None:
+        ctx.set_option("modelSkip", args.model_skip)
     if args.sort_rays is not None:
         ctx.set_option("sortRays", args.sort_rays)
     if args.tail_lanes is not None:
@@ -376,6 +383,7 @@ def main():
                     help="N > 1: one NCCL all-gather of finished tiles per frame, or pixels stored into the peers' images by the trace kernel (CUDA-IPC over NVLink)")
     ap.add_argument("--kernel", type=int, default=None, help="0 = megakernel, 1 = persistent threads, 2 = pooled wavefront (default)")
     ap.add_argument("--pool-slots", type=int, default=None, help="paths per warp pool of kernel 2 (32, 64, 96)")
+    ap.add_argument("--model-skip", type=int, default=None, help="kernels 1/2: skip models the ray cannot reach (1 default / 0)")
     ap.add_argument("--sort-rays", type=int, default=None, help="kernel 2: group the ray queue by direction octant (1/0)")
     ap.add_argument("--tail-lanes", type=int, default=None, help="kernel 2: leave the trace phase when this few lanes still trace")
     ap.add_argument("--smem-nodes", type=int, default=None, help="node pairs staged in shared memory (-1 = auto)")

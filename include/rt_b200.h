@@ -141,6 +141,9 @@ int rtGetDevicePointer(RtContext* ctx, const char* name, void** devPtr, size_t* 
  *   "smemNodes"   number of top-of-tree node pairs staged in shared memory by TMA bulk copy (0 = off; -1 = automatic, which
  *                 is currently 0: measured, the staging never beat leaving that shared memory to L1)
  *   "poolSlots"   paths per warp pool of kernel 2: 32, 64 (default) or 96
+ *   "modelSkip"   1 (default) = kernels 1 and 2 skip a model when the ray misses its padded world-space box or enters it beyond
+ *                 the closest hit so far (exact: such a model cannot change the result); 0 = walk every model like the
+ *                 reference.  Always 0 when "countStats" = 1, so that the test counts equal the reference's
  *   "extInstantiation"  1 = launch the kernel instantiation that carries the extensions (peer stores, sphere accelerator)
  *                 even when none is active — for testing that instantiation on one GPU
  *   "sortRays"    kernel 2: 1 = group each warp's ray queue by direction octant before tracing, 0 = slot order (default;

@@ -813,7 +813,7 @@ int rtSetOption(RtContext* c, const char* name, int value)
     if (!c || !name) return fail(c, RT_E_INVALID, "rtSetOption: bad argument");
     std::string n(name);
     if (n == "threads") { c->threads = value < 1 ? 1 : value; return RT_OK; }
-    if (n == "kernel" || n == "countStats" || n == "smemNodes" || n == "poolSlots" || n == "tailLanes" || n == "sortRays" || n == "extInstantiation") return RT_OK;   // accepted, meaningless on the CPU
+    if (n == "kernel" || n == "countStats" || n == "smemNodes" || n == "poolSlots" || n == "tailLanes" || n == "sortRays" || n == "extInstantiation" || n == "modelSkip") return RT_OK;   // accepted, meaningless on the CPU
     return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetOption: unknown option ") + name);
 }
 

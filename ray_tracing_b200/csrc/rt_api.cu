@@ -65,7 +65,7 @@ struct RtContext
     float4* peerFrame[RT_MAX_PEERS]; float4* peerAccum[RT_MAX_PEERS]; int nPeers = 0;
 
     // options
-    int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16, optSortRays = 0, optForceExt = 0;   // kernel -1 = automatic   // smemPairs -1 = automatic
+    int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16, optSortRays = 0, optForceExt = 0, optModelSkip = 1;   // kernel -1 = automatic   // smemPairs -1 = automatic
 
     // counters / timing
     unsigned long long* dCounters = nullptr;   // 5
@@ -318,6 +318,7 @@ int rtSetOption(RtContext* c, const char* name, int value)
     if (n == "kernel") { if (value < -1 || value > 2) return fail(c, RT_E_INVALID, "rtSetOption: kernel must be -1 (auto), 0, 1 or 2"); c->optKernel = value; }
     else if (n == "countStats") c->optCountStats = value != 0;
     else if (n == "smemNodes") c->optSmemPairs = value;
+    else if (n == "modelSkip") c->optModelSkip = value != 0;
     else if (n == "extInstantiation") c->optForceExt = value != 0;
     else if (n == "sortRays") c->optSortRays = value != 0;
     else if (n == "tailLanes") { if (value < 0 || value > 31) return fail(c, RT_E_INVALID, "rtSetOption: tailLanes must be in [0, 31]"); c->optTailLanes = value; }
@@ -436,7 +437,7 @@ int rtDispatch(RtContext* c, int kernelIndex, int gx, int gy, int gz)
     P.sphRootStart = c->repack.sphRootStart; P.sphRootCount = c->repack.sphRootCount; P.smemPairs = c->repack.smemPairs; P.tailLanes = c->optTailLanes; P.sortRays = c->optSortRays;
     P.FrameRender = c->frame.p; P.AccumulatedRender = c->accum.p;
     P.counters = c->dCounters; P.workCounter = c->dWork;
-    P.nPeers = c->nPeers; P.forceExt = c->optForceExt;
+    P.nPeers = c->nPeers; P.forceExt = c->optForceExt; P.modelSkip = c->optModelSkip;
     for (int k = 0; k < c->nPeers; k++) { P.peerFrame[k] = c->peerFrame[k]; P.peerAccum[k] = c->peerAccum[k]; }
 
     EventPair ev;

@@ -125,6 +125,8 @@ struct DevParams
     float4* peerFrame[RT_MAX_PEERS];
     float4* peerAccum[RT_MAX_PEERS];
     int   nPeers;
+    int   modelSkip;                        // skip models whose padded world box the ray cannot reach (exact; default on)
+    int   pad7;
     int   forceExt;                         // testing: run the <EXT = true> instantiation although no extension is active
     unsigned long long* counters;           // [0] rays [1] boxTests [2] triTests [3] sphereTests [4] sphere-accelerator box tests
     unsigned int* workCounter;              // persistent kernel: next job

@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                     model++;
                     // skip the models this ray cannot reach before its current best hit (not in the instrumented build, which
                     // walks every model like the reference so that the test counts stay identical)
-                    if (!STATS && model >= 0)
+                    if (!STATS && P.modelSkip && model >= 0)
                     {
                         const f3 rayInv = rcp3(rayDir);
                         while (model < P.modelCount && ModelOutOfReach(reinterpret_cast<const float4*>(P.models + model), rayPos, rayInv, resDst)) model++;

@@ -168,7 +168,7 @@ RT_DI Hit Intersect(const DevParams& P, const float4* __restrict__ smemPairs, co
         const float4* mr = reinterpret_cast<const float4*>(m);
         // the instrumented build walks every model like the reference (identical test counts); otherwise models the ray cannot
         // reach before its current best hit are skipped — they could not have changed the result
-        if (!STATS && ModelOutOfReach(mr, rayPos, rayInv, result.dst)) continue;
+        if (!STATS && P.modelSkip && ModelOutOfReach(mr, rayPos, rayInv, result.dst)) continue;
         float w2l[12];
         {
             const float4 r0 = __ldg(mr), r1 = __ldg(mr + 1), r2 = __ldg(mr + 2);

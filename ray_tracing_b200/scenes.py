@@ -239,6 +239,25 @@ def knot_room(width=1920, height=1080, max_bounces=8, rays_per_pixel=1, nu=1210,
                  settings=dict(maxBounceCount=max_bounces, numRaysPerPixel=rays_per_pixel))
 
 
+def instanced_knots(width=1920, height=1080, max_bounces=8, rays_per_pixel=1, instances=23, seed=9) -> Scene:
+    """Many Model components sharing one mesh (instancing through nodeOffset / triOffset, RayComputeManager.cs:209-232) in a
+    room: the shape of the reference's shipped scenes (10 - 28 models each)."""
+    rng = np.random.RandomState(seed)
+    meshes = [knot_mesh(nu=160, nv=24), room_mesh(), quad_mesh((-0.8, 3.98, -0.4), (0.8, 3.98, -0.4), (0.8, 3.98, 1.2), (-0.8, 3.98, 1.2))]
+    ident = np.eye(4)
+    models = [ModelDesc(1, ident, ident, material(diffuse=(0.78, 0.78, 0.78), specularProbability=0.0)),
+              ModelDesc(2, ident, ident, material(diffuse=(0, 0, 0), emission=(1, 1, 1), emissionStrength=15.0, specularProbability=0.0))]
+    for i in range(instances):
+        l2w, w2l = trs(position=(rng.uniform(-2.2, 2.2), rng.uniform(0.4, 3.4), rng.uniform(-1.5, 2.2)), euler_deg=tuple(rng.uniform(0, 360, 3)),
+                       scale=tuple(rng.uniform(0.07, 0.16, 3)))
+        mat = (material(flag=MAT_GLASS, ior=1.5, smoothness=0.9, specularProbability=0.9, absorption=(0.6, 0.3, 0.1), absorptionStrength=1.0) if i % 3 == 0 else
+               material(diffuse=tuple(rng.uniform(0.2, 0.9, 3)), smoothness=0.5, specularProbability=0.1))
+        models.append(ModelDesc(0, l2w, w2l, mat))
+    cam, _ = trs(position=(0.0, 1.9, -5.67))
+    return Scene(name="instanced_knots", width=width, height=height, meshes=meshes, models=models, cam_local_to_world=cam, fov=54.5,
+                 settings=dict(maxBounceCount=max_bounces, numRaysPerPixel=rays_per_pixel))
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # c4: "~870k triangles, deep BVH" — ten transformed copies of the knot merged into ONE mesh (871,200 tris), glass
 # ---------------------------------------------------------------------------------------------------------------------
