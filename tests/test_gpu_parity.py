@@ -332,3 +332,67 @@ def test_stated_tolerance_on_averaged_rgb():
     avg_o, avg_g = ao[..., :3] / ao[..., 3:4], ag[..., :3] / ag[..., 3:4]
     assert np.array_equal(np.isnan(avg_o), np.isnan(avg_g))
     assert np.nanmax(np.abs(avg_o - avg_g)) <= 1e-4
+
+
+def _animated_run(lib, options=None):
+    """Three frames with per-frame changes, as the reference's UpdateModels / SetShaderParams allow (RayComputeManager.cs:163-204):
+    a model moves and changes material, the sphere list changes, the camera moves, then the screen is resized and the
+    accumulation restarted."""
+    sc = scenes.knot_room(112, 64, max_bounces=4, rays_per_pixel=2, nu=90, nv=8)
+    sc.spheres = np.zeros(3, dtype=scenes.SPHERE_DTYPE)
+    for i in range(3):
+        sc.spheres[i] = scenes._sphere((-1.5 + 1.5 * i, 0.5, -1.0), 0.45, scenes.material(diffuse=(0.9, 0.4 + 0.2 * i, 0.2), specularProbability=0.0))
+    mgr = rt.RayComputeManager(lib)
+    scenes.apply(sc, mgr)
+    for k, v in (options or {}).items():
+        mgr.context.set_option(k, v)
+    mgr.OnEnable()
+    out = []
+    mgr.RenderFrame()
+    mgr.set_model_transform(0, *scenes.trs(position=(0.6, 1.4, 0.2), euler_deg=(10, 80, 30), scale=(0.35, 0.5, 0.4)))     # knot moves, non-uniform scale
+    mgr.set_model_material(0, scenes.material(flag=scenes.MAT_GLASS, ior=1.45, smoothness=0.9, specularProbability=0.9))
+    mgr.RenderFrame()
+    sph = sc.spheres[:2].copy()
+    sph["centre"][0] = (30.0, 0.5, 40.0)                             # a sphere far outside the old scene bounds
+    mgr.set_spheres(sph)
+    mgr.set_camera(48.0, scenes.trs(position=(0.4, 2.1, -6.3), euler_deg=(3, -4, 0))[0])
+    mgr.maxBounceCount = 6
+    mgr.RenderFrame()
+    out.append(mgr.accumulatedResult.copy())
+    mgr.set_screen(80, 48)                                            # Screen size change: new textures, accumulation restarts
+    mgr.ResetAccumulatedRender()
+    mgr.RenderFrame()
+    out.append(mgr.accumulatedResult.copy())
+    mgr.OnDestroy()
+    return out
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_per_frame_updates_models_spheres_camera_resize(kernel):
+    ref = _animated_run(ORACLE_LIB)
+    got = _animated_run(CUDA_LIB, {"kernel": kernel})
+    assert ref[0].shape == (64, 112, 4) and ref[1].shape == (48, 80, 4)
+    assert_bit_equal(got[0], ref[0], "after three frames with changing models / spheres / camera")
+    assert_bit_equal(got[1], ref[1], "after resize + ResetAccumulatedRender")
+    assert np.all(ref[0][..., 3] == 3.0) and np.all(ref[1][..., 3] == 1.0)
+
+
+def test_sphere_accelerator_with_extreme_radii_and_distant_camera():
+    """Padding of the sphere accelerator scales with (D^2 + r^2) / r: mix of tiny and huge spheres seen from far away, where the
+    reference's own cancellation error is largest."""
+    rng = np.random.RandomState(17)
+    n = 1500
+    sph = np.zeros(n, dtype=scenes.SPHERE_DTYPE)
+    sph["centre"] = rng.uniform(-60, 60, (n, 3)).astype(np.float32)
+    sph["radius"] = np.exp(rng.uniform(np.log(0.02), np.log(25.0), n)).astype(np.float32)
+    for i in range(n):
+        glass = i % 5 == 0
+        sph["material"][i] = (scenes.material(flag=scenes.MAT_GLASS, ior=1.5, smoothness=1.0, specularProbability=1.0) if glass else
+                              scenes.material(diffuse=tuple(rng.uniform(0.2, 1, 3)), emission=tuple(rng.uniform(0, 1, 3)), emissionStrength=float(i % 7 == 0),
+                                              specularProbability=0.2, smoothness=0.5))
+    sc = scenes.Scene(name="radii", width=128, height=96, spheres=sph, cam_local_to_world=scenes.trs(position=(0, 0, -260.0))[0], fov=40.0,
+                      settings=dict(maxBounceCount=6, numRaysPerPixel=2, useSky=True), sun_forward=(0.2, -0.7, 0.6))
+    fo, _ = render(ORACLE_LIB, sc, frames=1)
+    for kernel in KERNELS:
+        fg, _ = render(CUDA_LIB, sc, frames=1, options={"kernel": kernel})
+        assert_bit_equal(fg, fo, f"kernel {kernel}")
