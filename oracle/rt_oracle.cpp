@@ -18,7 +18,7 @@
  * implementation) plus or* helpers for tests.  Plain C-style C++; std::thread over rows.
  */
 #include "../include/rt_b200.h"
-#include "rt_oracle_math.h"
+#include "rt_oracle_math.h"   // HL = Assets/Scripts/Tracer/RayCommon.hlsl of the reference in the comments below
 
 #include <atomic>
 #include <chrono>
@@ -166,12 +166,12 @@ struct Shader
         float3 skyGradient = lerp(SkyColourHorizon, SkyColourZenith, skyGradientT);
         float s = 1000.0f * 1.0f / SunFocus;
         float sun = orc::pow(orc::max(0.0f, dot(dir, dirToSun)), s) * SunIntensity;
-        // Combine ground, sky, and sun
+        // (HL:180)
         float3 composite = lerp(GroundColour, skyGradient, groundToSkyT) + sun * SunColour * (groundToSkyT >= 1.0f ? 1.0f : 0.0f);
         return composite;
     }
 
-    // --- Ray Intersection Functions ---
+    // (HL:185)
     static TriangleHitInfo RayTriangle(const Ray& ray, const RtTriangle& tri, bool cullBackface)   // :188-215
     {
         float3 posA = mk3(tri.posA), posB = mk3(tri.posB), posC = mk3(tri.posC);
@@ -183,13 +183,13 @@ struct Shader
         float determinant = -dot(ray.dir, triFaceVector);
         float invDet = 1.0f / determinant;
 
-        // Calculate hit-dst and barycentric coordinates
+        // (HL:198)
         float dst = dot(vertRayOffset, triFaceVector) * invDet;
         float u = dot(edgeAC, rayOffsetPerp) * invDet;
         float v = -dot(edgeAB, rayOffsetPerp) * invDet;
         float w = 1.0f - u - v;
 
-        // Initialize hit info
+        // (HL:204)
         TriangleHitInfo hitInfo;
         bool keep = cullBackface ? determinant >= 1E-8f : orc::abs(determinant) >= 1E-8f;
         hitInfo.didHit = keep && dst > 0.0f && u >= 0.0f && v >= 0.0f && w >= 0.0f;
@@ -258,7 +258,7 @@ struct Shader
                 float dstB = RayBoundingBoxDst(ray, mk3(childB.boundsMin), mk3(childB.boundsMax));
                 nBox += 2; // count bounding box intersection tests                   :271
 
-                // We want to look at closest child node first, so push it last
+                // (HL:273)
                 bool isNearestA = dstA <= dstB;
                 float dstNear = isNearestA ? dstA : dstB;
                 float dstFar = isNearestA ? dstB : dstA;
@@ -338,17 +338,17 @@ struct Shader
             float4x4 worldToLocalMatrix, localToWorldMatrix;
             memcpy(worldToLocalMatrix.m, model.worldToLocal, 64);
             memcpy(localToWorldMatrix.m, model.localToWorld, 64);
-            // Transform ray into model's local coordinate space
+            // (HL:350)
             localRay.pos = mul_xyz(worldToLocalMatrix, mk4(worldRay.pos, 1.0f));
             localRay.dir = mul_xyz(worldToLocalMatrix, mk4(worldRay.dir, 0.0f));
             localRay.invDir = 1.0f / localRay.dir;
 
             bool cullBackface = model.material.flag != MATERIAL_GLASS;
             if (forceDontCullBack) cullBackface = false;
-            // Traverse bvh to find closest triangle intersection with current model
+            // (HL:358)
             TriangleHitInfo hit = RayTriangleBVH(localRay, result.dst, model.nodeOffset, model.triOffset, cullBackface);
 
-            // Record closest hit
+            // (HL:361)
             if (hit.dst < result.dst)
             {
                 result.didHit = true;
@@ -381,14 +381,14 @@ struct Shader
 
         if (orc::min(denominatorPerpendicular, denominatorParallel) < 1E-8f) return 1.0f;
 
-        // Perpendicular polarization
+        // (HL:396)
         float rPerpendicular = (iorA * cosAngleIn - iorB * cosAngleOfRefraction) / denominatorPerpendicular;
         rPerpendicular *= rPerpendicular;
-        // Parallel polarization
+        // (HL:399)
         float rParallel = (iorB * cosAngleIn - iorA * cosAngleOfRefraction) / denominatorParallel;
         rParallel *= rParallel;
 
-        // Return the average of the perpendicular and parallel polarizations
+        // (HL:403)
         return (rPerpendicular + rParallel) / 2.0f;
     }
 
@@ -412,11 +412,11 @@ struct Shader
     {
         LightResponse result;
 
-        // Calculate the two directions that light can take
+        // (HL:428)
         result.reflectDir = Reflect(inDir, normal);
         result.refractDir = Refract(inDir, normal, iorA, iorB);
 
-        // Calculate the proportion of light [0, 1] that takes each path
+        // (HL:432)
         result.reflectWeight = CalculateReflectance(inDir, normal, iorA, iorB);
         result.refractWeight = 1.0f - result.reflectWeight;
 
@@ -459,7 +459,7 @@ struct Shader
         float3 totalLight = mk3(0.0f);
         Ray ray = initialRay;
 
-        // Bounce the ray around the world to gather light
+        // (HL:484)
         for (int i = ray.bounceCount; i <= MaxBounceCount; i++)
         {
             ModelHitInfo hit = CalculateRayCollision(ray, false);
@@ -476,20 +476,20 @@ struct Shader
 
             if (material.flag == MATERIAL_GLASS) // Glass-like material
             {
-                // Absorb some amount of light as it travels through the object
+                // (HL:501)
                 if (hit.isBackface) ray.transmittance *= orc::exp(-hit.dst * mk3(material.absorption) * material.absorptionStrength);
 
                 float iorCurrent = hit.isBackface ? material.ior : 1.0f;
                 float iorNext = hit.isBackface ? 1.0f : material.ior;
                 LightResponse lr = CalculateReflectionAndRefraction(ray.dir, hit.normal, iorCurrent, iorNext);
 
-                // Calculate random direction in hemisphere around surface normal (cosine-weighted)
+                // (HL:508)
                 float3 diffuseDir = normalize(hit.normal + RandomDirection(rngState));
-                // Randomize the reflect/refract directions based on smoothness for a frosted effect
+                // (HL:510)
                 lr.reflectDir = normalize(lerp(diffuseDir, lr.reflectDir, material.specularProbability));
                 lr.refractDir = normalize(lerp(-diffuseDir, lr.refractDir, material.smoothness));
 
-                // Choose between reflection and refraction probabilistically based on proportion of light going each way
+                // (HL:514)
                 bool followReflection = RandomValue(rngState) <= lr.reflectWeight;
                 ray.dir = followReflection ? lr.reflectDir : lr.refractDir;
                 ray.pos = hit.pos + epsilon * hit.normal * sign(dot(hit.normal, ray.dir));
@@ -498,19 +498,19 @@ struct Shader
             {
                 bool isSpecularBounce = material.specularProbability >= RandomValue(rngState);
 
-                // Redirect ray based on collision info
+                // (HL:523)
                 ray.pos = hit.pos + (hit.normal * epsilon);
                 float3 diffuseDir = normalize(hit.normal + RandomDirection(rngState));
                 float3 specularDir = reflect(ray.dir, hit.normal);
                 ray.dir = normalize(lerp(diffuseDir, specularDir, material.smoothness * (isSpecularBounce ? 1.0f : 0.0f)));
 
-                // Update light info
+                // (HL:529)
                 float3 emittedLight = mk3(material.emissionCol) * material.emissionStrength;
                 totalLight += emittedLight * ray.transmittance;
                 ray.transmittance *= GetMaterialColour(material, hit.pos, hit.normal, isSpecularBounce);
             }
 
-            // Randomly early-exit paths, with probability based on how little light can be transmitted along it
+            // (HL:535)
             float p = orc::max(ray.transmittance.x, orc::max(ray.transmittance.y, ray.transmittance.z));
             if (RandomValue(rngState) >= p) break;
             ray.transmittance *= 1.0f / p; // scale by inverse probability so result averages out over many iterations
@@ -523,24 +523,24 @@ struct Shader
     {
         float3 camOrigin = mul_xyz(CamLocalToWorldMatrix, mk4(mk3(0.0f, 0.0f, 0.0f), 1.0f));
 
-        // Create seed for random number generator
+        // (HL:549)
         uint pixelCoordX = (uint)(uv.x * (float)numPixels[0]);
         uint pixelCoordY = (uint)(uv.y * (float)numPixels[1]);
         uint pixelIndex = pixelCoordY * numPixels[0] + pixelCoordX;
         uint rngState = pixelIndex + (uint)Frame * 719393u + (uint)renderSeed;
 
-        // Calculate focus point
+        // (HL:554)
         float3 focusPointLocal = mk3(uv.x - 0.5f, uv.y - 0.5f, 1.0f) * ViewParams;
         float3 focusPoint = mul_xyz(CamLocalToWorldMatrix, mk4(focusPointLocal, 1.0f));
         float3 camRight = mk3(M(CamLocalToWorldMatrix,0,0), M(CamLocalToWorldMatrix,1,0), M(CamLocalToWorldMatrix,2,0));
         float3 camUp = mk3(M(CamLocalToWorldMatrix,0,1), M(CamLocalToWorldMatrix,1,1), M(CamLocalToWorldMatrix,2,1));
 
-        // Trace multiple rays and average together
+        // (HL:560)
         float3 totalIncomingLight = mk3(0.0f);
 
         for (int rayIndex = 0; rayIndex < NumRaysPerPixel; rayIndex++)
         {
-            // -- Calculate ray origin and direction --
+            // (HL:565)
             float2 defocusJitter = RandomPointInCircle(rngState) * DefocusStrength / (float)numPixels[0];
             float3 rayOrigin = camOrigin + camRight * defocusJitter.x + camUp * defocusJitter.y;
 
