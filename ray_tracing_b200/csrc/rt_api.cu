@@ -630,6 +630,32 @@ int rtSetPeers(RtContext* c, int nPeers, const void* handles, size_t bytes)
     return RT_OK;
 }
 
+/* Device-free test hook (not part of include/rt_b200.h): the breadth-first pair layout the upload would build.
+ * pairsOut: capacity pairCap records of 64 bytes; rootsOut: 2 ints (start, count) per model.  Returns the number of pair
+ * records, or a negative RT_E_* code with the reason in msg. */
+int rtxPlanPairs(const RtNode* nodes, int nodeCount, const RtModel* models, int modelCount, int triCount, int smemBudget,
+                 void* pairsOut, int pairCap, int* smemPairsOut, int* rootsOut, char* msg, int msgCap)
+{
+    if (!nodes || !models || nodeCount <= 0 || modelCount < 0 || !pairsOut || !rootsOut) return RT_E_INVALID;
+    std::vector<RtNode> n(nodes, nodes + nodeCount);
+    std::vector<RtModel> m(models, models + modelCount);
+    for (int i = 0; i < modelCount; i++)
+        if (m[i].nodeOffset < 0 || m[i].nodeOffset >= nodeCount) { if (msg && msgCap > 0) snprintf(msg, msgCap, "model nodeOffset out of range"); return RT_E_STATE; }
+    RepackState st;
+    std::vector<NodePair> out; std::string why;
+    st.planScene(n, m, modelCount, (size_t)triCount, smemBudget, out, why);
+    if (!why.empty()) { if (msg && msgCap > 0) snprintf(msg, msgCap, "%s", why.c_str()); return RT_E_STATE; }
+    if ((int)out.size() > pairCap) return RT_E_INVALID;
+    if (!out.empty()) memcpy(pairsOut, out.data(), out.size() * sizeof(NodePair));
+    if (smemPairsOut) *smemPairsOut = st.smemPairs;
+    for (int i = 0; i < modelCount; i++)
+    {
+        const MeshRoot& r = st.roots[std::make_pair(m[i].nodeOffset, m[i].triOffset)];
+        rootsOut[2 * i] = r.rootStart; rootsOut[2 * i + 1] = r.rootCount;
+    }
+    return (int)out.size();
+}
+
 int rtGetStats(RtContext* c, RtStats* out)
 {
     if (!c || !out) return fail(c, RT_E_INVALID, "rtGetStats: bad argument");

@@ -59,11 +59,12 @@ struct RepackState
 
     void release() { pairs.release(); triGeom.release(); triNormals.release(); models.release(); spheres.release(); sphPairs.release(); sphLeaves.release(); roots.clear(); }
 
-    // Breadth-first renumbering of every distinct mesh referenced by the first modelCount models.
-    cudaError_t buildScene(const std::vector<RtNode>& nodes, const std::vector<RtModel>& mdl, int modelCount,
-                           const RtTriangle* dTris, size_t triCount, int smemOpt, cudaStream_t stream, std::string& msg)
+    // Breadth-first renumbering of every distinct mesh referenced by the first modelCount models.  Host only (no CUDA call):
+    // fills `out`, `roots`, `smemPairs`, `totalPairs`; a non-empty `msg` reports a malformed BVH.
+    void planScene(const std::vector<RtNode>& nodes, const std::vector<RtModel>& mdl, int modelCount, size_t triCount, int smemOpt,
+                   std::vector<NodePair>& out, std::string& msg)
     {
-        roots.clear(); smemPairs = 0; totalPairs = 0;
+        roots.clear(); smemPairs = 0; totalPairs = 0; out.clear();
         struct Mesh { int nodeOffset, triOffset; std::vector<int> order; /* global node index of first child, in BFS pair order */ size_t hot = 0, hotBase = 0, coldBase = 0; };
         std::vector<Mesh> meshes;
         for (int i = 0; i < modelCount; i++)
@@ -81,8 +82,8 @@ struct RepackState
                 {
                     const RtNode& nd = nodes[queue[q]];
                     const long long a = (long long)m.nodeOffset + nd.startIndex;
-                    if (a < 0 || a + 1 >= (long long)nodes.size()) { msg = "BVH child index out of range"; return cudaSuccess; }
-                    if (queue.size() > nodes.size()) { msg = "BVH has a cycle"; return cudaSuccess; }
+                    if (a < 0 || a + 1 >= (long long)nodes.size()) { msg = "BVH child index out of range"; return; }
+                    if (queue.size() > nodes.size()) { msg = "BVH has a cycle"; return; }
                     m.order.push_back((int)a);
                     if (nodes[a].triangleCount <= 0) queue.push_back((int)a);
                     if (nodes[a + 1].triangleCount <= 0) queue.push_back((int)a + 1);
@@ -113,7 +114,7 @@ struct RepackState
         size_t coldTotal = hotTotal; for (auto& m : meshes) { m.coldBase = coldTotal; coldTotal += m.order.size() - m.hot; }
         smemPairs = (int)hotTotal;
 
-        std::vector<NodePair> out(totalPairs);
+        out.assign(totalPairs, NodePair());
         for (auto& m : meshes)
         {
             auto globalPair = [&](size_t local) { return (int)(local < m.hot ? m.hotBase + local : m.coldBase + (local - m.hot)); };
@@ -133,14 +134,22 @@ struct RepackState
                 p.aMaxX = A.boundsMax[0]; p.aMaxY = A.boundsMax[1]; p.aMaxZ = A.boundsMax[2];
                 p.bMinX = B.boundsMin[0]; p.bMinY = B.boundsMin[1]; p.bMinZ = B.boundsMin[2];
                 p.bMaxX = B.boundsMax[0]; p.bMaxY = B.boundsMax[1]; p.bMaxZ = B.boundsMax[2];
-                if (A.triangleCount > 0) { p.aStart = m.triOffset + A.startIndex; p.aCount = A.triangleCount; if (p.aStart < 0 || (size_t)p.aStart + p.aCount > triCount) { msg = "BVH leaf triangle range out of bounds"; return cudaSuccess; } }
+                if (A.triangleCount > 0) { p.aStart = m.triOffset + A.startIndex; p.aCount = A.triangleCount; if (p.aStart < 0 || (size_t)p.aStart + p.aCount > triCount) { msg = "BVH leaf triangle range out of bounds"; return; } }
                 else { p.aStart = globalPair(nextChildPair++); p.aCount = 0; }
-                if (B.triangleCount > 0) { p.bStart = m.triOffset + B.startIndex; p.bCount = B.triangleCount; if (p.bStart < 0 || (size_t)p.bStart + p.bCount > triCount) { msg = "BVH leaf triangle range out of bounds"; return cudaSuccess; } }
+                if (B.triangleCount > 0) { p.bStart = m.triOffset + B.startIndex; p.bCount = B.triangleCount; if (p.bStart < 0 || (size_t)p.bStart + p.bCount > triCount) { msg = "BVH leaf triangle range out of bounds"; return; } }
                 else { p.bStart = globalPair(nextChildPair++); p.bCount = 0; }
                 out[globalPair(k)] = p;
             }
-            if (root.triangleCount > 0 && ((size_t)r.rootStart + r.rootCount > triCount)) { msg = "BVH root triangle range out of bounds"; return cudaSuccess; }
+            if (root.triangleCount > 0 && ((size_t)r.rootStart + r.rootCount > triCount)) { msg = "BVH root triangle range out of bounds"; return; }
         }
+    }
+
+    cudaError_t buildScene(const std::vector<RtNode>& nodes, const std::vector<RtModel>& mdl, int modelCount,
+                           const RtTriangle* dTris, size_t triCount, int smemOpt, cudaStream_t stream, std::string& msg)
+    {
+        std::vector<NodePair> out;
+        planScene(nodes, mdl, modelCount, triCount, smemOpt, out, msg);
+        if (!msg.empty()) return cudaSuccess;
         cudaError_t e;
         if ((e = pairs.ensure(std::max<size_t>(totalPairs, 1))) != cudaSuccess) return e;
         if (totalPairs && (e = cudaMemcpyAsync(pairs.p, out.data(), totalPairs * sizeof(NodePair), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;

@@ -1,0 +1,109 @@
+"""CPU tests of the upload-time repack (csrc/rt_repack.cuh: planScene) through its device-free hook rtxPlanPairs: the
+breadth-first NodePair layout must describe exactly the tree the host uploaded (same children, same order, same leaf ranges),
+for every shared-memory budget, for shared meshes, and malformed trees must be refused."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import CUDA_LIB
+import ray_tracing_b200 as rt
+from ray_tracing_b200 import capi, scenes
+
+PAIR_DTYPE = np.dtype([("aMin", "<f4", 3), ("aMax", "<f4", 3), ("aStart", "<i4"), ("aCount", "<i4"),
+                       ("bMin", "<f4", 3), ("bMax", "<f4", 3), ("bStart", "<i4"), ("bCount", "<i4")])
+assert PAIR_DTYPE.itemsize == 64
+
+
+def _plan(nodes, models, tri_count, budget):
+    L = C.CDLL(CUDA_LIB)                                   # host code only: no CUDA call is made
+    pairs = np.zeros(max(len(nodes), 1), dtype=PAIR_DTYPE)
+    roots = np.zeros(2 * len(models), dtype=np.int32)
+    smem = C.c_int()
+    msg = C.create_string_buffer(256)
+    n = L.rtxPlanPairs(nodes.ctypes.data_as(C.c_void_p), len(nodes), models.ctypes.data_as(C.c_void_p), len(models), tri_count, budget,
+                       pairs.ctypes.data_as(C.c_void_p), len(pairs), C.byref(smem), roots.ctypes.data_as(C.c_void_p), msg, 256)
+    return n, pairs[:max(n, 0)], roots.reshape(-1, 2), smem.value, msg.value.decode()
+
+
+def _scene_buffers():
+    knot = scenes.knot_mesh(nu=80, nv=8)
+    room = scenes.room_mesh()
+    t0, n0, _ = rt.build_bvh(knot.vertices, knot.indices, knot.normals)
+    t1, n1, _ = rt.build_bvh(room.vertices, room.indices, room.normals)
+    nodes = np.concatenate([n0, n1])
+    models = np.zeros(3, dtype=capi.MODEL_DTYPE)                                   # two instances of the knot + the room
+    models["nodeOffset"] = [0, 0, len(n0)]
+    models["triOffset"] = [0, 0, len(t0)]
+    return nodes, models, len(t0) + len(t1), (len(n0), len(t0))
+
+
+def _check_subtree(nodes, node_offset, tri_offset, node_index, pairs, ref, seen):
+    """The device reference (start, count) of `node_index` must describe the same subtree as the uploaded node."""
+    nd = nodes[node_offset + node_index] if node_index >= 0 else None
+    start, count = ref
+    if nd["triangleCount"] > 0:
+        assert count == nd["triangleCount"] and start == tri_offset + nd["startIndex"]
+        return 1
+    assert count == 0
+    p = pairs[start]
+    seen.add(int(start))
+    a, b = nodes[node_offset + nd["startIndex"]], nodes[node_offset + nd["startIndex"] + 1]
+    assert np.array_equal(p["aMin"], a["boundsMin"]) and np.array_equal(p["aMax"], a["boundsMax"])       # child order A, B is kept
+    assert np.array_equal(p["bMin"], b["boundsMin"]) and np.array_equal(p["bMax"], b["boundsMax"])
+    return (_check_subtree(nodes, node_offset, tri_offset, int(nd["startIndex"]), pairs, (p["aStart"], p["aCount"]), seen)
+            + _check_subtree(nodes, node_offset, tri_offset, int(nd["startIndex"]) + 1, pairs, (p["bStart"], p["bCount"]), seen))
+
+
+@pytest.mark.parametrize("budget", [0, 1, 5, 64, 100000])
+def test_pair_layout_describes_the_uploaded_trees(budget):
+    import sys
+    sys.setrecursionlimit(10000)
+    nodes, models, tri_count, (n_knot, t_knot) = _scene_buffers()
+    n, pairs, roots, smem, msg = _plan(nodes, models, tri_count, budget)
+    inner = int((nodes["triangleCount"] <= 0).sum())
+    assert n == inner and msg == ""                                                # one pair record per inner node
+    assert smem == min(budget, 3072, inner)                                        # hot records are the front of the array
+    assert np.array_equal(roots[0], roots[1])                                      # shared mesh -> shared records
+    seen = set()
+    leaves = _check_subtree(nodes, 0, 0, 0, pairs, tuple(roots[0]), seen)
+    leaves += _check_subtree(nodes, n_knot, t_knot, 0, pairs, tuple(roots[2]), seen)
+    assert leaves == int((nodes["triangleCount"] > 0).sum()) and len(seen) == inner   # every record reached exactly once
+    if 0 < smem < inner:
+        # breadth-first: the staged records are the TOP of the trees — every parent of a staged record is staged too
+        parent = {}
+        for i, p in enumerate(pairs):
+            for s, c in ((p["aStart"], p["aCount"]), (p["bStart"], p["bCount"])):
+                if c == 0:
+                    parent[int(s)] = i
+        assert all(parent[i] < smem for i in range(smem) if i in parent)
+
+
+def test_malformed_trees_are_refused():
+    nodes, models, tri_count, _ = _scene_buffers()
+    bad = nodes.copy()
+    inner = np.flatnonzero(bad["triangleCount"] <= 0)
+    bad["startIndex"][inner[3]] = len(bad) + 7                                     # child index outside the buffer
+    n, _, _, _, msg = _plan(bad, models, tri_count, 0)
+    assert n == capi.RT_E_STATE and "out of range" in msg
+    bad = nodes.copy()
+    bad["startIndex"][inner[5]] = 0                                                # a child pointing back at the root: cycle
+    n, _, _, _, msg = _plan(bad, models, tri_count, 0)
+    assert n == capi.RT_E_STATE and msg != ""
+    bad = nodes.copy()
+    leaf = np.flatnonzero(bad["triangleCount"] > 0)[0]
+    bad["startIndex"][leaf] = tri_count                                            # leaf range beyond the Triangles buffer
+    n, _, _, _, msg = _plan(bad, models, tri_count, 0)
+    assert n == capi.RT_E_STATE and "triangle range" in msg
+    m2 = models.copy()
+    m2["nodeOffset"][1] = len(nodes) + 1
+    n, _, _, _, msg = _plan(nodes, m2, tri_count, 0)
+    assert n == capi.RT_E_STATE
+
+
+def test_single_leaf_mesh_has_no_pairs():
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=np.float32)
+    tris, nodes, _ = rt.build_bvh(v, np.array([0, 1, 2], dtype=np.int32), np.tile(np.float32([[0, 0, 1]]), (3, 1)))
+    models = np.zeros(1, dtype=capi.MODEL_DTYPE)
+    n, pairs, roots, smem, msg = _plan(nodes, models, 1, 16)
+    assert n == 0 and smem == 0 and tuple(roots[0]) == (0, 1)                      # root is the leaf: (first triangle, count)
