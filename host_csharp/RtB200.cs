@@ -1,0 +1,33 @@
+// Shipped as source (no C# toolchain in the build image): the P/Invoke host for librt_b200.so.
+// Compiled twin: ray_tracing_b200/host/RayComputeManager.cpp.  See INTEGRATION.md.
+// Assets/Scripts/Tracer/RtB200.cs
+using System;
+using System.Runtime.InteropServices;
+
+public static class RtB200
+{
+    const string Lib = "rt_b200";            // librt_b200.so next to the player / in Assets/Plugins/x86_64
+
+    [DllImport(Lib)] public static extern int rtCreate(out IntPtr ctx, int device);
+    [DllImport(Lib)] public static extern int rtDestroy(IntPtr ctx);
+    [DllImport(Lib)] public static extern IntPtr rtLastError(IntPtr ctx);
+    [DllImport(Lib)] public static extern int rtSetBuffer(IntPtr ctx, string name, BVH.Triangle[] data, int count, int stride);
+    [DllImport(Lib)] public static extern int rtSetBuffer(IntPtr ctx, string name, BVH.Node[] data, int count, int stride);
+    [DllImport(Lib)] public static extern int rtSetBuffer(IntPtr ctx, string name, RayTracingManager.MeshInfo[] data, int count, int stride);
+    [DllImport(Lib)] public static extern int rtSetBuffer(IntPtr ctx, string name, RayTracingManager.Sphere[] data, int count, int stride);
+    [DllImport(Lib)] public static extern int rtSetInt(IntPtr ctx, string name, int value);
+    [DllImport(Lib)] public static extern int rtSetInts(IntPtr ctx, string name, int[] values, int n);
+    [DllImport(Lib)] public static extern int rtSetFloat(IntPtr ctx, string name, float value);
+    [DllImport(Lib)] public static extern int rtSetVector(IntPtr ctx, string name, ref UnityEngine.Vector4 value);
+    [DllImport(Lib)] public static extern int rtSetMatrix(IntPtr ctx, string name, ref UnityEngine.Matrix4x4 value);   // column-major, as Unity stores it
+    [DllImport(Lib)] public static extern int rtSetBool(IntPtr ctx, string name, int value);
+    [DllImport(Lib)] public static extern int rtResize(IntPtr ctx, int width, int height);
+    [DllImport(Lib)] public static extern int rtDispatch(IntPtr ctx, int kernelIndex, int gx, int gy, int gz);
+    [DllImport(Lib)] public static extern int rtReadback(IntPtr ctx, string tex, float[] dst, UIntPtr bytes);
+    [DllImport(Lib)] public static extern int rtSynchronize(IntPtr ctx);
+
+    public static void Check(IntPtr ctx, int rc)
+    {
+        if (rc != 0) throw new InvalidOperationException("rt_b200: " + Marshal.PtrToStringAnsi(rtLastError(ctx)));
+    }
+}

@@ -268,3 +268,30 @@ def test_cpp_example_drives_the_abi_like_the_reference_manager(tmp_path, oracle_
     if not os.path.exists("/dev/nvidiactl"):
         r = subprocess.run([exe, CUDA_LIB, "1"], capture_output=True, text=True, timeout=120)
         assert r.returncode == 2 and "no CPU path" in r.stderr
+
+
+def test_manager_error_paths_and_rebuild(oracle_path):
+    m = scenes.knot_mesh(nu=30, nv=6)
+    mgr = rt.RayComputeManager(oracle_path)
+    mgr.set_screen(24, 16)
+    mgr.set_camera(60.0, np.eye(4))
+    mid = mgr.add_mesh(m.vertices, m.indices, m.normals)
+    mgr.add_model(mid, *scenes.trs((0, 0, 6), (0, 0, 0), (0.5, 0.5, 0.5)), scenes.material(emission=(1, 1, 1), emissionStrength=1.0))
+    mgr.OnEnable(); mgr.RenderFrame()
+    first = mgr.raytraceFrameTex
+    assert first[..., :3].sum() > 0 and len(mgr.bvh_stats()) == 1
+    # adding a model later invalidates the BVH: the next frame rebuilds and uploads both (RayComputeManager.cs:143-161)
+    mgr.add_model(mid, *scenes.trs((1.5, 1.0, 7), (0, 45, 0), (0.4, 0.4, 0.4)), scenes.material(emission=(1, 1, 1), emissionStrength=2.0))
+    mgr.RenderFrame()
+    assert mgr.raytraceFrameTex[..., :3].sum() > first[..., :3].sum()
+    # a mesh with an out-of-range index is refused by the builder and reported through the manager, not crashed on
+    bad = rt.RayComputeManager(oracle_path)
+    bad.set_screen(8, 8)
+    bad.set_camera(60.0, np.eye(4))
+    mid = bad.add_mesh(m.vertices[:10], m.indices, m.normals[:10])
+    bad.add_model(mid, np.eye(4), np.eye(4), scenes.material())
+    with pytest.raises(capi.RtError) as e:
+        bad.OnEnable()
+    assert "index out of range" in str(e.value)
+    with pytest.raises(capi.RtError):
+        mgr.add_model(99, np.eye(4), np.eye(4), scenes.material())
