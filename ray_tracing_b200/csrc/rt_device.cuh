@@ -274,6 +274,15 @@ RT_DI bool RaySphereCore(f3 rayPos, f3 rayDir, f3 centre, float r2, float& dst, 
     const float discriminant = b * b - (4.0f * a) * c;
     if (discriminant >= 0.0f)
     {
+#ifdef RT_SPHERE_SKIP_SQRT
+        // Experimental (off by default, not yet measured): a sphere the ray is moving away from (b > 0) is hit only if
+        // sqrt(disc) >= b.  With bb = fl(b*b) in b^2 (1 +- 2^-24):  disc < bb (1 - 2^-21)  =>  disc < b^2 (1 - 2^-22)  =>
+        // sqrt_rn(disc) < b  =>  -b + s < 0  =>  the reference's dstFar < 0  =>  no hit.  Saves the sqrt; never changes an answer.
+        {
+            const float den0 = 2.0f * a;
+            if (b > 0.0f && den0 > 0.0f && den0 < inf32() && discriminant < (b * b) * 0.99999952f) return false;
+        }
+#endif
         const float s = sqrtf(discriminant);
         const float den = 2.0f * a;
         const float numFar = -b + s;

@@ -10,7 +10,7 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
 ORACLE_LIB = os.path.join(REPO, "oracle", "liboracle.so")
-CUDA_LIB = os.path.join(REPO, "ray_tracing_b200", "librt_b200.so")
+CUDA_LIB = os.environ.get("RT_B200_LIB") or os.path.join(REPO, "ray_tracing_b200", "librt_b200.so")   # RT_B200_LIB: test an experimental build
 GOLDEN = os.path.join(REPO, "tests", "golden")
 
 
