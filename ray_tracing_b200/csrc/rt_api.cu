@@ -451,7 +451,7 @@ int rtDispatch(RtContext* c, int kernelIndex, int gx, int gy, int gz)
     {
         CK(cudaEventRecord(ev.a, c->stream));
         dim3 grid((limX + 7) / 8, (limY + 7) / 8, 1), block(8, 8, 1);
-        k_raytrace_mega<<<grid, block, 0, c->stream>>>(P);
+        RT_LAUNCH(grid, block, 0, c->stream, k_raytrace_mega, P);
         CK(cudaEventRecord(ev.b, c->stream));
     }
     else if (kernel == 1)
@@ -492,7 +492,7 @@ int rtDisplay(RtContext* c, int useAccumulated, int Frame, uint8_t* dst, size_t 
     if (bytes != n * 4) return fail(c, RT_E_INVALID, "rtDisplay: bytes must equal W*H*4");
     CK(cudaSetDevice(c->device));
     CK(c->display.ensure(n));
-    k_display<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(useAccumulated ? c->accum.p : c->frame.p, c->display.p, n, (float)Frame);
+    RT_LAUNCH((unsigned)((n + 255) / 256), 256, 0, c->stream, k_display, useAccumulated ? c->accum.p : c->frame.p, c->display.p, n, (float)Frame);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(dst, c->display.p, bytes, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

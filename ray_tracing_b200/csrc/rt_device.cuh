@@ -185,7 +185,7 @@ RT_DI f3 RandomDirection(uint32_t& state)
     return normalize3(make_f3(x, y, z));
 }
 // (not inlined: two call sites per camera sample; keeping one copy shrinks the kernels' instruction footprint)
-__device__ __noinline__ f2 RandomPointInCircle(uint32_t& state)
+RT_DNI f2 RandomPointInCircle(uint32_t& state)
 {
     const float angle = (RandomValue(state) * 2.0f) * 3.1415f;       // PI = 3.1415 (HL:2,161)
     float s, c; sincos_rt(angle, s, c);
@@ -196,7 +196,7 @@ __device__ __noinline__ f2 RandomPointInCircle(uint32_t& state)
 // ---- environment (HL:167-183) -----------------------------------------------------------------------------------
 
 // (not inlined: two pow() bodies that only sky scenes execute, on miss)
-__device__ __noinline__ f3 GetEnvironmentLight(const DevParams& P, f3 dir)
+RT_DNI f3 GetEnvironmentLight(const DevParams& P, f3 dir)
 {
     if (P.UseSky == 0) return splat3(0.0f);
     const f3 GroundColour = make_f3(0.35f, 0.3f, 0.35f);
@@ -320,7 +320,7 @@ RT_DI bool RaySphereCore(f3 rayPos, f3 rayDir, f3 centre, float r2, float& dst, 
 //     a computed hit point always lies inside its sphere's box;
 //   * a box is skipped only if its entry distance, reduced by a relative 2^-18 and an absolute 1e-6, still exceeds the best
 //     dst so far (strictly), so equal-distance candidates with a smaller index are never lost.
-__device__ __noinline__ void TraverseSpheres(const DevParams& P, f3 rayPos, f3 rayDir, float& bestDst, int& bestIndex, bool& bestInside, int& bestFlag,
+RT_DNI void TraverseSpheres(const DevParams& P, f3 rayPos, f3 rayDir, float& bestDst, int& bestIndex, bool& bestInside, int& bestFlag,
                            Counters& cnt, bool countStats)
 {
     const f3 invDir = rcp3(rayDir);
@@ -425,7 +425,7 @@ RT_DI f3 GetMaterialColour(const RtMaterial* mat, f3 pos, f3 normal, bool isSpec
 }
 
 // exp of three components (not inlined: glass back-face hits only)
-__device__ __noinline__ f3 exp3_rt(f3 a) { return make_f3(exp_rt(a.x), exp_rt(a.y), exp_rt(a.z)); }
+RT_DNI f3 exp3_rt(f3 a) { return make_f3(exp_rt(a.x), exp_rt(a.y), exp_rt(a.z)); }
 
 struct PathState
 {

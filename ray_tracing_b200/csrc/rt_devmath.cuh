@@ -20,6 +20,18 @@ struct f2 { float x, y; };
 struct f3 { float x, y, z; };
 
 #define RT_DI __device__ __forceinline__
+// out-of-line device function.  (RT_SIMT_EMU: the test-only host build of these kernels, tests/simt — never defined in the product build)
+#ifdef RT_SIMT_EMU
+#define RT_DNI __attribute__((noinline))
+#else
+#define RT_DNI __device__ __noinline__
+#endif
+// kernel launch: kernel<<<grid, block, smem, stream>>>(args).  RT_K() protects the commas of a template-id.
+#define RT_K(...) __VA_ARGS__
+#ifndef RT_SIMT_EMU
+#define RT_LAUNCH(grid, block, smem, stream, kern, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define RT_DYNAMIC_SMEM(name) extern __shared__ __align__(128) unsigned char name[]      // the CTA's dynamic shared memory
+#endif
 
 RT_DI f2 make_f2(float x, float y) { f2 r; r.x = x; r.y = y; return r; }
 RT_DI f3 make_f3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -38,12 +50,12 @@ RT_DI f3 rcp3(f3 a) { return make_f3(1.0f / a.x, 1.0f / a.y, 1.0f / a.z); }
 RT_DI float dot3(f3 a, f3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 RT_DI f3 cross3(f3 a, f3 b) { return make_f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 #ifdef RT_NOINLINE_NORMALIZE
-__device__ __noinline__ f3 normalize3(f3 v) { float inv = 1.0f / sqrtf(dot3(v, v)); return v * inv; }
+RT_DNI f3 normalize3(f3 v) { float inv = 1.0f / sqrtf(dot3(v, v)); return v * inv; }
 #else
 RT_DI f3 normalize3(f3 v) { float inv = 1.0f / sqrtf(dot3(v, v)); return v * inv; }
 #endif
 // IEEE quotient behind a call: for divisions on rarely taken paths, so the compiler cannot speculate them
-__device__ __noinline__ float div_cold(float a, float b) { return a / b; }
+RT_DNI float div_cold(float a, float b) { return a / b; }
 RT_DI f3 lerp3(f3 a, f3 b, float t) { return a + t * (b - a); }
 RT_DI f3 reflect3(f3 i, f3 n) { return i - (2.0f * dot3(n, i)) * n; }
 RT_DI float sign1(float a) { return (a > 0.0f ? 1.0f : 0.0f) - (a < 0.0f ? 1.0f : 0.0f); }

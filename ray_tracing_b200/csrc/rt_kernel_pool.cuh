@@ -124,7 +124,7 @@ template <bool STATS, bool EXT, int M>
 __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_constant__ DevParams P, const unsigned int totalJobs,
                                                                   const unsigned int tilesX, const unsigned int ownedRows)
 {
-    extern __shared__ __align__(128) unsigned char smemRaw[];
+    RT_DYNAMIC_SMEM(smemRaw);
     WaveSmemHeader* hdr = reinterpret_cast<WaveSmemHeader*>(smemRaw);
     float4* smemPairs = reinterpret_cast<float4*>(smemRaw + sizeof(WaveSmemHeader));
     DevSphere* smemSpheres = reinterpret_cast<DevSphere*>(smemRaw + sizeof(WaveSmemHeader) + (size_t)P.smemPairs * sizeof(NodePair));
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
     if (threadIdx.x == 0)
     {
         mbar_init(mbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     __syncthreads();
     if (P.smemPairs > 0 && threadIdx.x == 0)
@@ -589,10 +589,10 @@ template <int M> inline cudaError_t pool_launch_m(const DevParams& P, int numSMs
     if ((e = cudaMemsetAsync(P.workCounter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(evA, stream)) != cudaSuccess) return e;
     const bool ext = P.nPeers > 0 || P.sphBvh != 0 || P.forceExt != 0;   // extensions compiled into their own instantiation
-    if (P.countStats) { if (ext) k_raytrace_pool<true, true, M><<<grid, POOL_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows);
-                        else k_raytrace_pool<true, false, M><<<grid, POOL_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows); }
-    else { if (ext) k_raytrace_pool<false, true, M><<<grid, POOL_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows);
-           else k_raytrace_pool<false, false, M><<<grid, POOL_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows); }
+    if (P.countStats) { if (ext) RT_LAUNCH(grid, POOL_THREADS, smemBytes, stream, RT_K(k_raytrace_pool<true, true, M>), P, totalJobs, tilesX, ownedRows);
+                        else RT_LAUNCH(grid, POOL_THREADS, smemBytes, stream, RT_K(k_raytrace_pool<true, false, M>), P, totalJobs, tilesX, ownedRows); }
+    else { if (ext) RT_LAUNCH(grid, POOL_THREADS, smemBytes, stream, RT_K(k_raytrace_pool<false, true, M>), P, totalJobs, tilesX, ownedRows);
+           else RT_LAUNCH(grid, POOL_THREADS, smemBytes, stream, RT_K(k_raytrace_pool<false, false, M>), P, totalJobs, tilesX, ownedRows); }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     return cudaEventRecord(evB, stream);
 }

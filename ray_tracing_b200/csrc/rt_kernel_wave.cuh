@@ -36,6 +36,7 @@ struct WaveSmemHeader
     unsigned int pad[14];
 };
 
+#ifndef RT_SIMT_EMU      // (the test-only host build, tests/simt, supplies its own versions of these six helpers)
 RT_DI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 RT_DI void mbar_init(uint32_t mbar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory"); }
@@ -52,6 +53,8 @@ RT_DI bool mbar_try_wait(uint32_t mbar, uint32_t parity)
                  : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
     return ok != 0;
 }
+RT_DI void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+#endif
 
 struct NodeRef { int start, count; };
 
@@ -212,7 +215,7 @@ template <bool STATS, bool EXT>
 __global__ void __launch_bounds__(WAVE_THREADS, RT_WAVE_MINBLOCKS) k_raytrace_wave(const __grid_constant__ DevParams P, const unsigned int totalJobs,
                                                                const unsigned int tilesX, const unsigned int ownedRows)
 {
-    extern __shared__ __align__(128) unsigned char smemRaw[];
+    RT_DYNAMIC_SMEM(smemRaw);
     WaveSmemHeader* hdr = reinterpret_cast<WaveSmemHeader*>(smemRaw);
     float4* smemPairs = reinterpret_cast<float4*>(smemRaw + sizeof(WaveSmemHeader));
     DevSphere* smemSpheres = reinterpret_cast<DevSphere*>(smemRaw + sizeof(WaveSmemHeader) + (size_t)P.smemPairs * sizeof(NodePair));
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, RT_WAVE_MINBLOCKS) k_raytrace_wa
     if (threadIdx.x == 0)
     {
         mbar_init(mbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     __syncthreads();
     if (P.smemPairs > 0 && threadIdx.x == 0)
@@ -367,7 +370,7 @@ template <bool S, bool X> inline cudaError_t wave_launch_one(const DevParams& P,
     if (grid > ctasNeeded) grid = ctasNeeded ? ctasNeeded : 1;
     if ((e = cudaMemsetAsync(P.workCounter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(evA, stream)) != cudaSuccess) return e;
-    k_raytrace_wave<S, X><<<grid, WAVE_THREADS, smemBytes, stream>>>(P, totalJobs, tilesX, ownedRows);
+    RT_LAUNCH(grid, WAVE_THREADS, smemBytes, stream, RT_K(k_raytrace_wave<S, X>), P, totalJobs, tilesX, ownedRows);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     return cudaEventRecord(evB, stream);
 }

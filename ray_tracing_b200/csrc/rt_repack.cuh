@@ -158,7 +158,7 @@ struct RepackState
         if ((e = triNormals.ensure(std::max<size_t>(triCount, 1))) != cudaSuccess) return e;
         if (triCount)
         {
-            k_repack_tris<<<(unsigned)((triCount + 255) / 256), 256, 0, stream>>>(dTris, triGeom.p, triNormals.p, triCount);
+            RT_LAUNCH((unsigned)((triCount + 255) / 256), 256, 0, stream, k_repack_tris, dTris, triGeom.p, triNormals.p, triCount);
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
         }
         return cudaSuccess;
@@ -388,12 +388,12 @@ __global__ void k_display(const float4* __restrict__ tex, uchar4* __restrict__ o
 inline void launch_pack_tile(const float4* frame, const float4* accum, float4* send, int W, int H, int rank, int world, int bandRows, int rowsPerRank, cudaStream_t s)
 {
     dim3 grid((W + 255) / 256, rowsPerRank, 1);
-    k_pack_tile<<<grid, 256, 0, s>>>(frame, accum, send, W, H, rank, world, bandRows, rowsPerRank);
+    RT_LAUNCH(grid, 256, 0, s, k_pack_tile, frame, accum, send, W, H, rank, world, bandRows, rowsPerRank);
 }
 inline void launch_unpack_tiles(const float4* recv, float4* frame, float4* accum, int W, int H, int world, int bandRows, int rowsPerRank, cudaStream_t s)
 {
     dim3 grid((W + 255) / 256, rowsPerRank, world);
-    k_unpack_tiles<<<grid, 256, 0, s>>>(recv, frame, accum, W, H, world, bandRows, rowsPerRank);
+    RT_LAUNCH(grid, 256, 0, s, k_unpack_tiles, recv, frame, accum, W, H, world, bandRows, rowsPerRank);
 }
 
 } // namespace rtd

@@ -116,6 +116,22 @@ def test_product_library_has_no_oracle_dependency():
     assert "oracle/" not in src and "rt_oracle" not in src
 
 
+def test_product_does_not_reference_the_simt_build():
+    """tests/simt (the SIMT interpreter build of the kernels) is test infrastructure: neither the package, the bench nor the
+    driver entry points may know about it, and the product build never defines its macro."""
+    files = [os.path.join(REPO, "bench.py"), os.path.join(REPO, "__graft_entry__.py")]
+    pkg = os.path.join(REPO, "ray_tracing_b200")
+    files += [os.path.join(pkg, f) for f in os.listdir(pkg) if f.endswith(".py")]
+    files += [os.path.join(pkg, "host", f) for f in os.listdir(os.path.join(pkg, "host"))]
+    for f in files:
+        text = open(f).read()
+        assert "simt" not in text.lower(), f
+    from ray_tracing_b200 import build
+    assert not any("SIMT" in flag for flag in build.NVCC_FLAGS + build.GXX_FLAGS)
+    syms = subprocess.run(["nm", "-D", "--defined-only", CUDA_LIB], capture_output=True, text=True).stdout
+    assert "simt" not in syms
+
+
 @pytest.mark.skipif(os.path.exists("/dev/nvidiactl"), reason="a GPU is present")
 def test_cuda_library_fails_loudly_without_a_gpu():
     with pytest.raises(capi.RtError) as e:

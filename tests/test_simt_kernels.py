@@ -1,0 +1,94 @@
+"""The CUDA kernels' own source, executed on the CPU by the SIMT interpreter of tests/simt (test infrastructure, see
+tests/simt/shim/cuda_runtime.h): rt_api.cu with every kernel it includes is compiled by g++ against a stand-in for
+<cuda_runtime.h> in which a CTA's threads are fibers and warp collectives really rendezvous.  What runs is the product's
+code — the pooled wavefront state machine, ballot compaction, shared-memory pools, the persistent work queue, the repack,
+the C-ABI host logic — so these tests check, without a GPU, everything about the kernels except how nvcc lowers them and
+how fast they are.  The bodies are the GPU parity tests themselves (tests/test_gpu_parity.py), pointed at the interpreter
+build instead of librt_b200.so; the same tests run on the B200 under `-m gpu`.
+
+The product never loads the interpreter build (tests/test_host.py::test_product_does_not_reference_the_simt_build).
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ORACLE_LIB, REPO, assert_bit_equal, render
+import ray_tracing_b200 as rt
+from ray_tracing_b200 import scenes
+import test_gpu_parity as G
+
+sys.path.insert(0, os.path.join(REPO, "tests", "simt"))
+import build as simt_build   # noqa: E402
+
+
+@pytest.fixture(scope="session")
+def simt_lib():
+    return simt_build.build()
+
+
+@pytest.fixture(autouse=True)
+def _point_parity_tests_at_the_interpreter(monkeypatch, simt_lib):
+    monkeypatch.setattr(G, "CUDA_LIB", simt_lib)
+
+
+# Left to the GPU run: the three full-size cases (minutes of interpretation) and the one that needs torch CUDA tensors.
+_GPU_ONLY = {"test_config4_shape_deep_bvh_sparse_pixels", "test_config5_shape_million_triangles_sparse_pixels", "test_full_size_properties",
+             "test_row_band_tiles_reassemble_to_the_single_gpu_image", "test_config2_size_sparse_pixels_against_oracle"}
+for _name in sorted(dir(G)):
+    if _name.startswith("test_") and _name not in _GPU_ONLY:
+        globals()["test_simt_" + _name[5:]] = getattr(G, _name)
+
+
+def test_simt_row_band_tiles_reassemble(simt_lib):
+    """rtSetTile / rtPackTile / rtUnpackTiles with three 'ranks' (bands of 8 rows, 150 rows: ranks own 56 / 48 / 46 rows, so the
+    padding of the short ranks is exercised): the concatenation of the TileSend buffers — what the all-gather delivers — unpacks
+    to the single-context image.  Device pointers of the interpreter build are host pointers."""
+    sc = scenes.cornell_spheres(200, 150, 4, 2)
+    fref, aref = render(simt_lib, sc, frames=2)
+    world, band = 3, 8
+    mgrs, sends = [], []
+    for r in range(world):
+        m = rt.RayComputeManager(simt_lib)
+        scenes.apply(sc, m)
+        m.context.set_tile(r, world, band)
+        m.OnEnable(); m.RenderFrame(); m.RenderFrame()
+        m.context.pack_tile(); m.context.synchronize()
+        ptr, nbytes = m.context.device_pointer("TileSend")
+        sends.append(C.string_at(ptr, nbytes))
+        mgrs.append(m)
+    ctx0 = mgrs[0].context
+    ptr, nbytes = ctx0.device_pointer("TileRecv")
+    blob = b"".join(sends)
+    assert len(blob) == nbytes
+    C.memmove(ptr, blob, nbytes)
+    ctx0.unpack_tiles(); ctx0.synchronize()
+    assert_bit_equal(mgrs[0].raytraceFrameTex, fref, "FrameRender reassembled")
+    assert_bit_equal(mgrs[0].accumulatedResult, aref, "AccumulatedRender reassembled")
+    for m in mgrs:
+        m.OnDestroy()
+
+
+def test_simt_corner_pixels_of_a_ragged_frame(simt_lib):
+    """Quirk Q1 (seed aliasing of the last column / row) and partial 8x8 groups at a size that is not a multiple of 8, all kernels."""
+    sc = scenes.cornell_spheres(75, 41, 5, 3)
+    fo, ao = render(ORACLE_LIB, sc, frames=2)
+    for kernel in (0, 1, 2):
+        fg, ag = render(simt_lib, sc, frames=2, options={"kernel": kernel})
+        assert_bit_equal(ag, ao, f"kernel {kernel}")
+
+
+def test_simt_tail_lanes_and_ray_sorting_are_schedule_only(simt_lib):
+    """Every scheduling knob of the pooled kernel — when the trace phase hands over to shading, the queue order, the pool size,
+    how many CTAs / 'SMs' share the work queue — leaves pixels and traversal counters untouched."""
+    sc = scenes.knot_room(72, 40, max_bounces=6, rays_per_pixel=2, nu=80, nv=8, glass=True)
+    fo, ao, so = render(ORACLE_LIB, sc, frames=1, want_stats=True)
+    for tail in (0, 1, 16, 31):
+        for sort_rays in (0, 1):
+            fg, ag, sg = render(simt_lib, sc, frames=1, options={"kernel": 2, "tailLanes": tail, "sortRays": sort_rays, "countStats": 1, "poolSlots": 32 + 32 * (tail % 3)},
+                                want_stats=True)
+            assert_bit_equal(fg, fo, f"tailLanes={tail} sortRays={sort_rays}")
+            for k in ("rays", "boxTests", "triTests"):
+                assert sg[k] == so[k]
