@@ -4,8 +4,9 @@ It recovers exactly what RayComputeManager pulls from the Unity scene graph at r
 fields (RayComputeManager.cs:9-42), Camera.main (field of view + transform), and every active `Model` component with its
 material, its mesh and its transform (RayComputeManager.cs:118,192-204).  Meshes are resolved by asset guid through the
 `.meta` files next to the `.obj` assets (loaded with host/ObjLoader.cpp) or built here for Unity's built-in Cube / Quad
-(fileID 10202 / 10210 of the built-in resources, not part of any repository).  `.fbx` meshes (Text, Water) are binary and
-not supported: scenes that need them raise unless `skip_unsupported=True`.
+(fileID 10202 / 10210 of the built-in resources, not part of any repository).  `.fbx` meshes (Text, Water) are read by
+fbx_mesh.py (binary FBX container, Unity's handedness / normal import settings) and picked by the sub-asset fileID the
+scene stores.  Any other mesh reference raises unless `skip_unsupported=True`.
 
 Not recoverable from the YAML: the run-time instance-ID order of FindObjectsByType (it only decides exact-tie winners
 between models, RayCommon.hlsl:362) — file order is used — and `renderSeed`, which the reference re-rolls in OnEnable
@@ -21,6 +22,7 @@ import numpy as np
 
 from . import scenes
 from .manager import load_obj
+from .fbx_mesh import load_fbx_meshes
 
 MODEL_SCRIPT_GUID = "cacf7f4e77ad8814ca6868b309a77322"       # Assets/Scripts/Types/Model.cs.meta
 MANAGER_SCRIPT_GUID = "5a097d4e14022bb47ae63bb730d39172"     # Assets/Scripts/Tracer/RayComputeManager.cs.meta
@@ -127,6 +129,7 @@ def load_unity_scene(scene_path: str, graphics_dir: Optional[str] = None, width:
 
     mesh_filters = {int(f["m_GameObject"]["fileID"]): f for _, (cid, _, f) in docs.items() if cid == 33}
     meshes, mesh_index, models = [], {}, []
+    fbx_cache: dict = {}
     for fid, (cid, _, f) in docs.items():
         if cid != 114 or f.get("m_Script", {}).get("guid") != MODEL_SCRIPT_GUID or not int(f.get("m_Enabled", 1)):
             continue
@@ -142,6 +145,14 @@ def load_unity_scene(scene_path: str, graphics_dir: Optional[str] = None, width:
                 mesh = builtin_quad()
             elif key[0] in guids and guids[key[0]].lower().endswith(".obj"):
                 mesh = scenes.MeshDesc(*load_obj(guids[key[0]]))
+            elif key[0] in guids and guids[key[0]].lower().endswith(".fbx"):
+                path = guids[key[0]]
+                if path not in fbx_cache:
+                    fbx_cache[path] = load_fbx_meshes(path)
+                if key[1] not in fbx_cache[path]:
+                    raise NotImplementedError(f"mesh fileID {key[1]} of '{game_objects[go].get('m_Name')}' is not a Mesh sub-asset of {path} "
+                                              f"(it holds {sorted(n for n, _ in fbx_cache[path].values())})")
+                mesh = fbx_cache[path][key[1]][1]
             elif skip_unsupported:
                 continue
             else:

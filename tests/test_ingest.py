@@ -150,6 +150,123 @@ def test_reference_scenes_load_with_the_serialized_settings(oracle_path):
     sc.settings["numRaysPerPixel"] = 16
     frame, _ = render(oracle_path, sc)
     assert np.isfinite(frame).all() and (frame[..., :3].sum(-1) > 0).mean() > 0.1
-    # scenes that need binary .fbx meshes say so instead of rendering something else
-    with pytest.raises(NotImplementedError):
-        unity_scene.load_unity_scene(os.path.join(SCENES_DIR, "Text.unity"))
+
+
+# ---- binary FBX (Text.fbx / Water.fbx of the reference) -----------------------------------------------------------------------
+
+def _fbx_node(name, props=b"", nprops=0, children=b"", version=7400):
+    """One FBX node record (32-bit offsets); the caller fixes up the absolute end offset."""
+    return (name.encode(), nprops, props, children)
+
+
+def _write_fbx(path, tree, version=7400):
+    import struct
+    wide = version >= 7500
+    out = bytearray(b"Kaydara FBX Binary  \x00\x1a\x00" + struct.pack("<I", version))
+    null = b"\x00" * (25 if wide else 13)
+
+    def emit(node):
+        name, nprops, props, children = node
+        start = len(out)
+        out.extend(b"\x00" * (24 if wide else 12)); out.append(len(name)); out.extend(name); out.extend(props)
+        for c in children:
+            emit(c)
+        if children:
+            out.extend(null)
+        struct.pack_into("<QQQ" if wide else "<III", out, start, len(out), nprops, len(props))
+    for n in tree:
+        emit(n)
+    out.extend(null)
+    out.extend(b"\x00" * 200)                                      # footer padding
+    open(path, "wb").write(bytes(out))
+
+
+def _p_str(s):
+    import struct
+    b = s.encode()
+    return b"S" + struct.pack("<I", len(b)) + b
+
+
+def _p_arr(code, arr, deflate):
+    import struct, zlib
+    raw = arr.tobytes()
+    body = zlib.compress(raw) if deflate else raw
+    return code.encode() + struct.pack("<III", arr.size, 1 if deflate else 0, len(body)) + body
+
+
+def _p_i64(v):
+    import struct
+    return b"L" + struct.pack("<q", v)
+
+
+@pytest.mark.parametrize("version", [7400, 7500])
+def test_fbx_reader_on_a_synthetic_file(tmp_path, version):
+    """Container (both offset widths, raw and deflated arrays), polygon end markers, fan triangulation, ByPolygonVertex /
+    IndexToDirect normals, node-name ownership through Connections, Unity handedness."""
+    from ray_tracing_b200 import fbx_mesh
+    verts = np.array([0, 0, 0, 1, 0, 0, 1, 1, 0, 0, 1, 0, 2, 0, 1], dtype="<f8")
+    pvi = np.array([0, 1, 2, ~3, 1, 4, ~2], dtype="<i4")            # a quad and a triangle
+    normals = np.array([0, 0, 1, 0, 1, 0], dtype="<f8")
+    nidx = np.array([0, 0, 0, 0, 1, 1, 1], dtype="<i4")
+    layer = _fbx_node("LayerElementNormal", children=[
+        _fbx_node("MappingInformationType", _p_str("ByPolygonVertex"), 1), _fbx_node("ReferenceInformationType", _p_str("IndexToDirect"), 1),
+        _fbx_node("Normals", _p_arr("d", normals, False), 1), _fbx_node("NormalsIndex", _p_arr("i", nidx, True), 1)])
+    geom = _fbx_node("Geometry", _p_i64(77) + _p_str("geo\x00\x01Geometry") + _p_str("Mesh"), 3, children=[
+        _fbx_node("Vertices", _p_arr("d", verts, True), 1), _fbx_node("PolygonVertexIndex", _p_arr("i", pvi, False), 1), layer])
+    model = _fbx_node("Model", _p_i64(88) + _p_str("Sign.001\x00\x01Model") + _p_str("Mesh"), 3)
+    conns = _fbx_node("Connections", children=[_fbx_node("C", _p_str("OO") + _p_i64(88) + _p_i64(0), 3), _fbx_node("C", _p_str("OO") + _p_i64(77) + _p_i64(88), 3)])
+    path = tmp_path / "t.fbx"
+    _write_fbx(str(path), [_fbx_node("Objects", children=[geom, model]), conns], version)
+    meshes = fbx_mesh.load_fbx_meshes(str(path))
+    (fid, (name, m)), = meshes.items()
+    assert name == "Sign.001" and fid == fbx_mesh.unity_mesh_file_id("Sign.001")
+    assert m.triangle_count == 3
+    tri = m.vertices.reshape(3, 3, 3)
+    assert np.array_equal(tri[0], [[-1, 1, 0], [-1, 0, 0], [0, 0, 0]])          # (0,1,2) reversed, X negated
+    assert np.array_equal(tri[1], [[0, 1, 0], [-1, 1, 0], [0, 0, 0]])           # (0,2,3) reversed
+    assert np.array_equal(m.normals[:6], [[0, 0, 1]] * 6) and np.array_equal(m.normals[6:], [[0, 1, 0]] * 3)
+    a, b, c = tri[0]
+    assert np.dot(np.cross(b - a, c - a), m.normals[0]) > 0                     # orientation survives the two flips
+    # recomputed normals (normalImportMode 1): flat faces more than the smoothing angle apart keep their own face normal
+    calc = fbx_mesh.load_fbx_meshes(str(path), normal_import_mode=1, smooth_angle_deg=30.0)[fid][1]
+    assert np.allclose(calc.normals[:6], [[0, 0, 1]] * 6, atol=1e-6)
+    assert np.allclose(np.linalg.norm(calc.normals, axis=1), 1.0, atol=1e-6)
+    with pytest.raises(ValueError):
+        (tmp_path / "ascii.fbx").write_text("; FBX 7.4.0 project file\n")
+        fbx_mesh.load_fbx_meshes(str(tmp_path / "ascii.fbx"))
+
+
+def test_unity_mesh_file_ids_known_answers():
+    """XXH64 against its published test vectors, and the sub-asset ids the reference's scenes store for its two .fbx files
+    (Text.unity:317-5749, Splash.unity) — fileID = XXH64("Type:Mesh->" + name + "0")."""
+    from ray_tracing_b200 import fbx_mesh
+    assert fbx_mesh.xxh64(b"") == 0xEF46DB3751D8E999 and fbx_mesh.xxh64(b"abc") == 0x44BC2CF5AD770999
+    assert fbx_mesh.xxh64(b"Nobody inspects the spammish repetition") == 0xFBCEA83C8A378BF1
+    pinned = {"Text": 6686097678407549244, "Text.001": 4882115322962003972, "Text.002": 2210965410299338194, "Text.003": -7432939776326845586,
+              "Text.004": 3038654674045518180, "Text.005": -3932407843921001191, "Text.006": 552887423116881197, "Text.007": -5082522871635176651,
+              "Text.008": -8413837161920484157, "Text.009": -1661537731292281231, "waterTest2": 1552480332205418273}
+    for name, fid in pinned.items():
+        assert fbx_mesh.unity_mesh_file_id(name) == fid, name
+
+
+@pytest.mark.skipif(not os.path.isdir(SCENES_DIR), reason="reference scenes not mounted")
+def test_reference_fbx_scenes_load_and_trace(oracle_path):
+    """Text.unity (ten glyph meshes of Text.fbx, normals recomputed as its .meta asks) and Splash.unity (Water.fbx, 656,796
+    triangles, bvhQuality Low): every mesh id resolves, the geometry sits inside the room, the scene traces."""
+    from ray_tracing_b200 import unity_scene
+    sc = unity_scene.load_unity_scene(os.path.join(SCENES_DIR, "Text.unity"), width=64, height=36)
+    glyphs = sorted(m.triangle_count for m in sc.meshes if m.triangle_count not in (2, 12, 87130))
+    assert glyphs == [284, 284, 2444, 2736, 3740, 4364, 4364, 6048, 6048, 6956] and len(sc.models) == 18      # the ten glyph meshes of Text.fbx
+    for md in sc.models:
+        m = sc.meshes[md.mesh]
+        w = (md.local_to_world[:3, :3] @ m.vertices.T.astype(np.float64)).T + md.local_to_world[:3, 3]
+        assert w[:, 0].min() > -3.1 and w[:, 0].max() < 3.1 and w[:, 1].min() > -0.2 and w[:, 1].max() < 4.2      # inside the 5.6 x 4 room
+    sc.settings.update(numRaysPerPixel=16, maxBounceCount=8)
+    frame, _ = render(oracle_path, sc)
+    assert np.isfinite(frame).all() and (frame[..., :3].sum(-1) > 0).mean() > 0.05     # one small ceiling light: a dark, noisy room
+    sp = unity_scene.load_unity_scene(os.path.join(SCENES_DIR, "Splash.unity"), width=48, height=27)
+    water = [m for m in sp.models if sp.meshes[m.mesh].triangle_count == 656796]
+    assert len(water) == 1 and sp.settings["bvhQuality"] == 0
+    m = sp.meshes[water[0].mesh]
+    w = (water[0].local_to_world[:3, :3] @ m.vertices.T.astype(np.float64)).T + water[0].local_to_world[:3, 3]
+    assert np.allclose(w.min(0), [-3.95, -0.04, -1.93], atol=0.02) and np.allclose(w.max(0), [3.95, 5.85, 2.02], atol=0.02)   # fills the room wall to wall
