@@ -38,6 +38,23 @@ namespace rtd {
 #ifndef RT_POOL_WARPS
 #define RT_POOL_WARPS 24      // measured (profiles/r01_sweeps.log): 16 -> 24 warps per SM: knot 33.8 -> 31.7 ms, 871k-triangle scene 109.8 -> 93.4 ms
 #endif
+// Round-2 candidates, compiled out by default (each is bit-exact on the SIMT interpreter build; none measured on the GPU yet):
+//   RT_STACK_TOP_REG   the top entry of the traversal stack lives in two registers: a pop hands it over at once and issues
+//                      the local-memory load of the entry below, which is only needed at the next pop / push — the pop's
+//                      load latency (17 % of the stall samples on the 1M-triangle scene, profiles/r01_f_soup4k_*) overlaps
+//                      the fetch and box tests of the popped node instead of preceding them
+//   RT_CACHE_RAYINV    1 / world ray direction (model skipping) computed once per ray instead of at every model step
+//   RT_LEAF_REPEAT=n   n leaf primitives per census (like RT_INNER_REPEAT for inner nodes)
+#ifdef RT_STACK_TOP_REG
+#define RT_PUSH(x) do { if (stackCount > 0) stack[stackCount - 1] = stackTop; stackTop = (x); stackCount++; } while (0)
+#define RT_POP(dst) do { (dst) = stackTop; --stackCount; if (stackCount > 0) stackTop = stack[stackCount - 1]; } while (0)
+#else
+#define RT_PUSH(x) stack[stackCount++] = (x)
+#define RT_POP(dst) (dst) = stack[--stackCount]
+#endif
+#ifndef RT_LEAF_REPEAT
+#define RT_LEAF_REPEAT 1
+#endif
 constexpr int POOL_WARPS = RT_POOL_WARPS;      // warps per CTA (one persistent CTA per SM)
 constexpr int POOL_THREADS = POOL_WARPS * 32;
 constexpr int POOL_WORDS = 24;                 // 32-bit words of state per path slot
@@ -181,6 +198,12 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
     int leafK = 0;
     NodeRef stack[WAVE_STACK];
     int stackCount = 0;
+#ifdef RT_STACK_TOP_REG
+    NodeRef stackTop; stackTop.start = 0; stackTop.count = 0;
+#endif
+#ifdef RT_CACHE_RAYINV
+    f3 rayInvW = splat3(0.0f);
+#endif
 
     for (;;)
     {
@@ -364,6 +387,9 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                     pool.u(F_INFO, myEntry) = (pool.u(F_INFO, myEntry) & ~15u) | PS_FLIGHT;
                     rayPos = pool.get3(F_POS, myEntry); rayDir = pool.get3(F_DIR, myEntry);
                     cnt.rays++;
+#ifdef RT_CACHE_RAYINV
+                    rayInvW = rcp3(rayDir);
+#endif
                     resDst = inf32(); resPrim = 0; resModel = 0; resKind = PS_HIT_MISS; resU = resV = resDet = 0.0f;
                     // spheres first (extension; where the reference's commented call sits, HL:341)
                     // A large Spheres buffer is searched through its accelerator by the same state machine as the meshes
@@ -416,7 +442,11 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                     // walks every model like the reference so that the test counts stay identical)
                     if (!STATS && P.modelSkip && model >= 0)
                     {
+#ifdef RT_CACHE_RAYINV
+                        const f3 rayInv = rayInvW;
+#else
                         const f3 rayInv = rcp3(rayDir);
+#endif
                         while (model < P.modelCount && ModelOutOfReach(reinterpret_cast<const float4*>(P.models + model), rayPos, rayInv, resDst)) model++;
                     }
                     if (EXT && P.sphBvh && model == -1)
@@ -486,15 +516,19 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                     // meshes: the reference's push-time test dst < best (HL:280-281).  Sphere boxes: conservative slack, ties kept
                     // (x*1 - 0 is x exactly, so the mesh comparison is unchanged; inf stays inf and never passes)
                     const float cs = sph ? 0.99999619f : 1.0f, cb = sph ? 1e-6f : 0.0f;
-                    if ((dstFar * cs - cb) < bestDst && stackCount < WAVE_STACK) stack[stackCount++] = farRef;   // (prefetching the far record here was measured: -2 %)
+                    if ((dstFar * cs - cb) < bestDst && stackCount < WAVE_STACK) RT_PUSH(farRef);   // (prefetching the far record here was measured: -2 %)
                     if ((dstNear * cs - cb) < bestDst) { cur = nearRef; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
-                    else if (stackCount > 0) { cur = stack[--stackCount]; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
+                    else if (stackCount > 0) { RT_POP(cur); leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
                     else mode = T_NEXT;
                 }
             }
             else
             {
                 // ---- one leaf triangle: HL:248-260 ----
+#if RT_LEAF_REPEAT > 1
+#pragma unroll 1
+                for (int rep = 0; rep < RT_LEAF_REPEAT; rep++)
+#endif
                 if (EXT && P.sphBvh && mode == T_LEAF && model < 0)
                 {
                     // one sphere of the accelerator's leaf (reference test, first-index rule on equal dst)
@@ -510,7 +544,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                     leafK++;
                     if (leafK >= cur.count)
                     {
-                        if (stackCount > 0) { cur = stack[--stackCount]; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
+                        if (stackCount > 0) { RT_POP(cur); leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
                         else mode = T_NEXT;
                     }
                 }
@@ -526,7 +560,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                     leafK++;
                     if (leafK >= cur.count)
                     {
-                        if (stackCount > 0) { cur = stack[--stackCount]; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
+                        if (stackCount > 0) { RT_POP(cur); leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
                         else mode = T_NEXT;
                     }
                 }

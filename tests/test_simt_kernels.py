@@ -92,3 +92,22 @@ def test_simt_tail_lanes_and_ray_sorting_are_schedule_only(simt_lib):
             assert_bit_equal(fg, fo, f"tailLanes={tail} sortRays={sort_rays}")
             for k in ("rays", "boxTests", "triTests"):
                 assert sg[k] == so[k]
+
+
+@pytest.mark.skipif(not os.environ.get("RT_SIMT_VARIANTS"), reason="four extra interpreter builds (~3 min): set RT_SIMT_VARIANTS=1")
+@pytest.mark.parametrize("defines", [("RT_STACK_TOP_REG",), ("RT_CACHE_RAYINV",), ("RT_LEAF_REPEAT=2",), ("RT_SPHERE_SKIP_SQRT",),
+                                     ("RT_STACK_TOP_REG", "RT_CACHE_RAYINV", "RT_LEAF_REPEAT=2", "RT_INNER_REPEAT=1")])
+def test_simt_compile_time_variants_are_bit_exact(defines, tmp_path):
+    """The A/B candidates of tools/round2_sweep.sh change scheduling / instruction selection only: same pixels, same counters."""
+    lib = simt_build.build(force=True, defines=defines, out=str(tmp_path / "variant.so"))
+    flat = scenes.knot_room(48, 27, max_bounces=3, rays_per_pixel=1, nu=40, nv=6)
+    flat.settings["bvhQuality"] = 2
+    for sc, frames in ((scenes.knot_room(96, 54, max_bounces=6, rays_per_pixel=2, nu=120, nv=10, glass=True), 2),
+                       (scenes.random_soup(64, 64, max_bounces=6, rays_per_pixel=2, triangles=20000, spheres=300), 1),
+                       (scenes.cornell_spheres(64, 48, 5, 3), 2), (flat, 1)):
+        fo, ao, so = render(ORACLE_LIB, sc, frames=frames, want_stats=True)
+        for opts in ({"kernel": 2, "countStats": 1}, {"kernel": 2, "poolSlots": 32, "tailLanes": 3}, {"kernel": 1}, {"kernel": 0}):
+            fg, ag, sg = render(lib, sc, frames=frames, options=opts, want_stats=True)
+            assert_bit_equal(ag, ao, f"{defines} {sc.name} {opts}")
+            if opts.get("countStats"):
+                assert all(sg[k] == so[k] for k in ("rays", "boxTests", "triTests"))

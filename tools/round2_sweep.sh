@@ -1,13 +1,16 @@
 #!/bin/bash
-# A/B candidates prepared at the end of round 1 (compile-time variants, all off by default, none measured yet).
+# A/B candidates prepared at the end of round 1 (compile-time variants, all off by default, none measured yet; the pool-kernel
+# ones are bit-exact on the SIMT interpreter build: RT_SIMT_VARIANTS=1 python -m pytest tests/test_simt_kernels.py -k variants).
 # Build them next to the default library and compare on one GPU:   bash tools/round2_sweep.sh   (under gpurun)
 python - <<'PY'
 from ray_tracing_b200 import build
 import os
 P = build.PKG_DIR
-for name, defs in [("skipsqrt", ("RT_SPHERE_SKIP_SQRT",)), ("mb5", ("RT_WAVE_MINBLOCKS=5",)), ("ir1", ("RT_INNER_REPEAT=1",)), ("pw20", ("RT_POOL_WARPS=20",))]:
+for name, defs in [("skipsqrt", ("RT_SPHERE_SKIP_SQRT",)), ("mb5", ("RT_WAVE_MINBLOCKS=5",)), ("ir1", ("RT_INNER_REPEAT=1",)), ("pw20", ("RT_POOL_WARPS=20",)),
+                   ("stacktop", ("RT_STACK_TOP_REG",)), ("rayinv", ("RT_CACHE_RAYINV",)), ("leaf2", ("RT_LEAF_REPEAT=2",)),
+                   ("stacktop_leaf2", ("RT_STACK_TOP_REG", "RT_LEAF_REPEAT=2"))]:
     build.build_cuda(force=True, defines=defs, out=os.path.join(P, f"librt_b200_{name}.so"))
 PY
 RT_B200_LIB=ray_tracing_b200/librt_b200_skipsqrt.so python -m pytest tests -m gpu -q -k "cornell or sphere or soup" 2>&1 | tail -3
 bash tools/gpu_ab.sh r2 librt_b200.so librt_b200_skipsqrt.so librt_b200_mb5.so
-bash tools/gpu_ab2.sh r2 librt_b200.so librt_b200_ir1.so librt_b200_pw20.so
+bash tools/gpu_ab2.sh r2 librt_b200.so librt_b200_ir1.so librt_b200_pw20.so librt_b200_stacktop.so librt_b200_rayinv.so librt_b200_leaf2.so librt_b200_stacktop_leaf2.so
