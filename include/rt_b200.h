@@ -149,6 +149,9 @@ int rtGetDevicePointer(RtContext* ctx, const char* name, void** devPtr, size_t* 
  *   "sortRays"    kernel 2: 1 = group each warp's ray queue by direction octant before tracing, 0 = slot order (default;
  *                 measured: the grouping changes throughput by -3 % .. +1.5 %)
  *   "tailLanes"   kernel 2 leaves its trace phase when the ray queue is empty and at most this many lanes still trace
+ *   "pairOrder"   order of the repacked node-pair records inside a mesh: 0 = breadth-first (default), d = 1..32 = treelets of d
+ *                 levels laid out depth-first (1 = plain pre-order: child A's record follows its parent's).  Layout only: the
+ *                 traversal visits the same nodes in the same order; not yet measured on the GPU
  * Unknown names return RT_E_UNKNOWN_NAME. */
 int rtSetOption(RtContext* ctx, const char* name, int value);
 

@@ -65,7 +65,7 @@ struct RtContext
     float4* peerFrame[RT_MAX_PEERS]; float4* peerAccum[RT_MAX_PEERS]; int nPeers = 0;
 
     // options
-    int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16, optSortRays = 0, optForceExt = 0, optModelSkip = 1;   // kernel -1 = automatic   // smemPairs -1 = automatic
+    int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16, optSortRays = 0, optForceExt = 0, optModelSkip = 1, optPairOrder = 0;   // kernel -1 = automatic   // smemPairs -1 = automatic
 
     // counters / timing
     unsigned long long* dCounters = nullptr;   // 5
@@ -321,6 +321,7 @@ int rtSetOption(RtContext* c, const char* name, int value)
     else if (n == "modelSkip") c->optModelSkip = value != 0;
     else if (n == "extInstantiation") c->optForceExt = value != 0;
     else if (n == "sortRays") c->optSortRays = value != 0;
+    else if (n == "pairOrder") { if (value < 0 || value > 32) return fail(c, RT_E_INVALID, "rtSetOption: pairOrder must be 0 (breadth-first) or a treelet depth 1..32"); c->optPairOrder = value; }
     else if (n == "tailLanes") { if (value < 0 || value > 31) return fail(c, RT_E_INVALID, "rtSetOption: tailLanes must be in [0, 31]"); c->optTailLanes = value; }
     else if (n == "poolSlots") { if (value != 32 && value != 64 && value != 96) return fail(c, RT_E_INVALID, "rtSetOption: poolSlots must be 32, 64 or 96"); c->optPoolSlots = value; }
     else return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetOption: unknown option ") + name);
@@ -351,11 +352,11 @@ static int prepareScene(RtContext* c)
     const int kernelSel = effectiveKernel(c);
     if (kernelSel == 2) { const int mx = pool_max_smem_pairs(c->optPoolSlots, (int)c->spheres.count); if (budget > mx) budget = mx; }
     else if (kernelSel == 0) budget = 0;
-    if (budget != c->repack.budgetUsed) c->sceneDirty = true;
+    if (budget != c->repack.budgetUsed || c->optPairOrder != c->repack.orderUsed) c->sceneDirty = true;
     if (c->sceneDirty)
     {
         std::string msg;
-        cudaError_t e = c->repack.buildScene(c->hNodes, c->hModels, c->P.modelCount, c->tris.p, c->tris.count, budget, c->stream, msg);
+        cudaError_t e = c->repack.buildScene(c->hNodes, c->hModels, c->P.modelCount, c->tris.p, c->tris.count, budget, c->stream, msg, c->optPairOrder);
         if (e != cudaSuccess) return failCuda(c, e, "repack scene");
         if (!msg.empty()) return fail(c, RT_E_STATE, "rtDispatch: " + msg);
         c->sceneDirty = false; c->modelsDirty = true;
@@ -633,8 +634,15 @@ int rtSetPeers(RtContext* c, int nPeers, const void* handles, size_t bytes)
 /* Device-free test hook (not part of include/rt_b200.h): the breadth-first pair layout the upload would build.
  * pairsOut: capacity pairCap records of 64 bytes; rootsOut: 2 ints (start, count) per model.  Returns the number of pair
  * records, or a negative RT_E_* code with the reason in msg. */
+int rtxPlanPairsOrdered(const RtNode* nodes, int nodeCount, const RtModel* models, int modelCount, int triCount, int smemBudget, int treeletDepth,
+                        void* pairsOut, int pairCap, int* smemPairsOut, int* rootsOut, char* msg, int msgCap);
 int rtxPlanPairs(const RtNode* nodes, int nodeCount, const RtModel* models, int modelCount, int triCount, int smemBudget,
                  void* pairsOut, int pairCap, int* smemPairsOut, int* rootsOut, char* msg, int msgCap)
+{
+    return rtxPlanPairsOrdered(nodes, nodeCount, models, modelCount, triCount, smemBudget, 0, pairsOut, pairCap, smemPairsOut, rootsOut, msg, msgCap);
+}
+int rtxPlanPairsOrdered(const RtNode* nodes, int nodeCount, const RtModel* models, int modelCount, int triCount, int smemBudget, int treeletDepth,
+                        void* pairsOut, int pairCap, int* smemPairsOut, int* rootsOut, char* msg, int msgCap)
 {
     if (!nodes || !models || nodeCount <= 0 || modelCount < 0 || !pairsOut || !rootsOut) return RT_E_INVALID;
     std::vector<RtNode> n(nodes, nodes + nodeCount);
@@ -643,7 +651,7 @@ int rtxPlanPairs(const RtNode* nodes, int nodeCount, const RtModel* models, int 
         if (m[i].nodeOffset < 0 || m[i].nodeOffset >= nodeCount) { if (msg && msgCap > 0) snprintf(msg, msgCap, "model nodeOffset out of range"); return RT_E_STATE; }
     RepackState st;
     std::vector<NodePair> out; std::string why;
-    st.planScene(n, m, modelCount, (size_t)triCount, smemBudget, out, why);
+    st.planScene(n, m, modelCount, (size_t)triCount, smemBudget, out, why, treeletDepth);
     if (!why.empty()) { if (msg && msgCap > 0) snprintf(msg, msgCap, "%s", why.c_str()); return RT_E_STATE; }
     if ((int)out.size() > pairCap) return RT_E_INVALID;
     if (!out.empty()) memcpy(pairsOut, out.data(), out.size() * sizeof(NodePair));

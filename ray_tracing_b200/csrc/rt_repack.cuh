@@ -55,17 +55,26 @@ struct RepackState
     std::map<std::pair<int,int>, MeshRoot> roots;     // (nodeOffset, triOffset) -> encoded root
     int smemPairs = 0;
     int budgetUsed = -1;
+    int orderUsed = 0;                              // treeletDepth of the current pair layout
     size_t totalPairs = 0;
 
     void release() { pairs.release(); triGeom.release(); triNormals.release(); models.release(); spheres.release(); sphPairs.release(); sphLeaves.release(); roots.clear(); }
 
-    // Breadth-first renumbering of every distinct mesh referenced by the first modelCount models.  Host only (no CUDA call):
+    // Renumbering of every distinct mesh referenced by the first modelCount models.  Host only (no CUDA call):
     // fills `out`, `roots`, `smemPairs`, `totalPairs`; a non-empty `msg` reports a malformed BVH.
+    // Record order inside a mesh (it changes where records live, never what a traversal visits):
+    //   treeletDepth = 0   breadth-first (the default: the top of the tree is one contiguous range)
+    //   treeletDepth = d   treelets of d levels, breadth-first inside a treelet, treelets in depth-first order (first child's
+    //                      subtree first): a descent stays inside one or two 128-byte lines for d levels, and with d = 1
+    //                      (plain pre-order) the record of child A directly follows its parent's.  The first `hot` records
+    //                      (shared-memory staging) stay the breadth-first top whatever the order of the rest.
     void planScene(const std::vector<RtNode>& nodes, const std::vector<RtModel>& mdl, int modelCount, size_t triCount, int smemOpt,
-                   std::vector<NodePair>& out, std::string& msg)
+                   std::vector<NodePair>& out, std::string& msg, int treeletDepth = 0)
     {
         roots.clear(); smemPairs = 0; totalPairs = 0; out.clear();
-        struct Mesh { int nodeOffset, triOffset; std::vector<int> order; /* global node index of first child, in BFS pair order */ size_t hot = 0, hotBase = 0, coldBase = 0; };
+        struct Mesh { int nodeOffset, triOffset; std::vector<int> order; /* global node index of first child, in BFS pair order */
+                      std::vector<int> kidA, kidB; /* BFS pair id of the inner children of pair k, -1 for a leaf */
+                      std::vector<int> perm; /* BFS pair id -> position inside the mesh */ size_t hot = 0, hotBase = 0, coldBase = 0; };
         std::vector<Mesh> meshes;
         for (int i = 0; i < modelCount; i++)
         {
@@ -85,8 +94,8 @@ struct RepackState
                     if (a < 0 || a + 1 >= (long long)nodes.size()) { msg = "BVH child index out of range"; return; }
                     if (queue.size() > nodes.size()) { msg = "BVH has a cycle"; return; }
                     m.order.push_back((int)a);
-                    if (nodes[a].triangleCount <= 0) queue.push_back((int)a);
-                    if (nodes[a + 1].triangleCount <= 0) queue.push_back((int)a + 1);
+                    if (nodes[a].triangleCount <= 0) { m.kidA.push_back((int)queue.size()); queue.push_back((int)a); } else m.kidA.push_back(-1);
+                    if (nodes[a + 1].triangleCount <= 0) { m.kidB.push_back((int)queue.size()); queue.push_back((int)a + 1); } else m.kidB.push_back(-1);
                 }
             }
             meshes.push_back(std::move(m));
@@ -117,8 +126,34 @@ struct RepackState
         out.assign(totalPairs, NodePair());
         for (auto& m : meshes)
         {
-            auto globalPair = [&](size_t local) { return (int)(local < m.hot ? m.hotBase + local : m.coldBase + (local - m.hot)); };
-            // second pass in the same BFS order: the k-th inner node met owns pair k; its inner children get the next free ids
+            // position of every pair inside the mesh
+            const size_t n = m.order.size();
+            m.perm.assign(n, -1);
+            if (treeletDepth <= 0) for (size_t k = 0; k < n; k++) m.perm[k] = (int)k;
+            else if (n > 0)
+            {
+                int next = (int)m.hot;
+                for (size_t k = 0; k < m.hot; k++) m.perm[k] = (int)k;
+                std::vector<int> todo(1, 0), level, below;                 // treelet roots still to lay out (depth-first: a stack)
+                while (!todo.empty())
+                {
+                    level.assign(1, todo.back()); todo.pop_back();
+                    for (int d = 0; d < treeletDepth && !level.empty(); d++)
+                    {
+                        below.clear();
+                        for (int k : level)
+                        {
+                            if (m.perm[k] < 0) m.perm[k] = next++;
+                            if (m.kidA[k] >= 0) below.push_back(m.kidA[k]);
+                            if (m.kidB[k] >= 0) below.push_back(m.kidB[k]);
+                        }
+                        level.swap(below);
+                    }
+                    for (size_t i = level.size(); i-- > 0;) todo.push_back(level[i]);     // leftmost treelet next
+                }
+            }
+            auto globalPair = [&](size_t bfsId) { const size_t local = (size_t)m.perm[bfsId]; return (int)(local < m.hot ? m.hotBase + local : m.coldBase + (local - m.hot)); };
+            // second pass in BFS order: the k-th inner node met owns pair k; its inner children are the next ones the BFS met
             size_t nextChildPair = 1;       // pair 0 belongs to the root
             const RtNode& root = nodes[m.nodeOffset];
             MeshRoot r;
@@ -145,10 +180,11 @@ struct RepackState
     }
 
     cudaError_t buildScene(const std::vector<RtNode>& nodes, const std::vector<RtModel>& mdl, int modelCount,
-                           const RtTriangle* dTris, size_t triCount, int smemOpt, cudaStream_t stream, std::string& msg)
+                           const RtTriangle* dTris, size_t triCount, int smemOpt, cudaStream_t stream, std::string& msg, int treeletDepth = 0)
     {
         std::vector<NodePair> out;
-        planScene(nodes, mdl, modelCount, triCount, smemOpt, out, msg);
+        planScene(nodes, mdl, modelCount, triCount, smemOpt, out, msg, treeletDepth);
+        orderUsed = treeletDepth;
         if (!msg.empty()) return cudaSuccess;
         cudaError_t e;
         if ((e = pairs.ensure(std::max<size_t>(totalPairs, 1))) != cudaSuccess) return e;

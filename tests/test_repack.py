@@ -15,14 +15,18 @@ PAIR_DTYPE = np.dtype([("aMin", "<f4", 3), ("aMax", "<f4", 3), ("aStart", "<i4")
 assert PAIR_DTYPE.itemsize == 64
 
 
-def _plan(nodes, models, tri_count, budget):
+def _plan(nodes, models, tri_count, budget, treelet_depth=None):
     L = C.CDLL(CUDA_LIB)                                   # host code only: no CUDA call is made
     pairs = np.zeros(max(len(nodes), 1), dtype=PAIR_DTYPE)
     roots = np.zeros(2 * len(models), dtype=np.int32)
     smem = C.c_int()
     msg = C.create_string_buffer(256)
-    n = L.rtxPlanPairs(nodes.ctypes.data_as(C.c_void_p), len(nodes), models.ctypes.data_as(C.c_void_p), len(models), tri_count, budget,
-                       pairs.ctypes.data_as(C.c_void_p), len(pairs), C.byref(smem), roots.ctypes.data_as(C.c_void_p), msg, 256)
+    if treelet_depth is None:
+        n = L.rtxPlanPairs(nodes.ctypes.data_as(C.c_void_p), len(nodes), models.ctypes.data_as(C.c_void_p), len(models), tri_count, budget,
+                           pairs.ctypes.data_as(C.c_void_p), len(pairs), C.byref(smem), roots.ctypes.data_as(C.c_void_p), msg, 256)
+    else:
+        n = L.rtxPlanPairsOrdered(nodes.ctypes.data_as(C.c_void_p), len(nodes), models.ctypes.data_as(C.c_void_p), len(models), tri_count, budget, treelet_depth,
+                                  pairs.ctypes.data_as(C.c_void_p), len(pairs), C.byref(smem), roots.ctypes.data_as(C.c_void_p), msg, 256)
     return n, pairs[:max(n, 0)], roots.reshape(-1, 2), smem.value, msg.value.decode()
 
 
@@ -107,3 +111,35 @@ def test_single_leaf_mesh_has_no_pairs():
     models = np.zeros(1, dtype=capi.MODEL_DTYPE)
     n, pairs, roots, smem, msg = _plan(nodes, models, 1, 16)
     assert n == 0 and smem == 0 and tuple(roots[0]) == (0, 1)                      # root is the leaf: (first triangle, count)
+
+
+@pytest.mark.parametrize("depth,budget", [(1, 0), (2, 0), (3, 0), (5, 0), (32, 0), (1, 40), (3, 700)])
+def test_treelet_orders_describe_the_same_trees(depth, budget):
+    """The "pairOrder" layouts (treelets of `depth` levels in depth-first order) are permutations of the breadth-first one: the same
+    trees hang off the same roots, every record is reached exactly once, the staged (hot) front is unchanged."""
+    import sys
+    sys.setrecursionlimit(10000)
+    nodes, models, tri_count, (n_knot, t_knot) = _scene_buffers()
+    n0, bfs, roots0, smem0, _ = _plan(nodes, models, tri_count, budget)
+    n, pairs, roots, smem, msg = _plan(nodes, models, tri_count, budget, depth)
+    assert n == n0 and msg == "" and smem == smem0
+    seen = set()
+    leaves = _check_subtree(nodes, 0, 0, 0, pairs, tuple(roots[0]), seen)
+    leaves += _check_subtree(nodes, n_knot, t_knot, 0, pairs, tuple(roots[2]), seen)
+    assert leaves == int((nodes["triangleCount"] > 0).sum()) and len(seen) == n
+    for f in ("aMin", "aMax", "bMin", "bMax"):                                        # the hot front holds the same nodes (child ids inside may differ)
+        assert np.array_equal(pairs[f][:smem], bfs[f][:smem])
+    if depth >= 32:
+        # one treelet spans the whole tree: breadth-first again
+        assert np.array_equal(pairs.view(np.uint8), bfs.view(np.uint8))
+    if depth == 1 and budget == 0:
+        # plain pre-order: the record of an inner child A directly follows its parent's record
+        inner_a = pairs["aCount"] == 0
+        assert np.array_equal(pairs["aStart"][inner_a], np.flatnonzero(inner_a) + 1)
+    if depth == 3 and budget == 0:
+        # a descent of two steps from a treelet root stays within the treelet's 7 records
+        root = int(roots[0][0])
+        for s1 in (pairs[root]["aStart"], pairs[root]["bStart"]):
+            assert root < s1 <= root + 2
+            for s2, c2 in ((pairs[s1]["aStart"], pairs[s1]["aCount"]), (pairs[s1]["bStart"], pairs[s1]["bCount"])):
+                assert c2 > 0 or root + 2 < s2 <= root + 6

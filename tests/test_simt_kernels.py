@@ -94,6 +94,20 @@ def test_simt_tail_lanes_and_ray_sorting_are_schedule_only(simt_lib):
                 assert sg[k] == so[k]
 
 
+def test_simt_pair_record_order_is_layout_only(simt_lib):
+    """"pairOrder" (treelets in depth-first order instead of breadth-first records): same pixels, same traversal counters, with
+    and without tree tops staged in shared memory, shared and unshared meshes."""
+    scs = [scenes.knot_room(72, 40, max_bounces=5, rays_per_pixel=2, nu=100, nv=10, glass=True),
+           scenes.random_soup(48, 48, max_bounces=5, rays_per_pixel=2, triangles=8000, spheres=12)]
+    for sc in scs:
+        fo, ao, so = render(ORACLE_LIB, sc, frames=1, want_stats=True)
+        for order in (1, 2, 3, 6):
+            for kernel, smem in ((2, 0), (2, 300), (1, 0), (1, 64)):
+                fg, ag, sg = render(simt_lib, sc, frames=1, options={"kernel": kernel, "pairOrder": order, "smemNodes": smem, "countStats": 1}, want_stats=True)
+                assert_bit_equal(fg, fo, f"{sc.name} pairOrder={order} kernel={kernel} smemNodes={smem}")
+                assert all(sg[k] == so[k] for k in ("rays", "boxTests", "triTests"))
+
+
 @pytest.mark.skipif(not os.environ.get("RT_SIMT_VARIANTS"), reason="four extra interpreter builds (~3 min): set RT_SIMT_VARIANTS=1")
 @pytest.mark.parametrize("defines", [("RT_STACK_TOP_REG",), ("RT_CACHE_RAYINV",), ("RT_LEAF_REPEAT=2",), ("RT_SPHERE_SKIP_SQRT",),
                                      ("RT_STACK_TOP_REG", "RT_CACHE_RAYINV", "RT_LEAF_REPEAT=2", "RT_INNER_REPEAT=1")])

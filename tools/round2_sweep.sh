@@ -14,3 +14,14 @@ PY
 RT_B200_LIB=ray_tracing_b200/librt_b200_skipsqrt.so python -m pytest tests -m gpu -q -k "cornell or sphere or soup" 2>&1 | tail -3
 bash tools/gpu_ab.sh r2 librt_b200.so librt_b200_skipsqrt.so librt_b200_mb5.so
 bash tools/gpu_ab2.sh r2 librt_b200.so librt_b200_ir1.so librt_b200_pw20.so librt_b200_stacktop.so librt_b200_rayinv.so librt_b200_leaf2.so librt_b200_stacktop_leaf2.so
+# node-pair record order (host-side layout only; kernel unchanged): breadth-first (0, default) vs treelets laid out depth-first
+OUT=gpurun_out; mkdir -p $OUT
+for wl in knot64 cluster4k soup4k; do for po in 0 1 2 3 4 6; do
+  echo "== $wl --pair-order $po" | tee -a $OUT/sweep_r2_pairorder.log
+  timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --workload $wl --pair-order $po 2>&1 | tail -1 | python -c "
+import sys,json
+l=sys.stdin.read().strip()
+try:
+    d=json.loads(l); print(d['value'],'Mrays/s', d['ms_per_step'],'ms', 'frac',d['roofline']['frac'])
+except Exception as e: print('ERR',l[-600:])" | tee -a $OUT/sweep_r2_pairorder.log
+done; done
