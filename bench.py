@@ -233,6 +233,8 @@ def run_gpu(args, w):
         ctx.set_option("tailLanes", args.tail_lanes)
     if args.pair_order is not None:
         ctx.set_option("pairOrder", args.pair_order)
+    if args.grid_fit is not None:
+        ctx.set_option("gridFit", args.grid_fit)
     mgr.OnEnable()
     if tiled.fused:
         with torch.cuda.stream(stream):
@@ -351,7 +353,7 @@ def run_gpu(args, w):
                                    if tiled.fused else "one NCCL all-gather of finished tiles per frame")) if world > 1 else "single GPU",
                        "l2": "flushed between steps (256 MiB write inside the timed region)",
                        "kernel": kernel_label,
-                       "pool_slots": args.pool_slots, "smem_nodes": args.smem_nodes, "pair_order": args.pair_order},
+                       "pool_slots": args.pool_slots, "smem_nodes": args.smem_nodes, "pair_order": args.pair_order, "grid_fit": args.grid_fit},
             "ms_per_frame": round(ms_total / args.steps, 4),
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": W * H * 16,
@@ -388,6 +390,7 @@ def main():
     ap.add_argument("--model-skip", type=int, default=None, help="kernels 1/2: skip models the ray cannot reach (1 default / 0)")
     ap.add_argument("--sort-rays", type=int, default=None, help="kernel 2: group the ray queue by direction octant (1/0)")
     ap.add_argument("--tail-lanes", type=int, default=None, help="kernel 2: leave the trace phase when this few lanes still trace")
+    ap.add_argument("--grid-fit", type=int, default=None, help="1 = size the persistent grid for a whole number of pixels per lane (multi-GPU tail), 0 = default")
     ap.add_argument("--pair-order", type=int, default=None, help="node-pair record order: 0 = breadth-first (default), d = treelets of d levels, depth-first")
     ap.add_argument("--smem-nodes", type=int, default=None, help="node pairs staged in shared memory (-1 = auto)")
     ap.add_argument("--lib", default=None, help="alternative build of librt_b200.so (A/B experiments)")

@@ -149,6 +149,9 @@ int rtGetDevicePointer(RtContext* ctx, const char* name, void** devPtr, size_t* 
  *   "sortRays"    kernel 2: 1 = group each warp's ray queue by direction octant before tracing, 0 = slot order (default;
  *                 measured: the grouping changes throughput by -3 % .. +1.5 %)
  *   "tailLanes"   kernel 2 leaves its trace phase when the ray queue is empty and at most this many lanes still trace
+ *   "gridFit"     kernels 1 and 2: 1 = shrink the persistent grid so that every lane (pool slot) gets a whole number of pixels
+ *                 — fewer, fully occupied rounds instead of a last round of mostly empty warps when the image is small for the
+ *                 machine (multi-GPU tiles); 0 = one CTA set filling the machine (default; not yet measured)
  *   "pairOrder"   order of the repacked node-pair records inside a mesh: 0 = breadth-first (default), d = 1..32 = treelets of d
  *                 levels laid out depth-first (1 = plain pre-order: child A's record follows its parent's).  Layout only: the
  *                 traversal visits the same nodes in the same order; not yet measured on the GPU

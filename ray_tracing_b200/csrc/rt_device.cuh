@@ -116,7 +116,7 @@ struct DevParams
     int   smemPairs;                        // number of leading pair records staged in shared memory
     int   tailLanes;                        // pooled kernel: leave the trace phase when this few lanes are still tracing
     int   sortRays;                         // pooled kernel: group the ray queue by direction octant
-    int   pad4;
+    int   gridFit;                          // host only: size the persistent grid so that every lane gets a whole number of pixels
 
     float4* FrameRender;
     float4* AccumulatedRender;

@@ -619,6 +619,7 @@ template <int M> inline cudaError_t pool_launch_m(const DevParams& P, int numSMs
     const unsigned slots = POOL_WARPS * M;
     const unsigned ctasNeeded = (totalJobs + slots - 1) / slots;
     if (grid > ctasNeeded) grid = ctasNeeded ? ctasNeeded : 1;
+    grid = fit_persistent_grid(P.gridFit, grid, slots, totalJobs);
     cudaError_t e;
     if ((e = cudaMemsetAsync(P.workCounter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(evA, stream)) != cudaSuccess) return e;

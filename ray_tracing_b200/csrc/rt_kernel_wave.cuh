@@ -344,6 +344,20 @@ __global__ void __launch_bounds__(WAVE_THREADS, RT_WAVE_MINBLOCKS) k_raytrace_wa
     }
 }
 
+// "gridFit": a pixel's samples cannot be split (one RNG chain), so a persistent lane works through whole pixels.  When the image
+// gives every lane only a few (8 GPUs, config 2: 2.3 pixels per lane) the last round runs with mostly empty warps.  With the
+// option on, the grid is shrunk so that pixels / lanes is just under a whole number k = ceil(pixels / maxLanes): the same k
+// rounds, every one of them with full warps, on fewer resident warps.  Scheduling only; off by default (not yet measured).
+inline unsigned int fit_persistent_grid(int enabled, unsigned int grid, unsigned int lanesPerCta, unsigned int totalJobs)
+{
+    if (!enabled || grid == 0 || totalJobs == 0) return grid;
+    const unsigned long long lanes = (unsigned long long)grid * lanesPerCta;
+    const unsigned long long k = (totalJobs + lanes - 1) / lanes;                    // rounds at full size
+    const unsigned long long fitLanes = (totalJobs + k - 1) / k;                     // lanes that keep k rounds full
+    const unsigned long long fit = (fitLanes + lanesPerCta - 1) / lanesPerCta;
+    return fit < grid ? (unsigned int)(fit ? fit : 1) : grid;
+}
+
 template <bool S, bool X> inline cudaError_t wave_configure_one()
 {
     return cudaFuncSetAttribute(k_raytrace_wave<S, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
@@ -368,6 +382,7 @@ template <bool S, bool X> inline cudaError_t wave_launch_one(const DevParams& P,
     const unsigned int warpsNeeded = (totalJobs + 31u) / 32u;
     const unsigned int ctasNeeded = (warpsNeeded + (WAVE_THREADS / 32) - 1) / (WAVE_THREADS / 32);
     if (grid > ctasNeeded) grid = ctasNeeded ? ctasNeeded : 1;
+    grid = fit_persistent_grid(P.gridFit, grid, WAVE_THREADS, totalJobs);
     if ((e = cudaMemsetAsync(P.workCounter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(evA, stream)) != cudaSuccess) return e;
     RT_LAUNCH(grid, WAVE_THREADS, smemBytes, stream, RT_K(k_raytrace_wave<S, X>), P, totalJobs, tilesX, ownedRows);

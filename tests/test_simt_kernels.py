@@ -94,6 +94,20 @@ def test_simt_tail_lanes_and_ray_sorting_are_schedule_only(simt_lib):
                 assert sg[k] == so[k]
 
 
+def test_simt_grid_fit_is_schedule_only(simt_lib, monkeypatch):
+    """"gridFit" changes how many persistent CTAs share the pixel queue (a whole number of pixels per lane), nothing else — checked with
+    several machine sizes so that the fitted grid is really smaller than the full one (e.g. 3 'SMs' x 2 CTAs x 128 lanes = 768 lanes for
+    60 x 33 = 1980 pixels + padding: 3 rounds -> 5 CTAs instead of 6)."""
+    scs = [scenes.cornell_spheres(60, 33, 4, 3), scenes.knot_room(60, 33, max_bounces=4, rays_per_pixel=2, nu=60, nv=8)]
+    for sms in ("1", "3", "5"):
+        monkeypatch.setenv("RT_SIMT_SMS", sms)
+        for sc in scs:
+            fo, ao = render(ORACLE_LIB, sc, frames=2)
+            for kernel in (1, 2):
+                fg, ag = render(simt_lib, sc, frames=2, options={"kernel": kernel, "gridFit": 1, "poolSlots": 32})
+                assert_bit_equal(ag, ao, f"{sc.name} gridFit kernel={kernel} SMs={sms}")
+
+
 def test_simt_pair_record_order_is_layout_only(simt_lib):
     """"pairOrder" (treelets in depth-first order instead of breadth-first records): same pixels, same traversal counters, with
     and without tree tops staged in shared memory, shared and unshared meshes."""

@@ -17,3 +17,12 @@ def test_pair_record_order_is_layout_only_on_gpu(order):
         fg, ag, sg = render(CUDA_LIB, sc, frames=1, options={"kernel": kernel, "pairOrder": order, "smemNodes": smem, "countStats": 1}, want_stats=True)
         assert_bit_equal(fg, fo, f"pairOrder={order} kernel={kernel} smemNodes={smem}")
         assert all(sg[k] == so[k] for k in ("rays", "boxTests", "triTests"))
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_grid_fit_is_schedule_only_on_gpu(kernel):
+    """A frame small enough that the B200 gets about two pixels per persistent lane, so the fitted grid differs from the full one."""
+    sc = scenes.cornell_spheres(640, 360, 6, 4) if kernel == 1 else scenes.knot_room(640, 360, max_bounces=5, rays_per_pixel=2, nu=120, nv=10)
+    fo, ao = render(CUDA_LIB, sc, frames=2, options={"kernel": kernel})
+    fg, ag = render(CUDA_LIB, sc, frames=2, options={"kernel": kernel, "gridFit": 1})
+    assert_bit_equal(ag, ao, f"gridFit kernel={kernel}")

@@ -25,3 +25,9 @@ try:
     d=json.loads(l); print(d['value'],'Mrays/s', d['ms_per_step'],'ms', 'frac',d['roofline']['frac'])
 except Exception as e: print('ERR',l[-600:])" | tee -a $OUT/sweep_r2_pairorder.log
 done; done
+# gridFit (whole pixels per persistent lane): matters when a GPU has few pixels per lane, i.e. on multi-GPU tiles.  Single GPU
+# check of the same regime: a quarter-size frame.  On N GPUs:  torchrun ... bench.py --gpus N --grid-fit 1  (tools/gpu_multi.sh).
+for gf in 0 1; do
+  echo "== cornell64 --grid-fit $gf" | tee -a $OUT/sweep_r2_gridfit.log
+  timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --workload cornell64 --grid-fit $gf 2>&1 | tail -1 | cut -c1-200 | tee -a $OUT/sweep_r2_gridfit.log
+done
