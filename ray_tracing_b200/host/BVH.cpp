@@ -6,10 +6,15 @@
 #include <cmath>
 #include <cstdio>
 #include <stdexcept>
+#include <thread>
 
 namespace Seb {
 
+int BVH::BuildThreads = 0;
+
 namespace {
+
+constexpr int kParallelMinTris = 16384;      // below this a subtree is built by one thread
 
 struct Box
 {
@@ -38,6 +43,15 @@ inline RtNode makeNode(const Box& b, int start, int count)
 }
 
 } // namespace
+
+static void mergeStats(BVH::BuildStats& a, const BVH::BuildStats& b)
+{
+    a.TriangleCount += b.TriangleCount; a.TotalNodeCount += b.TotalNodeCount; a.LeafNodeCount += b.LeafNodeCount; a.LeafDepthSum += b.LeafDepthSum;
+    if (b.LeafDepthMax > a.LeafDepthMax) a.LeafDepthMax = b.LeafDepthMax;
+    if (b.LeafDepthMin < a.LeafDepthMin) a.LeafDepthMin = b.LeafDepthMin;
+    if (b.LeafMaxTriCount > a.LeafMaxTriCount) a.LeafMaxTriCount = b.LeafMaxTriCount;
+    if (b.LeafMinTriCount < a.LeafMinTriCount) a.LeafMinTriCount = b.LeafMinTriCount;
+}
 
 void BVH::BuildStats::RecordNode(int depth, bool isLeaf, int triCount)
 {
@@ -75,27 +89,59 @@ BVH::BVH(const Vector3* verts, int vertCount, const int* indices, int indexCount
         if (indices[i] < 0 || indices[i] >= vertCount) throw std::invalid_argument("BVH: vertex index out of range");
 
     const int triCount = indexCount / 3;
-    buildTris.resize(triCount);
-    Box all;
-    for (int i = 0; i < indexCount; i += 3)                       // BVH.cs:44-59
+    int threads = BuildThreads > 0 ? BuildThreads : (int)std::thread::hardware_concurrency();
+    if (threads < 1) threads = 1;
+    if (threads > 128) threads = 128;
+    if (triCount < kParallelMinTris) threads = 1;
+    // run f(t, lo, hi) on `threads` slices of [0, triCount)
+    auto parallelSlices = [&](auto&& f)
     {
-        const Vector3 a = verts[indices[i]], b = verts[indices[i + 1]], c = verts[indices[i + 2]];
-        BuildTri t;
-        t.cx = (a.x + b.x + c.x) / 3; t.cy = (a.y + b.y + c.y) / 3; t.cz = (a.z + b.z + c.z) / 3;
-        t.minX = min3(a.x, b.x, c.x); t.minY = min3(a.y, b.y, c.y); t.minZ = min3(a.z, b.z, c.z);
-        t.maxX = max3(a.x, b.x, c.x); t.maxY = max3(a.y, b.y, c.y); t.maxZ = max3(a.z, b.z, c.z);
-        t.index = i;
-        buildTris[i / 3] = t;
-        all.grow(t);
-    }
+        std::vector<std::thread> pool;
+        for (int t = 1; t < threads; t++) pool.emplace_back([&, t]() { f(t, (int)((long long)triCount * t / threads), (int)((long long)triCount * (t + 1) / threads)); });
+        f(0, 0, (int)((long long)triCount / threads));
+        for (auto& th : pool) th.join();
+    };
+
+    buildTris.resize(triCount);
+    std::vector<Box> sliceBox(threads);
+    parallelSlices([&](int t, int lo, int hi)
+    {
+        for (int k = lo; k < hi; k++)                               // BVH.cs:44-59
+        {
+            const int i = 3 * k;
+            const Vector3 a = verts[indices[i]], b = verts[indices[i + 1]], c = verts[indices[i + 2]];
+            BuildTri tr;
+            tr.cx = (a.x + b.x + c.x) / 3; tr.cy = (a.y + b.y + c.y) / 3; tr.cz = (a.z + b.z + c.z) / 3;
+            tr.minX = min3(a.x, b.x, c.x); tr.minY = min3(a.y, b.y, c.y); tr.minZ = min3(a.z, b.z, c.z);
+            tr.maxX = max3(a.x, b.x, c.x); tr.maxY = max3(a.y, b.y, c.y); tr.maxZ = max3(a.z, b.z, c.z);
+            tr.index = i;
+            buildTris[k] = tr;
+            sliceBox[t].grow(tr);
+        }
+    });
+    Box all;
+    for (const Box& b : sliceBox) for (int a = 0; a < 3; a++) { if (b.lo[a] < all.lo[a]) all.lo[a] = b.lo[a]; if (b.hi[a] > all.hi[a]) all.hi[a] = b.hi[a]; }
 
     Nodes.reserve(256);
     AddNode(makeNode(all, -1, -1));                               // BVH.cs:61
     if (quality == Quality::Disabled) { Nodes[0].startIndex = 0; Nodes[0].triangleCount = triCount; }
-    else Split(0, 0, triCount, 0);
+    else if (threads == 1 || triCount < kParallelMinTris) Split(Nodes, stats, 0, 0, triCount, 0);
+    else
+    {
+        // the same recursion, its independent subtrees built by different threads and concatenated in the reference's order
+        Block blk;
+        RtNode root = BuildBlock(Nodes[0], 0, triCount, 0, blk, threads);
+        if (root.triangleCount <= 0) root.startIndex = 1;                 // B(root) starts right after the root
+        for (RtNode& n : blk.nodes) if (n.triangleCount <= 0) n.startIndex += 1;
+        Nodes[0] = root;
+        Nodes.insert(Nodes.end(), blk.nodes.begin(), blk.nodes.end());
+        mergeStats(stats, blk.stats);
+    }
 
     Triangles.resize(triCount);                                   // BVH.cs:69-80: leaf order
-    for (int i = 0; i < triCount; i++)
+    parallelSlices([&](int, int lo, int hi)
+    {
+    for (int i = lo; i < hi; i++)
     {
         const int base = buildTris[i].index;
         RtTriangle& o = Triangles[i];
@@ -108,6 +154,7 @@ BVH::BVH(const Vector3* verts, int vertCount, const int* indices, int indexCount
         o.normB[0] = n[1]->x; o.normB[1] = n[1]->y; o.normB[2] = n[1]->z;
         o.normC[0] = n[2]->x; o.normC[1] = n[2]->y; o.normC[2] = n[2]->z;
     }
+    });
     std::vector<BuildTri>().swap(buildTris);
     stats.TimeMs = (int)std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
 }
@@ -137,7 +184,11 @@ float BVH::EvaluateSplit(int splitAxis, float splitPos, int start, int count) co
     return costA + costB;
 }
 
-BVH::SplitChoice BVH::ChooseSplit(const RtNode& node, int start, int count) const     // BVH.cs:183-250
+namespace {
+struct CandidateAcc { Box left, right; int numOnLeft = 0, numOnRight = 0; };
+}
+
+BVH::SplitChoice BVH::ChooseSplit(const RtNode& node, int start, int count, int threads) const     // BVH.cs:183-250
 {
     if (count <= 1) return SplitChoice{0, 0.0f, INFINITY};
     const float size[3] = {node.boundsMax[0] - node.boundsMin[0], node.boundsMax[1] - node.boundsMin[1], node.boundsMax[2] - node.boundsMin[2]};
@@ -155,6 +206,7 @@ BVH::SplitChoice BVH::ChooseSplit(const RtNode& node, int start, int count) cons
     if (size[1] > maxAxis) maxAxis = size[1];
     if (size[2] > maxAxis) maxAxis = size[2];
 
+    int candAxis[15]; float candPos[15]; int numCand = 0;
     for (int axis = 0; axis < 3; axis++)
     {
         const float ratio = size[axis] / maxAxis * maxSplitTests;
@@ -165,15 +217,64 @@ BVH::SplitChoice BVH::ChooseSplit(const RtNode& node, int start, int count) cons
         for (int i = 0; i < numSplitTests; i++)
         {
             const float splitT = (i + 1) / (numSplitTests + 1.0f);
-            const float splitPos = node.boundsMin[axis] + size[axis] * splitT;
-            const float cost = EvaluateSplit(axis, splitPos, start, count);
-            if (cost < best.cost) { best.cost = cost; best.pos = splitPos; best.axis = axis; }
+            candAxis[numCand] = axis; candPos[numCand] = node.boundsMin[axis] + size[axis] * splitT; numCand++;
         }
+    }
+    if (threads <= 1 || count < kParallelMinTris)
+    {
+        for (int c = 0; c < numCand; c++)
+        {
+            const float cost = EvaluateSplit(candAxis[c], candPos[c], start, count);
+            if (cost < best.cost) { best.cost = cost; best.pos = candPos[c]; best.axis = candAxis[c]; }
+        }
+        return best;
+    }
+    // large node: every thread takes a slice of the triangles and evaluates all candidates on it in one pass; boxes merge by
+    // min / max and counts by sum, which are exact in any order, so the costs are the serial EvaluateSplit's bit for bit
+    std::vector<std::vector<CandidateAcc>> part(threads, std::vector<CandidateAcc>(numCand));
+    auto slice = [&](int t)
+    {
+        const int lo = start + (int)((long long)count * t / threads), hi = start + (int)((long long)count * (t + 1) / threads);
+        std::vector<CandidateAcc>& acc = part[t];
+        for (int i = lo; i < hi; i++)
+        {
+            const BuildTri& tri = buildTris[i];
+            for (int c = 0; c < numCand; c++)
+            {
+                const float centre = candAxis[c] == 0 ? tri.cx : candAxis[c] == 1 ? tri.cy : tri.cz;
+                if (centre < candPos[c]) { acc[c].left.grow(tri); acc[c].numOnLeft++; }
+                else { acc[c].right.grow(tri); acc[c].numOnRight++; }
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(slice, t);
+    slice(0);
+    for (auto& th : pool) th.join();
+    for (int c = 0; c < numCand; c++)
+    {
+        CandidateAcc total;
+        for (int t = 0; t < threads; t++)
+        {
+            const CandidateAcc& a = part[t][c];
+            for (int k = 0; k < 3; k++)
+            {
+                if (a.left.lo[k] < total.left.lo[k]) total.left.lo[k] = a.left.lo[k];
+                if (a.left.hi[k] > total.left.hi[k]) total.left.hi[k] = a.left.hi[k];
+                if (a.right.lo[k] < total.right.lo[k]) total.right.lo[k] = a.right.lo[k];
+                if (a.right.hi[k] > total.right.hi[k]) total.right.hi[k] = a.right.hi[k];
+            }
+            total.numOnLeft += a.numOnLeft; total.numOnRight += a.numOnRight;
+        }
+        const float costA = NodeCost(total.left.hi[0] - total.left.lo[0], total.left.hi[1] - total.left.lo[1], total.left.hi[2] - total.left.lo[2], total.numOnLeft);
+        const float costB = NodeCost(total.right.hi[0] - total.right.lo[0], total.right.hi[1] - total.right.lo[1], total.right.hi[2] - total.right.lo[2], total.numOnRight);
+        const float cost = costA + costB;
+        if (cost < best.cost) { best.cost = cost; best.pos = candPos[c]; best.axis = candAxis[c]; }
     }
     return best;
 }
 
-void BVH::Split(int parentIndex, int triGlobalStart, int triNum, int depth)           // BVH.cs:89-181
+void BVH::Split(std::vector<RtNode>& Nodes, BuildStats& stats, int parentIndex, int triGlobalStart, int triNum, int depth)           // BVH.cs:89-181
 {
     const int MaxDepth = 32;
     const RtNode parent = Nodes[parentIndex];
@@ -201,12 +302,14 @@ void BVH::Split(int parentIndex, int triGlobalStart, int triNum, int depth)     
             else right.grow(t);
         }
         const int numOnRight = triNum - numOnLeft;
-        const int childIndexLeft = AddNode(makeNode(left, triGlobalStart, 0));
-        const int childIndexRight = AddNode(makeNode(right, triGlobalStart + numOnLeft, 0));
+        Nodes.push_back(makeNode(left, triGlobalStart, 0));
+        const int childIndexLeft = (int)Nodes.size() - 1;
+        Nodes.push_back(makeNode(right, triGlobalStart + numOnLeft, 0));
+        const int childIndexRight = childIndexLeft + 1;
         Nodes[parentIndex].startIndex = childIndexLeft;
         stats.RecordNode(depth, false);
-        Split(childIndexLeft, triGlobalStart, numOnLeft, depth + 1);
-        Split(childIndexRight, triGlobalStart + numOnLeft, numOnRight, depth + 1);
+        Split(Nodes, stats, childIndexLeft, triGlobalStart, numOnLeft, depth + 1);
+        Split(Nodes, stats, childIndexRight, triGlobalStart + numOnLeft, numOnRight, depth + 1);
     }
     else
     {
@@ -214,6 +317,71 @@ void BVH::Split(int parentIndex, int triGlobalStart, int triNum, int depth)     
         Nodes[parentIndex].triangleCount = triNum;
         stats.RecordNode(depth, true, triNum);
     }
+}
+
+// The subtree below `node` (its triangles are buildTris[triGlobalStart .. +triNum)), built with up to `threads` threads.
+// Takes exactly the decisions Split() takes — same ChooseSplit, same in-place partition — and returns the node with its leaf
+// range or, for an inner node, startIndex = 0 (block-relative); blk receives B(node).
+RtNode BVH::BuildBlock(RtNode node, int triGlobalStart, int triNum, int depth, Block& blk, int threads)
+{
+    if (threads <= 1 || triNum < kParallelMinTris)
+    {
+        std::vector<RtNode> local;
+        local.reserve((size_t)triNum / 2 + 16);
+        local.push_back(node);
+        Split(local, blk.stats, 0, triGlobalStart, triNum, depth);
+        node = local[0];
+        blk.nodes.assign(local.begin() + 1, local.end());
+        for (RtNode& n : blk.nodes) if (n.triangleCount <= 0) n.startIndex -= 1;      // local index -> block-relative
+        if (node.triangleCount <= 0) node.startIndex = 0;
+        return node;
+    }
+    const int MaxDepth = 32;
+    const float parentCost = NodeCost(node.boundsMax[0] - node.boundsMin[0], node.boundsMax[1] - node.boundsMin[1], node.boundsMax[2] - node.boundsMin[2], triNum);
+    const SplitChoice split = ChooseSplit(node, triGlobalStart, triNum, threads);
+    if (!(split.cost < parentCost && depth < MaxDepth))
+    {
+        node.startIndex = triGlobalStart; node.triangleCount = triNum;
+        blk.stats.RecordNode(depth, true, triNum);
+        return node;
+    }
+    Box left, right;
+    int numOnLeft = 0;
+    for (int i = triGlobalStart; i < triGlobalStart + triNum; i++)          // the reference's partition, sequential: its order is part of the result
+    {
+        const BuildTri t = buildTris[i];
+        const float c = split.axis == 0 ? t.cx : split.axis == 1 ? t.cy : t.cz;
+        if (c < split.pos)
+        {
+            left.grow(t);
+            const BuildTri other = buildTris[triGlobalStart + numOnLeft];
+            buildTris[triGlobalStart + numOnLeft] = t;
+            buildTris[i] = other;
+            numOnLeft++;
+        }
+        else right.grow(t);
+    }
+    const int numOnRight = triNum - numOnLeft;
+    RtNode childL = makeNode(left, triGlobalStart, 0), childR = makeNode(right, triGlobalStart + numOnLeft, 0);
+    blk.stats.RecordNode(depth, false);
+    int threadsL = (int)((long long)threads * numOnLeft / triNum);
+    if (threadsL < 1) threadsL = 1;
+    if (threadsL > threads - 1) threadsL = threads - 1;
+    Block bl, br;
+    std::thread worker([&]() { childL = BuildBlock(childL, triGlobalStart, numOnLeft, depth + 1, bl, threadsL); });
+    childR = BuildBlock(childR, triGlobalStart + numOnLeft, numOnRight, depth + 1, br, threads - threadsL);
+    worker.join();
+    // B(node) = [L, R] + B(L) + B(R)
+    const int offL = 2, offR = 2 + (int)bl.nodes.size();
+    if (childL.triangleCount <= 0) childL.startIndex = offL;
+    if (childR.triangleCount <= 0) childR.startIndex = offR;
+    blk.nodes.reserve(2 + bl.nodes.size() + br.nodes.size());
+    blk.nodes.push_back(childL); blk.nodes.push_back(childR);
+    for (RtNode& n : bl.nodes) { if (n.triangleCount <= 0) n.startIndex += offL; blk.nodes.push_back(n); }
+    for (RtNode& n : br.nodes) { if (n.triangleCount <= 0) n.startIndex += offR; blk.nodes.push_back(n); }
+    mergeStats(blk.stats, bl.stats); mergeStats(blk.stats, br.stats);
+    node.startIndex = 0;
+    return node;
 }
 
 } // namespace Seb

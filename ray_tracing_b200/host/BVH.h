@@ -43,6 +43,10 @@ public:
     // verts / normals: per-vertex arrays; indices: 3 per triangle (Unity Mesh.vertices / .triangles / .normals)
     BVH(const Vector3* verts, int vertCount, const int* indices, int indexCount, const Vector3* normals, Quality quality = Quality::High);
 
+    // Host threads a build may use (0 = all hardware threads, 1 = the reference's single-threaded recursion).  The result does not
+    // depend on it: the same nodes in the same order, the same triangle order, byte for byte (tests/test_host.py).
+    static int BuildThreads;
+
 private:
     struct BuildTri { float cx, cy, cz, minX, minY, minZ, maxX, maxY, maxZ; int index; };   // BVH.cs:459-496
     struct SplitChoice { int axis; float pos; float cost; };
@@ -50,9 +54,14 @@ private:
     std::vector<BuildTri> buildTris;
     Quality quality;
 
+    // B(n) of a node n: everything Split(n) appends to Nodes — [left child, right child] + B(left) + B(right) — with child
+    // indices relative to the first entry of the block, so that independently built blocks concatenate by adding offsets
+    struct Block { std::vector<RtNode> nodes; BuildStats stats; };
+
     int  AddNode(const RtNode& n);
-    void Split(int parentIndex, int triGlobalStart, int triNum, int depth);
-    SplitChoice ChooseSplit(const RtNode& node, int start, int count) const;
+    void Split(std::vector<RtNode>& nodes, BuildStats& st, int parentIndex, int triGlobalStart, int triNum, int depth);
+    RtNode BuildBlock(RtNode node, int triGlobalStart, int triNum, int depth, Block& blk, int threads);
+    SplitChoice ChooseSplit(const RtNode& node, int start, int count, int threads = 1) const;
     float EvaluateSplit(int splitAxis, float splitPos, int start, int count) const;
     static float NodeCost(float x, float y, float z, int numTriangles);
 };

@@ -51,6 +51,10 @@ int rthBuildBVH(const float* verts, int vertCount, const int* indices, int index
     catch (const std::exception& e) { g_err = e.what(); return RT_E_INVALID; }
 }
 
+/* Host threads a BVH build may use: 0 = all hardware threads (default), 1 = single-threaded like the reference.  The built
+ * buffers do not depend on it.  Returns the previous value. */
+int rthSetBuildThreads(int threads) { const int old = BVH::BuildThreads; BVH::BuildThreads = threads < 0 ? 0 : threads; return old; }
+
 const char* rthLastError(void) { return g_err.c_str(); }
 
 /* ---- RayComputeManager ------------------------------------------------------------------------------------------------------ */

@@ -85,6 +85,11 @@ def build_bvh(vertices: np.ndarray, indices: np.ndarray, normals: np.ndarray, qu
     return tris[:ntri].copy(), nodes[:rc].copy(), dict(zip(STAT_NAMES, (int(s) for s in stats)))
 
 
+def set_build_threads(threads: int) -> int:
+    """Host threads a BVH build may use (0 = all, 1 = single-threaded like the reference); the result does not depend on it."""
+    return int(host_lib().rthSetBuildThreads(int(threads)))
+
+
 def load_obj(path: str, unity_handedness: bool = True):
     """Wavefront OBJ -> (vertices (n,3) f32, indices (3t,) i32, normals (n,3) f32) as Unity's importer hands them to the
     reference's manager (host/ObjLoader.cpp)."""

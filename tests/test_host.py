@@ -74,6 +74,25 @@ def test_bvh_is_deterministic_and_splits_reduce_cost():
     assert a[2]["LeafMaxTriCount"] < 64 and a[2]["LeafNodeCount"] > m.triangle_count // 16
 
 
+def test_bvh_build_does_not_depend_on_the_thread_count():
+    """The multi-threaded build (independent subtrees on different threads, slices of a large node evaluated in parallel) returns the
+    single-threaded recursion's buffers byte for byte: same node order, same bounds, same triangle order, same statistics."""
+    knot = scenes.knot_mesh(nu=400, nv=24)                                          # 19,200 triangles: above the parallel threshold
+    soup = max(scenes.random_soup(16, 16, 2, 1, triangles=60000, spheres=1).meshes, key=lambda m: m.triangle_count)
+    try:
+        for mesh in (knot, soup):
+            for q in ("High", "Low", "Disabled"):
+                rt.set_build_threads(1)
+                t1, n1, s1 = rt.build_bvh(mesh.vertices, mesh.indices, mesh.normals, q)
+                for threads in (2, 5, 16):
+                    rt.set_build_threads(threads)
+                    t, n, st = rt.build_bvh(mesh.vertices, mesh.indices, mesh.normals, q)
+                    assert np.array_equal(n.view(np.uint8), n1.view(np.uint8)) and np.array_equal(t.view(np.uint8), t1.view(np.uint8)), (q, threads)
+                    assert {k: v for k, v in st.items() if k != "TimeMs"} == {k: v for k, v in s1.items() if k != "TimeMs"}
+    finally:
+        rt.set_build_threads(0)
+
+
 def test_bvh_vs_brute_force_image(oracle_path):
     # same rays, tree vs one big leaf: identical closest hits except exact-distance ties between triangles sharing an edge
     sc = scenes.knot_room(96, 54, max_bounces=3, rays_per_pixel=1, nu=90, nv=8)
