@@ -133,6 +133,16 @@ int rtSetPeers(RtContext* ctx, int nPeers, const void* handles, size_t bytes);
  * name ∈ {"FrameRender","AccumulatedRender","TileSend","TileRecv"}. */
 int rtGetDevicePointer(RtContext* ctx, const char* name, void** devPtr, size_t* bytes);
 
+/* Replaces `new BVH(mesh.vertices, mesh.triangles, mesh.normals, quality)` (BVH.cs:26; called once per shared mesh from
+ * RayComputeManager.CreateAllMeshData, RayComputeManager.cs:209-232) by a build on the GPU that takes the reference's decisions
+ * node for node — the same candidate planes, costs, split test and partition order — and therefore returns the Nodes and
+ * Triangles buffers the reference's builder returns (mesh-relative indices, children adjacent, left subtree first, triangles
+ * in leaf order).  verts / normals: vertCount x 3 floats; indices: 3 per triangle; quality: 0 Low, 1 High, 2 Disabled
+ * (BVH.cs:11-16).  outTris: indexCount / 3 entries; outNodes: nodeCapacity >= 2 * triangles + 1 entries; *outNodeCount
+ * receives the number of nodes written. */
+int rtBuildBVH(RtContext* ctx, const float* verts, int vertCount, const int* indices, int indexCount, const float* normals, int quality,
+               RtTriangle* outTris, RtNode* outNodes, int nodeCapacity, int* outNodeCount);
+
 /* Tuning / instrumentation switches.  name ∈
  *   "kernel"      0 = reference-shaped per-pixel megakernel, 1 = persistent threads (one path per lane),
  *                 2 = persistent-thread wavefront with per-warp path pools, sorting and ray compaction,

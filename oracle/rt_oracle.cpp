@@ -907,3 +907,169 @@ int orRaySphere(const float pos[3], const float dir[3], const float centre[3], f
 }
 
 } // extern "C"
+
+// ---- BVH builder: CPU restatement of Assets/Scripts/Types/BVH.cs:26-318 (BC below), the oracle of rtBuildBVH -------------------
+// Plain single-threaded recursion in the reference's own shape: one flat node list, in-place swap partition.  Test
+// infrastructure like the rest of this file.
+namespace BvhCs {
+
+struct BVHTriangle { float CentreX, CentreY, CentreZ, MinX, MinY, MinZ, MaxX, MaxY, MaxZ; int Index; };      // BC:459-496
+
+struct Builder
+{
+    int quality = 1;                                              // BC:11-16: 0 Low, 1 High, 2 Disabled
+    std::vector<BVHTriangle> buildTriangles;
+    std::vector<RtNode> nodes;
+
+    static RtNode Node(float minX, float minY, float minZ, float maxX, float maxY, float maxZ, int start, int count)   // BC:432-457
+    {
+        RtNode n; n.boundsMin[0] = minX; n.boundsMin[1] = minY; n.boundsMin[2] = minZ; n.boundsMax[0] = maxX; n.boundsMax[1] = maxY; n.boundsMax[2] = maxZ;
+        n.startIndex = start; n.triangleCount = count; return n;
+    }
+    static float NodeCost(float sizeX, float sizeY, float sizeZ, int numTriangles)     // BC:313-318
+    {
+        if (numTriangles == 0) return 0;
+        float area = sizeX * sizeY + sizeX * sizeZ + sizeY * sizeZ;
+        return area * numTriangles;
+    }
+    float EvaluateSplit(int splitAxis, float splitPos, int start, int count) const    // BC:253-311
+    {
+        float lo[2][3], hi[2][3]; int num[2] = {0, 0};
+        for (int s = 0; s < 2; s++) for (int a = 0; a < 3; a++) { lo[s][a] = 3.402823466e+38f; hi[s][a] = -3.402823466e+38f; }
+        for (int i = start; i < start + count; i++)
+        {
+            const BVHTriangle& tri = buildTriangles[i];
+            const float c = splitAxis == 0 ? tri.CentreX : splitAxis == 1 ? tri.CentreY : tri.CentreZ;
+            const int s = c < splitPos ? 0 : 1;
+            if (tri.MinX < lo[s][0]) lo[s][0] = tri.MinX;
+            if (tri.MinY < lo[s][1]) lo[s][1] = tri.MinY;
+            if (tri.MinZ < lo[s][2]) lo[s][2] = tri.MinZ;
+            if (tri.MaxX > hi[s][0]) hi[s][0] = tri.MaxX;
+            if (tri.MaxY > hi[s][1]) hi[s][1] = tri.MaxY;
+            if (tri.MaxZ > hi[s][2]) hi[s][2] = tri.MaxZ;
+            num[s]++;
+        }
+        const float costA = NodeCost(hi[0][0] - lo[0][0], hi[0][1] - lo[0][1], hi[0][2] - lo[0][2], num[0]);
+        const float costB = NodeCost(hi[1][0] - lo[1][0], hi[1][1] - lo[1][1], hi[1][2] - lo[1][2], num[1]);
+        return costA + costB;
+    }
+    void ChooseSplit(const RtNode& node, int start, int count, int& axisOut, float& posOut, float& costOut) const     // BC:183-250
+    {
+        axisOut = 0; posOut = 0; costOut = INFINITY;
+        if (count <= 1) return;
+        const float size[3] = {node.boundsMax[0] - node.boundsMin[0], node.boundsMax[1] - node.boundsMin[1], node.boundsMax[2] - node.boundsMin[2]};
+        if (quality == 0)
+        {
+            const int largest = size[0] > size[1] && size[0] > size[2] ? 0 : size[1] > size[2] ? 1 : 2;
+            posOut = node.boundsMin[largest] + size[largest] * 0.5f; axisOut = largest;
+            costOut = EvaluateSplit(largest, posOut, start, count);
+            return;
+        }
+        const int maxSplitTests = count < 10 ? 3 : 5;
+        float maxAxis = size[0] > size[1] ? size[0] : size[1];                 // Mathf.Max of three
+        if (size[2] > maxAxis) maxAxis = size[2];
+        float bestCost = 3.402823466e+38f;
+        for (int axis = 0; axis < 3; axis++)
+        {
+            const float scaled = size[axis] / maxAxis * maxSplitTests;
+            int numSplitTests = scaled != scaled ? -2147483647 - 1 : (int)ceil((double)scaled);     // Mathf.CeilToInt; (int)NaN is int.MinValue in C#
+            if (numSplitTests < 1) numSplitTests = 1;
+            if (numSplitTests > maxSplitTests) numSplitTests = maxSplitTests;
+            for (int i = 0; i < numSplitTests; i++)
+            {
+                const float splitT = (i + 1) / (numSplitTests + 1.0f);
+                const float splitPos = node.boundsMin[axis] + size[axis] * splitT;
+                const float cost = EvaluateSplit(axis, splitPos, start, count);
+                if (cost < bestCost) { bestCost = cost; posOut = splitPos; axisOut = axis; }
+            }
+        }
+        costOut = bestCost;
+    }
+    void Split(int parentIndex, int triGlobalStart, int triNum, int depth)     // BC:89-181
+    {
+        const RtNode parent = nodes[parentIndex];
+        const float parentCost = NodeCost(parent.boundsMax[0] - parent.boundsMin[0], parent.boundsMax[1] - parent.boundsMin[1], parent.boundsMax[2] - parent.boundsMin[2], triNum);
+        int splitAxis; float splitPos, cost;
+        ChooseSplit(parent, triGlobalStart, triNum, splitAxis, splitPos, cost);
+        if (cost < parentCost && depth < 32)
+        {
+            float lo[2][3], hi[2][3];
+            for (int s = 0; s < 2; s++) for (int a = 0; a < 3; a++) { lo[s][a] = 3.402823466e+38f; hi[s][a] = -3.402823466e+38f; }
+            int numOnLeft = 0;
+            for (int i = triGlobalStart; i < triGlobalStart + triNum; i++)
+            {
+                const BVHTriangle tri = buildTriangles[i];
+                const float c = splitAxis == 0 ? tri.CentreX : splitAxis == 1 ? tri.CentreY : tri.CentreZ;
+                const int s = c < splitPos ? 0 : 1;
+                if (tri.MinX < lo[s][0]) lo[s][0] = tri.MinX;
+                if (tri.MinY < lo[s][1]) lo[s][1] = tri.MinY;
+                if (tri.MinZ < lo[s][2]) lo[s][2] = tri.MinZ;
+                if (tri.MaxX > hi[s][0]) hi[s][0] = tri.MaxX;
+                if (tri.MaxY > hi[s][1]) hi[s][1] = tri.MaxY;
+                if (tri.MaxZ > hi[s][2]) hi[s][2] = tri.MaxZ;
+                if (s == 0)
+                {
+                    const BVHTriangle swap = buildTriangles[triGlobalStart + numOnLeft];
+                    buildTriangles[triGlobalStart + numOnLeft] = tri;
+                    buildTriangles[i] = swap;
+                    numOnLeft++;
+                }
+            }
+            const int numOnRight = triNum - numOnLeft;
+            nodes.push_back(Node(lo[0][0], lo[0][1], lo[0][2], hi[0][0], hi[0][1], hi[0][2], triGlobalStart, 0));
+            const int childIndexLeft = (int)nodes.size() - 1;
+            nodes.push_back(Node(lo[1][0], lo[1][1], lo[1][2], hi[1][0], hi[1][1], hi[1][2], triGlobalStart + numOnLeft, 0));
+            nodes[parentIndex].startIndex = childIndexLeft;
+            Split(childIndexLeft, triGlobalStart, numOnLeft, depth + 1);
+            Split(childIndexLeft + 1, triGlobalStart + numOnLeft, numOnRight, depth + 1);
+        }
+        else { nodes[parentIndex].startIndex = triGlobalStart; nodes[parentIndex].triangleCount = triNum; }
+    }
+};
+
+} // namespace BvhCs
+
+extern "C" int rtBuildBVH(RtContext* ctx, const float* verts, int vertCount, const int* indices, int indexCount, const float* normals, int quality,
+                          RtTriangle* outTris, RtNode* outNodes, int nodeCapacity, int* outNodeCount)
+{
+    if (!ctx || !verts || !indices || !normals || !outTris || !outNodes || !outNodeCount || quality < 0 || quality > 2 || indexCount <= 0 || indexCount % 3 != 0 || vertCount <= 0)
+        return RT_E_INVALID;
+    for (int i = 0; i < indexCount; i++) if (indices[i] < 0 || indices[i] >= vertCount) return RT_E_INVALID;
+    BvhCs::Builder b; b.quality = quality;
+    const int triCount = indexCount / 3;
+    if (nodeCapacity < 2 * triCount + 1) return RT_E_INVALID;
+    b.buildTriangles.resize(triCount);
+    float lo[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, hi[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+    for (int i = 0; i < indexCount; i += 3)                                   // BC:44-59
+    {
+        const float* a = verts + 3 * (size_t)indices[i]; const float* bb = verts + 3 * (size_t)indices[i + 1]; const float* c = verts + 3 * (size_t)indices[i + 2];
+        BvhCs::BVHTriangle t;
+        t.CentreX = (a[0] + bb[0] + c[0]) / 3; t.CentreY = (a[1] + bb[1] + c[1]) / 3; t.CentreZ = (a[2] + bb[2] + c[2]) / 3;
+        float mn[3], mx[3];
+        for (int d = 0; d < 3; d++)
+        {
+            mn[d] = a[d] < bb[d] ? (a[d] < c[d] ? a[d] : c[d]) : (bb[d] < c[d] ? bb[d] : c[d]);
+            mx[d] = a[d] > bb[d] ? (a[d] > c[d] ? a[d] : c[d]) : (bb[d] > c[d] ? bb[d] : c[d]);
+            if (mn[d] < lo[d]) lo[d] = mn[d];
+            if (mx[d] > hi[d]) hi[d] = mx[d];
+        }
+        t.MinX = mn[0]; t.MinY = mn[1]; t.MinZ = mn[2]; t.MaxX = mx[0]; t.MaxY = mx[1]; t.MaxZ = mx[2]; t.Index = i;
+        b.buildTriangles[i / 3] = t;
+    }
+    b.nodes.push_back(BvhCs::Builder::Node(lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], -1, -1));     // BC:61
+    if (quality == 2) { b.nodes[0].startIndex = 0; b.nodes[0].triangleCount = triCount; }
+    else b.Split(0, 0, triCount, 0);
+    for (int i = 0; i < triCount; i++)                                           // BC:69-80
+    {
+        const int base = b.buildTriangles[i].Index;
+        RtTriangle& o = outTris[i];
+        for (int d = 0; d < 3; d++)
+        {
+            o.posA[d] = verts[3 * (size_t)indices[base] + d]; o.posB[d] = verts[3 * (size_t)indices[base + 1] + d]; o.posC[d] = verts[3 * (size_t)indices[base + 2] + d];
+            o.normA[d] = normals[3 * (size_t)indices[base] + d]; o.normB[d] = normals[3 * (size_t)indices[base + 1] + d]; o.normC[d] = normals[3 * (size_t)indices[base + 2] + d];
+        }
+    }
+    memcpy(outNodes, b.nodes.data(), b.nodes.size() * sizeof(RtNode));
+    *outNodeCount = (int)b.nodes.size();
+    return RT_OK;
+}

@@ -85,10 +85,11 @@ class RtLib:
             "rtSetPeers": ([vp, ci, vp, C.c_size_t], ci),
             "rtGetStats": ([vp, C.POINTER(RtStats)], ci),
             "rtResetStats": ([vp], ci),
+            "rtBuildBVH": ([vp, vp, ci, vp, ci, vp, ci, vp, vp, ci, C.POINTER(ci)], ci),
         }
         for name, (args, res) in sig.items():
             if not hasattr(L, name):
-                if name in ("rtGetIpcHandles", "rtSetPeers"):      # absent from older experimental builds used in A/B runs
+                if name in ("rtGetIpcHandles", "rtSetPeers", "rtBuildBVH"):      # absent from older experimental builds used in A/B runs
                     continue
                 raise AttributeError(f"{self.path} does not export {name}")
             fn = getattr(L, name)
@@ -220,6 +221,19 @@ class RtContext:
         """handles: one 144-byte blob (ipc_handles()) per peer rank."""
         blob = b"".join(handles)
         self._ck(self._L.rtSetPeers(self._h, len(handles), blob if handles else None, len(blob)))
+
+    def build_bvh(self, vertices, indices, normals, quality: int = 1):
+        """rtBuildBVH: BVH(verts, indices, normals, quality) of the reference (BVH.cs:26), built by the backend -> (triangles, nodes)."""
+        v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+        n = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+        idx = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1)
+        ntri = idx.size // 3
+        tris = np.zeros(max(ntri, 1), dtype=TRIANGLE_DTYPE)
+        nodes = np.zeros(2 * max(ntri, 1) + 1, dtype=NODE_DTYPE)
+        count = C.c_int()
+        self._ck(self._L.rtBuildBVH(self._h, v.ctypes.data, v.shape[0], idx.ctypes.data, idx.size, n.ctypes.data, int(quality),
+                                    tris.ctypes.data, nodes.ctypes.data, nodes.shape[0], C.byref(count)))
+        return tris[:ntri].copy(), nodes[:count.value].copy()
 
     def set_option(self, name: str, v: int):
         self._ck(self._L.rtSetOption(self._h, name.encode(), int(v)))

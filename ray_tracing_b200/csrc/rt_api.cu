@@ -10,6 +10,7 @@
 #include "rt_kernel_wave.cuh"
 #include "rt_kernel_pool.cuh"
 #include "rt_repack.cuh"
+#include "rt_bvh_build.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -629,6 +630,39 @@ int rtSetPeers(RtContext* c, int nPeers, const void* handles, size_t bytes)
         c->peerAccum[k] = (float4*)((char*)base[1] + h[2 * k + 1].offset);
     }
     c->nPeers = nPeers;
+    return RT_OK;
+}
+
+// BVH(verts, indices, normals, quality) of the reference (BVH.cs:26, called per mesh from RayComputeManager.cs:209-232), built on the GPU:
+// the same Nodes / Triangles the host builder returns (rt_bvh_build.cuh).  Host arrays in, host arrays out.
+int rtBuildBVH(RtContext* c, const float* verts, int vertCount, const int* indices, int indexCount, const float* normals, int quality,
+               RtTriangle* outTris, RtNode* outNodes, int nodeCapacity, int* outNodeCount)
+{
+    if (!c || !verts || !indices || !normals || !outTris || !outNodes || !outNodeCount) return fail(c, RT_E_INVALID, "rtBuildBVH: bad argument");
+    if (quality < 0 || quality > 2) return fail(c, RT_E_INVALID, "rtBuildBVH: quality must be 0 (Low), 1 (High) or 2 (Disabled)");
+    if (indexCount <= 0 || indexCount % 3 != 0) return fail(c, RT_E_INVALID, "rtBuildBVH: index count must be a positive multiple of 3");
+    if (vertCount <= 0) return fail(c, RT_E_INVALID, "rtBuildBVH: no vertices");
+    for (int i = 0; i < indexCount; i++)
+        if (indices[i] < 0 || indices[i] >= vertCount) return fail(c, RT_E_INVALID, "rtBuildBVH: vertex index out of range");
+    const int triCount = indexCount / 3;
+    if (nodeCapacity < 2 * triCount + 1) return fail(c, RT_E_INVALID, "rtBuildBVH: outNodes must hold 2 * triangles + 1 entries");
+    CK(cudaSetDevice(c->device));
+    DevBuf<float> dV, dN; DevBuf<int> dI; DevBuf<RtNode> dNodes; DevBuf<RtTriangle> dTris;
+    auto release = [&]() { dV.release(); dN.release(); dI.release(); dNodes.release(); dTris.release(); };
+    cudaError_t e;
+    if ((e = dV.ensure((size_t)vertCount * 3)) != cudaSuccess || (e = dN.ensure((size_t)vertCount * 3)) != cudaSuccess || (e = dI.ensure((size_t)indexCount)) != cudaSuccess ||
+        (e = dNodes.ensure((size_t)2 * triCount + 1)) != cudaSuccess || (e = dTris.ensure((size_t)triCount)) != cudaSuccess) { release(); return failCuda(c, e, "rtBuildBVH: cudaMalloc"); }
+    if ((e = cudaMemcpyAsync(dV.p, verts, (size_t)vertCount * 12, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(dN.p, normals, (size_t)vertCount * 12, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(dI.p, indices, (size_t)indexCount * 4, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) { release(); return failCuda(c, e, "rtBuildBVH: upload"); }
+    BvhBuildResult res; std::string msg;
+    e = bvh_build_device(dV.p, dN.p, dI.p, triCount, quality, dNodes.p, dTris.p, c->stream, res, msg);
+    if (e != cudaSuccess) { release(); return msg.empty() ? failCuda(c, e, "rtBuildBVH") : fail(c, RT_E_STATE, "rtBuildBVH: " + msg); }
+    if ((e = cudaMemcpyAsync(outNodes, dNodes.p, (size_t)res.nodeCount * sizeof(RtNode), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(outTris, dTris.p, (size_t)triCount * sizeof(RtTriangle), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { release(); return failCuda(c, e, "rtBuildBVH: download"); }
+    release();
+    *outNodeCount = res.nodeCount;
     return RT_OK;
 }
 

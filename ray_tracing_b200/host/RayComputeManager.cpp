@@ -7,6 +7,7 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <random>
+#include <stdexcept>
 
 namespace Seb {
 
@@ -21,6 +22,7 @@ std::string RtApi::Load(const char* path)
     RESOLVE(SetBool, "rtSetBool") RESOLVE(Resize, "rtResize") RESOLVE(Dispatch, "rtDispatch")
     RESOLVE(Readback, "rtReadback") RESOLVE(Synchronize, "rtSynchronize")
 #undef RESOLVE
+    BuildBVH = reinterpret_cast<decltype(BuildBVH)>(dlsym(dl, "rtBuildBVH"));
     return "";
 }
 
@@ -175,11 +177,29 @@ RayComputeManager::MeshDataLists RayComputeManager::CreateAllMeshData()
         if (!meshLookup.count(mesh))
         {
             meshLookup[mesh] = std::make_pair((int)allData.nodes.size(), (int)allData.triangles.size());
+            if (buildBVHOnDevice && api.BuildBVH && ctx)
+            {
+                // the same Nodes / Triangles, built by the backend (rtBuildBVH); statistics are the host builder's business
+                const int triCount = (int)mesh->triangles.size() / 3;
+                std::vector<RtTriangle> t((size_t)(triCount > 0 ? triCount : 1));
+                std::vector<RtNode> n((size_t)2 * (triCount > 0 ? triCount : 1) + 1);
+                int nodeCount = 0;
+                const int rc = api.BuildBVH(ctx, &mesh->vertices[0].x, (int)mesh->vertices.size(), mesh->triangles.data(), (int)mesh->triangles.size(),
+                                            &mesh->normals[0].x, (int)bvhQuality, t.data(), n.data(), (int)n.size(), &nodeCount);
+                if (rc != RT_OK) throw std::runtime_error(std::string("rtBuildBVH: ") + api.LastError(ctx));
+                BVH::BuildStats st; st.quality = bvhQuality; st.TriangleCount = triCount; st.TotalNodeCount = nodeCount;
+                bvhStats.push_back(st);
+                allData.triangles.insert(allData.triangles.end(), t.begin(), t.begin() + triCount);
+                allData.nodes.insert(allData.nodes.end(), n.begin(), n.begin() + nodeCount);
+            }
+            else
+            {
             BVH bvh(mesh->vertices.data(), (int)mesh->vertices.size(), mesh->triangles.data(), (int)mesh->triangles.size(),
                     mesh->normals.data(), bvhQuality);
             bvhStats.push_back(bvh.stats);
             allData.triangles.insert(allData.triangles.end(), bvh.Triangles.begin(), bvh.Triangles.end());
             allData.nodes.insert(allData.nodes.end(), bvh.Nodes.begin(), bvh.Nodes.end());
+            }
         }
         RtModel info;
         memset(&info, 0, sizeof(info));

@@ -52,6 +52,7 @@ struct RtApi
     decltype(&rtSetFloat) SetFloat = nullptr; decltype(&rtSetVector) SetVector = nullptr; decltype(&rtSetMatrix) SetMatrix = nullptr;
     decltype(&rtSetBool) SetBool = nullptr; decltype(&rtResize) Resize = nullptr; decltype(&rtDispatch) Dispatch = nullptr;
     decltype(&rtReadback) Readback = nullptr; decltype(&rtSynchronize) Synchronize = nullptr;
+    decltype(&rtBuildBVH) BuildBVH = nullptr;   // optional: absent from older builds of the library
     std::string Load(const char* path);        // returns "" on success, else the error text
     void Unload();
 };
@@ -63,6 +64,7 @@ public:
     bool rayTracingEnabled = true;
     bool accumulate = true;
     BVH::Quality bvhQuality = BVH::Quality::High;
+    bool buildBVHOnDevice = false;              // not in the reference: build each mesh's BVH with rtBuildBVH (same buffers) instead of on the host
     int maxBounceCount = 4;
     int numRaysPerPixel = 1;
     float defocusStrength = 0;

@@ -93,6 +93,7 @@ int rcmSetInt(void* hv, const char* field, int v)
     else if (f == "numAccumulatedFrames") m.numAccumulatedFrames = v;
     else if (f == "bvhQuality") { if (v < 0 || v > 2) return RT_E_INVALID; m.bvhQuality = (BVH::Quality)v; }
     else if (f == "rayTracingEnabled") m.rayTracingEnabled = v != 0;
+    else if (f == "buildBVHOnDevice") m.buildBVHOnDevice = v != 0;
     else if (f == "accumulate") m.accumulate = v != 0;
     else if (f == "useSky") m.useSky = v != 0;
     else if (f == "randomizeSeedOnEnable") m.randomizeSeedOnEnable = v != 0;
@@ -111,6 +112,7 @@ int rcmGetInt(void* hv, const char* field, int* out)
     else if (f == "numAccumulatedFrames") *out = m.numAccumulatedFrames;
     else if (f == "bvhQuality") *out = (int)m.bvhQuality;
     else if (f == "accumulate") *out = m.accumulate;
+    else if (f == "buildBVHOnDevice") *out = m.buildBVHOnDevice;
     else if (f == "useSky") *out = m.useSky;
     else { m.lastError = "unknown int field " + f; return RT_E_UNKNOWN_NAME; }
     return RT_OK;

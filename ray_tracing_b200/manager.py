@@ -113,7 +113,7 @@ class RayComputeManager:
     """Mirror of the reference's RayComputeManager (public fields + ResetAccumulatedRender / RenderFrame)."""
 
     _INT_FIELDS = ("maxBounceCount", "numRaysPerPixel", "renderSeed", "numAccumulatedFrames", "bvhQuality",
-                   "rayTracingEnabled", "accumulate", "useSky", "randomizeSeedOnEnable")
+                   "rayTracingEnabled", "accumulate", "useSky", "randomizeSeedOnEnable", "buildBVHOnDevice")
     _FLOAT_FIELDS = ("defocusStrength", "divergeStrength", "focusDistance", "sunFocus", "sunIntensity")
 
     def __init__(self, backend_library: Optional[str] = None, device: int = 0):

@@ -41,6 +41,7 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #define __align__(n) __attribute__((aligned(n)))
 #define __grid_constant__
+#define __shared__ static thread_local      /* a static __shared__ array: one copy per worker thread = per resident CTA */
 #define __launch_bounds__(...)
 
 // ---- vector types -----------------------------------------------------------------------------------------------------------
@@ -92,10 +93,16 @@ static inline void __syncwarp(unsigned int mask = 0xffffffffu) { simt::collectiv
 static inline unsigned int __shfl_sync(unsigned int mask, unsigned int v, int srcLane) { return (unsigned int)simt::collective(simt::OP_SHFL, mask, v, srcLane); }
 static inline int __shfl_sync(unsigned int mask, int v, int srcLane) { return (int)(unsigned int)simt::collective(simt::OP_SHFL, mask, (unsigned int)v, srcLane); }
 static inline float __shfl_sync(unsigned int mask, float v, int srcLane) { return __uint_as_float((unsigned int)simt::collective(simt::OP_SHFL, mask, __float_as_uint(v), srcLane)); }
+static inline unsigned int __shfl_down_sync(unsigned int mask, unsigned int v, unsigned int delta) { const unsigned int l = simt::lane_id(); return (unsigned int)simt::collective(simt::OP_SHFL, mask, v, l + delta < 32u ? (int)(l + delta) : (int)l); }
+static inline int __shfl_down_sync(unsigned int mask, int v, unsigned int delta) { return (int)__shfl_down_sync(mask, (unsigned int)v, delta); }
+static inline unsigned int __shfl_up_sync(unsigned int mask, unsigned int v, unsigned int delta) { const unsigned int l = simt::lane_id(); return (unsigned int)simt::collective(simt::OP_SHFL, mask, v, l >= delta ? (int)(l - delta) : (int)l); }
+static inline int __shfl_up_sync(unsigned int mask, int v, unsigned int delta) { return (int)__shfl_up_sync(mask, (unsigned int)v, delta); }
 static inline void __syncthreads() { simt::syncthreads(); }
 
 static inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned int atomicMin(unsigned int* p, unsigned int v) { unsigned int old = __atomic_load_n(p, __ATOMIC_RELAXED); while (v < old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { } return old; }
+static inline unsigned int atomicMax(unsigned int* p, unsigned int v) { unsigned int old = __atomic_load_n(p, __ATOMIC_RELAXED); while (v > old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { } return old; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 
 // ---- runtime API (the subset rt_api.cu / rt_repack.cuh call) ---------------------------------------------------------------------

@@ -81,6 +81,8 @@ inline void yield()
     simt_switch(&c->fibers[c->cur].sp, c->schedSp);
 }
 
+inline unsigned int lane_id() { return tl_cta->cur & 31u; }
+
 inline unsigned int activemask()
 {
     // any subset of the converged lanes that contains the caller is a legal answer; the smallest one needs no rendezvous

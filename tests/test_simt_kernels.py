@@ -94,6 +94,47 @@ def test_simt_tail_lanes_and_ray_sorting_are_schedule_only(simt_lib):
                 assert sg[k] == so[k]
 
 
+def _bvh_meshes():
+    rng = np.random.RandomState(5)
+    knot = scenes.knot_mesh(nu=160, nv=10)
+    shuffled = scenes.MeshDesc(knot.vertices, knot.indices.reshape(-1, 3)[rng.permutation(knot.triangle_count)].reshape(-1), knot.normals)
+    soup = max(scenes.random_soup(16, 16, 2, 1, triangles=9000, spheres=1).meshes, key=lambda m: m.triangle_count)
+    one = scenes.MeshDesc(np.float32([[0, 0, 0], [1, 0, 0], [0, 1, 0]]), np.int32([0, 1, 2]), np.float32([[0, 0, 1]] * 3))
+    flat = scenes.MeshDesc(np.float32([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]]), np.int32([0, 1, 2] * 40 + [1, 3, 2] * 40), np.float32([[0, 0, 1]] * 4))   # 80 coincident triangles: no plane separates them
+    return [("knot", knot), ("knot, shuffled triangle order", shuffled), ("soup", soup), ("room", scenes.room_mesh()), ("one triangle", one), ("coincident", flat)]
+
+
+def test_simt_device_bvh_build_returns_the_reference_builders_buffers(simt_lib):
+    """rtBuildBVH (level-synchronous GPU build, csrc/rt_bvh_build.cuh) against the host builder and the oracle's restatement of BVH.cs:
+    Nodes and Triangles byte for byte — node order, bounds, leaf ranges AND the triangle order the reference's swap partition
+    leaves behind — for all three quality modes, meshes in authored and in shuffled triangle order, degenerate inputs."""
+    from ray_tracing_b200 import capi
+    gpu, orc = capi.RtLib(simt_lib).create(0), capi.RtLib(ORACLE_LIB).create(0)
+    for name, m in _bvh_meshes():
+        for q in (1, 0, 2):
+            th, nh, _ = rt.build_bvh(m.vertices, m.indices, m.normals, q)
+            to, no = orc.build_bvh(m.vertices, m.indices, m.normals, q)
+            tg, ng = gpu.build_bvh(m.vertices, m.indices, m.normals, q)
+            assert np.array_equal(no.view(np.uint8), nh.view(np.uint8)) and np.array_equal(to.view(np.uint8), th.view(np.uint8)), f"oracle vs host: {name} q={q}"
+            assert len(ng) == len(nh) and np.array_equal(ng.view(np.uint8), nh.view(np.uint8)), f"device nodes: {name} q={q}"
+            assert np.array_equal(tg.view(np.uint8), th.view(np.uint8)), f"device triangle order: {name} q={q}"
+    with pytest.raises(capi.RtError):
+        gpu.build_bvh(np.zeros((3, 3), np.float32), np.int32([0, 1, 7]), np.zeros((3, 3), np.float32))      # index out of range
+    gpu.destroy(); orc.destroy()
+
+
+def test_simt_manager_can_build_on_the_device(simt_lib):
+    """buildBVHOnDevice: the host manager takes its Nodes / Triangles from rtBuildBVH instead of the host builder — same frame."""
+    sc = scenes.knot_room(64, 36, max_bounces=4, rays_per_pixel=2, nu=60, nv=8)
+    fo, ao = render(ORACLE_LIB, sc, frames=2)
+    mgr = rt.RayComputeManager(simt_lib)
+    scenes.apply(sc, mgr)
+    mgr.buildBVHOnDevice = 1
+    mgr.OnEnable(); mgr.RenderFrame(); mgr.RenderFrame()
+    assert_bit_equal(mgr.accumulatedResult, ao, "device-built BVH")
+    mgr.OnDestroy()
+
+
 def test_simt_grid_fit_is_schedule_only(simt_lib, monkeypatch):
     """"gridFit" changes how many persistent CTAs share the pixel queue (a whole number of pixels per lane), nothing else — checked with
     several machine sizes so that the fitted grid is really smaller than the full one (e.g. 3 'SMs' x 2 CTAs x 128 lanes = 768 lanes for

@@ -31,3 +31,5 @@ for gf in 0 1; do
   echo "== cornell64 --grid-fit $gf" | tee -a $OUT/sweep_r2_gridfit.log
   timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --workload cornell64 --grid-fit $gf 2>&1 | tail -1 | cut -c1-200 | tee -a $OUT/sweep_r2_gridfit.log
 done
+# BVH builder row: host (1 thread / all threads) vs rtBuildBVH, identical buffers required
+python tools/bvh_build_bench.py 2>&1 | tee -a $OUT/sweep_r2_bvhbuild.log
