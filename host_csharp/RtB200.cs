@@ -25,6 +25,9 @@ public static class RtB200
     [DllImport(Lib)] public static extern int rtDispatch(IntPtr ctx, int kernelIndex, int gx, int gy, int gz);
     [DllImport(Lib)] public static extern int rtReadback(IntPtr ctx, string tex, float[] dst, UIntPtr bytes);
     [DllImport(Lib)] public static extern int rtSynchronize(IntPtr ctx);
+    // optional: new BVH(verts, indices, normals, quality) built on the GPU — the same Triangles / Nodes arrays (BVH.cs:26)
+    [DllImport(Lib)] public static extern int rtBuildBVH(IntPtr ctx, UnityEngine.Vector3[] verts, int vertCount, int[] indices, int indexCount, UnityEngine.Vector3[] normals,
+                                                         int quality, [Out] BVH.Triangle[] tris, [Out] BVH.Node[] nodes, int nodeCapacity, out int nodeCount);
 
     public static void Check(IntPtr ctx, int rc)
     {
