@@ -3,7 +3,8 @@
 It recovers exactly what RayComputeManager pulls from the Unity scene graph at run time: the manager's inspector
 fields (RayComputeManager.cs:9-42), Camera.main (field of view + transform), and every active `Model` component with its
 material, its mesh and its transform (RayComputeManager.cs:118,192-204).  Meshes are resolved by asset guid through the
-`.meta` files next to the `.obj` assets (loaded with host/ObjLoader.cpp) or built here for Unity's built-in Cube / Quad
+`.meta` files next to the `.obj` assets (loaded with host/ObjLoader.cpp; normals recomputed when the `.meta` says
+`normalImportMode: 1`, as for Icosphere.obj) or built here for Unity's built-in Cube / Quad
 (fileID 10202 / 10210 of the built-in resources, not part of any repository).  `.fbx` meshes (Text, Water) are read by
 fbx_mesh.py (binary FBX container, Unity's handedness / normal import settings) and picked by the sub-asset fileID the
 scene stores.  Any other mesh reference raises unless `skip_unsupported=True`.
@@ -22,7 +23,7 @@ import numpy as np
 
 from . import scenes
 from .manager import load_obj
-from .fbx_mesh import load_fbx_meshes
+from .fbx_mesh import load_fbx_meshes, _calculated_normals, _meta_settings
 
 MODEL_SCRIPT_GUID = "cacf7f4e77ad8814ca6868b309a77322"       # Assets/Scripts/Types/Model.cs.meta
 MANAGER_SCRIPT_GUID = "5a097d4e14022bb47ae63bb730d39172"     # Assets/Scripts/Tracer/RayComputeManager.cs.meta
@@ -145,6 +146,14 @@ def load_unity_scene(scene_path: str, graphics_dir: Optional[str] = None, width:
                 mesh = builtin_quad()
             elif key[0] in guids and guids[key[0]].lower().endswith(".obj"):
                 mesh = scenes.MeshDesc(*load_obj(guids[key[0]]))
+                mode, angle = _meta_settings(guids[key[0]])
+                if mode == 1:
+                    # `normalImportMode: 1` in the .meta (Icosphere.obj): Unity discards the file's normals and recomputes them
+                    corners = mesh.vertices[mesh.indices].astype(np.float64)
+                    tri = np.arange(len(corners)).reshape(-1, 3)
+                    normals = _calculated_normals(corners, tri, angle)
+                    mesh = scenes.MeshDesc(np.ascontiguousarray(corners, dtype=np.float32), np.arange(len(corners), dtype=np.int32),
+                                           np.ascontiguousarray(normals, dtype=np.float32))
             elif key[0] in guids and guids[key[0]].lower().endswith(".fbx"):
                 path = guids[key[0]]
                 if path not in fbx_cache:
