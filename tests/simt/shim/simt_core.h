@@ -191,10 +191,24 @@ inline void run_cta(Cta& c)
     tl_cta = &c;
     tl_blockIdx = c.bidx; tl_blockDim = c.block; tl_gridDim = c.grid;
     unsigned long long lastProgress = ~0ull; unsigned long long idleRounds = 0;
+    // Order in which the scheduler visits the threads of the CTA in a round (RT_SIMT_ORDER): 0 = ascending (default), 1 = descending,
+    // 2 = a fresh pseudo-random order every round.  A race between lanes that is masked by one order shows up under another.
+    const int orderMode = env_int("RT_SIMT_ORDER", 0);
+    std::vector<unsigned int> order(n);
+    for (unsigned int t = 0; t < n; t++) order[t] = orderMode == 1 ? n - 1 - t : t;
+    unsigned long long rng = 0x9E3779B97F4A7C15ull ^ ((unsigned long long)c.bidx.x << 32) ^ c.bidx.y;
     while (c.liveThreads > 0)
     {
-        for (unsigned int t = 0; t < n; t++)
+        if (orderMode == 2)
+            for (unsigned int i = n; i > 1; i--)
+            {
+                rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                const unsigned int j = (unsigned int)((rng >> 33) % i);
+                const unsigned int tmp = order[i - 1]; order[i - 1] = order[j]; order[j] = tmp;
+            }
+        for (unsigned int k = 0; k < n; k++)
         {
+            const unsigned int t = order[k];
             if (c.fibers[t].done) continue;
             c.cur = t;
             set_builtins(&c, t);
