@@ -235,6 +235,8 @@ def run_gpu(args, w):
         ctx.set_option("pairOrder", args.pair_order)
     if args.grid_fit is not None:
         ctx.set_option("gridFit", args.grid_fit)
+    if args.l2_persist is not None:
+        ctx.set_option("l2Persist", args.l2_persist)
     mgr.OnEnable()
     if tiled.fused:
         with torch.cuda.stream(stream):
@@ -390,6 +392,7 @@ def main():
     ap.add_argument("--model-skip", type=int, default=None, help="kernels 1/2: skip models the ray cannot reach (1 default / 0)")
     ap.add_argument("--sort-rays", type=int, default=None, help="kernel 2: group the ray queue by direction octant (1/0)")
     ap.add_argument("--tail-lanes", type=int, default=None, help="kernel 2: leave the trace phase when this few lanes still trace")
+    ap.add_argument("--l2-persist", type=int, default=None, help="1 = persisting L2 window over the node-pair records")
     ap.add_argument("--grid-fit", type=int, default=None, help="1 = size the persistent grid for a whole number of pixels per lane (multi-GPU tail), 0 = default")
     ap.add_argument("--pair-order", type=int, default=None, help="node-pair record order: 0 = breadth-first (default), d = treelets of d levels, depth-first")
     ap.add_argument("--smem-nodes", type=int, default=None, help="node pairs staged in shared memory (-1 = auto)")

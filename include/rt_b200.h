@@ -162,6 +162,8 @@ int rtBuildBVH(RtContext* ctx, const float* verts, int vertCount, const int* ind
  *   "gridFit"     kernels 1 and 2: 1 = shrink the persistent grid so that every lane (pool slot) gets a whole number of pixels
  *                 — fewer, fully occupied rounds instead of a last round of mostly empty warps when the image is small for the
  *                 machine (multi-GPU tiles); 0 = one CTA set filling the machine (default; not yet measured)
+ *   "l2Persist"   1 = persisting L2 access-policy window over the node-pair records on the dispatch stream (0 = default; not yet
+ *                 measured)
  *   "pairOrder"   order of the repacked node-pair records inside a mesh: 0 = breadth-first (default), d = 1..32 = treelets of d
  *                 levels laid out depth-first (1 = plain pre-order: child A's record follows its parent's).  Layout only: the
  *                 traversal visits the same nodes in the same order; not yet measured on the GPU

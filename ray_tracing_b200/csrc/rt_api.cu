@@ -66,7 +66,8 @@ struct RtContext
     float4* peerFrame[RT_MAX_PEERS]; float4* peerAccum[RT_MAX_PEERS]; int nPeers = 0;
 
     // options
-    int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16, optSortRays = 0, optForceExt = 0, optModelSkip = 1, optPairOrder = 0, optGridFit = 0;   // kernel -1 = automatic   // smemPairs -1 = automatic
+    int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16, optSortRays = 0, optForceExt = 0, optModelSkip = 1, optPairOrder = 0, optGridFit = 0, optL2Persist = 0;
+    int l2PersistApplied = 0; const void* l2PersistBase = nullptr; size_t l2PersistBytes = 0;   // kernel -1 = automatic   // smemPairs -1 = automatic
 
     // counters / timing
     unsigned long long* dCounters = nullptr;   // 5
@@ -323,6 +324,7 @@ int rtSetOption(RtContext* c, const char* name, int value)
     else if (n == "extInstantiation") c->optForceExt = value != 0;
     else if (n == "sortRays") c->optSortRays = value != 0;
     else if (n == "gridFit") c->optGridFit = value != 0;
+    else if (n == "l2Persist") c->optL2Persist = value != 0;
     else if (n == "pairOrder") { if (value < 0 || value > 32) return fail(c, RT_E_INVALID, "rtSetOption: pairOrder must be 0 (breadth-first) or a treelet depth 1..32"); c->optPairOrder = value; }
     else if (n == "tailLanes") { if (value < 0 || value > 31) return fail(c, RT_E_INVALID, "rtSetOption: tailLanes must be in [0, 31]"); c->optTailLanes = value; }
     else if (n == "poolSlots") { if (value != 32 && value != 64 && value != 96) return fail(c, RT_E_INVALID, "rtSetOption: poolSlots must be 32, 64 or 96"); c->optPoolSlots = value; }
@@ -336,6 +338,38 @@ static int effectiveKernel(const RtContext* c)
 {
     if (c->optKernel >= 0) return c->optKernel;
     return c->P.modelCount > 0 ? 2 : 1;
+}
+
+// "l2Persist": ask the L2 to keep the node-pair records (persisting access-policy window on the dispatch stream; every ray walks
+// them, the triangle stream is marked streaming by omission).  The scenes already hit L2 at 76-86 % (profiles/), so this is a
+// candidate for the misses' latency, not for bandwidth; off by default, not yet measured.
+static void applyL2Persistence(RtContext* c)
+{
+#ifndef RT_SIMT_EMU
+    const void* base = c->repack.pairs.p;
+    const size_t bytes = c->repack.totalPairs * sizeof(NodePair);
+    const int want = c->optL2Persist && base && bytes > 0;
+    if (want == c->l2PersistApplied && (!want || (base == c->l2PersistBase && bytes == c->l2PersistBytes))) return;
+    cudaStreamAttrValue attr; memset(&attr, 0, sizeof(attr));
+    if (want)
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess || prop.persistingL2CacheMaxSize <= 0) return;
+        size_t setAside = bytes < (size_t)prop.persistingL2CacheMaxSize ? bytes : (size_t)prop.persistingL2CacheMaxSize;
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setAside) != cudaSuccess) { cudaGetLastError(); return; }
+        size_t window = bytes < (size_t)prop.accessPolicyMaxWindowSize ? bytes : (size_t)prop.accessPolicyMaxWindowSize;
+        attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+        attr.accessPolicyWindow.num_bytes = window;
+        attr.accessPolicyWindow.hitRatio = window > 0 ? (float)((double)setAside / (double)window > 1.0 ? 1.0 : (double)setAside / (double)window) : 0.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    }
+    if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) { cudaGetLastError(); return; }
+    if (!want) cudaCtxResetPersistingL2Cache();
+    c->l2PersistApplied = want; c->l2PersistBase = base; c->l2PersistBytes = bytes;
+#else
+    (void)c;
+#endif
 }
 
 static int prepareScene(RtContext* c)
@@ -428,6 +462,7 @@ int rtDispatch(RtContext* c, int kernelIndex, int gx, int gy, int gz)
 
     int rc = prepareScene(c);
     if (rc != RT_OK) return rc;
+    applyL2Persistence(c);
 
     DevParams P = c->P;
     P.limX = limX; P.limY = limY;

@@ -10,6 +10,29 @@
 
 namespace rtd {
 
+// ---- cache policy of the triangle stream (round-2 candidate, compiled out by default) --------------------------------------
+// Leaf triangles (48-byte TriGeom records, the normals of a winner) are touched once per test and rarely again soon, while the
+// node-pair records of the upper tree are re-read by every ray: L1 capacity was the lever in round 1 (no shared-memory tree
+// tops, 64-slot pools).  RT_TRI_LOAD_POLICY = 1 loads triangle data with L1::no_allocate, 2 with L1::evict_first, so that they do
+// not displace node records; 0 (default) = plain read-only loads.  Same values either way.
+#ifndef RT_TRI_LOAD_POLICY
+#define RT_TRI_LOAD_POLICY 0
+#endif
+RT_DI float4 ldg_tri(const float4* p)
+{
+#if RT_TRI_LOAD_POLICY == 0 || defined(RT_SIMT_EMU)
+    return __ldg(p);
+#else
+    float4 v;
+#if RT_TRI_LOAD_POLICY == 1
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+#else
+    asm volatile("ld.global.nc.L1::evict_first.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+#endif
+    return v;
+#endif
+}
+
 // ---- repacked device-side scene records (built at upload time by rt_repack.cu) ---------------------------
 
 // Two sibling BVH nodes in one 64-byte, 64-byte-aligned record (children are allocated adjacently by the

@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                             const int model = pool.i(F_HMODEL, e);
                             const float det = pool.f(F_HDET, e);
                             const float4* nq = reinterpret_cast<const float4*>(P.triNormals + prim);
-                            const float4 n0 = __ldg(nq), n1 = __ldg(nq + 1), n2 = __ldg(nq + 2);
+                            const float4 n0 = ldg_tri(nq), n1 = ldg_tri(nq + 1), n2 = ldg_tri(nq + 2);
                             const f3 n = TriangleSmoothNormal(make_f3(n0.x, n0.y, n0.z), make_f3(n0.w, n1.x, n1.y), make_f3(n1.z, n1.w, n2.x),
                                                               pool.f(F_HU, e), pool.f(F_HV, e), det);
                             const float4* mr = reinterpret_cast<const float4*>(P.models + model) + 3;
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                 else if (mode == T_LEAF)
                 {
                     const float4* g = reinterpret_cast<const float4*>(P.triGeom + cur.start + leafK);
-                    const float4 g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2);
+                    const float4 g0 = ldg_tri(g), g1 = ldg_tri(g + 1), g2 = ldg_tri(g + 2);
                     float dst, u, v, det;
                     const bool didHit = RayTriangleCore(lpos, ldir, make_f3(g0.x, g0.y, g0.z), make_f3(g0.w, g1.x, g1.y), make_f3(g1.z, g1.w, g2.x),
                                                         make_f3(g2.y, g2.z, g2.w), cull, dst, u, v, det);

@@ -90,7 +90,7 @@ RT_DI void TraverseMesh(const DevParams& P, const float4* __restrict__ smemPairs
             const float4* g = reinterpret_cast<const float4*>(P.triGeom + cur.start);
             for (int i = 0; i < cur.count; i++, g += 3)
             {
-                const float4 g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2);
+                const float4 g0 = ldg_tri(g), g1 = ldg_tri(g + 1), g2 = ldg_tri(g + 2);
                 float dst, u, v, det;
                 const bool didHit = RayTriangleCore(pos, dir, make_f3(g0.x, g0.y, g0.z), make_f3(g0.w, g1.x, g1.y), make_f3(g1.z, g1.w, g2.x),
                                                     make_f3(g2.y, g2.z, g2.w), cullBackface, dst, u, v, det);
@@ -189,7 +189,7 @@ RT_DI Hit Intersect(const DevParams& P, const float4* __restrict__ smemPairs, co
         if (dst < result.dst)
         {
             const float4* nq = reinterpret_cast<const float4*>(P.triNormals + tri);
-            const float4 n0 = __ldg(nq), n1 = __ldg(nq + 1), n2 = __ldg(nq + 2);
+            const float4 n0 = ldg_tri(nq), n1 = ldg_tri(nq + 1), n2 = ldg_tri(nq + 2);
             const f3 n = TriangleSmoothNormal(make_f3(n0.x, n0.y, n0.z), make_f3(n0.w, n1.x, n1.y), make_f3(n1.z, n1.w, n2.x), u, v, det);
             float l2w[12];
             {

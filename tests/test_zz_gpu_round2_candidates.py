@@ -41,3 +41,10 @@ def test_device_bvh_build_equals_the_host_builder_on_gpu():
             tg, ng = gpu.build_bvh(m.vertices, m.indices, m.normals, q)
             assert len(ng) == len(nh) and np.array_equal(ng.view(np.uint8), nh.view(np.uint8)) and np.array_equal(tg.view(np.uint8), th.view(np.uint8))
     gpu.destroy()
+
+
+def test_l2_persistence_window_changes_nothing_but_caching():
+    sc = scenes.knot_room(160, 90, max_bounces=5, rays_per_pixel=2, nu=200, nv=12)
+    fo, ao = render(CUDA_LIB, sc, frames=2)
+    fg, ag = render(CUDA_LIB, sc, frames=2, options={"l2Persist": 1})
+    assert_bit_equal(ag, ao, "l2Persist")

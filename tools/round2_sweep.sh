@@ -8,12 +8,12 @@ import os
 P = build.PKG_DIR
 for name, defs in [("skipsqrt", ("RT_SPHERE_SKIP_SQRT",)), ("mb5", ("RT_WAVE_MINBLOCKS=5",)), ("ir1", ("RT_INNER_REPEAT=1",)), ("pw20", ("RT_POOL_WARPS=20",)),
                    ("stacktop", ("RT_STACK_TOP_REG",)), ("rayinv", ("RT_CACHE_RAYINV",)), ("leaf2", ("RT_LEAF_REPEAT=2",)),
-                   ("stacktop_leaf2", ("RT_STACK_TOP_REG", "RT_LEAF_REPEAT=2"))]:
+                   ("stacktop_leaf2", ("RT_STACK_TOP_REG", "RT_LEAF_REPEAT=2")), ("tri_na", ("RT_TRI_LOAD_POLICY=1",)), ("tri_ef", ("RT_TRI_LOAD_POLICY=2",))]:
     build.build_cuda(force=True, defines=defs, out=os.path.join(P, f"librt_b200_{name}.so"))
 PY
 RT_B200_LIB=ray_tracing_b200/librt_b200_skipsqrt.so python -m pytest tests -m gpu -q -k "cornell or sphere or soup" 2>&1 | tail -3
 bash tools/gpu_ab.sh r2 librt_b200.so librt_b200_skipsqrt.so librt_b200_mb5.so
-bash tools/gpu_ab2.sh r2 librt_b200.so librt_b200_ir1.so librt_b200_pw20.so librt_b200_stacktop.so librt_b200_rayinv.so librt_b200_leaf2.so librt_b200_stacktop_leaf2.so
+bash tools/gpu_ab2.sh r2 librt_b200.so librt_b200_ir1.so librt_b200_pw20.so librt_b200_stacktop.so librt_b200_rayinv.so librt_b200_leaf2.so librt_b200_stacktop_leaf2.so librt_b200_tri_na.so librt_b200_tri_ef.so
 # node-pair record order (host-side layout only; kernel unchanged): breadth-first (0, default) vs treelets laid out depth-first
 OUT=gpurun_out; mkdir -p $OUT
 for wl in knot64 cluster4k soup4k; do for po in 0 1 2 3 4 6; do
@@ -33,3 +33,8 @@ for gf in 0 1; do
 done
 # BVH builder row: host (1 thread / all threads) vs rtBuildBVH, identical buffers required
 python tools/bvh_build_bench.py 2>&1 | tee -a $OUT/sweep_r2_bvhbuild.log
+# persisting L2 window over the node-pair records
+for wl in knot64 cluster4k soup4k; do for lp in 0 1; do
+  echo "== $wl --l2-persist $lp" | tee -a $OUT/sweep_r2_l2persist.log
+  timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --workload $wl --l2-persist $lp 2>&1 | tail -1 | cut -c1-160 | tee -a $OUT/sweep_r2_l2persist.log
+done; done
