@@ -45,6 +45,7 @@ namespace rtd {
 //                      the fetch and box tests of the popped node instead of preceding them
 //   RT_CACHE_RAYINV    1 / world ray direction (model skipping) computed once per ray instead of at every model step
 //   RT_LEAF_REPEAT=n   n leaf primitives per census (like RT_INNER_REPEAT for inner nodes)
+//   RT_PREFETCH_NEXT_PAIR   L1 prefetch of the record after the one being fetched (meant for "pairOrder" = 1, where that is child A's)
 #ifdef RT_STACK_TOP_REG
 #define RT_PUSH(x) do { if (stackCount > 0) stack[stackCount - 1] = stackTop; stackTop = (x); stackCount++; } while (0)
 #define RT_POP(dst) do { (dst) = stackTop; --stackCount; if (stackCount > 0) stackTop = stack[stackCount - 1]; } while (0)
@@ -501,6 +502,11 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                     else
                     {
                         LoadPair(P, smemPairs, cur.start, q0, q1, q2, q3);
+#if defined(RT_PREFETCH_NEXT_PAIR) && !defined(RT_SIMT_EMU)
+                        // with "pairOrder" = 1 (pre-order records) the record of an inner child A is the next one: ask for it while this one is
+                        // still in flight, so that a descent into A finds it in L1 (a wasted 64-byte prefetch when the ray goes to B or up)
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(P.pairs + cur.start + 1));
+#endif
                         if (STATS) cnt.box += 2;
                     }
                     const float dstA = RayBoundingBoxDst(lpos, linv, make_f3(q0.x, q0.y, q0.z), make_f3(q0.w, q1.x, q1.y));
