@@ -237,6 +237,8 @@ def run_gpu(args, w):
         ctx.set_option("gridFit", args.grid_fit)
     if args.l2_persist is not None:
         ctx.set_option("l2Persist", args.l2_persist)
+    if args.treelet_prefetch is not None:
+        ctx.set_option("treeletPrefetch", args.treelet_prefetch)
     mgr.OnEnable()
     if tiled.fused:
         with torch.cuda.stream(stream):
@@ -392,6 +394,7 @@ def main():
     ap.add_argument("--model-skip", type=int, default=None, help="kernels 1/2: skip models the ray cannot reach (1 default / 0)")
     ap.add_argument("--sort-rays", type=int, default=None, help="kernel 2: group the ray queue by direction octant (1/0)")
     ap.add_argument("--tail-lanes", type=int, default=None, help="kernel 2: leave the trace phase when this few lanes still trace")
+    ap.add_argument("--treelet-prefetch", type=int, default=None, help="1 = flagged two-level treelets + L1 prefetch of both next records (needs --lib built with RT_TREELET_PREFETCH)")
     ap.add_argument("--l2-persist", type=int, default=None, help="1 = persisting L2 window over the node-pair records")
     ap.add_argument("--grid-fit", type=int, default=None, help="1 = size the persistent grid for a whole number of pixels per lane (multi-GPU tail), 0 = default")
     ap.add_argument("--pair-order", type=int, default=None, help="node-pair record order: 0 = breadth-first (default), d = treelets of d levels, depth-first")

@@ -164,6 +164,8 @@ int rtBuildBVH(RtContext* ctx, const float* verts, int vertCount, const int* ind
  *                 machine (multi-GPU tiles); 0 = one CTA set filling the machine (default; not yet measured)
  *   "l2Persist"   1 = persisting L2 access-policy window over the node-pair records on the dispatch stream (0 = default; not yet
  *                 measured)
+ *   "treeletPrefetch"  1 = two-level treelet layout with flagged treelet roots and an L1 prefetch of both possible next records
+ *                 (only in a library built with -DRT_TREELET_PREFETCH; the default build returns RT_E_INVALID; not yet measured)
  *   "pairOrder"   order of the repacked node-pair records inside a mesh: 0 = breadth-first (default), d = 1..32 = treelets of d
  *                 levels laid out depth-first (1 = plain pre-order: child A's record follows its parent's).  Layout only: the
  *                 traversal visits the same nodes in the same order; not yet measured on the GPU

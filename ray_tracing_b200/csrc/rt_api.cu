@@ -66,7 +66,7 @@ struct RtContext
     float4* peerFrame[RT_MAX_PEERS]; float4* peerAccum[RT_MAX_PEERS]; int nPeers = 0;
 
     // options
-    int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16, optSortRays = 0, optForceExt = 0, optModelSkip = 1, optPairOrder = 0, optGridFit = 0, optL2Persist = 0;
+    int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16, optSortRays = 0, optForceExt = 0, optModelSkip = 1, optPairOrder = 0, optGridFit = 0, optL2Persist = 0, optTreeletPrefetch = 0;
     int l2PersistApplied = 0; const void* l2PersistBase = nullptr; size_t l2PersistBytes = 0;   // kernel -1 = automatic   // smemPairs -1 = automatic
 
     // counters / timing
@@ -325,6 +325,14 @@ int rtSetOption(RtContext* c, const char* name, int value)
     else if (n == "sortRays") c->optSortRays = value != 0;
     else if (n == "gridFit") c->optGridFit = value != 0;
     else if (n == "l2Persist") c->optL2Persist = value != 0;
+    else if (n == "treeletPrefetch")
+    {
+#ifdef RT_TREELET_PREFETCH
+        c->optTreeletPrefetch = value != 0;
+#else
+        if (value) return fail(c, RT_E_INVALID, "rtSetOption: treeletPrefetch needs a library built with RT_TREELET_PREFETCH (the default kernels do not strip the flag bit)");
+#endif
+    }
     else if (n == "pairOrder") { if (value < 0 || value > 32) return fail(c, RT_E_INVALID, "rtSetOption: pairOrder must be 0 (breadth-first) or a treelet depth 1..32"); c->optPairOrder = value; }
     else if (n == "tailLanes") { if (value < 0 || value > 31) return fail(c, RT_E_INVALID, "rtSetOption: tailLanes must be in [0, 31]"); c->optTailLanes = value; }
     else if (n == "poolSlots") { if (value != 32 && value != 64 && value != 96) return fail(c, RT_E_INVALID, "rtSetOption: poolSlots must be 32, 64 or 96"); c->optPoolSlots = value; }
@@ -386,13 +394,16 @@ static int prepareScene(RtContext* c)
     // automatic = 0: measured (profiles/r01_sweeps.log), staging tree tops never beat leaving that shared memory to L1
     int budget = c->optSmemPairs < 0 ? 0 : c->optSmemPairs;
     const int kernelSel = effectiveKernel(c);
+    const bool treelets = c->optTreeletPrefetch && kernelSel != 0;      // two-level treelets with flagged roots; no shared-memory staging with it
+    const int pairOrder = treelets ? 2 : c->optPairOrder;
+    if (treelets) budget = 0;
     if (kernelSel == 2) { const int mx = pool_max_smem_pairs(c->optPoolSlots, (int)c->spheres.count); if (budget > mx) budget = mx; }
     else if (kernelSel == 0) budget = 0;
-    if (budget != c->repack.budgetUsed || c->optPairOrder != c->repack.orderUsed) c->sceneDirty = true;
+    if (budget != c->repack.budgetUsed || pairOrder != c->repack.orderUsed || treelets != c->repack.flagsUsed) c->sceneDirty = true;
     if (c->sceneDirty)
     {
         std::string msg;
-        cudaError_t e = c->repack.buildScene(c->hNodes, c->hModels, c->P.modelCount, c->tris.p, c->tris.count, budget, c->stream, msg, c->optPairOrder);
+        cudaError_t e = c->repack.buildScene(c->hNodes, c->hModels, c->P.modelCount, c->tris.p, c->tris.count, budget, c->stream, msg, pairOrder, treelets);
         if (e != cudaSuccess) return failCuda(c, e, "repack scene");
         if (!msg.empty()) return fail(c, RT_E_STATE, "rtDispatch: " + msg);
         c->sceneDirty = false; c->modelsDirty = true;

@@ -58,9 +58,20 @@ RT_DI void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster
 
 struct NodeRef { int start, count; };
 
+// Round-2 candidate RT_TREELET_PREFETCH (compiled out by default; option "treeletPrefetch"): with records laid out as two-level
+// treelets — [record of a node, records of its inner children] contiguous, "pairOrder" = 2 — a reference to a treelet's first
+// record carries bit 30.  Fetching such a record also asks L1 for the one or two records behind it, i.e. for BOTH possible next
+// steps of the descent, before the box tests have decided which one it is: every second level of a descent then finds its
+// record in L1 instead of paying another trip to L2 — the dependent-fetch chain that stalls the mesh scenes (profiles/) is halved.
+constexpr int TREELET_ROOT_BIT = 0x40000000;
+
 // Fetch one 64-byte pair record: from the shared-memory copy of the tree tops, or from HBM/L2.
 RT_DI void LoadPair(const DevParams& P, const float4* __restrict__ smemPairs, int idx, float4& q0, float4& q1, float4& q2, float4& q3)
 {
+#ifdef RT_TREELET_PREFETCH
+    const bool treeletRoot = (idx & TREELET_ROOT_BIT) != 0;
+    idx &= ~TREELET_ROOT_BIT;
+#endif
     if (idx < P.smemPairs)
     {
         const float4* p = smemPairs + (size_t)idx * 4;
@@ -70,6 +81,13 @@ RT_DI void LoadPair(const DevParams& P, const float4* __restrict__ smemPairs, in
     {
         const float4* p = reinterpret_cast<const float4*>(P.pairs + idx);
         q0 = __ldg(p); q1 = __ldg(p + 1); q2 = __ldg(p + 2); q3 = __ldg(p + 3);
+#if defined(RT_TREELET_PREFETCH) && !defined(RT_SIMT_EMU)
+        if (treeletRoot)
+        {
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(p + 4));      // the records of the inner children (or, for a one-child
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(p + 8));      // treelet, the start of the next treelet: harmless)
+        }
+#endif
     }
 }
 

@@ -55,6 +55,7 @@ struct RepackState
     std::map<std::pair<int,int>, MeshRoot> roots;     // (nodeOffset, triOffset) -> encoded root
     int smemPairs = 0;
     int budgetUsed = -1;
+    bool flagsUsed = false;                         // references to treelet roots carry bit 30 (RT_TREELET_PREFETCH builds only)
     int orderUsed = 0;                              // treeletDepth of the current pair layout
     size_t totalPairs = 0;
 
@@ -69,12 +70,12 @@ struct RepackState
     //                      (plain pre-order) the record of child A directly follows its parent's.  The first `hot` records
     //                      (shared-memory staging) stay the breadth-first top whatever the order of the rest.
     void planScene(const std::vector<RtNode>& nodes, const std::vector<RtModel>& mdl, int modelCount, size_t triCount, int smemOpt,
-                   std::vector<NodePair>& out, std::string& msg, int treeletDepth = 0)
+                   std::vector<NodePair>& out, std::string& msg, int treeletDepth = 0, bool flagTreeletRoots = false)
     {
         roots.clear(); smemPairs = 0; totalPairs = 0; out.clear();
         struct Mesh { int nodeOffset, triOffset; std::vector<int> order; /* global node index of first child, in BFS pair order */
                       std::vector<int> kidA, kidB; /* BFS pair id of the inner children of pair k, -1 for a leaf */
-                      std::vector<int> perm; /* BFS pair id -> position inside the mesh */ size_t hot = 0, hotBase = 0, coldBase = 0; };
+                      std::vector<int> perm; /* BFS pair id -> position inside the mesh */ std::vector<char> troot; /* first record of a treelet */ size_t hot = 0, hotBase = 0, coldBase = 0; };
         std::vector<Mesh> meshes;
         for (int i = 0; i < modelCount; i++)
         {
@@ -129,6 +130,7 @@ struct RepackState
             // position of every pair inside the mesh
             const size_t n = m.order.size();
             m.perm.assign(n, -1);
+            m.troot.assign(n, 0);
             if (treeletDepth <= 0) for (size_t k = 0; k < n; k++) m.perm[k] = (int)k;
             else if (n > 0)
             {
@@ -138,6 +140,7 @@ struct RepackState
                 while (!todo.empty())
                 {
                     level.assign(1, todo.back()); todo.pop_back();
+                    m.troot[level[0]] = 1;
                     for (int d = 0; d < treeletDepth && !level.empty(); d++)
                     {
                         below.clear();
@@ -152,7 +155,10 @@ struct RepackState
                     for (size_t i = level.size(); i-- > 0;) todo.push_back(level[i]);     // leftmost treelet next
                 }
             }
-            auto globalPair = [&](size_t bfsId) { const size_t local = (size_t)m.perm[bfsId]; return (int)(local < m.hot ? m.hotBase + local : m.coldBase + (local - m.hot)); };
+            // (with flagTreeletRoots a reference to the first record of a treelet carries bit 30, see LoadPair)
+            auto globalPair = [&](size_t bfsId) { const size_t local = (size_t)m.perm[bfsId]; const int g = (int)(local < m.hot ? m.hotBase + local : m.coldBase + (local - m.hot));
+                                                  return (flagTreeletRoots && m.troot[bfsId]) ? (g | 0x40000000) : g; };
+            auto slotOf = [&](size_t bfsId) { const size_t local = (size_t)m.perm[bfsId]; return (size_t)(local < m.hot ? m.hotBase + local : m.coldBase + (local - m.hot)); };
             // second pass in BFS order: the k-th inner node met owns pair k; its inner children are the next ones the BFS met
             size_t nextChildPair = 1;       // pair 0 belongs to the root
             const RtNode& root = nodes[m.nodeOffset];
@@ -173,18 +179,19 @@ struct RepackState
                 else { p.aStart = globalPair(nextChildPair++); p.aCount = 0; }
                 if (B.triangleCount > 0) { p.bStart = m.triOffset + B.startIndex; p.bCount = B.triangleCount; if (p.bStart < 0 || (size_t)p.bStart + p.bCount > triCount) { msg = "BVH leaf triangle range out of bounds"; return; } }
                 else { p.bStart = globalPair(nextChildPair++); p.bCount = 0; }
-                out[globalPair(k)] = p;
+                out[slotOf(k)] = p;
             }
             if (root.triangleCount > 0 && ((size_t)r.rootStart + r.rootCount > triCount)) { msg = "BVH root triangle range out of bounds"; return; }
         }
     }
 
     cudaError_t buildScene(const std::vector<RtNode>& nodes, const std::vector<RtModel>& mdl, int modelCount,
-                           const RtTriangle* dTris, size_t triCount, int smemOpt, cudaStream_t stream, std::string& msg, int treeletDepth = 0)
+                           const RtTriangle* dTris, size_t triCount, int smemOpt, cudaStream_t stream, std::string& msg, int treeletDepth = 0,
+                           bool flagTreeletRoots = false)
     {
         std::vector<NodePair> out;
-        planScene(nodes, mdl, modelCount, triCount, smemOpt, out, msg, treeletDepth);
-        orderUsed = treeletDepth;
+        planScene(nodes, mdl, modelCount, triCount, smemOpt, out, msg, treeletDepth, flagTreeletRoots);
+        orderUsed = treeletDepth; flagsUsed = flagTreeletRoots;
         if (!msg.empty()) return cudaSuccess;
         cudaError_t e;
         if ((e = pairs.ensure(std::max<size_t>(totalPairs, 1))) != cudaSuccess) return e;

@@ -184,7 +184,7 @@ def test_simt_pair_record_order_is_layout_only(simt_lib):
 
 
 @pytest.mark.skipif(not os.environ.get("RT_SIMT_VARIANTS"), reason="four extra interpreter builds (~3 min): set RT_SIMT_VARIANTS=1")
-@pytest.mark.parametrize("defines", [("RT_STACK_TOP_REG",), ("RT_CACHE_RAYINV",), ("RT_LEAF_REPEAT=2",), ("RT_SPHERE_SKIP_SQRT",),
+@pytest.mark.parametrize("defines", [("RT_STACK_TOP_REG",), ("RT_CACHE_RAYINV",), ("RT_LEAF_REPEAT=2",), ("RT_SPHERE_SKIP_SQRT",), ("RT_TREELET_PREFETCH",),
                                      ("RT_STACK_TOP_REG", "RT_CACHE_RAYINV", "RT_LEAF_REPEAT=2", "RT_INNER_REPEAT=1")])
 def test_simt_compile_time_variants_are_bit_exact(defines, tmp_path):
     """The A/B candidates of tools/round2_sweep.sh change scheduling / instruction selection only: same pixels, same counters."""
@@ -196,7 +196,20 @@ def test_simt_compile_time_variants_are_bit_exact(defines, tmp_path):
                        (scenes.cornell_spheres(64, 48, 5, 3), 2), (flat, 1)):
         fo, ao, so = render(ORACLE_LIB, sc, frames=frames, want_stats=True)
         for opts in ({"kernel": 2, "countStats": 1}, {"kernel": 2, "poolSlots": 32, "tailLanes": 3}, {"kernel": 1}, {"kernel": 0}):
+            if "RT_TREELET_PREFETCH" in defines:
+                opts = dict(opts, treeletPrefetch=1, smemNodes=64)            # flagged treelet roots (the staging request is overridden)
             fg, ag, sg = render(lib, sc, frames=frames, options=opts, want_stats=True)
             assert_bit_equal(ag, ao, f"{defines} {sc.name} {opts}")
             if opts.get("countStats"):
                 assert all(sg[k] == so[k] for k in ("rays", "boxTests", "triTests"))
+
+
+def test_simt_default_build_refuses_flagged_treelet_roots(simt_lib):
+    """The default kernels do not strip the treelet-root flag from a record index, so the option that sets it must be refused."""
+    from ray_tracing_b200 import capi
+    ctx = capi.RtLib(simt_lib).create(0)
+    with pytest.raises(capi.RtError) as e:
+        ctx.set_option("treeletPrefetch", 1)
+    assert e.value.code == capi.RT_E_INVALID
+    ctx.set_option("treeletPrefetch", 0)
+    ctx.destroy()

@@ -8,7 +8,7 @@ import os
 P = build.PKG_DIR
 for name, defs in [("skipsqrt", ("RT_SPHERE_SKIP_SQRT",)), ("mb5", ("RT_WAVE_MINBLOCKS=5",)), ("ir1", ("RT_INNER_REPEAT=1",)), ("pw20", ("RT_POOL_WARPS=20",)),
                    ("stacktop", ("RT_STACK_TOP_REG",)), ("rayinv", ("RT_CACHE_RAYINV",)), ("leaf2", ("RT_LEAF_REPEAT=2",)),
-                   ("stacktop_leaf2", ("RT_STACK_TOP_REG", "RT_LEAF_REPEAT=2")), ("tri_na", ("RT_TRI_LOAD_POLICY=1",)), ("tri_ef", ("RT_TRI_LOAD_POLICY=2",)), ("pf", ("RT_PREFETCH_NEXT_PAIR",))]:
+                   ("stacktop_leaf2", ("RT_STACK_TOP_REG", "RT_LEAF_REPEAT=2")), ("tri_na", ("RT_TRI_LOAD_POLICY=1",)), ("tri_ef", ("RT_TRI_LOAD_POLICY=2",)), ("pf", ("RT_PREFETCH_NEXT_PAIR",)), ("treelet", ("RT_TREELET_PREFETCH",))]:
     build.build_cuda(force=True, defines=defs, out=os.path.join(P, f"librt_b200_{name}.so"))
 PY
 RT_B200_LIB=ray_tracing_b200/librt_b200_skipsqrt.so python -m pytest tests -m gpu -q -k "cornell or sphere or soup" 2>&1 | tail -3
@@ -42,4 +42,8 @@ done; done
 for wl in knot64 cluster4k soup4k; do
   echo "== $wl prefetch-next-pair + --pair-order 1" | tee -a $OUT/sweep_r2_pairorder.log
   timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --workload $wl --pair-order 1 --lib ray_tracing_b200/librt_b200_pf.so 2>&1 | tail -1 | cut -c1-160 | tee -a $OUT/sweep_r2_pairorder.log
+done
+for wl in knot64 cluster4k soup4k; do
+  echo "== $wl treelet prefetch" | tee -a $OUT/sweep_r2_pairorder.log
+  timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --workload $wl --treelet-prefetch 1 --lib ray_tracing_b200/librt_b200_treelet.so 2>&1 | tail -1 | cut -c1-160 | tee -a $OUT/sweep_r2_pairorder.log
 done
