@@ -94,6 +94,59 @@ def test_simt_tail_lanes_and_ray_sorting_are_schedule_only(simt_lib):
                 assert sg[k] == so[k]
 
 
+def _equal_to_oracle(lib, sc, frames=1, kernels=(0, 1, 2), extra=()):
+    fo, ao, so = render(ORACLE_LIB, sc, frames=frames, want_stats=True)
+    for k in kernels:
+        for opts in ({"kernel": k}, {"kernel": k, "countStats": 1}) + tuple(dict(o, kernel=k) for o in extra):
+            fg, ag, sg = render(lib, sc, frames=frames, options=opts, want_stats=True)
+            assert_bit_equal(ag, ao, f"{sc.name} {opts}")
+            assert_bit_equal(fg, fo, f"{sc.name} frame {opts}")
+            if opts.get("countStats"):
+                assert all(sg[key] == so[key] for key in ("rays", "boxTests", "triTests")), (sc.name, opts)
+
+
+@pytest.mark.parametrize("size", [(1, 1), (2, 1), (7, 3), (9, 9), (33, 5), (64, 1), (1, 64)])
+def test_simt_tiny_and_ragged_images(simt_lib, size):
+    _equal_to_oracle(simt_lib, scenes.cornell_spheres(size[0], size[1], 3, 2), frames=2)
+    _equal_to_oracle(simt_lib, scenes.knot_room(size[0], size[1], 3, 2, nu=20, nv=6))
+
+
+@pytest.mark.parametrize("bounces,spp", [(0, 1), (0, 5), (1, 1), (32, 1), (3, 17)])
+def test_simt_bounce_and_sample_extremes(simt_lib, bounces, spp):
+    _equal_to_oracle(simt_lib, scenes.cornell_spheres(24, 16, bounces, spp))
+    _equal_to_oracle(simt_lib, scenes.knot_room(24, 16, bounces, spp, nu=30, nv=6, glass=True))
+
+
+@pytest.mark.parametrize("n", [0, 1, 63, 64, 65, 255, 256, 257, 300])
+def test_simt_sphere_count_thresholds(simt_lib, n):
+    """64 / 65: linear scan vs sphere accelerator; 256 / 257: spheres staged in shared memory vs read from global memory."""
+    _equal_to_oracle(simt_lib, scenes.random_soup(24, 24, max_bounces=3, rays_per_pixel=1, triangles=300, spheres=n))
+
+
+def test_simt_degenerate_scenes(simt_lib):
+    """Nothing to hit (with and without sky), a mesh whose root is a leaf, 150 instanced models, a huge defocus disc."""
+    sc = scenes.cornell_spheres(16, 8, 3, 1); sc.spheres = sc.spheres[:0]
+    _equal_to_oracle(simt_lib, sc)
+    sc.settings["useSky"] = True
+    _equal_to_oracle(simt_lib, sc)
+    one = scenes.MeshDesc(np.float32([[-1, 0, 3], [1, 0, 3], [0, 1.5, 3]]), np.int32([0, 1, 2]), np.float32([[0, 0, -1]] * 3))
+    mat = scenes.material(diffuse=(0.8, 0.3, 0.3), emission=(1, 1, 1), emissionStrength=2.0)
+    _equal_to_oracle(simt_lib, scenes.Scene(name="tri", width=24, height=16, meshes=[one], models=[scenes.ModelDesc(0, np.eye(4), np.eye(4), mat)],
+                                            settings=dict(maxBounceCount=2, numRaysPerPixel=2, useSky=True)))
+    rng = np.random.RandomState(0)
+    models = []
+    for i in range(150):
+        l2w, w2l = scenes.trs(position=tuple(rng.uniform(-3, 3, 3) + np.array([0, 0, 6])), euler_deg=tuple(rng.uniform(0, 360, 3)), scale=tuple(rng.uniform(0.2, 0.6, 3)))
+        models.append(scenes.ModelDesc(i % 2, l2w, w2l, scenes.material(diffuse=tuple(rng.uniform(0.2, 1, 3)), flag=scenes.MAT_GLASS if i % 7 == 0 else 0, ior=1.4,
+                                                                         emission=(1, 1, 1), emissionStrength=float(i % 5 == 0))))
+    _equal_to_oracle(simt_lib, scenes.Scene(name="many", width=32, height=20, meshes=[scenes.knot_mesh(nu=16, nv=5), one], models=models,
+                                            settings=dict(maxBounceCount=4, numRaysPerPixel=1, useSky=True)), kernels=(1, 2))
+    sc = scenes.cornell_spheres(20, 12, 3, 2); sc.settings.update(defocusStrength=500.0, focusDistance=3.0, divergeStrength=0.0)
+    _equal_to_oracle(simt_lib, sc)
+    _equal_to_oracle(simt_lib, scenes.knot_room(40, 24, 5, 2, nu=40, nv=6, glass=True), kernels=(2,),
+                     extra=[{"poolSlots": 32, "tailLanes": 31}, {"poolSlots": 96, "tailLanes": 0, "sortRays": 1}, {"smemNodes": 100000}, {"modelSkip": 0}, {"gridFit": 1, "pairOrder": 1}])
+
+
 @pytest.mark.parametrize("order", ["1", "2"])
 def test_simt_results_do_not_depend_on_the_lane_schedule(simt_lib, monkeypatch, order):
     """The interpreter visits the threads of a CTA in descending or freshly shuffled order every round instead of ascending: a
