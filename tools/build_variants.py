@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Builds the compile-time A/B variants of librt_b200.so HERE (nvcc cross-compiles without a GPU) into ray_tracing_b200/variants/,
+so that a gpurun call spends its minutes measuring, not compiling.  The .so files are git-ignored but travel with the snapshot.
+
+    python tools/build_variants.py [name ...]        (no names: all)
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ray_tracing_b200 import build   # noqa: E402
+
+VARIANTS = {
+    "treelet": ("RT_TREELET_PREFETCH",),
+    "treelet_stacktop": ("RT_TREELET_PREFETCH", "RT_STACK_TOP_REG"),
+    "stacktop": ("RT_STACK_TOP_REG",),
+    "tri_na": ("RT_TRI_LOAD_POLICY=1",),
+    "tri_ef": ("RT_TRI_LOAD_POLICY=2",),
+    "pf": ("RT_PREFETCH_NEXT_PAIR",),
+    "leaf2": ("RT_LEAF_REPEAT=2",),
+    "ir1": ("RT_INNER_REPEAT=1",),
+    "ir3": ("RT_INNER_REPEAT=3",),
+    "rayinv": ("RT_CACHE_RAYINV",),
+    "pw20": ("RT_POOL_WARPS=20",),
+    "pw16": ("RT_POOL_WARPS=16",),
+    "skipsqrt": ("RT_SPHERE_SKIP_SQRT",),
+    "mb5": ("RT_WAVE_MINBLOCKS=5",),
+    "all_mesh": ("RT_TREELET_PREFETCH", "RT_STACK_TOP_REG", "RT_TRI_LOAD_POLICY=1", "RT_LEAF_REPEAT=2"),
+}
+OUT_DIR = os.path.join(build.PKG_DIR, "variants")
+
+
+def path(name: str) -> str:
+    return os.path.join(OUT_DIR, f"librt_b200_{name}.so")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT_DIR, exist_ok=True)
+    names = sys.argv[1:] or list(VARIANTS)
+    for n in names:
+        build.build_cuda(force=True, defines=VARIANTS[n], out=path(n))
+    print("built", len(names), "variants in", OUT_DIR)

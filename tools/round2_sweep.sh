@@ -1,4 +1,6 @@
 #!/bin/bash
+# SUPERSEDED for quick ranking by tools/build_variants.py (run locally) + tools/sweep.py --stage 1|2|3 (one process per workload, no
+# compiling on the GPU box); this script is the long form that goes through bench.py for every configuration.
 # A/B candidates prepared at the end of round 1 (compile-time variants, all off by default, none measured yet; the pool-kernel
 # ones are bit-exact on the SIMT interpreter build: RT_SIMT_VARIANTS=1 python -m pytest tests/test_simt_kernels.py -k variants).
 # Build them next to the default library and compare on one GPU:   bash tools/round2_sweep.sh   (under gpurun)

@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""A/B sweep of kernel variants and options in ONE process per workload (the scene is generated once; every configuration gets a
+fresh context on it).  Kernel time = CUDA events around the dispatches (rtGetStats kernelMs), after warm-up; a 256 MiB write
+between frames evicts L2.  For ranking candidates; the numbers that count are bench.py's.
+
+    python tools/build_variants.py                      (here, before gpurun)
+    python tools/sweep.py --stage 1                     (on the GPU box; writes gpurun_out/sweep_r2.jsonl)
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tools"))
+import bench                                         # noqa: E402  (workload table, scene factory, algorithmic bytes)
+from build_variants import path as variant           # noqa: E402
+
+# (label, variant library or None, options)
+STAGES = {
+    1: (["knot64", "soup4k"], [
+        ("default", None, {}),
+        ("treelet", "treelet", {"treeletPrefetch": 1}),
+        ("treelet+stacktop", "treelet_stacktop", {"treeletPrefetch": 1}),
+        ("stacktop", "stacktop", {}),
+        ("tri no_allocate", "tri_na", {}),
+        ("tri evict_first", "tri_ef", {}),
+        ("pairOrder 1", None, {"pairOrder": 1}),
+        ("pairOrder 2", None, {"pairOrder": 2}),
+        ("pairOrder 3", None, {"pairOrder": 3}),
+        ("pairOrder 1 + next-pair prefetch", "pf", {"pairOrder": 1}),
+        ("all_mesh", "all_mesh", {"treeletPrefetch": 1}),
+    ]),
+    2: (["knot64", "cluster4k", "soup4k"], [
+        ("default", None, {}),
+        ("leaf2", "leaf2", {}), ("ir1", "ir1", {}), ("ir3", "ir3", {}), ("rayinv", "rayinv", {}), ("pw20", "pw20", {}), ("pw16", "pw16", {}),
+        ("l2Persist", None, {"l2Persist": 1}), ("pairOrder 4", None, {"pairOrder": 4}), ("pairOrder 6", None, {"pairOrder": 6}),
+        ("poolSlots 96 + treelet", "treelet", {"treeletPrefetch": 1, "poolSlots": 96}),
+    ]),
+    3: (["cornell64", "cornell1"], [
+        ("default", None, {}), ("skipsqrt", "skipsqrt", {}), ("mb5", "mb5", {}), ("gridFit", None, {"gridFit": 1}), ("kernel 2", None, {"kernel": 2}),
+    ]),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--stage", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--workloads", nargs="*", default=None)
+    args = ap.parse_args()
+    import torch
+    import ray_tracing_b200 as rt
+    from ray_tracing_b200 import build as b, scenes
+    workloads, configs = STAGES[args.stage]
+    os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
+    log = open(os.path.join(REPO, "gpurun_out", "sweep_r2.jsonl"), "a")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for wl in (args.workloads or workloads):
+        w = bench.WORKLOADS[wl]
+        sc = bench.make_scene(w)
+        base = None
+        for label, var, opts in configs:
+            lib = variant(var) if var else b.LIB_CUDA
+            if not os.path.exists(lib):
+                print(f"-- {wl}: {label}: {lib} not built", flush=True)
+                continue
+            try:
+                mgr = rt.RayComputeManager(lib)
+                scenes.apply(sc, mgr)
+                ctx = mgr.context
+                for k, v in opts.items():
+                    ctx.set_option(k, v)
+                mgr.OnEnable()
+                for i in range(args.warmup):
+                    ctx.set_int("Frame", 1 + i); ctx.dispatch_full(0)
+                ctx.synchronize(); ctx.reset_stats()
+                for i in range(args.steps):
+                    flush.zero_(); torch.cuda.synchronize()
+                    ctx.set_int("Frame", 1 + args.warmup + i); ctx.dispatch_full(0)
+                st = ctx.stats()
+                ms = st["kernelMs"] / args.steps
+                mrays = st["rays"] / (st["kernelMs"] * 1e-3) / 1e6
+                mgr.OnDestroy()
+            except Exception as e:                      # a variant that fails must not stop the sweep
+                print(f"-- {wl}: {label}: {type(e).__name__}: {str(e)[:200]}", flush=True)
+                continue
+            if base is None:
+                base = ms
+            row = {"workload": wl, "config": label, "kernel_ms": round(ms, 4), "Mrays_s": round(mrays, 1), "vs_default": round(base / ms, 4), "options": opts, "lib": os.path.basename(lib)}
+            print(json.dumps(row), flush=True)
+            log.write(json.dumps(row) + "\n"); log.flush()
+
+
+if __name__ == "__main__":
+    main()
