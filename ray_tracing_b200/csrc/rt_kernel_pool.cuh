@@ -45,6 +45,7 @@ namespace rtd {
 //                      the fetch and box tests of the popped node instead of preceding them
 //   RT_CACHE_RAYINV    1 / world ray direction (model skipping) computed once per ray instead of at every model step
 //   RT_LEAF_REPEAT=n   n leaf primitives per census (like RT_INNER_REPEAT for inner nodes)
+//   (RT_PREFETCH_CUR: below)
 //   RT_PREFETCH_NEXT_PAIR   L1 prefetch of the record after the one being fetched (meant for "pairOrder" = 1, where that is child A's)
 #ifdef RT_STACK_TOP_REG
 #define RT_PUSH(x) do { if (stackCount > 0) stack[stackCount - 1] = stackTop; stackTop = (x); stackCount++; } while (0)
@@ -55,6 +56,16 @@ namespace rtd {
 #endif
 #ifndef RT_LEAF_REPEAT
 #define RT_LEAF_REPEAT 1
+#endif
+//   RT_PREFETCH_CUR    the moment a lane learns which node it visits next (descent, pop, start of a model) it asks L1 for that node's
+//                      record (or the leaf's first triangle): the census, the vote and the other step kinds of the following
+//                      iterations run while the line travels, instead of the load being issued at the top of the step that needs it
+#if defined(RT_PREFETCH_CUR) && !defined(RT_SIMT_EMU)
+#define RT_PF_CUR() do { const void* pfAddr = cur.count > 0 ? (EXT && P.sphBvh && model < 0 ? (const void*)(P.sphLeaves + cur.start) : (const void*)(P.triGeom + cur.start)) \
+                                                             : (EXT && P.sphBvh && model < 0 ? (const void*)(P.sphPairs + cur.start) : (const void*)(P.pairs + (cur.start & 0x3fffffff))); \
+                         asm volatile("prefetch.global.L1 [%0];" :: "l"(pfAddr)); } while (0)
+#else
+#define RT_PF_CUR() do { } while (0)
 #endif
 constexpr int POOL_WARPS = RT_POOL_WARPS;      // warps per CTA (one persistent CTA per SM)
 constexpr int POOL_THREADS = POOL_WARPS * 32;
@@ -456,7 +467,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                         lpos = rayPos; ldir = rayDir; linv = rcp3(rayDir);
                         bestDst = inf32(); bestTri = 0x7fffffff; bestDet = 1.0f; bestU = 0.0f;
                         cur.start = P.sphRootStart; cur.count = P.sphRootCount; leafK = 0; stackCount = 0;
-                        mode = cur.count > 0 ? T_LEAF : T_INNER;
+                        mode = cur.count > 0 ? T_LEAF : T_INNER; RT_PF_CUR();
                     }
                     else if (model < P.modelCount)
                     {
@@ -470,7 +481,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                         cull = meta.z != 0;
                         bestDst = resDst; bestTri = -1;              // result.dst is the ray length shared across models (HL:359)
                         cur.start = meta.x; cur.count = meta.y; leafK = 0; stackCount = 0;
-                        mode = cur.count > 0 ? T_LEAF : T_INNER;
+                        mode = cur.count > 0 ? T_LEAF : T_INNER; RT_PF_CUR();
                     }
                     else
                     {
@@ -523,8 +534,8 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                     // (x*1 - 0 is x exactly, so the mesh comparison is unchanged; inf stays inf and never passes)
                     const float cs = sph ? 0.99999619f : 1.0f, cb = sph ? 1e-6f : 0.0f;
                     if ((dstFar * cs - cb) < bestDst && stackCount < WAVE_STACK) RT_PUSH(farRef);   // (prefetching the far record here was measured: -2 %)
-                    if ((dstNear * cs - cb) < bestDst) { cur = nearRef; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
-                    else if (stackCount > 0) { RT_POP(cur); leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
+                    if ((dstNear * cs - cb) < bestDst) { cur = nearRef; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; RT_PF_CUR(); }
+                    else if (stackCount > 0) { RT_POP(cur); leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; RT_PF_CUR(); }
                     else mode = T_NEXT;
                 }
             }
@@ -550,7 +561,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                     leafK++;
                     if (leafK >= cur.count)
                     {
-                        if (stackCount > 0) { RT_POP(cur); leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
+                        if (stackCount > 0) { RT_POP(cur); leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; RT_PF_CUR(); }
                         else mode = T_NEXT;
                     }
                 }
@@ -566,7 +577,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                     leafK++;
                     if (leafK >= cur.count)
                     {
-                        if (stackCount > 0) { RT_POP(cur); leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; }
+                        if (stackCount > 0) { RT_POP(cur); leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; RT_PF_CUR(); }
                         else mode = T_NEXT;
                     }
                 }

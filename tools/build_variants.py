@@ -17,6 +17,9 @@ VARIANTS = {
     "tri_na": ("RT_TRI_LOAD_POLICY=1",),
     "tri_ef": ("RT_TRI_LOAD_POLICY=2",),
     "pf": ("RT_PREFETCH_NEXT_PAIR",),
+    "pfcur": ("RT_PREFETCH_CUR",),
+    "pfcur_ir1": ("RT_PREFETCH_CUR", "RT_INNER_REPEAT=1"),
+    "pfcur_treelet": ("RT_PREFETCH_CUR", "RT_TREELET_PREFETCH"),
     "leaf2": ("RT_LEAF_REPEAT=2",),
     "ir1": ("RT_INNER_REPEAT=1",),
     "ir3": ("RT_INNER_REPEAT=3",),

@@ -25,6 +25,9 @@ STAGES = {
         ("treelet", "treelet", {"treeletPrefetch": 1}),
         ("treelet+stacktop", "treelet_stacktop", {"treeletPrefetch": 1}),
         ("stacktop", "stacktop", {}),
+        ("prefetch cur", "pfcur", {}),
+        ("prefetch cur, 1 inner visit per census", "pfcur_ir1", {}),
+        ("prefetch cur + treelet", "pfcur_treelet", {"treeletPrefetch": 1}),
         ("tri no_allocate", "tri_na", {}),
         ("tri evict_first", "tri_ef", {}),
         ("pairOrder 1", None, {"pairOrder": 1}),
