@@ -47,12 +47,31 @@ namespace rtd {
 //   RT_LEAF_REPEAT=n   n leaf primitives per census (like RT_INNER_REPEAT for inner nodes)
 //   (RT_PREFETCH_CUR: below)
 //   RT_PREFETCH_NEXT_PAIR   L1 prefetch of the record after the one being fetched (meant for "pairOrder" = 1, where that is child A's)
-#ifdef RT_STACK_TOP_REG
+//   RT_SMEM_STACK=N    (N a power of two) the top N entries of every lane's traversal stack live in shared memory — a ring, word-major
+//                      across the warp, so lane = bank and a push or pop is two conflict-free 4-byte accesses instead of a local-memory
+//                      access that touches up to 32 different lines (divergent stack depths); deeper entries spill to the local
+//                      array, oldest first.  Costs N * 6 KB of shared memory per CTA (taken from L1).
+#if defined(RT_SMEM_STACK)
+static_assert((RT_SMEM_STACK & (RT_SMEM_STACK - 1)) == 0 && RT_SMEM_STACK >= 2, "RT_SMEM_STACK must be a power of two");
+// entries [stackSpilled, stackCount) are in the ring at index (i & (N - 1)); entries [0, stackSpilled) in the local array
+#define RT_PUSH(x) do { if (stackCount - stackSpilled == RT_SMEM_STACK) { NodeRef sp_; const int r_ = (stackSpilled & (RT_SMEM_STACK - 1)) * 64; \
+                            sp_.start = ring[r_ + (int)lane]; sp_.count = ring[r_ + 32 + (int)lane]; stack[stackSpilled++] = sp_; } \
+                        const NodeRef px_ = (x); const int w_ = (stackCount & (RT_SMEM_STACK - 1)) * 64; ring[w_ + (int)lane] = px_.start; ring[w_ + 32 + (int)lane] = px_.count; stackCount++; } while (0)
+#define RT_POP(dst) do { --stackCount; if (stackCount < stackSpilled) { (dst) = stack[--stackSpilled]; } \
+                         else { const int w_ = (stackCount & (RT_SMEM_STACK - 1)) * 64; (dst).start = ring[w_ + (int)lane]; (dst).count = ring[w_ + 32 + (int)lane]; } } while (0)
+#elif defined(RT_STACK_TOP_REG)
 #define RT_PUSH(x) do { if (stackCount > 0) stack[stackCount - 1] = stackTop; stackTop = (x); stackCount++; } while (0)
 #define RT_POP(dst) do { (dst) = stackTop; --stackCount; if (stackCount > 0) stackTop = stack[stackCount - 1]; } while (0)
 #else
 #define RT_PUSH(x) stack[stackCount++] = (x)
 #define RT_POP(dst) (dst) = stack[--stackCount]
+#endif
+#ifdef RT_SMEM_STACK
+#define RT_STACK_RESET() stackSpilled = 0
+#define RT_STACK_SMEM_BYTES ((size_t)POOL_THREADS * RT_SMEM_STACK * 8)
+#else
+#define RT_STACK_RESET() do { } while (0)
+#define RT_STACK_SMEM_BYTES ((size_t)0)
 #endif
 #ifndef RT_LEAF_REPEAT
 #define RT_LEAF_REPEAT 1
@@ -167,6 +186,10 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
     PoolView<M> pool;
     pool.w = reinterpret_cast<float*>(poolBase + (size_t)warp * POOL_BYTES);
     pool.order = reinterpret_cast<unsigned char*>(pool.w + POOL_WORDS * M);
+#ifdef RT_SMEM_STACK
+    int* ring = reinterpret_cast<int*>(poolBase + (size_t)POOL_WARPS * POOL_BYTES) + (size_t)warp * (RT_SMEM_STACK * 64);     // this warp's N x 2 x 32 words
+    int stackSpilled = 0;
+#endif
 
     // ---- stage the tree tops (TMA bulk copy) and the spheres; initialise the pool -------------------------------------
     const uint32_t mbar = smem_u32(&hdr->mbar);
@@ -466,7 +489,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                         // sphere phase: world-space ray against the accelerator of the Spheres buffer (semantics of TraverseSpheres)
                         lpos = rayPos; ldir = rayDir; linv = rcp3(rayDir);
                         bestDst = inf32(); bestTri = 0x7fffffff; bestDet = 1.0f; bestU = 0.0f;
-                        cur.start = P.sphRootStart; cur.count = P.sphRootCount; leafK = 0; stackCount = 0;
+                        cur.start = P.sphRootStart; cur.count = P.sphRootCount; leafK = 0; stackCount = 0; RT_STACK_RESET();
                         mode = cur.count > 0 ? T_LEAF : T_INNER; RT_PF_CUR();
                     }
                     else if (model < P.modelCount)
@@ -480,7 +503,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                         linv = rcp3(ldir);
                         cull = meta.z != 0;
                         bestDst = resDst; bestTri = -1;              // result.dst is the ray length shared across models (HL:359)
-                        cur.start = meta.x; cur.count = meta.y; leafK = 0; stackCount = 0;
+                        cur.start = meta.x; cur.count = meta.y; leafK = 0; stackCount = 0; RT_STACK_RESET();
                         mode = cur.count > 0 ? T_LEAF : T_INNER; RT_PF_CUR();
                     }
                     else
@@ -599,7 +622,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
 template <int M> inline size_t pool_smem_bytes(const DevParams& P)
 {
     const int nS = P.sphereCount < WAVE_MAX_SMEM_SPHERES ? P.sphereCount : WAVE_MAX_SMEM_SPHERES;
-    return sizeof(WaveSmemHeader) + (size_t)P.smemPairs * sizeof(NodePair) + (size_t)nS * sizeof(DevSphere) + (size_t)POOL_WARPS * (POOL_WORDS * M * 4 + M);
+    return sizeof(WaveSmemHeader) + (size_t)P.smemPairs * sizeof(NodePair) + (size_t)nS * sizeof(DevSphere) + (size_t)POOL_WARPS * (POOL_WORDS * M * 4 + M) + RT_STACK_SMEM_BYTES;
 }
 
 template <int M> inline cudaError_t pool_configure_one()
@@ -623,7 +646,7 @@ inline int pool_max_smem_pairs(int M, int sphereCount)
 {
     const int nS = sphereCount < WAVE_MAX_SMEM_SPHERES ? sphereCount : WAVE_MAX_SMEM_SPHERES;
     const long long left = 227LL * 1024 - (long long)sizeof(WaveSmemHeader) - (long long)nS * (long long)sizeof(DevSphere)
-                         - (long long)POOL_WARPS * (POOL_WORDS * M * 4 + M) - 1024;
+                         - (long long)POOL_WARPS * (POOL_WORDS * M * 4 + M) - (long long)RT_STACK_SMEM_BYTES - 1024;
     return left <= 0 ? 0 : (int)(left / (long long)sizeof(NodePair));
 }
 

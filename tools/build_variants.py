@@ -20,6 +20,8 @@ VARIANTS = {
     "pfcur": ("RT_PREFETCH_CUR",),
     "pfcur_ir1": ("RT_PREFETCH_CUR", "RT_INNER_REPEAT=1"),
     "pfcur_treelet": ("RT_PREFETCH_CUR", "RT_TREELET_PREFETCH"),
+    "smemstack4": ("RT_SMEM_STACK=4",),
+    "smemstack8": ("RT_SMEM_STACK=8",),
     "leaf2": ("RT_LEAF_REPEAT=2",),
     "ir1": ("RT_INNER_REPEAT=1",),
     "ir3": ("RT_INNER_REPEAT=3",),

@@ -25,6 +25,8 @@ STAGES = {
         ("treelet", "treelet", {"treeletPrefetch": 1}),
         ("treelet+stacktop", "treelet_stacktop", {"treeletPrefetch": 1}),
         ("stacktop", "stacktop", {}),
+        ("smem stack 4", "smemstack4", {}),
+        ("smem stack 8", "smemstack8", {}),
         ("prefetch cur", "pfcur", {}),
         ("prefetch cur, 1 inner visit per census", "pfcur_ir1", {}),
         ("prefetch cur + treelet", "pfcur_treelet", {"treeletPrefetch": 1}),
