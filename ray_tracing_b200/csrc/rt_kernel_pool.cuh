@@ -76,6 +76,21 @@ static_assert((RT_SMEM_STACK & (RT_SMEM_STACK - 1)) == 0 && RT_SMEM_STACK >= 2, 
 #ifndef RT_LEAF_REPEAT
 #define RT_LEAF_REPEAT 1
 #endif
+//   RT_VOTE_WI / RT_VOTE_WL / RT_VOTE_WN   weights of the vote: the warp runs the step kind with the largest lanes x weight.  A leaf step
+//                      (one triangle) costs about a third of an inner step (two node visits) and returns its lanes to the inner
+//                      population sooner; counted on the SIMT interpreter build (step counts are exact there, the instruction cost per
+//                      step kind is an estimate from the SASS line profile: census 20, inner 150, leaf 55, next 90), weights 1 / 3 / 2
+//                      cut the inner steps of the 200k-triangle soup by 22 % (they run with 20 lanes instead of 15.6) and the estimated
+//                      instruction count by 17 %; 5-7 % on the knot scenes and on 24 instanced models.  Default 1 / 1 / 1 until measured.
+#ifndef RT_VOTE_WI
+#define RT_VOTE_WI 1
+#endif
+#ifndef RT_VOTE_WL
+#define RT_VOTE_WL 1
+#endif
+#ifndef RT_VOTE_WN
+#define RT_VOTE_WN 1
+#endif
 //   RT_PREFETCH_CUR    the moment a lane learns which node it visits next (descent, pop, start of a model) it asks L1 for that node's
 //                      record (or the leaf's first triangle): the census, the vote and the other step kinds of the following
 //                      iterations run while the line travels, instead of the load being issued at the top of the step that needs it
@@ -456,7 +471,9 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
             // Lanes are independent state machines (inner node / leaf triangle / next model); executing every kind each
             // iteration would run each at a fraction of the warp.  One kind per iteration keeps the executed block dense,
             // the others catch up when their kind becomes the majority.  The per-ray visiting order is unchanged.
-            if (nNext >= nInner && nNext >= nLeaf)
+            // (RT_VOTE_W*: cost-weighted vote, see the macro block at the top; all weights 1 = the plain majority)
+            const int scoreInner = nInner * RT_VOTE_WI, scoreLeaf = nLeaf * RT_VOTE_WL, scoreNext = nNext * RT_VOTE_WN;
+            if (scoreNext >= scoreInner && scoreNext >= scoreLeaf)
             {
                 // ---- advance to the next model / finish the ray ----
                 bool fin = false;
@@ -517,7 +534,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                 }
                 if (__any_sync(0xffffffffu, fin)) finishedAny = true;
             }
-            else if (nInner >= nLeaf)
+            else if (scoreInner >= scoreLeaf)
             {
                 // ---- inner nodes: HL:262-282 ----  (RT_INNER_REPEAT visits per census: most lanes stay in this mode after a
                 // visit, and the census / vote / loop control of an iteration costs about a third of a visit)

@@ -11,6 +11,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ray_tracing_b200 import build   # noqa: E402
 
 VARIANTS = {
+    "vote132": ("RT_VOTE_WL=3", "RT_VOTE_WN=2"),
+    "vote142": ("RT_VOTE_WL=4", "RT_VOTE_WN=2"),
+    "vote274": ("RT_VOTE_WI=2", "RT_VOTE_WL=7", "RT_VOTE_WN=4"),
+    "vote163": ("RT_VOTE_WL=6", "RT_VOTE_WN=3"),
+    "vote132_pfcur": ("RT_VOTE_WL=3", "RT_VOTE_WN=2", "RT_PREFETCH_CUR"),
+    "vote132_pfcur_treelet": ("RT_VOTE_WL=3", "RT_VOTE_WN=2", "RT_PREFETCH_CUR", "RT_TREELET_PREFETCH"),
     "treelet": ("RT_TREELET_PREFETCH",),
     "treelet_stacktop": ("RT_TREELET_PREFETCH", "RT_STACK_TOP_REG"),
     "stacktop": ("RT_STACK_TOP_REG",),

@@ -22,6 +22,12 @@ from build_variants import path as variant           # noqa: E402
 STAGES = {
     1: (["knot64", "soup4k"], [
         ("default", None, {}),
+        ("vote 1/3/2", "vote132", {}),
+        ("vote 1/4/2", "vote142", {}),
+        ("vote 2/7/4", "vote274", {}),
+        ("vote 1/6/3", "vote163", {}),
+        ("vote 1/3/2 + prefetch cur", "vote132_pfcur", {}),
+        ("vote 1/3/2 + prefetch cur + treelet", "vote132_pfcur_treelet", {"treeletPrefetch": 1}),
         ("treelet", "treelet", {"treeletPrefetch": 1}),
         ("treelet+stacktop", "treelet_stacktop", {"treeletPrefetch": 1}),
         ("stacktop", "stacktop", {}),
