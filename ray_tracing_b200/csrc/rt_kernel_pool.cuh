@@ -91,6 +91,23 @@ static_assert((RT_SMEM_STACK & (RT_SMEM_STACK - 1)) == 0 && RT_SMEM_STACK >= 2, 
 #ifndef RT_VOTE_WN
 #define RT_VOTE_WN 1
 #endif
+// Schedule profiler of the SIMT interpreter build (tools/simt_schedule_profile.py; never defined in the product build): the
+// scheduling knobs become run-time values and the kernel counts census iterations, the lanes per step kind, phases and batches.
+#if defined(RT_SIMT_PROFILE) && defined(RT_SIMT_EMU)
+#undef RT_VOTE_WI
+#undef RT_VOTE_WL
+#undef RT_VOTE_WN
+#undef RT_INNER_REPEAT
+#undef RT_LEAF_REPEAT
+#define RT_VOTE_WI simt::knob[0]
+#define RT_VOTE_WL simt::knob[1]
+#define RT_VOTE_WN simt::knob[2]
+#define RT_INNER_REPEAT simt::knob[3]
+#define RT_LEAF_REPEAT_RUNTIME simt::knob[4]
+#define RT_PROF(i, v) simt::prof_add(i, (unsigned long long)(v))
+#else
+#define RT_PROF(i, v) do { } while (0)
+#endif
 //   RT_PREFETCH_CUR    the moment a lane learns which node it visits next (descent, pop, start of a model) it asks L1 for that node's
 //                      record (or the leaf's first triangle): the census, the vote and the other step kinds of the following
 //                      iterations run while the line travels, instead of the load being issued at the top of the step that needs it
@@ -261,6 +278,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
         // (1) shade the slots that came back from tracing, sorted by hit kind
         {
             const int n = CompactByState<M>(pool, lane, PS_HIT_MISS, PS_HIT_GLASS);
+            if (lane == 0) { RT_PROF(14, 1); RT_PROF(15, (n + 31) / 32); RT_PROF(16, n); }
             for (int i0 = 0; i0 < n; i0 += 32)
             {
                 const int i = i0 + (int)lane;
@@ -392,6 +410,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
         // (3) camera rays for the slots that start a sample (HL:567-576), in compacted batches
         {
             const int n = CompactByState<M>(pool, lane, PS_GEN, PS_GEN);
+            if (lane == 0) { RT_PROF(17, (n + 31) / 32); RT_PROF(18, n); }
             for (int i0 = 0; i0 < n; i0 += 32)
             {
                 const int i = i0 + (int)lane;
@@ -423,6 +442,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
             // ---- census: how many lanes wait in each mode (one warp reduction on byte-packed counters) ----
             const unsigned census = __reduce_add_sync(0xffffffffu, 1u << (8 * mode));
             const int nIdle = (int)(census & 255u), nInner = (int)((census >> 8) & 255u), nLeaf = (int)((census >> 16) & 255u), nNext = (int)(census >> 24);
+            if (lane == 0) { RT_PROF(0, 1); RT_PROF(1, nIdle); RT_PROF(2, nInner); RT_PROF(3, nLeaf); RT_PROF(4, nNext); }
 
             // ---- fetch: idle lanes pop the next rays of the warp queue (ballot rank, no atomics) ----
             if (nIdle != 0 && next < nRays)
@@ -475,6 +495,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
             const int scoreInner = nInner * RT_VOTE_WI, scoreLeaf = nLeaf * RT_VOTE_WL, scoreNext = nNext * RT_VOTE_WN;
             if (scoreNext >= scoreInner && scoreNext >= scoreLeaf)
             {
+                if (lane == 0) { RT_PROF(5, 1); RT_PROF(6, nNext); }
                 // ---- advance to the next model / finish the ray ----
                 bool fin = false;
                 if (mode == T_NEXT)
@@ -536,6 +557,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
             }
             else if (scoreInner >= scoreLeaf)
             {
+                if (lane == 0) { RT_PROF(7, 1); RT_PROF(8, nInner); }
                 // ---- inner nodes: HL:262-282 ----  (RT_INNER_REPEAT visits per census: most lanes stay in this mode after a
                 // visit, and the census / vote / loop control of an iteration costs about a third of a visit)
 #pragma unroll 1
@@ -553,6 +575,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                     else
                     {
                         LoadPair(P, smemPairs, cur.start, q0, q1, q2, q3);
+                        RT_PROF(13, 1);
 #if defined(RT_PREFETCH_NEXT_PAIR) && !defined(RT_SIMT_EMU)
                         // with "pairOrder" = 1 (pre-order records) the record of an inner child A is the next one: ask for it while this one is
                         // still in flight, so that a descent into A finds it in L1 (a wasted 64-byte prefetch when the ray goes to B or up)
@@ -573,7 +596,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
                     // meshes: the reference's push-time test dst < best (HL:280-281).  Sphere boxes: conservative slack, ties kept
                     // (x*1 - 0 is x exactly, so the mesh comparison is unchanged; inf stays inf and never passes)
                     const float cs = sph ? 0.99999619f : 1.0f, cb = sph ? 1e-6f : 0.0f;
-                    if ((dstFar * cs - cb) < bestDst && stackCount < WAVE_STACK) RT_PUSH(farRef);   // (prefetching the far record here was measured: -2 %)
+                    if ((dstFar * cs - cb) < bestDst && stackCount < WAVE_STACK) { RT_PUSH(farRef); RT_PROF(11, 1); RT_PROF(32 + (stackCount < 31 ? stackCount : 31), 1); }   // (prefetching the far record here was measured: -2 %)
                     if ((dstNear * cs - cb) < bestDst) { cur = nearRef; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; RT_PF_CUR(); }
                     else if (stackCount > 0) { RT_POP(cur); leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; RT_PF_CUR(); }
                     else mode = T_NEXT;
@@ -581,8 +604,11 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
             }
             else
             {
+                if (lane == 0) { RT_PROF(9, 1); RT_PROF(10, nLeaf); }
                 // ---- one leaf triangle: HL:248-260 ----
-#if RT_LEAF_REPEAT > 1
+#ifdef RT_LEAF_REPEAT_RUNTIME
+                for (int rep = 0; rep < RT_LEAF_REPEAT_RUNTIME; rep++)
+#elif RT_LEAF_REPEAT > 1
 #pragma unroll 1
                 for (int rep = 0; rep < RT_LEAF_REPEAT; rep++)
 #endif

@@ -81,6 +81,11 @@ inline void yield()
     simt_switch(&c->fibers[c->cur].sp, c->schedSp);
 }
 
+// schedule profiler (RT_SIMT_PROFILE builds): run-time scheduling knobs and counters, exported for tools/simt_schedule_profile.py
+extern "C" { inline int simtKnob[8] = {1, 1, 1, 2, 1, 0, 0, 0}; inline unsigned long long simtProf[64] = {}; }
+inline int* const knob = simtKnob;
+inline void prof_add(int i, unsigned long long v) { __atomic_fetch_add(&simtProf[i], v, __ATOMIC_RELAXED); }
+
 inline unsigned int lane_id() { return tl_cta->cur & 31u; }
 
 inline unsigned int activemask()
