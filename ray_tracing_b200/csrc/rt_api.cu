@@ -66,7 +66,7 @@ struct RtContext
     float4* peerFrame[RT_MAX_PEERS]; float4* peerAccum[RT_MAX_PEERS]; int nPeers = 0;
 
     // options
-    int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16, optSortRays = 0, optForceExt = 0, optModelSkip = 1, optPairOrder = 0, optGridFit = 0, optL2Persist = 0, optTreeletPrefetch = 0;
+    int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16, optSortRays = 0, optForceExt = 0, optModelSkip = 1, optPairOrder = 0, optGridFit = 0, optL2Persist = 0, optTreeletPrefetch = 0, optZeroDefocus = 1;
     int l2PersistApplied = 0; const void* l2PersistBase = nullptr; size_t l2PersistBytes = 0;   // kernel -1 = automatic   // smemPairs -1 = automatic
 
     // counters / timing
@@ -325,6 +325,7 @@ int rtSetOption(RtContext* c, const char* name, int value)
     else if (n == "sortRays") c->optSortRays = value != 0;
     else if (n == "gridFit") c->optGridFit = value != 0;
     else if (n == "l2Persist") c->optL2Persist = value != 0;
+    else if (n == "zeroDefocusShortcut") c->optZeroDefocus = value != 0;      // only RT_SKIP_ZERO_DEFOCUS builds read the flag it controls
     else if (n == "treeletPrefetch")
     {
 #ifdef RT_TREELET_PREFETCH
@@ -487,6 +488,16 @@ int rtDispatch(RtContext* c, int kernelIndex, int gx, int gy, int gz)
     P.FrameRender = c->frame.p; P.AccumulatedRender = c->accum.p;
     P.counters = c->dCounters; P.workCounter = c->dWork;
     P.nPeers = c->nPeers; P.forceExt = c->optForceExt; P.modelSkip = c->optModelSkip;
+    {
+        // camOrigin = M * (0,0,0,1) as SetupPixel computes it (left to right, unfused): exact zero components and non-finite axes rule the shortcut out
+        bool ok = c->P.DefocusStrength == 0.0f && c->optZeroDefocus != 0;
+        for (int a = 0; a < 3 && ok; a++)
+        {
+            const float o = ((P.cam[a] * 0.0f + P.cam[4 + a] * 0.0f) + P.cam[8 + a] * 0.0f) + P.cam[12 + a] * 1.0f;
+            ok = o != 0.0f && std::isfinite(o) && std::isfinite(P.cam[a]) && std::isfinite(P.cam[4 + a]);
+        }
+        P.zeroDefocus = ok ? 1 : 0;
+    }
     for (int k = 0; k < c->nPeers; k++) { P.peerFrame[k] = c->peerFrame[k]; P.peerAccum[k] = c->peerAccum[k]; }
 
     EventPair ev;

@@ -135,7 +135,8 @@ struct DevParams
     // leaf order (pad1 = index in the Spheres buffer)
     const NodePair*   sphPairs;
     const DevSphere*  sphLeaves;
-    int   sphBvh, sphRootStart, sphRootCount, pad6;
+    int   sphBvh, sphRootStart, sphRootCount;
+    int   zeroDefocus;                      // host: DefocusStrength == 0 and adding +-0 to the camera origin cannot change a bit of it (RT_SKIP_ZERO_DEFOCUS builds)
     int   smemPairs;                        // number of leading pair records staged in shared memory
     int   tailLanes;                        // pooled kernel: leave the trace phase when this few lanes are still tracing
     int   sortRays;                         // pooled kernel: group the ray queue by direction octant
@@ -574,9 +575,24 @@ RT_DI PixelSetup SetupPixel(const DevParams& P, unsigned int idx, unsigned int i
 RT_DI void GenerateCameraRay(const DevParams& P, const PixelSetup& s, uint32_t& rngState, PathState& ray)
 {
     const float numPixelsX = __uint2float_rn(P.W);
+#ifdef RT_SKIP_ZERO_DEFOCUS
+    // Round-2 candidate (compiled out by default): with DefocusStrength == 0 — every shipped scene but one — the defocus jitter is
+    // (finite * +-0) / W = +-0 and origin + camRight * +-0 + camUp * +-0 is the origin bit for bit as long as no origin component is
+    // itself a zero (whose sign could flip) and the camera axes are finite; the host checks that once per dispatch.  The two random
+    // numbers are still drawn (the stream must advance), only the sine, cosine, square root and two IEEE divisions are not evaluated.
+    f3 rayOrigin;
+    if (P.zeroDefocus) { NextRandom(rngState); NextRandom(rngState); rayOrigin = s.camOrigin; }
+    else
+    {
+        const f2 c0 = RandomPointInCircle(rngState);
+        const f2 defocusJitter = make_f2((c0.x * P.DefocusStrength) / numPixelsX, (c0.y * P.DefocusStrength) / numPixelsX);
+        rayOrigin = (s.camOrigin + s.camRight * defocusJitter.x) + s.camUp * defocusJitter.y;
+    }
+#else
     const f2 c0 = RandomPointInCircle(rngState);
     const f2 defocusJitter = make_f2((c0.x * P.DefocusStrength) / numPixelsX, (c0.y * P.DefocusStrength) / numPixelsX);
     const f3 rayOrigin = (s.camOrigin + s.camRight * defocusJitter.x) + s.camUp * defocusJitter.y;
+#endif
     const f2 c1 = RandomPointInCircle(rngState);
     const f2 jitter = make_f2((c1.x * P.DivergeStrength) / numPixelsX, (c1.y * P.DivergeStrength) / numPixelsX);
     const f3 jitteredFocusPoint = (s.focusPoint + s.camRight * jitter.x) + s.camUp * jitter.y;

@@ -27,6 +27,11 @@ def _sources() -> list[str]:
 
 
 def build(force: bool = False, defines: tuple = (), out: str = "") -> str:
+    """RT_SIMT_DEFINES=A,B=2 in the environment builds (and makes the test suite use) a variant with those macros defined."""
+    env_defs = tuple(d for d in os.environ.get("RT_SIMT_DEFINES", "").split(",") if d)
+    if env_defs and not defines and not out:
+        defines = env_defs
+        out = os.path.join(OUT_DIR, "librt_b200_simt_" + "_".join(d.replace("=", "") for d in env_defs) + ".so")
     target = out or LIB_SIMT
     os.makedirs(os.path.dirname(target), exist_ok=True)
     if not force and os.path.exists(target) and all(os.path.getmtime(s) <= os.path.getmtime(target) for s in _sources()):
