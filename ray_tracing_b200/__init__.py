@@ -14,6 +14,6 @@ entry points raise.
 from . import capi, scenes          # noqa: F401
 from .capi import RtLib, RtContext, RtError   # noqa: F401
 from .manager import RayComputeManager, build_bvh, load_obj, set_build_threads   # noqa: F401
-from .display import RayTraceDisplay, write_png   # noqa: F401
+from .display import RayTraceDisplay, write_png, write_exr, read_exr   # noqa: F401
 
-__all__ = ["capi", "scenes", "RtLib", "RtContext", "RtError", "RayComputeManager", "build_bvh", "load_obj", "RayTraceDisplay", "write_png"]
+__all__ = ["capi", "scenes", "RtLib", "RtContext", "RtError", "RayComputeManager", "build_bvh", "load_obj", "RayTraceDisplay", "write_png", "write_exr", "read_exr"]

@@ -117,6 +117,22 @@ def test_display_matches_oracle_on_gpu():
 SCENES_DIR = "/root/reference/Assets/Scenes"
 
 
+def test_exr_export_is_lossless(tmp_path, oracle_path):
+    """The float4 accumulation buffer through write_exr / read_exr: bit-identical, NaN and inf included; header fields as the format wants."""
+    _, accum = render(oracle_path, scenes.cornell_spheres(37, 21, 3, 2), frames=2)
+    img = accum[::-1].copy()                                       # display orientation: row 0 = top
+    img[0, 0] = (np.nan, np.inf, -np.inf, -0.0)
+    p = str(tmp_path / "a.exr")
+    rt.write_exr(p, img)
+    back = rt.read_exr(p)
+    assert back.shape == img.shape and np.array_equal(back.view(np.uint32), img.view(np.uint32))
+    raw = open(p, "rb").read()
+    assert raw[:4] == bytes([0x76, 0x2F, 0x31, 0x01]) and b"channels\x00chlist\x00" in raw and b"compression\x00compression\x00\x01\x00\x00\x00\x00" in raw
+    assert len(raw) > 21 * (8 + 37 * 16)                        # 21 scan-line blocks of 8 + 4 channels x 37 floats, plus header and offset table
+    with pytest.raises(ValueError):
+        rt.write_exr(p, np.zeros((4, 4, 3), np.float32))
+
+
 def test_builtin_unity_meshes():
     from ray_tracing_b200 import unity_scene
     cube, quad = unity_scene.builtin_cube(), unity_scene.builtin_quad()
