@@ -456,6 +456,30 @@ struct PathState
     f3 pos, dir, transmittance, totalLight;
 };
 
+#ifdef RT_GLASS_OUT_OF_LINE
+// Round-2 candidate (compiled out by default): the glass branch of ShadeSegment (HL:499-518) as one out-of-line function.  Three of 32
+// lanes take it on config 2; inlined it is ~150 instructions of the per-iteration footprint, and instruction fetch is a fifth of the
+// stall cycles of that issue-bound kernel (profiles/r01_f_cornell_*).  Same operations in the same order.
+RT_DNI void ShadeGlass(const RtMaterial* material, float hitDst, bool isBackface, f3 normal, f3 hitPos, f3 diffuseDir, float v7, PathState& ray)
+{
+    if (isBackface)
+    {
+        const f3 absorb = ((-hitDst) * make_f3(material->absorption[0], material->absorption[1], material->absorption[2])) * material->absorptionStrength;
+        ray.transmittance = ray.transmittance * exp3_rt(absorb);
+    }
+    const float iorCurrent = isBackface ? material->ior : 1.0f;
+    const float iorNext = isBackface ? 1.0f : material->ior;
+    f3 reflectDir = Reflect(ray.dir, normal);
+    f3 refractDir = Refract(ray.dir, normal, iorCurrent, iorNext);
+    const float reflectWeight = CalculateReflectance(ray.dir, normal, iorCurrent, iorNext);
+    reflectDir = normalize3(lerp3(diffuseDir, reflectDir, material->specularProbability));
+    refractDir = normalize3(lerp3(-diffuseDir, refractDir, material->smoothness));
+    const bool followReflection = v7 <= reflectWeight;
+    ray.dir = followReflection ? reflectDir : refractDir;
+    ray.pos = hitPos + (0.001f * normal) * sign1(dot3(normal, ray.dir));
+}
+#endif
+
 // One iteration of the bounce loop after the intersection (HL:488-538).
 // Returns true when the path continues with another segment.
 //
@@ -500,6 +524,9 @@ RT_DI bool ShadeSegment(const DevParams& P, const Hit& hit, PathState& ray, uint
 
     if (isGlass)
     {
+#ifdef RT_GLASS_OUT_OF_LINE
+        ShadeGlass(material, hit.dst, hit.isBackface, hit.normal, hit.pos, diffuseDir, v7, ray);
+#else
         if (hit.isBackface)
         {
             const f3 absorb = ((-hit.dst) * make_f3(material->absorption[0], material->absorption[1], material->absorption[2])) * material->absorptionStrength;
@@ -517,6 +544,7 @@ RT_DI bool ShadeSegment(const DevParams& P, const Hit& hit, PathState& ray, uint
         const bool followReflection = v7 <= reflectWeight;
         ray.dir = followReflection ? reflectDir : refractDir;
         ray.pos = hit.pos + (epsilon * hit.normal) * sign1(dot3(hit.normal, ray.dir));
+#endif
     }
     else
     {

@@ -36,6 +36,8 @@ VARIANTS = {
     "pw16": ("RT_POOL_WARPS=16",),
     "skipsqrt": ("RT_SPHERE_SKIP_SQRT",),
     "zerodefocus": ("RT_SKIP_ZERO_DEFOCUS",),
+    "glassool": ("RT_GLASS_OUT_OF_LINE",),
+    "cornell_all": ("RT_SKIP_ZERO_DEFOCUS", "RT_GLASS_OUT_OF_LINE", "RT_SPHERE_SKIP_SQRT"),
     "zerodefocus_skipsqrt": ("RT_SKIP_ZERO_DEFOCUS", "RT_SPHERE_SKIP_SQRT"),
     "mb5": ("RT_WAVE_MINBLOCKS=5",),
     "all_mesh": ("RT_TREELET_PREFETCH", "RT_STACK_TOP_REG", "RT_TRI_LOAD_POLICY=1", "RT_LEAF_REPEAT=2"),

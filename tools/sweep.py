@@ -51,7 +51,7 @@ STAGES = {
         ("poolSlots 96 + treelet", "treelet", {"treeletPrefetch": 1, "poolSlots": 96}),
     ]),
     3: (["cornell64", "cornell1"], [
-        ("default", None, {}), ("zero-defocus shortcut", "zerodefocus", {}), ("zero-defocus + skipsqrt", "zerodefocus_skipsqrt", {}), ("skipsqrt", "skipsqrt", {}), ("mb5", "mb5", {}), ("gridFit", None, {"gridFit": 1}), ("kernel 2", None, {"kernel": 2}),
+        ("default", None, {}), ("glass out of line", "glassool", {}), ("zero-defocus + glass out of line + skipsqrt", "cornell_all", {}), ("zero-defocus shortcut", "zerodefocus", {}), ("zero-defocus + skipsqrt", "zerodefocus_skipsqrt", {}), ("skipsqrt", "skipsqrt", {}), ("mb5", "mb5", {}), ("gridFit", None, {"gridFit": 1}), ("kernel 2", None, {"kernel": 2}),
     ]),
 }
 
