@@ -226,6 +226,15 @@ RT_DI Hit Intersect(const DevParams& P, const float4* __restrict__ smemPairs, co
     return result;
 }
 
+#if defined(RT_SIMT_PROFILE) && defined(RT_SIMT_EMU)
+#define WAVE_PROF(i, v) do { if ((threadIdx.x & 31u) == 0) simt::prof_add(i, (unsigned long long)(v)); } while (0)
+#define WAVE_PROF_LANES(i, pred) do { const unsigned m_ = __ballot_sync(0xffffffffu, (pred)); if ((threadIdx.x & 31u) == 0) { simt::prof_add(i, (unsigned long long)__popc(m_)); simt::prof_add((i) + 20, m_ ? 1u : 0u); } } while (0)
+#define WAVE_PROF_LANE(i, pred) do { if (pred) simt::prof_add(i, 1); } while (0)
+#else
+#define WAVE_PROF(i, v) do { } while (0)
+#define WAVE_PROF_LANES(i, pred) do { } while (0)
+#define WAVE_PROF_LANE(i, pred) do { } while (0)
+#endif
 #ifndef RT_WAVE_MINBLOCKS
 #define RT_WAVE_MINBLOCKS 6      // <= 85 registers: 24 warps per SM (measured: 31.0 ms vs 37.1 ms at 16 warps on config 2)
 #endif
@@ -321,6 +330,8 @@ __global__ void __launch_bounds__(WAVE_THREADS, RT_WAVE_MINBLOCKS) k_raytrace_wa
             continue;
         }
 
+        // (interpreter-only schedule profile, see rt_kernel_pool.cuh / tools/simt_schedule_profile.py)
+        WAVE_PROF(20, 1); WAVE_PROF_LANES(21, havePixel && !pathActive && sample < P.NumRaysPerPixel); WAVE_PROF_LANES(22, pathActive || (havePixel && sample < P.NumRaysPerPixel));
         // [generate] start the pixel's next sample
         if (havePixel && !pathActive && sample < P.NumRaysPerPixel)
         {
@@ -333,6 +344,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, RT_WAVE_MINBLOCKS) k_raytrace_wa
         if (pathActive)
         {
             const Hit hit = Intersect<STATS, EXT>(P, smemPairs, smemSpheres, ray.pos, ray.dir, cnt);
+            WAVE_PROF_LANE(23, !(hit.dst < inf32())); WAVE_PROF_LANE(24, hit.dst < inf32() && hit.material->flag == RT_MATERIAL_GLASS);
             const bool cont = ShadeSegment(P, hit, ray, rngState);
             bounce++;
             if (!cont || bounce > P.MaxBounceCount)
