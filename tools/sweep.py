@@ -7,6 +7,7 @@ between frames evicts L2.  For ranking candidates; the numbers that count are be
     python tools/sweep.py --stage 1                     (on the GPU box; writes gpurun_out/sweep_r2.jsonl)
 """
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -73,7 +74,7 @@ def main():
     for wl in (args.workloads or workloads):
         w = bench.WORKLOADS[wl]
         sc = bench.make_scene(w)
-        base = None
+        base, base_digest = None, None
         for label, var, opts in configs:
             lib = variant(var) if var else b.LIB_CUDA
             if not os.path.exists(lib):
@@ -95,13 +96,14 @@ def main():
                 st = ctx.stats()
                 ms = st["kernelMs"] / args.steps
                 mrays = st["rays"] / (st["kernelMs"] * 1e-3) / 1e6
+                digest = hashlib.sha256(mgr.accumulatedResult.tobytes()).hexdigest()[:16]     # same frames in every configuration: same bits expected
                 mgr.OnDestroy()
             except Exception as e:                      # a variant that fails must not stop the sweep
                 print(f"-- {wl}: {label}: {type(e).__name__}: {str(e)[:200]}", flush=True)
                 continue
             if base is None:
-                base = ms
-            row = {"workload": wl, "config": label, "kernel_ms": round(ms, 4), "Mrays_s": round(mrays, 1), "vs_default": round(base / ms, 4), "options": opts, "lib": os.path.basename(lib)}
+                base, base_digest = ms, digest
+            row = {"workload": wl, "config": label, "identical_to_default": digest == base_digest, "kernel_ms": round(ms, 4), "Mrays_s": round(mrays, 1), "vs_default": round(base / ms, 4), "options": opts, "lib": os.path.basename(lib)}
             print(json.dumps(row), flush=True)
             log.write(json.dumps(row) + "\n"); log.flush()
 
