@@ -74,3 +74,14 @@ def assert_bit_equal(a: np.ndarray, b: np.ndarray, what=""):
     diff = np.abs(a.astype(np.float64) - b.astype(np.float64))
     raise AssertionError(f"{what}: {len(bad)} of {ai.size} values differ bitwise; max |Δ| = {np.nanmax(diff):.3e}; first at {bad[0].tolist()} "
                          f"({a[tuple(bad[0])]!r} vs {b[tuple(bad[0])]!r})")
+
+
+def seed_forcing_draw(post_step_state, draw, pixel_index, frame=1):
+    """renderSeed that makes the `draw`-th NextRandom of a pixel leave the generator in `post_step_state` (RayCommon.hlsl:127-133,552:
+    rngState = pixelIndex + Frame * 719393 + renderSeed, then state = state * 747796405 + 2891336453 per draw — an invertible LCG)."""
+    a_inv, c, m = pow(747796405, -1, 1 << 32), 2891336453, 1 << 32
+    st = post_step_state
+    for _ in range(draw):
+        st = ((st - c) * a_inv) % m
+    seed = (st - pixel_index - frame * 719393) % m
+    return seed - m if seed >= (1 << 31) else seed

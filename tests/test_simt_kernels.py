@@ -15,7 +15,7 @@ import sys
 import numpy as np
 import pytest
 
-from conftest import ORACLE_LIB, REPO, assert_bit_equal, render
+from conftest import ORACLE_LIB, REPO, assert_bit_equal, render, seed_forcing_draw as _seed_forcing_draw
 import ray_tracing_b200 as rt
 from ray_tracing_b200 import scenes
 import test_gpu_parity as G
@@ -145,6 +145,27 @@ def test_simt_degenerate_scenes(simt_lib):
     _equal_to_oracle(simt_lib, sc)
     _equal_to_oracle(simt_lib, scenes.knot_room(40, 24, 5, 2, nu=40, nv=6, glass=True), kernels=(2,),
                      extra=[{"poolSlots": 32, "tailLanes": 31}, {"poolSlots": 96, "tailLanes": 0, "sortRays": 1}, {"smemNodes": 100000}, {"modelSkip": 0}, {"gridFit": 1, "pairOrder": 1}])
+
+
+def test_simt_random_value_exactly_zero_and_exactly_one(simt_lib):
+    """Quirk Q4 made to happen: RandomValue is inclusive at both ends.  PCG's output is 0 only from post-step state 0 and 2^32 - 1 only
+    from 515875080 (exhaustive search), and the seed arithmetic is invertible, so a seed can put either value at a chosen draw of a
+    chosen pixel.  (a) 0 as the rho draw of the first diffuse hit: log(0) = -inf, rho = +inf, the random direction becomes
+    (inf * 0 = NaN, 0, 0), the bounce direction NaN; the ray then misses everything and the sky — whose smoothstep / max are
+    NaN-ignoring — answers with the ground colour: a FINITE pixel, equal on both sides.  (b) 1.0 as the roulette draw:
+    `rv >= p` ends the path even for p = 1."""
+    W, H, x, y = 48, 32, 5, 7
+    sc = scenes.cornell_spheres(W, H, 4, 1)
+    sc.settings["useSky"] = True
+    for post_state, draw in ((0, 7), (515875080, 12)):             # draws 1-4 camera jitter, 5 specular test, 6 theta_x, 7 rho_x, ..., 12 roulette
+        sc.settings["renderSeed"] = _seed_forcing_draw(post_state, draw, y * W + x)
+        fo, _ = render(ORACLE_LIB, sc)
+        if post_state == 0:
+            wall = fo[y, x, :3] / np.float32([0.35, 0.3, 0.35])     # ground colour of GetEnvironmentLight times the colour of the wall that was hit
+            assert np.all(np.isfinite(fo[y, x])) and np.all(wall > 0) and np.all(wall <= 1.0 + 1e-6)
+        for kernel in (0, 1, 2):
+            fg, _ = render(simt_lib, sc, options={"kernel": kernel})
+            assert_bit_equal(fg, fo, f"forced draw {draw} kernel {kernel}")
 
 
 @pytest.mark.parametrize("order", ["1", "2"])

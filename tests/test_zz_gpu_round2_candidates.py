@@ -48,3 +48,18 @@ def test_l2_persistence_window_changes_nothing_but_caching():
     fo, ao = render(CUDA_LIB, sc, frames=2)
     fg, ag = render(CUDA_LIB, sc, frames=2, options={"l2Persist": 1})
     assert_bit_equal(ag, ao, "l2Persist")
+
+
+def test_random_value_exactly_zero_and_exactly_one_on_gpu():
+    """Quirk Q4 forced by seed construction (see tests/test_simt_kernels.py::test_simt_random_value_exactly_zero_and_exactly_one): log(0) in
+    Box-Muller and a roulette draw of exactly 1.0, on the B200, all three kernels."""
+    from conftest import seed_forcing_draw as _seed_forcing_draw
+    W, H, x, y = 48, 32, 5, 7
+    sc = scenes.cornell_spheres(W, H, 4, 1)
+    sc.settings["useSky"] = True
+    for post_state, draw in ((0, 7), (515875080, 12)):
+        sc.settings["renderSeed"] = _seed_forcing_draw(post_state, draw, y * W + x)
+        fo, _ = render(ORACLE_LIB, sc)
+        for kernel in (0, 1, 2):
+            fg, _ = render(CUDA_LIB, sc, options={"kernel": kernel})
+            assert_bit_equal(fg, fo, f"forced draw {draw} kernel {kernel}")
