@@ -301,4 +301,18 @@ def test_cpp_oracle_equals_the_python_restatement(oracle_path):
         assert np.count_nonzero(mine) > (len(xy) if use_sky else 10)   # the sample is not a black image
         assert_bit_equal(out[:, :3], mine, f"C++ oracle vs numpy restatement (UseSky={use_sky})")
         assert np.all(out[:, 3] == 1.0)
+    # quirk Q4 forced: seeds that put RandomValue = 0 (log(0) in Box-Muller) or = 1.0 at a chosen draw of one pixel (conftest.seed_forcing_draw)
+    from conftest import seed_forcing_draw
+    ctx.set_int("UseSky", 1)
+    sh.UseSky = 1
+    for (px, py), post_state, draw in (((W // 2, H // 2), 0, 6), ((W // 2, H // 2), 0, 7), ((5, 3), 0, 7), ((W // 2, H // 2), 515875080, 12), ((7, 20), 515875080, 5)):
+        forced = seed_forcing_draw(post_state, draw, py * W + px, frame=frame)
+        ctx.set_int("renderSeed", forced); ctx.set_int("Frame", frame)
+        sh.renderSeed, sh.Frame = forced, frame
+        one = np.array([[px, py]], dtype=np.int32)
+        out = np.zeros((1, 4), dtype=np.float32)
+        assert fn(ctx.handle, one.ctypes.data, 1, out.ctypes.data) == 0
+        with np.errstate(all="ignore"):
+            mine = np.array([sh.pixel(px, py)], dtype=np.float32)
+        assert_bit_equal(out[:, :3], mine, f"forced draw {draw} -> post-step state {post_state} at pixel ({px}, {py})")
     ctx.destroy()
