@@ -47,6 +47,9 @@ WORKLOADS = {
     "instances16": dict(kind="instances", width=1920, height=1080, bounces=8, spp=16,
                         desc="24 models sharing two meshes (a 7,680-triangle knot instanced 23 times, glass / opaque / emissive, + room), "
                              "1920x1080, 8 bounces, 16 spp per frame (the many-Model shape of the reference's shipped scenes)"),
+    "instances500": dict(kind="instances", width=1920, height=1080, bounces=8, spp=8, instances=498,
+                         desc="500 models sharing two meshes (a 7,680-triangle knot instanced 498 times + room + light), 1920x1080, 8 bounces, "
+                              "8 spp per frame (many-Model shape: the TLAS over the models' world boxes, option tlas, is on automatically above 64 models)"),
     "cluster4k": dict(kind="cluster", width=3840, height=2160, bounces=12, spp=4,
                       desc="871,212-triangle glass knot cluster (one mesh, one deep BVH) in a room, 3840x2160, 12 bounces, 4 spp per frame (configs[3] shape)"),
     "soup4k": dict(kind="soup", width=4096, height=4096, bounces=16, spp=2,
@@ -61,7 +64,7 @@ def make_scene(w):
     if w["kind"] == "cornell":
         return scenes.cornell_spheres(w["width"], w["height"], w["bounces"], w["spp"])
     if w["kind"] == "instances":
-        return scenes.instanced_knots(w["width"], w["height"], w["bounces"], w["spp"])
+        return scenes.instanced_knots(w["width"], w["height"], w["bounces"], w["spp"], instances=w.get("instances", 23))
     if w["kind"] == "cluster":
         return scenes.knot_cluster(w["width"], w["height"], w["bounces"], w["spp"])
     if w["kind"] == "soup":
@@ -239,6 +242,8 @@ def run_gpu(args, w):
         ctx.set_option("l2Persist", args.l2_persist)
     if args.treelet_prefetch is not None:
         ctx.set_option("treeletPrefetch", args.treelet_prefetch)
+    if args.tlas is not None:
+        ctx.set_option("tlas", args.tlas)
     mgr.OnEnable()
     if tiled.fused:
         with torch.cuda.stream(stream):
@@ -357,7 +362,7 @@ def run_gpu(args, w):
                                    if tiled.fused else "one NCCL all-gather of finished tiles per frame")) if world > 1 else "single GPU",
                        "l2": "flushed between steps (256 MiB write inside the timed region)",
                        "kernel": kernel_label,
-                       "pool_slots": args.pool_slots, "smem_nodes": args.smem_nodes, "pair_order": args.pair_order, "grid_fit": args.grid_fit},
+                       "pool_slots": args.pool_slots, "smem_nodes": args.smem_nodes, "pair_order": args.pair_order, "grid_fit": args.grid_fit, "tlas": args.tlas},
             "ms_per_frame": round(ms_total / args.steps, 4),
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": W * H * 16,
@@ -392,6 +397,7 @@ def main():
     ap.add_argument("--kernel", type=int, default=None, help="0 = megakernel, 1 = persistent threads, 2 = pooled wavefront (default)")
     ap.add_argument("--pool-slots", type=int, default=None, help="paths per warp pool of kernel 2 (32, 64, 96)")
     ap.add_argument("--model-skip", type=int, default=None, help="kernels 1/2: skip models the ray cannot reach (1 default / 0)")
+    ap.add_argument("--tlas", type=int, default=None, help="kernels 1/2: tree over the models' world boxes: -1 = automatic (above 64 models, default), 0 = linear test, 1 = on")
     ap.add_argument("--sort-rays", type=int, default=None, help="kernel 2: group the ray queue by direction octant (1/0)")
     ap.add_argument("--tail-lanes", type=int, default=None, help="kernel 2: leave the trace phase when this few lanes still trace")
     ap.add_argument("--treelet-prefetch", type=int, default=None, help="1 = flagged two-level treelets + L1 prefetch of both next records (needs --lib built with RT_TREELET_PREFETCH)")

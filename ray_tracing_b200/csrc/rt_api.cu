@@ -66,7 +66,7 @@ struct RtContext
     float4* peerFrame[RT_MAX_PEERS]; float4* peerAccum[RT_MAX_PEERS]; int nPeers = 0;
 
     // options
-    int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16, optSortRays = 0, optForceExt = 0, optModelSkip = 1, optPairOrder = 0, optGridFit = 0, optL2Persist = 0, optTreeletPrefetch = 0, optZeroDefocus = 1;
+    int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16, optSortRays = 0, optForceExt = 0, optModelSkip = 1, optPairOrder = 0, optGridFit = 0, optL2Persist = 0, optTreeletPrefetch = 0, optZeroDefocus = 1, optTlas = -1;
     int l2PersistApplied = 0; const void* l2PersistBase = nullptr; size_t l2PersistBytes = 0;   // kernel -1 = automatic   // smemPairs -1 = automatic
 
     // counters / timing
@@ -321,6 +321,11 @@ int rtSetOption(RtContext* c, const char* name, int value)
     else if (n == "countStats") c->optCountStats = value != 0;
     else if (n == "smemNodes") c->optSmemPairs = value;
     else if (n == "modelSkip") c->optModelSkip = value != 0;
+    else if (n == "tlas")
+    {
+        if (value < -1 || value > 1) return fail(c, RT_E_INVALID, "rtSetOption: tlas must be -1 (automatic), 0 or 1");
+        if (value != c->optTlas) { c->optTlas = value; c->modelsDirty = true; }
+    }
     else if (n == "extInstantiation") c->optForceExt = value != 0;
     else if (n == "sortRays") c->optSortRays = value != 0;
     else if (n == "gridFit") c->optGridFit = value != 0;
@@ -411,7 +416,7 @@ static int prepareScene(RtContext* c)
     }
     if (c->modelsDirty)
     {
-        cudaError_t e = c->repack.buildModels(c->hModels, c->hNodes, c->P.modelCount, c->stream);
+        cudaError_t e = c->repack.buildModels(c->hModels, c->hNodes, c->P.modelCount, c->stream, c->optTlas);
         if (e != cudaSuccess) return failCuda(c, e, "repack models");
         c->modelsDirty = false;
     }
@@ -488,6 +493,8 @@ int rtDispatch(RtContext* c, int kernelIndex, int gx, int gy, int gz)
     P.FrameRender = c->frame.p; P.AccumulatedRender = c->accum.p;
     P.counters = c->dCounters; P.workCounter = c->dWork;
     P.nPeers = c->nPeers; P.forceExt = c->optForceExt; P.modelSkip = c->optModelSkip;
+    P.tlasPairs = c->repack.tlasPairs.p; P.tlasLeaves = c->repack.tlasLeaves.p; P.tlas = c->repack.tlas;
+    P.tlasRootStart = c->repack.tlasRootStart; P.tlasRootCount = c->repack.tlasRootCount;
     {
         // camOrigin = M * (0,0,0,1) as SetupPixel computes it (left to right, unfused): exact zero components and non-finite axes rule the shortcut out
         bool ok = c->P.DefocusStrength == 0.0f && c->optZeroDefocus != 0;
@@ -753,6 +760,27 @@ int rtxPlanPairsOrdered(const RtNode* nodes, int nodeCount, const RtModel* model
         const MeshRoot& r = st.roots[std::make_pair(m[i].nodeOffset, m[i].triOffset)];
         rootsOut[2 * i] = r.rootStart; rootsOut[2 * i + 1] = r.rootCount;
     }
+    return (int)out.size();
+}
+
+/* Device-free test hook (not part of include/rt_b200.h): the TLAS the upload would build over `modelCount` world boxes
+ * (6 floats each: min xyz, max xyz).  pairsOut: capacity pairCap records of 64 bytes; leavesOut: modelCount model indices in leaf
+ * order; rootOut: 2 ints (start, count).  Returns the number of pair records or a negative RT_E_* code. */
+int rtxPlanTlas(const float* boxes, int modelCount, void* pairsOut, int pairCap, int* leavesOut, int* rootOut)
+{
+    if (!boxes || modelCount < 1 || modelCount > RT_TLAS_MAX_MODELS || !pairsOut || !leavesOut || !rootOut) return RT_E_INVALID;
+    std::vector<DevModel> dm(modelCount);
+    for (int i = 0; i < modelCount; i++)
+    {
+        memset(&dm[i], 0, sizeof(DevModel));
+        dm[i].wmin[0] = boxes[6 * i]; dm[i].wmin[1] = boxes[6 * i + 1]; dm[i].wmin[2] = boxes[6 * i + 2];
+        dm[i].wmaxx = boxes[6 * i + 3]; dm[i].wmaxy = boxes[6 * i + 4]; dm[i].wmaxz = boxes[6 * i + 5];
+    }
+    std::vector<NodePair> out; std::vector<int> order;
+    RepackState::planTlas(dm, modelCount, out, order, rootOut[0], rootOut[1]);
+    if ((int)out.size() > pairCap) return RT_E_INVALID;
+    if (!out.empty()) memcpy(pairsOut, out.data(), out.size() * sizeof(NodePair));
+    memcpy(leavesOut, order.data(), order.size() * sizeof(int));
     return (int)out.size();
 }
 

@@ -84,12 +84,32 @@ struct __align__(16) DevModel
 };
 static_assert(sizeof(DevModel) == 144, "DevModel layout");
 
+// Counters of the SIMT interpreter's profile build (tools/simt_*_profile.py; never defined in the product build):
+// [25] per-model box tests  [26] TLAS box tests  [27] TLAS walks
+#if defined(RT_SIMT_PROFILE) && defined(RT_SIMT_EMU)
+#define RT_DEV_PROF(i, v) simt::prof_add(i, (unsigned long long)(v))
+#else
+#define RT_DEV_PROF(i, v) do { } while (0)
+#endif
+
 // true when model record `mr` cannot change the current result: its padded world box is missed or lies beyond bestDst
 RT_DI bool ModelOutOfReach(const float4* __restrict__ mr, f3 rayPos, f3 rayInv, float bestDst)
 {
+    RT_DEV_PROF(25, 1);
     const float4 b0 = __ldg(mr + 7), b1 = __ldg(mr + 8);
     const f3 tMin = (make_f3(b0.x, b0.y, b0.z) - rayPos) * rayInv;
     const f3 tMax = (make_f3(b0.w, b1.x, b1.y) - rayPos) * rayInv;
+    const float tNear = fmaxf(fmaxf(fminf(tMin.x, tMax.x), fminf(tMin.y, tMax.y)), fminf(tMin.z, tMax.z));
+    const float tFar  = fminf(fminf(fmaxf(tMin.x, tMax.x), fmaxf(tMin.y, tMax.y)), fmaxf(tMin.z, tMax.z));
+    const bool hit = tFar >= tNear && tFar > 0.0f;
+    return !hit || (tNear * 0.99999619f - 1e-6f) > bestDst;
+}
+
+// The same test on a box of the TLAS (a box that encloses the padded world boxes of a set of models).
+RT_DI bool WorldBoxOutOfReach(f3 bmin, f3 bmax, f3 rayPos, f3 rayInv, float bestDst)
+{
+    const f3 tMin = (bmin - rayPos) * rayInv;
+    const f3 tMax = (bmax - rayPos) * rayInv;
     const float tNear = fmaxf(fmaxf(fminf(tMin.x, tMax.x), fminf(tMin.y, tMax.y)), fminf(tMin.z, tMax.z));
     const float tFar  = fminf(fminf(fmaxf(tMin.x, tMax.x), fmaxf(tMin.y, tMax.y)), fmaxf(tMin.z, tMax.z));
     const bool hit = tFar >= tNear && tFar > 0.0f;
@@ -154,6 +174,11 @@ struct DevParams
     int   forceExt;                         // testing: run the <EXT = true> instantiation although no extension is active
     unsigned long long* counters;           // [0] rays [1] boxTests [2] triTests [3] sphereTests [4] sphere-accelerator box tests
     unsigned int* workCounter;              // persistent kernel: next job
+    // TLAS over the models' padded world boxes (many-model scenes; only the <TLAS> kernels read these — appended so that the
+    // parameter offsets of everything above stay where they were)
+    const NodePair* tlasPairs;              // inner records: two child boxes each; count > 0 <=> leaf, start -> tlasLeaves
+    const int*      tlasLeaves;             // model indices in leaf order
+    int   tlas, tlasRootStart, tlasRootCount, pad8;
 };
 
 struct Counters { unsigned int rays, box, tri, sph, sbox; };
@@ -390,6 +415,67 @@ RT_DNI void TraverseSpheres(const DevParams& P, f3 rayPos, f3 rayDir, float& bes
             else { if (stackCount == 0) return; cur = stack[--stackCount]; }
         }
     }
+}
+
+// ---- TLAS over the models (many-model scenes) ------------------------------------------------------------------
+// The reference walks every Model for every ray segment, in buffer order, with one running result (HL:347-371).  Exactness pins
+// the ORDER in which models are processed (a model's traversal is culled against the result of the models before it), so the
+// TLAS does not reorder anything: one walk per ray segment marks, in a bit mask, the models whose padded world box the ray can
+// reach before its current best hit; the model loop then visits the marked models in ascending buffer index and repeats the
+// per-model test (ModelOutOfReach) against the result as it stands by then.  A model is therefore skipped only if its own box
+// test — or the same test on a TLAS box that encloses its box — fails, and either means its traversal could not have changed
+// the result ("Models a ray cannot reach are skipped").  Whatever the walk cannot decide (stack full)
+// it marks, so the mask is always a superset of what the linear test would keep at the same bestDst.
+constexpr int RT_TLAS_MAX_MODELS = 4096;                 // mask words per lane = 128 (local memory, touched only up to modelCount / 32)
+constexpr int RT_TLAS_WORDS = RT_TLAS_MAX_MODELS / 32;
+constexpr int RT_TLAS_STACK = 24;                        // median-split tree over <= 4096 models: depth <= 12
+
+RT_DNI void TlasCollect(const DevParams& P, f3 rayPos, f3 rayInv, float bestDst, unsigned int* __restrict__ mask)
+{
+    const int words = (P.modelCount + 31) >> 5;
+    for (int w = 0; w < words; w++) mask[w] = 0u;
+    int2 stack[RT_TLAS_STACK];
+    int stackCount = 0;
+    int2 cur = make_int2(P.tlasRootStart, P.tlasRootCount);
+    RT_DEV_PROF(27, 1);
+    for (;;)
+    {
+        if (cur.y > 0)
+        {
+            for (int k = 0; k < cur.y; k++) { const int m = __ldg(P.tlasLeaves + cur.x + k); mask[m >> 5] |= 1u << (m & 31); }
+            if (stackCount == 0) return;
+            cur = stack[--stackCount];
+        }
+        else
+        {
+            const float4* p = reinterpret_cast<const float4*>(P.tlasPairs + cur.x);
+            const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+            RT_DEV_PROF(26, 2);
+            const bool skipA = WorldBoxOutOfReach(make_f3(q0.x, q0.y, q0.z), make_f3(q0.w, q1.x, q1.y), rayPos, rayInv, bestDst);
+            const bool skipB = WorldBoxOutOfReach(make_f3(q2.x, q2.y, q2.z), make_f3(q2.w, q3.x, q3.y), rayPos, rayInv, bestDst);
+            const int2 a = make_int2(__float_as_int(q1.z), __float_as_int(q1.w)), b = make_int2(__float_as_int(q3.z), __float_as_int(q3.w));
+            if (!skipA && !skipB)
+            {
+                if (stackCount == RT_TLAS_STACK) { for (int w = 0; w < words; w++) mask[w] = 0xffffffffu; return; }   // cannot happen with the host's tree; stay conservative
+                stack[stackCount++] = b; cur = a;
+            }
+            else if (!skipA) cur = a;
+            else if (!skipB) cur = b;
+            else { if (stackCount == 0) return; cur = stack[--stackCount]; }
+        }
+    }
+}
+
+// smallest marked model index >= from, or modelCount
+RT_DI int TlasNext(const unsigned int* __restrict__ mask, int from, int modelCount)
+{
+    const int words = (modelCount + 31) >> 5;
+    int w = from >> 5;
+    if (from >= modelCount || w >= words) return modelCount;
+    unsigned int bits = mask[w] & (0xffffffffu << (from & 31));
+    while (bits == 0u) { if (++w >= words) return modelCount; bits = mask[w]; }
+    const int m = (w << 5) + __ffs((int)bits) - 1;
+    return m < modelCount ? m : modelCount;
 }
 
 // ---- hit record -----------------------------------------------------------------------------------------------------------

@@ -200,9 +200,11 @@ template <int M> RT_DI int CompactRaysByOctant(const PoolView<M>& pool, unsigned
     return base;
 }
 
-template <bool STATS, bool EXT, int M>
-__global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_constant__ DevParams P, const unsigned int totalJobs,
-                                                                  const unsigned int tilesX, const unsigned int ownedRows)
+// The kernel body.  TLAS = the many-model instantiation (k_raytrace_pool_tlas): at the start of a ray's model loop one walk of the
+// TLAS marks the models the ray can reach (TlasCollect, rt_device.cuh); the T_NEXT step then jumps from marked model to marked model,
+// in buffer order, re-testing each against the running result.  The kernels measured in round 1 are the TLAS = false instantiations.
+template <bool STATS, bool EXT, bool TLAS, int M>
+RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const unsigned int tilesX, const unsigned int ownedRows)
 {
     RT_DYNAMIC_SMEM(smemRaw);
     WaveSmemHeader* hdr = reinterpret_cast<WaveSmemHeader*>(smemRaw);
@@ -271,6 +273,8 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
 #ifdef RT_CACHE_RAYINV
     f3 rayInvW = splat3(0.0f);
 #endif
+    unsigned int tlasMask[TLAS ? RT_TLAS_WORDS : 1];                 // models this lane's ray can reach (valid from its first model step)
+    const bool useTlas = TLAS && !STATS && P.modelSkip && P.tlas;
 
     for (;;)
     {
@@ -520,6 +524,17 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
 #else
                         const f3 rayInv = rcp3(rayDir);
 #endif
+                        if (useTlas)
+                        {
+                            if (model == 0) TlasCollect(P, rayPos, rayInv, resDst, tlasMask);
+                            for (;;)
+                            {
+                                model = TlasNext(tlasMask, model, P.modelCount);
+                                if (model >= P.modelCount || !ModelOutOfReach(reinterpret_cast<const float4*>(P.models + model), rayPos, rayInv, resDst)) break;
+                                model++;
+                            }
+                        }
+                        else
                         while (model < P.modelCount && ModelOutOfReach(reinterpret_cast<const float4*>(P.models + model), rayPos, rayInv, resDst)) model++;
                     }
                     if (EXT && P.sphBvh && model == -1)
@@ -662,6 +677,21 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_
     }
 }
 
+template <bool STATS, bool EXT, int M>
+__global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_constant__ DevParams P, const unsigned int totalJobs,
+                                                                  const unsigned int tilesX, const unsigned int ownedRows)
+{
+    pool_body<STATS, EXT, false, M>(P, totalJobs, tilesX, ownedRows);
+}
+
+// many-model scenes: every extension + the TLAS (never instrumented: the counting build walks every model like the reference)
+template <int M>
+__global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool_tlas(const __grid_constant__ DevParams P, const unsigned int totalJobs,
+                                                                       const unsigned int tilesX, const unsigned int ownedRows)
+{
+    pool_body<false, true, true, M>(P, totalJobs, tilesX, ownedRows);
+}
+
 template <int M> inline size_t pool_smem_bytes(const DevParams& P)
 {
     const int nS = P.sphereCount < WAVE_MAX_SMEM_SPHERES ? P.sphereCount : WAVE_MAX_SMEM_SPHERES;
@@ -674,6 +704,7 @@ template <int M> inline cudaError_t pool_configure_one()
     if ((e = cudaFuncSetAttribute(k_raytrace_pool<false, false, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_raytrace_pool<true, false, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_raytrace_pool<false, true, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_raytrace_pool_tlas<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_raytrace_pool<true, true, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 inline cudaError_t pool_configure()
@@ -709,6 +740,7 @@ template <int M> inline cudaError_t pool_launch_m(const DevParams& P, int numSMs
     const bool ext = P.nPeers > 0 || P.sphBvh != 0 || P.forceExt != 0;   // extensions compiled into their own instantiation
     if (P.countStats) { if (ext) RT_LAUNCH(grid, POOL_THREADS, smemBytes, stream, RT_K(k_raytrace_pool<true, true, M>), P, totalJobs, tilesX, ownedRows);
                         else RT_LAUNCH(grid, POOL_THREADS, smemBytes, stream, RT_K(k_raytrace_pool<true, false, M>), P, totalJobs, tilesX, ownedRows); }
+    else if (P.tlas && P.modelSkip) RT_LAUNCH(grid, POOL_THREADS, smemBytes, stream, RT_K(k_raytrace_pool_tlas<M>), P, totalJobs, tilesX, ownedRows);
     else { if (ext) RT_LAUNCH(grid, POOL_THREADS, smemBytes, stream, RT_K(k_raytrace_pool<false, true, M>), P, totalJobs, tilesX, ownedRows);
            else RT_LAUNCH(grid, POOL_THREADS, smemBytes, stream, RT_K(k_raytrace_pool<false, false, M>), P, totalJobs, tilesX, ownedRows); }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;

@@ -142,7 +142,7 @@ RT_DI void TraverseMesh(const DevParams& P, const float4* __restrict__ smemPairs
 }
 
 // HL:335-374 (+ sphere extension) on the repacked streams
-template <bool STATS, bool EXT>
+template <bool STATS, bool EXT, bool TLAS>
 RT_DI Hit Intersect(const DevParams& P, const float4* __restrict__ smemPairs, const DevSphere* __restrict__ smemSpheres,
                     f3 rayPos, f3 rayDir, Counters& cnt)
 {
@@ -183,8 +183,14 @@ RT_DI Hit Intersect(const DevParams& P, const float4* __restrict__ smemPairs, co
     }
 
     const f3 rayInv = rcp3(rayDir);
+    // many-model scenes (<TLAS> kernels only): one walk of the TLAS marks the models this ray can reach at all; the loop below
+    // then jumps from marked model to marked model, still in buffer order and still re-testing each against the running result
+    unsigned int tlasMask[TLAS ? RT_TLAS_WORDS : 1];
+    const bool useTlas = TLAS && !STATS && P.modelSkip && P.tlas;
+    if (useTlas) TlasCollect(P, rayPos, rayInv, result.dst, tlasMask);
     for (int i = 0; i < P.modelCount; i++)
     {
+        if (useTlas) { i = TlasNext(tlasMask, i, P.modelCount); if (i >= P.modelCount) break; }
         const DevModel* m = P.models + i;
         const float4* mr = reinterpret_cast<const float4*>(m);
         // the instrumented build walks every model like the reference (identical test counts); otherwise models the ray cannot
@@ -238,9 +244,10 @@ RT_DI Hit Intersect(const DevParams& P, const float4* __restrict__ smemPairs, co
 #ifndef RT_WAVE_MINBLOCKS
 #define RT_WAVE_MINBLOCKS 6      // <= 85 registers: 24 warps per SM (measured: 31.0 ms vs 37.1 ms at 16 warps on config 2)
 #endif
-template <bool STATS, bool EXT>
-__global__ void __launch_bounds__(WAVE_THREADS, RT_WAVE_MINBLOCKS) k_raytrace_wave(const __grid_constant__ DevParams P, const unsigned int totalJobs,
-                                                               const unsigned int tilesX, const unsigned int ownedRows)
+// The kernel body.  TLAS = the many-model instantiation (its own kernel, k_raytrace_wave_tlas, so that the kernels measured in
+// round 1 keep their code: the TLAS walk and its mask exist only there).
+template <bool STATS, bool EXT, bool TLAS>
+RT_DI void wave_body(const DevParams& P, const unsigned int totalJobs, const unsigned int tilesX, const unsigned int ownedRows)
 {
     RT_DYNAMIC_SMEM(smemRaw);
     WaveSmemHeader* hdr = reinterpret_cast<WaveSmemHeader*>(smemRaw);
@@ -343,7 +350,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, RT_WAVE_MINBLOCKS) k_raytrace_wa
         // [intersect] + [shade]
         if (pathActive)
         {
-            const Hit hit = Intersect<STATS, EXT>(P, smemPairs, smemSpheres, ray.pos, ray.dir, cnt);
+            const Hit hit = Intersect<STATS, EXT, TLAS>(P, smemPairs, smemSpheres, ray.pos, ray.dir, cnt);
             WAVE_PROF_LANE(23, !(hit.dst < inf32())); WAVE_PROF_LANE(24, hit.dst < inf32() && hit.material->flag == RT_MATERIAL_GLASS);
             const bool cont = ShadeSegment(P, hit, ray, rngState);
             bounce++;
@@ -374,6 +381,20 @@ __global__ void __launch_bounds__(WAVE_THREADS, RT_WAVE_MINBLOCKS) k_raytrace_wa
     }
 }
 
+template <bool STATS, bool EXT>
+__global__ void __launch_bounds__(WAVE_THREADS, RT_WAVE_MINBLOCKS) k_raytrace_wave(const __grid_constant__ DevParams P, const unsigned int totalJobs,
+                                                               const unsigned int tilesX, const unsigned int ownedRows)
+{
+    wave_body<STATS, EXT, false>(P, totalJobs, tilesX, ownedRows);
+}
+
+// many-model scenes: every extension + the TLAS walk (never instrumented: the counting build walks every model like the reference)
+__global__ void __launch_bounds__(WAVE_THREADS, RT_WAVE_MINBLOCKS) k_raytrace_wave_tlas(const __grid_constant__ DevParams P, const unsigned int totalJobs,
+                                                                    const unsigned int tilesX, const unsigned int ownedRows)
+{
+    wave_body<false, true, true>(P, totalJobs, tilesX, ownedRows);
+}
+
 // "gridFit": a pixel's samples cannot be split (one RNG chain), so a persistent lane works through whole pixels.  When the image
 // gives every lane only a few (8 GPUs, config 2: 2.3 pixels per lane) the last round runs with mostly empty warps.  With the
 // option on, the grid is shrunk so that pixels / lanes is just under a whole number k = ceil(pixels / maxLanes): the same k
@@ -398,14 +419,16 @@ inline cudaError_t wave_configure()
     if ((e = wave_configure_one<false, false>()) != cudaSuccess) return e;
     if ((e = wave_configure_one<true, false>()) != cudaSuccess) return e;
     if ((e = wave_configure_one<false, true>()) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_raytrace_wave_tlas, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)) != cudaSuccess) return e;
     return wave_configure_one<true, true>();
 }
 
-template <bool S, bool X> inline cudaError_t wave_launch_one(const DevParams& P, int numSMs, size_t smemBytes, unsigned totalJobs, unsigned tilesX, unsigned ownedRows,
+template <bool S, bool X, bool T = false> inline cudaError_t wave_launch_one(const DevParams& P, int numSMs, size_t smemBytes, unsigned totalJobs, unsigned tilesX, unsigned ownedRows,
                                                              cudaStream_t stream, cudaEvent_t evA, cudaEvent_t evB)
 {
     int ctasPerSM = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, k_raytrace_wave<S, X>, WAVE_THREADS, smemBytes);
+    cudaError_t e = T ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, k_raytrace_wave_tlas, WAVE_THREADS, smemBytes)
+                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, k_raytrace_wave<S, X>, WAVE_THREADS, smemBytes);
     if (e != cudaSuccess) return e;
     if (ctasPerSM < 1) return cudaErrorInvalidConfiguration;
     unsigned int grid = (unsigned int)(numSMs * ctasPerSM);                  // persistent: a multiple of the SM count
@@ -415,7 +438,8 @@ template <bool S, bool X> inline cudaError_t wave_launch_one(const DevParams& P,
     grid = fit_persistent_grid(P.gridFit, grid, WAVE_THREADS, totalJobs);
     if ((e = cudaMemsetAsync(P.workCounter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(evA, stream)) != cudaSuccess) return e;
-    RT_LAUNCH(grid, WAVE_THREADS, smemBytes, stream, RT_K(k_raytrace_wave<S, X>), P, totalJobs, tilesX, ownedRows);
+    if (T) RT_LAUNCH(grid, WAVE_THREADS, smemBytes, stream, k_raytrace_wave_tlas, P, totalJobs, tilesX, ownedRows);
+    else RT_LAUNCH(grid, WAVE_THREADS, smemBytes, stream, RT_K(k_raytrace_wave<S, X>), P, totalJobs, tilesX, ownedRows);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     return cudaEventRecord(evB, stream);
 }
@@ -436,6 +460,7 @@ inline cudaError_t wave_launch(const DevParams& P, int numSMs, cudaStream_t stre
     const bool ext = P.nPeers > 0 || P.sphBvh != 0 || P.forceExt != 0;   // extensions compiled into their own instantiation
     if (P.countStats) return ext ? wave_launch_one<true, true>(P, numSMs, smemBytes, totalJobs, tilesX, ownedRows, stream, evA, evB)
                                  : wave_launch_one<true, false>(P, numSMs, smemBytes, totalJobs, tilesX, ownedRows, stream, evA, evB);
+    if (P.tlas && P.modelSkip) return wave_launch_one<false, true, true>(P, numSMs, smemBytes, totalJobs, tilesX, ownedRows, stream, evA, evB);
     return ext ? wave_launch_one<false, true>(P, numSMs, smemBytes, totalJobs, tilesX, ownedRows, stream, evA, evB)
                : wave_launch_one<false, false>(P, numSMs, smemBytes, totalJobs, tilesX, ownedRows, stream, evA, evB);
 }

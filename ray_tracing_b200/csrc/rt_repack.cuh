@@ -49,6 +49,55 @@ template <class T> struct RBuf
 
 struct MeshRoot { int rootStart, rootCount; };
 
+// Host only: binary tree over n axis-aligned boxes in NodePair records (two child boxes per record; count > 0 <=> leaf whose
+// items are order[start .. start + count)).  Median split of the item centres on the widest centre axis (ties by item index, so
+// the tree is a function of the input alone), leaves of at most `leafSize` items, records emitted parent before children —
+// depth <= ceil(log2(n / leafSize)) + 1.  Used for the sphere accelerator and for the TLAS over the models' world boxes; both
+// only decide what a ray may skip, so its shape never changes a result.
+inline void BuildMedianSplitPairs(const std::vector<float>& lo, const std::vector<float>& hi, const std::vector<float>& cen, size_t n, int leafSize,
+                                  std::vector<int>& order, std::vector<NodePair>& pairsOut, int& rootStart, int& rootCount)
+{
+    order.resize(n);
+    for (size_t i = 0; i < n; i++) order[i] = (int)i;
+    pairsOut.clear(); pairsOut.reserve(n);
+    auto boundsOf = [&](int start, int count, float blo[3], float bhi[3]) {
+        for (int a = 0; a < 3; a++) { blo[a] = INFINITY; bhi[a] = -INFINITY; }
+        for (int k = start; k < start + count; k++) for (int a = 0; a < 3; a++) { blo[a] = std::min(blo[a], lo[3 * order[k] + a]); bhi[a] = std::max(bhi[a], hi[3 * order[k] + a]); }
+    };
+    struct Work { int pairIndex, side, start, count; };
+    std::vector<Work> work;
+    auto splitRange = [&](int start, int count) -> int {
+        float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int k = start; k < start + count; k++) for (int a = 0; a < 3; a++) { clo[a] = std::min(clo[a], cen[3 * order[k] + a]); chi[a] = std::max(chi[a], cen[3 * order[k] + a]); }
+        int axis = 0; for (int a = 1; a < 3; a++) if (chi[a] - clo[a] > chi[axis] - clo[axis]) axis = a;
+        const int mid = start + count / 2;
+        std::nth_element(order.begin() + start, order.begin() + mid, order.begin() + start + count,
+                         [&](int x, int y) { return cen[3 * x + axis] < cen[3 * y + axis] || (cen[3 * x + axis] == cen[3 * y + axis] && x < y); });
+        return mid;
+    };
+    if ((int)n <= leafSize) { rootStart = 0; rootCount = (int)n; return; }
+    rootStart = 0; rootCount = 0;
+    pairsOut.push_back(NodePair());
+    work.push_back(Work{0, -1, 0, (int)n});
+    for (size_t w = 0; w < work.size(); w++)
+    {
+        const Work cur = work[w];
+        const int mid = splitRange(cur.start, cur.count);
+        const int cs[2] = {cur.start, mid}, cc[2] = {mid - cur.start, cur.start + cur.count - mid};
+        for (int side = 0; side < 2; side++)
+        {
+            float blo[3], bhi[3];
+            boundsOf(cs[side], cc[side], blo, bhi);
+            int st, ct;
+            if (cc[side] <= leafSize) { st = cs[side]; ct = cc[side]; }
+            else { st = (int)pairsOut.size(); ct = 0; pairsOut.push_back(NodePair()); work.push_back(Work{st, side, cs[side], cc[side]}); }
+            NodePair& q = pairsOut[cur.pairIndex];       // (push_back may have moved the vector)
+            if (side == 0) { q.aMinX = blo[0]; q.aMinY = blo[1]; q.aMinZ = blo[2]; q.aMaxX = bhi[0]; q.aMaxY = bhi[1]; q.aMaxZ = bhi[2]; q.aStart = st; q.aCount = ct; }
+            else           { q.bMinX = blo[0]; q.bMinY = blo[1]; q.bMinZ = blo[2]; q.bMaxX = bhi[0]; q.bMaxY = bhi[1]; q.bMaxZ = bhi[2]; q.bStart = st; q.bCount = ct; }
+        }
+    }
+}
+
 struct RepackState
 {
     RBuf<NodePair> pairs; RBuf<TriGeom> triGeom; RBuf<TriNormals> triNormals; RBuf<DevModel> models; RBuf<DevSphere> spheres;
@@ -59,7 +108,7 @@ struct RepackState
     int orderUsed = 0;                              // treeletDepth of the current pair layout
     size_t totalPairs = 0;
 
-    void release() { pairs.release(); triGeom.release(); triNormals.release(); models.release(); spheres.release(); sphPairs.release(); sphLeaves.release(); roots.clear(); }
+    void release() { pairs.release(); triGeom.release(); triNormals.release(); models.release(); spheres.release(); sphPairs.release(); sphLeaves.release(); tlasPairs.release(); tlasLeaves.release(); tlas = 0; roots.clear(); }
 
     // Renumbering of every distinct mesh referenced by the first modelCount models.  Host only (no CUDA call):
     // fills `out`, `roots`, `smemPairs`, `totalPairs`; a non-empty `msg` reports a malformed BVH.
@@ -207,7 +256,56 @@ struct RepackState
         return cudaSuccess;
     }
 
-    cudaError_t buildModels(const std::vector<RtModel>& mdl, const std::vector<RtNode>& nodes, int modelCount, cudaStream_t stream)
+    // ---- TLAS over the models' padded world boxes --------------------------------------------------------------
+    // Rebuilt with the model records, i.e. whenever ModelInfo is re-sent (the reference re-sends it every frame, RCM:192-204): a
+    // median-split tree over a few hundred to a few thousand boxes is microseconds of host work next to a frame.
+    RBuf<NodePair> tlasPairs; RBuf<int> tlasLeaves;
+    int tlas = 0, tlasRootStart = 0, tlasRootCount = 0;
+    static constexpr int TLAS_AUTO_THRESHOLD = 64;                   // below this the linear test of resident 32-byte boxes is cheaper (shipped scenes: 10-28 models)
+
+    // mode: 0 = off, 1 = on whenever it is possible, -1 = automatic (more than TLAS_AUTO_THRESHOLD models)
+    static bool tlasWanted(int mode, int modelCount)
+    {
+        if (modelCount < 1 || modelCount > RT_TLAS_MAX_MODELS) return false;
+        return mode > 0 || (mode < 0 && modelCount > TLAS_AUTO_THRESHOLD);
+    }
+
+    // Host only (no CUDA call).  A model whose matrices are not inverses of each other carries an infinite box (buildModels); it
+    // makes every TLAS box above it infinite, so it is always marked — conservative, like the linear test.
+    static void planTlas(const std::vector<DevModel>& dm, int modelCount, std::vector<NodePair>& pairsOut, std::vector<int>& order, int& rootStart, int& rootCount)
+    {
+        const size_t n = (size_t)modelCount;
+        std::vector<float> lo(3 * n), hi(3 * n), cen(3 * n);
+        for (size_t i = 0; i < n; i++)
+        {
+            const float bmin[3] = {dm[i].wmin[0], dm[i].wmin[1], dm[i].wmin[2]}, bmax[3] = {dm[i].wmaxx, dm[i].wmaxy, dm[i].wmaxz};
+            for (int a = 0; a < 3; a++)
+            {
+                lo[3 * i + a] = bmin[a]; hi[3 * i + a] = bmax[a];
+                const float c = 0.5f * bmin[a] + 0.5f * bmax[a];
+                cen[3 * i + a] = std::isfinite(c) ? c : 0.0f;
+            }
+        }
+        BuildMedianSplitPairs(lo, hi, cen, n, 4, order, pairsOut, rootStart, rootCount);
+    }
+
+    cudaError_t buildTlas(const std::vector<DevModel>& dm, int modelCount, int mode, cudaStream_t stream)
+    {
+        tlas = 0;
+        if (!tlasWanted(mode, modelCount)) return cudaSuccess;
+        std::vector<NodePair> pairsOut; std::vector<int> order;
+        planTlas(dm, modelCount, pairsOut, order, tlasRootStart, tlasRootCount);
+        cudaError_t e;
+        if ((e = tlasPairs.ensure(std::max<size_t>(pairsOut.size(), 1))) != cudaSuccess) return e;
+        if ((e = tlasLeaves.ensure(order.size())) != cudaSuccess) return e;
+        if (!pairsOut.empty() && (e = cudaMemcpyAsync(tlasPairs.p, pairsOut.data(), pairsOut.size() * sizeof(NodePair), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(tlasLeaves.p, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;      // the vectors are locals
+        tlas = 1;
+        return cudaSuccess;
+    }
+
+    cudaError_t buildModels(const std::vector<RtModel>& mdl, const std::vector<RtNode>& nodes, int modelCount, cudaStream_t stream, int tlasMode = 0)
     {
         std::vector<DevModel> out(std::max(modelCount, 1));
         for (int i = 0; i < modelCount; i++)
@@ -259,7 +357,8 @@ struct RepackState
         cudaError_t e;
         if ((e = models.ensure(out.size())) != cudaSuccess) return e;
         if ((e = cudaMemcpyAsync(models.p, out.data(), out.size() * sizeof(DevModel), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
-        return cudaStreamSynchronize(stream);
+        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+        return buildTlas(out, modelCount, tlasMode, stream);
     }
 
     // ---- spheres ------------------------------------------------------------------------------------------------------------
@@ -323,53 +422,9 @@ struct RepackState
             }
         }
         // median split on the widest centroid axis, leaves of <= 4 spheres; pairs emitted parent-before-children
-        std::vector<int> order(n);
-        for (size_t i = 0; i < n; i++) order[i] = (int)i;
-        std::vector<NodePair> pairsOut; pairsOut.reserve(n);
-        struct Ref { int start, count; float lo[3], hi[3]; };
-        auto boundsOf = [&](int start, int count, float blo[3], float bhi[3]) {
-            for (int a = 0; a < 3; a++) { blo[a] = INFINITY; bhi[a] = -INFINITY; }
-            for (int k = start; k < start + count; k++) for (int a = 0; a < 3; a++) { blo[a] = std::min(blo[a], lo[3 * order[k] + a]); bhi[a] = std::max(bhi[a], hi[3 * order[k] + a]); }
-        };
-        struct Work { int pairIndex, side, start, count; };
-        std::vector<Work> work;
-        auto splitRange = [&](int start, int count) -> int {
-            float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
-            for (int k = start; k < start + count; k++) for (int a = 0; a < 3; a++) { clo[a] = std::min(clo[a], cen[3 * order[k] + a]); chi[a] = std::max(chi[a], cen[3 * order[k] + a]); }
-            int axis = 0; for (int a = 1; a < 3; a++) if (chi[a] - clo[a] > chi[axis] - clo[axis]) axis = a;
-            const int mid = start + count / 2;
-            std::nth_element(order.begin() + start, order.begin() + mid, order.begin() + start + count,
-                             [&](int x, int y) { return cen[3 * x + axis] < cen[3 * y + axis] || (cen[3 * x + axis] == cen[3 * y + axis] && x < y); });
-            return mid;
-        };
-        // root
-        const int LEAF = 4;
-        if ((int)n <= LEAF) { sphRootStart = 0; sphRootCount = (int)n; }
-        else
-        {
-            sphRootStart = 0; sphRootCount = 0;
-            pairsOut.push_back(NodePair());
-            work.push_back(Work{0, -1, 0, (int)n});
-            for (size_t w = 0; w < work.size(); w++)
-            {
-                const Work cur = work[w];
-                const int mid = splitRange(cur.start, cur.count);
-                const int cs[2] = {cur.start, mid}, cc[2] = {mid - cur.start, cur.start + cur.count - mid};
-                NodePair& p = pairsOut[cur.pairIndex];
-                for (int side = 0; side < 2; side++)
-                {
-                    float blo[3], bhi[3];
-                    boundsOf(cs[side], cc[side], blo, bhi);
-                    int st, ct;
-                    if (cc[side] <= LEAF) { st = cs[side]; ct = cc[side]; }
-                    else { st = (int)pairsOut.size(); ct = 0; pairsOut.push_back(NodePair()); work.push_back(Work{st, side, cs[side], cc[side]}); }
-                    NodePair& q = pairsOut[cur.pairIndex];       // (push_back may have moved the vector)
-                    if (side == 0) { q.aMinX = blo[0]; q.aMinY = blo[1]; q.aMinZ = blo[2]; q.aMaxX = bhi[0]; q.aMaxY = bhi[1]; q.aMaxZ = bhi[2]; q.aStart = st; q.aCount = ct; }
-                    else           { q.bMinX = blo[0]; q.bMinY = blo[1]; q.bMinZ = blo[2]; q.bMaxX = bhi[0]; q.bMaxY = bhi[1]; q.bMaxZ = bhi[2]; q.bStart = st; q.bCount = ct; }
-                }
-                (void)p;
-            }
-        }
+        std::vector<int> order;
+        std::vector<NodePair> pairsOut;
+        BuildMedianSplitPairs(lo, hi, cen, n, 4, order, pairsOut, sphRootStart, sphRootCount);
         std::vector<DevSphere> leaves(n);
         for (size_t k = 0; k < n; k++) leaves[k] = out[order[k]];
         if ((e = sphPairs.ensure(std::max<size_t>(pairsOut.size(), 1))) != cudaSuccess) return e;

@@ -143,3 +143,60 @@ def test_treelet_orders_describe_the_same_trees(depth, budget):
             assert root < s1 <= root + 2
             for s2, c2 in ((pairs[s1]["aStart"], pairs[s1]["aCount"]), (pairs[s1]["bStart"], pairs[s1]["bCount"])):
                 assert c2 > 0 or root + 2 < s2 <= root + 6
+
+
+# ---- TLAS over the models' world boxes (planTlas through the device-free hook rtxPlanTlas) -------------------------------------------
+
+def _plan_tlas(boxes):
+    L = C.CDLL(CUDA_LIB)                                   # host code only: no CUDA call is made
+    n = len(boxes)
+    pairs = np.zeros(max(n, 1), dtype=PAIR_DTYPE)
+    leaves = np.full(n, -1, dtype=np.int32)
+    root = np.zeros(2, dtype=np.int32)
+    b = np.ascontiguousarray(boxes, dtype=np.float32)
+    k = L.rtxPlanTlas(b.ctypes.data_as(C.c_void_p), n, pairs.ctypes.data_as(C.c_void_p), len(pairs), leaves.ctypes.data_as(C.c_void_p), root.ctypes.data_as(C.c_void_p))
+    return k, pairs[:max(k, 0)], leaves, root
+
+
+def _tlas_walk(pairs, leaves, boxes, ref, lo, hi, depth, seen, depths):
+    """Every box of the tree must enclose the boxes of all the models below it; returns the models below `ref`."""
+    start, count = ref
+    if count > 0:
+        assert count <= 4
+        below = [int(m) for m in leaves[start:start + count]]
+        depths.append(depth)
+    else:
+        assert start not in seen
+        seen.add(int(start))
+        p = pairs[start]
+        below = (_tlas_walk(pairs, leaves, boxes, (p["aStart"], p["aCount"]), p["aMin"], p["aMax"], depth + 1, seen, depths)
+                 + _tlas_walk(pairs, leaves, boxes, (p["bStart"], p["bCount"]), p["bMin"], p["bMax"], depth + 1, seen, depths))
+    if lo is not None:
+        for m in below:
+            assert np.all(lo <= boxes[m, :3]) and np.all(hi >= boxes[m, 3:]), "a TLAS box does not enclose a model below it"
+    return below
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 64, 65, 1000, 4096])
+def test_tlas_plan_encloses_every_model_exactly_once(n):
+    rng = np.random.RandomState(n)
+    centre = rng.uniform(-50, 50, (n, 3))
+    half = np.exp(rng.uniform(np.log(0.01), np.log(8.0), (n, 3)))
+    boxes = np.concatenate([centre - half, centre + half], axis=1).astype(np.float32)
+    if n >= 64:
+        boxes[7] = [-np.inf] * 3 + [np.inf] * 3              # a model without trustworthy world bounds (buildModels)
+        boxes[11, :] = boxes[12, :]                          # coincident boxes
+    k, pairs, leaves, root = _plan_tlas(boxes)
+    assert k >= 0
+    assert sorted(leaves.tolist()) == list(range(n)), "every model is in exactly one leaf"
+    seen, depths = set(), []
+    below = _tlas_walk(pairs, leaves, boxes, (int(root[0]), int(root[1])), None, None, 0, seen, depths)
+    assert sorted(below) == list(range(n)) and len(seen) == k
+    assert max(depths) <= 12, "the device walk keeps a stack of 24 entries"
+    if n <= 4:
+        assert k == 0 and root[1] == n                       # the root is a leaf
+
+
+def test_tlas_plan_refuses_more_models_than_the_device_mask_holds():
+    boxes = np.zeros((4097, 6), dtype=np.float32)
+    assert _plan_tlas(boxes)[0] < 0

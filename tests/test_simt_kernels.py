@@ -19,6 +19,7 @@ from conftest import ORACLE_LIB, REPO, assert_bit_equal, render, seed_forcing_dr
 import ray_tracing_b200 as rt
 from ray_tracing_b200 import scenes
 import test_gpu_parity as G
+import test_zz_gpu_round2_candidates as Z
 
 sys.path.insert(0, os.path.join(REPO, "tests", "simt"))
 import build as simt_build   # noqa: E402
@@ -32,6 +33,7 @@ def simt_lib():
 @pytest.fixture(autouse=True)
 def _point_parity_tests_at_the_interpreter(monkeypatch, simt_lib):
     monkeypatch.setattr(G, "CUDA_LIB", simt_lib)
+    monkeypatch.setattr(Z, "CUDA_LIB", simt_lib)
 
 
 # Left to the GPU run: the three full-size cases (minutes of interpretation) and the one that needs torch CUDA tensors.
@@ -40,6 +42,12 @@ _GPU_ONLY = {"test_config4_shape_deep_bvh_sparse_pixels", "test_config5_shape_mi
 for _name in sorted(dir(G)):
     if _name.startswith("test_") and _name not in _GPU_ONLY:
         globals()["test_simt_" + _name[5:]] = getattr(G, _name)
+
+
+# the TLAS tests of the round-2 GPU file run here too (the other tests of that file have interpreter versions of their own below)
+for _name in sorted(dir(Z)):
+    if _name.startswith("test_tlas_"):
+        globals()["test_simt_" + _name[5:]] = getattr(Z, _name)
 
 
 def test_simt_row_band_tiles_reassemble(simt_lib):

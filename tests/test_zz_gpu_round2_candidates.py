@@ -63,3 +63,87 @@ def test_random_value_exactly_zero_and_exactly_one_on_gpu():
         for kernel in (0, 1, 2):
             fg, _ = render(CUDA_LIB, sc, options={"kernel": kernel})
             assert_bit_equal(fg, fo, f"forced draw {draw} kernel {kernel}")
+
+
+# ---- TLAS over the models: option "tlas" -----------------------------------------------------------------------------
+
+def _tlas_scene(instances, width=96, height=54, bounces=5, spp=2):
+    return scenes.instanced_knots(width, height, max_bounces=bounces, rays_per_pixel=spp, instances=instances)
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_tlas_many_models_bitwise(kernel):
+    """152 Model components (instancing of one mesh + room + light): above 64 models the TLAS is used automatically; forced on, forced
+    off and automatic must all give the oracle's bits (the oracle walks every model like the reference)."""
+    sc = _tlas_scene(150)
+    fo, ao = render(ORACLE_LIB, sc, frames=2)
+    for tlas in (-1, 1, 0):
+        fg, ag = render(CUDA_LIB, sc, frames=2, options={"kernel": kernel, "tlas": tlas})
+        assert_bit_equal(ag, ao, f"kernel {kernel} tlas {tlas}")
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_tlas_forced_on_for_few_models(kernel):
+    """The TLAS kernels with a root that is a leaf (3 models) and with a two-level tree (14 models); also together with the image split
+    into row bands (rank 1 of 3)."""
+    for sc in (scenes.knot_room(96, 54, max_bounces=5, rays_per_pixel=2, nu=90, nv=8, glass=True), _tlas_scene(12)):
+        fo, ao = render(ORACLE_LIB, sc, frames=2)
+        fg, ag = render(CUDA_LIB, sc, frames=2, options={"kernel": kernel, "tlas": 1})
+        assert_bit_equal(ag, ao, f"{sc.name} kernel {kernel}")
+    ft, at = render(CUDA_LIB, sc, frames=2, options={"kernel": kernel, "tlas": 1}, tile=(1, 3, 8))
+    rows = [y for y in range(sc.height) if (y // 8) % 3 == 1]
+    assert_bit_equal(at[rows], ao[rows], "row bands of rank 1 of 3")
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_tlas_follows_per_frame_model_updates(kernel):
+    """The reference re-sends ModelInfo every frame (RayComputeManager.cs:192-204): models move, change scale and material between
+    frames, one leaves the scene's old bounds — the TLAS is rebuilt with the model records."""
+    import numpy as np
+    import ray_tracing_b200 as rt
+
+    def run(lib, options):
+        sc = _tlas_scene(80, 80, 48, 4, 1)
+        rng = np.random.RandomState(3)
+        mgr = rt.RayComputeManager(lib)
+        scenes.apply(sc, mgr)
+        for k, v in options.items():
+            mgr.context.set_option(k, v)
+        mgr.OnEnable()
+        for frame in range(3):
+            mgr.RenderFrame()
+            for m in rng.choice(np.arange(2, 82), 12, replace=False):
+                pos = (rng.uniform(-2.2, 2.2), rng.uniform(0.4, 3.4), rng.uniform(-1.5, 2.2)) if m % 5 else (rng.uniform(8, 12), 1.0, rng.uniform(8, 12))
+                mgr.set_model_transform(int(m), *scenes.trs(position=pos, euler_deg=tuple(rng.uniform(0, 360, 3)), scale=tuple(rng.uniform(0.07, 0.3, 3))))
+            mgr.set_model_material(int(rng.randint(2, 82)), scenes.material(flag=scenes.MAT_GLASS, ior=1.45, smoothness=0.9, specularProbability=0.9))
+        mgr.RenderFrame()
+        out = mgr.accumulatedResult.copy()
+        mgr.OnDestroy()
+        return out
+
+    ref = run(ORACLE_LIB, {})
+    assert_bit_equal(run(CUDA_LIB, {"kernel": kernel}), ref, "automatic TLAS, 82 models, four frames")
+    assert_bit_equal(run(CUDA_LIB, {"kernel": kernel, "tlas": 0}), ref, "linear model test")
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_tlas_with_sphere_accelerator_and_a_model_without_world_bounds(kernel):
+    """70 models + 300 spheres (sphere accelerator and TLAS in one launch) + one model whose two matrices are not inverses of each
+    other: the ray test only uses worldToLocal, so no world box can be trusted for it — it carries an infinite box and is always a
+    candidate (linear test and TLAS alike)."""
+    import numpy as np
+    sc = _tlas_scene(68)
+    rng = np.random.RandomState(21)
+    sph = np.zeros(300, dtype=scenes.SPHERE_DTYPE)
+    for i in range(300):
+        sph[i] = scenes._sphere((rng.uniform(-2.4, 2.4), rng.uniform(0.2, 3.6), rng.uniform(-1.5, 2.4)), rng.uniform(0.03, 0.12),
+                                scenes.material(diffuse=tuple(rng.uniform(0.2, 0.9, 3)), specularProbability=0.3, smoothness=0.6) if i % 4 else
+                                scenes.material(flag=scenes.MAT_GLASS, ior=1.5, smoothness=1.0, specularProbability=1.0))
+    sc.spheres = sph
+    l2w, _ = scenes.trs(position=(0.5, 1.0, 0.5), scale=(0.2, 0.2, 0.2))
+    _, w2l = scenes.trs(position=(-0.8, 2.2, 0.3), euler_deg=(20, 40, 60), scale=(0.25, 0.2, 0.3))       # where the rays really meet it
+    sc.models[5] = scenes.ModelDesc(0, l2w, w2l, sc.models[5].material)
+    fo, ao = render(ORACLE_LIB, sc, frames=2)
+    for tlas in (-1, 0):
+        fg, ag = render(CUDA_LIB, sc, frames=2, options={"kernel": kernel, "tlas": tlas})
+        assert_bit_equal(ag, ao, f"kernel {kernel} tlas {tlas}")

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Memory check of the kernels without a GPU: the SIMT interpreter build (tests/simt) compiled with AddressSanitizer — device buffers
 # are heap blocks with red zones, the dynamic shared memory is a static array with red zones — runs all three trace kernels (plain /
-# instrumented / EXT instantiations, staged tree tops, treelet order, sphere accelerator) and the device BVH build against the oracle.
+# instrumented / EXT / TLAS instantiations, staged tree tops, treelet order, sphere accelerator) and the device BVH build against the oracle.
 # Needs the system g++ (libasan); ~2 min.   bash tools/simt_asan.sh
 set -e
 cd "$(dirname "$0")/.."
@@ -31,6 +31,14 @@ for sc, frames in ((scenes.cornell_spheres(48, 32, 4, 2), 2), (scenes.knot_room(
         fg, ag = render(LIB, sc, frames=frames, options=opts)
         assert_bit_equal(ag, ao, f"{sc.name} {opts}")
     print(sc.name, "clean", flush=True)
+# TLAS kernels: 70 models (automatic), 12 models (forced, two-level tree), 3 models (forced, the root is a leaf)
+for sc, tlas in ((scenes.instanced_knots(48, 28, 4, 2, instances=68), -1), (scenes.instanced_knots(48, 28, 4, 2, instances=10), 1),
+                 (scenes.knot_room(48, 28, 4, 2, nu=60, nv=8), 1)):
+    fo, ao = render(ORACLE_LIB, sc, frames=2)
+    for kernel in (1, 2):
+        fg, ag = render(LIB, sc, frames=2, options={"kernel": kernel, "tlas": tlas, "poolSlots": 32 if kernel == 2 else 64})
+        assert_bit_equal(ag, ao, f"{sc.name} tlas {tlas} kernel {kernel}")
+print("TLAS kernels clean", flush=True)
 gpu = capi.RtLib(LIB).create(0)
 m = scenes.knot_mesh(nu=100, nv=8)
 for q in (1, 0, 2):

@@ -51,6 +51,10 @@ STAGES = {
         ("l2Persist", None, {"l2Persist": 1}), ("pairOrder 4", None, {"pairOrder": 4}), ("pairOrder 6", None, {"pairOrder": 6}),
         ("poolSlots 96 + treelet", "treelet", {"treeletPrefetch": 1, "poolSlots": 96}),
     ]),
+    4: (["instances500", "instances16"], [       # TLAS over the models' world boxes (automatic above 64 models) against the linear per-model test
+        ("default", None, {}), ("tlas off", None, {"tlas": 0}), ("tlas on", None, {"tlas": 1}), ("tlas on, kernel 1", None, {"tlas": 1, "kernel": 1}),
+        ("tlas off, kernel 1", None, {"tlas": 0, "kernel": 1}), ("no model skipping at all", None, {"modelSkip": 0}),
+    ]),
     3: (["cornell64", "cornell1"], [
         ("default", None, {}), ("glass out of line", "glassool", {}), ("zero-defocus + glass out of line + skipsqrt", "cornell_all", {}), ("zero-defocus shortcut", "zerodefocus", {}), ("zero-defocus + skipsqrt", "zerodefocus_skipsqrt", {}), ("skipsqrt", "skipsqrt", {}), ("mb5", "mb5", {}), ("gridFit", None, {"gridFit": 1}), ("kernel 2", None, {"kernel": 2}),
     ]),
