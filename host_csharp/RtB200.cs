@@ -29,6 +29,25 @@ public static class RtB200
     [DllImport(Lib)] public static extern int rtBuildBVH(IntPtr ctx, UnityEngine.Vector3[] verts, int vertCount, int[] indices, int indexCount, UnityEngine.Vector3[] normals,
                                                          int quality, [Out] BVH.Triangle[] tris, [Out] BVH.Node[] nodes, int nodeCapacity, out int nodeCount);
 
+    // Display.shader:42-47 (tex / Frame, sRGB 8-bit): RayTraceDisplay.OnRenderImage and the screenshot of RayComputeManager.cs:106-111
+    [DllImport(Lib)] public static extern int rtDisplay(IntPtr ctx, int useAccumulated, int frame, byte[] rgba, UIntPtr bytes);
+
+    // ---- extensions (no counterpart in the reference) ----
+    [DllImport(Lib)] public static extern int rtGetVersion();
+    [DllImport(Lib)] public static extern int rtSetOption(IntPtr ctx, string name, int value);           // "kernel", "tlas", "modelSkip", ... (rt_b200.h)
+    [DllImport(Lib)] public static extern int rtSetStream(IntPtr ctx, IntPtr cudaStream);
+    [StructLayout(LayoutKind.Sequential)]
+    public struct Stats { public ulong rays, boxTests, triTests, sphereTests, dispatches; public double kernelMs; public ulong sphereBoxTests; }
+    [DllImport(Lib)] public static extern int rtGetStats(IntPtr ctx, out Stats stats);
+    [DllImport(Lib)] public static extern int rtResetStats(IntPtr ctx);
+    // multi-GPU row bands: one process per GPU; the all-gather of TileSend into TileRecv is the host's (NCCL)
+    [DllImport(Lib)] public static extern int rtSetTile(IntPtr ctx, int rank, int worldSize, int bandRows);
+    [DllImport(Lib)] public static extern int rtPackTile(IntPtr ctx);
+    [DllImport(Lib)] public static extern int rtUnpackTiles(IntPtr ctx);
+    [DllImport(Lib)] public static extern int rtGetDevicePointer(IntPtr ctx, string name, out IntPtr devPtr, out UIntPtr bytes);
+    [DllImport(Lib)] public static extern int rtGetIpcHandles(IntPtr ctx, byte[] handles, UIntPtr bytes);
+    [DllImport(Lib)] public static extern int rtSetPeers(IntPtr ctx, int nPeers, byte[] handles, UIntPtr bytes);
+
     public static void Check(IntPtr ctx, int rc)
     {
         if (rc != 0) throw new InvalidOperationException("rt_b200: " + Marshal.PtrToStringAnsi(rtLastError(ctx)));

@@ -330,3 +330,17 @@ def test_manager_error_paths_and_rebuild(oracle_path):
     assert "index out of range" in str(e.value)
     with pytest.raises(capi.RtError):
         mgr.add_model(99, np.eye(4), np.eye(4), scenes.material())
+
+
+def test_csharp_binding_declares_every_entry_point_of_the_header():
+    """host_csharp/RtB200.cs (shipped as source: no C# toolchain here) must bind every function include/rt_b200.h declares."""
+    import re
+    header = open(os.path.join(REPO, "include", "rt_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(rt[A-Z]\w*)\s*\(", header, flags=re.M))
+    assert len(declared) >= 27
+    cs = open(os.path.join(REPO, "host_csharp", "RtB200.cs")).read()
+    bound = set(re.findall(r"static extern \w+ (rt[A-Z]\w*)\(", cs))
+    assert declared <= bound, f"not bound in RtB200.cs: {sorted(declared - bound)}"
+    m = re.search(r"public struct Stats \{([^}]*)\}", cs)
+    fields = re.findall(r"(\w+)[,;]", m.group(1))
+    assert [f for f in fields if f not in ("ulong", "double", "public")] == ["rays", "boxTests", "triTests", "sphereTests", "dispatches", "kernelMs", "sphereBoxTests"]
