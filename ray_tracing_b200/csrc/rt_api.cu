@@ -125,7 +125,15 @@ int rtCreate(RtContext** out, int device)
     c->P.tileWorld = 1; c->P.bandRows = 1;
     const float ident[16] = {1,0,0,0, 0,1,0,0, 0,0,1,0, 0,0,0,1};
     memcpy(c->P.cam, ident, sizeof(ident));
-    auto bail = [&](cudaError_t err, const char* what) { std::string m = std::string(what) + ": " + cudaGetErrorString(err); delete c; return fail(nullptr, RT_E_CUDA, m); };
+    auto bail = [&](cudaError_t err, const char* what)
+    {
+        const std::string m = std::string(what) + ": " + cudaGetErrorString(err);
+        if (c->dCounters) cudaFree(c->dCounters);
+        if (c->dWork) cudaFree(c->dWork);
+        if (c->ownStream) cudaStreamDestroy(c->ownStream);
+        delete c;
+        return fail(nullptr, RT_E_CUDA, m);
+    };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");

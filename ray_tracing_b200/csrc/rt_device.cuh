@@ -33,6 +33,25 @@ RT_DI float4 ldg_tri(const float4* p)
 #endif
 }
 
+// ---- 256-bit record loads (round-2 candidate RT_LDG256, compiled out by default) -----------------------------------------------
+// The L1 serves a load instruction one 128-byte line at a time (B300_MICROARCH.md: ~2 cycles per line touched within one LDG), and
+// in the node loop every lane reads its own 64-byte record: the four LDG.128 of a record cost 4 x (lanes) passes of the L1 data
+// pipe, which the round-1 profiles show 57-73 % busy on the mesh scenes.  sm_100 has 256-bit global loads (LDG.E.256): the same
+// record is two loads, i.e. half the passes.  Same bytes, same values; only the instruction count of the fetch changes.
+// Only used where it is inlined into a kernel: inside the out-of-line device functions (TraverseSpheres, TlasCollect) the v8 load
+// makes ptxas 12.9.86 crash (segmentation fault when the module is assembled as a whole), and those are not the hot fetches.
+RT_DI void ldg_record64(const float4* p, float4& q0, float4& q1, float4& q2, float4& q3)      // p: 64-byte aligned, read-only data
+{
+#if defined(RT_LDG256) && !defined(RT_SIMT_EMU)
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w), "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w) : "l"(p));
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w), "=f"(q3.x), "=f"(q3.y), "=f"(q3.z), "=f"(q3.w) : "l"(p + 2));
+#else
+    q0 = __ldg(p); q1 = __ldg(p + 1); q2 = __ldg(p + 2); q3 = __ldg(p + 3);
+#endif
+}
+
 // ---- repacked device-side scene records (built at upload time by rt_repack.cu) ---------------------------
 
 // Two sibling BVH nodes in one 64-byte, 64-byte-aligned record (children are allocated adjacently by the
@@ -50,12 +69,44 @@ struct __align__(64) NodePair
 // Triangle geometry as the intersection test consumes it: vertex A, the two edges and the face vector
 // cross(AB, AC) — each the single IEEE operation sequence of HL:190-192, evaluated once at upload
 // instead of once per test (same bits).  48 bytes = 3 × float4.
+// Round-2 candidate RT_TRI_PAD64 (compiled out by default): the record padded to 64 bytes, 64-byte aligned — one LDG.E.256 + one
+// LDG.128 instead of three LDG.128 (the L1 works through a load one line at a time, see ldg_record64), and a record never straddles
+// a 128-byte line (a 48-byte one does in three of eight positions); costs a third more triangle bytes in L2 / HBM.
+#ifdef RT_TRI_PAD64
+struct __align__(64) TriGeom
+{
+    float ax, ay, az, abx;
+    float aby, abz, acx, acy;
+    float acz, nx, ny, nz;
+    float pad[4];
+};
+#else
 struct __align__(16) TriGeom
 {
     float ax, ay, az, abx;
     float aby, abz, acx, acy;
     float acz, nx, ny, nz;
 };
+#endif
+constexpr int TRI_GEOM_F4 = (int)(sizeof(TriGeom) / 16);     // float4 stride from one record to the next
+
+// the three float4 of a TriGeom record (g points at the record)
+RT_DI void ldg_trigeom(const float4* g, float4& g0, float4& g1, float4& g2)
+{
+#if defined(RT_TRI_PAD64) && !defined(RT_SIMT_EMU)
+#if RT_TRI_LOAD_POLICY == 1
+    asm("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+#elif RT_TRI_LOAD_POLICY == 2
+    asm("ld.global.nc.L1::evict_first.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+#else
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+#endif
+        : "=f"(g0.x), "=f"(g0.y), "=f"(g0.z), "=f"(g0.w), "=f"(g1.x), "=f"(g1.y), "=f"(g1.z), "=f"(g1.w) : "l"(g));
+    g2 = ldg_tri(g + 2);
+#else
+    g0 = ldg_tri(g); g1 = ldg_tri(g + 1); g2 = ldg_tri(g + 2);
+#endif
+}
 
 // Vertex normals, fetched only for the winning triangle of a traversal.  48 bytes = 3 × float4.
 struct __align__(16) TriNormals
@@ -402,7 +453,7 @@ RT_DNI void TraverseSpheres(const DevParams& P, f3 rayPos, f3 rayDir, float& bes
         else
         {
             const float4* p = reinterpret_cast<const float4*>(P.sphPairs + cur.x);
-            const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+            const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);   // (not ldg_record64: see there)
             const float dA = RayBoundingBoxDst(rayPos, invDir, make_f3(q0.x, q0.y, q0.z), make_f3(q0.w, q1.x, q1.y));
             const float dB = RayBoundingBoxDst(rayPos, invDir, make_f3(q2.x, q2.y, q2.z), make_f3(q2.w, q3.x, q3.y));
             if (countStats) cnt.sbox += 2;
@@ -449,7 +500,7 @@ RT_DNI void TlasCollect(const DevParams& P, f3 rayPos, f3 rayInv, float bestDst,
         else
         {
             const float4* p = reinterpret_cast<const float4*>(P.tlasPairs + cur.x);
-            const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+            const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);   // (not ldg_record64: see there)
             RT_DEV_PROF(26, 2);
             const bool skipA = WorldBoxOutOfReach(make_f3(q0.x, q0.y, q0.z), make_f3(q0.w, q1.x, q1.y), rayPos, rayInv, bestDst);
             const bool skipB = WorldBoxOutOfReach(make_f3(q2.x, q2.y, q2.z), make_f3(q2.w, q3.x, q3.y), rayPos, rayInv, bestDst);

@@ -584,7 +584,7 @@ RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const uns
                     if (sph)
                     {
                         const float4* p = reinterpret_cast<const float4*>(P.sphPairs + cur.start);
-                        q0 = __ldg(p); q1 = __ldg(p + 1); q2 = __ldg(p + 2); q3 = __ldg(p + 3);
+                        ldg_record64(p, q0, q1, q2, q3);
                         if (STATS) cnt.sbox += 2;
                     }
                     else
@@ -649,7 +649,8 @@ RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const uns
                 else if (mode == T_LEAF)
                 {
                     const float4* g = reinterpret_cast<const float4*>(P.triGeom + cur.start + leafK);
-                    const float4 g0 = ldg_tri(g), g1 = ldg_tri(g + 1), g2 = ldg_tri(g + 2);
+                    float4 g0, g1, g2;
+                    ldg_trigeom(g, g0, g1, g2);
                     float dst, u, v, det;
                     const bool didHit = RayTriangleCore(lpos, ldir, make_f3(g0.x, g0.y, g0.z), make_f3(g0.w, g1.x, g1.y), make_f3(g1.z, g1.w, g2.x),
                                                         make_f3(g2.y, g2.z, g2.w), cull, dst, u, v, det);

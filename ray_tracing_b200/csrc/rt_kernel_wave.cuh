@@ -80,7 +80,7 @@ RT_DI void LoadPair(const DevParams& P, const float4* __restrict__ smemPairs, in
     else
     {
         const float4* p = reinterpret_cast<const float4*>(P.pairs + idx);
-        q0 = __ldg(p); q1 = __ldg(p + 1); q2 = __ldg(p + 2); q3 = __ldg(p + 3);
+        ldg_record64(p, q0, q1, q2, q3);
 #if defined(RT_TREELET_PREFETCH) && !defined(RT_SIMT_EMU)
         if (treeletRoot)
         {
@@ -106,9 +106,10 @@ RT_DI void TraverseMesh(const DevParams& P, const float4* __restrict__ smemPairs
         if (cur.count > 0)
         {
             const float4* g = reinterpret_cast<const float4*>(P.triGeom + cur.start);
-            for (int i = 0; i < cur.count; i++, g += 3)
+            for (int i = 0; i < cur.count; i++, g += TRI_GEOM_F4)
             {
-                const float4 g0 = ldg_tri(g), g1 = ldg_tri(g + 1), g2 = ldg_tri(g + 2);
+                float4 g0, g1, g2;
+                ldg_trigeom(g, g0, g1, g2);
                 float dst, u, v, det;
                 const bool didHit = RayTriangleCore(pos, dir, make_f3(g0.x, g0.y, g0.z), make_f3(g0.w, g1.x, g1.y), make_f3(g1.z, g1.w, g2.x),
                                                     make_f3(g2.y, g2.z, g2.w), cullBackface, dst, u, v, det);

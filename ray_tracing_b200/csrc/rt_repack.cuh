@@ -31,6 +31,9 @@ __global__ void k_repack_tris(const RtTriangle* __restrict__ in, TriGeom* __rest
     TriGeom g;
     g.ax = A.x; g.ay = A.y; g.az = A.z; g.abx = edgeAB.x; g.aby = edgeAB.y; g.abz = edgeAB.z;
     g.acx = edgeAC.x; g.acy = edgeAC.y; g.acz = edgeAC.z; g.nx = N.x; g.ny = N.y; g.nz = N.z;
+#ifdef RT_TRI_PAD64
+    g.pad[0] = g.pad[1] = g.pad[2] = g.pad[3] = 0.0f;
+#endif
     geom[i] = g;
     TriNormals q;
     q.nax = t.normA[0]; q.nay = t.normA[1]; q.naz = t.normA[2];

@@ -266,7 +266,7 @@ def test_simt_pair_record_order_is_layout_only(simt_lib):
 
 
 @pytest.mark.skipif(not os.environ.get("RT_SIMT_VARIANTS"), reason="four extra interpreter builds (~3 min): set RT_SIMT_VARIANTS=1")
-@pytest.mark.parametrize("defines", [("RT_STACK_TOP_REG",), ("RT_CACHE_RAYINV",), ("RT_LEAF_REPEAT=2",), ("RT_SPHERE_SKIP_SQRT",), ("RT_TREELET_PREFETCH",), ("RT_SMEM_STACK=2",), ("RT_SKIP_ZERO_DEFOCUS", "RT_GLASS_OUT_OF_LINE"), ("RT_VOTE_WL=3", "RT_VOTE_WN=2"), ("RT_VOTE_WI=2", "RT_VOTE_WL=7", "RT_VOTE_WN=4", "RT_LEAF_REPEAT=2"), ("RT_SMEM_STACK=8", "RT_PREFETCH_CUR"),
+@pytest.mark.parametrize("defines", [("RT_STACK_TOP_REG",), ("RT_CACHE_RAYINV",), ("RT_LEAF_REPEAT=2",), ("RT_SPHERE_SKIP_SQRT",), ("RT_TREELET_PREFETCH",), ("RT_SMEM_STACK=2",), ("RT_SKIP_ZERO_DEFOCUS", "RT_GLASS_OUT_OF_LINE"), ("RT_VOTE_WL=3", "RT_VOTE_WN=2"), ("RT_VOTE_WI=2", "RT_VOTE_WL=7", "RT_VOTE_WN=4", "RT_LEAF_REPEAT=2"), ("RT_SMEM_STACK=8", "RT_PREFETCH_CUR"), ("RT_LDG256", "RT_TRI_PAD64"),
                                      ("RT_STACK_TOP_REG", "RT_CACHE_RAYINV", "RT_LEAF_REPEAT=2", "RT_INNER_REPEAT=1")])
 def test_simt_compile_time_variants_are_bit_exact(defines, tmp_path):
     """The A/B candidates of tools/round2_sweep.sh change scheduling / instruction selection only: same pixels, same counters."""
@@ -284,6 +284,14 @@ def test_simt_compile_time_variants_are_bit_exact(defines, tmp_path):
             assert_bit_equal(ag, ao, f"{defines} {sc.name} {opts}")
             if opts.get("countStats"):
                 assert all(sg[k] == so[k] for k in ("rays", "boxTests", "triTests"))
+    # the TLAS kernels of the variant (their model step is the one RT_CACHE_RAYINV and the stack variants touch)
+    many = scenes.instanced_knots(64, 36, max_bounces=4, rays_per_pixel=2, instances=70)
+    fo, ao = render(ORACLE_LIB, many, frames=1)
+    for opts in ({"kernel": 2}, {"kernel": 1}):
+        if "RT_TREELET_PREFETCH" in defines:
+            opts = dict(opts, treeletPrefetch=1)
+        fg, ag = render(lib, many, frames=1, options=opts)
+        assert_bit_equal(ag, ao, f"{defines} TLAS {opts}")
 
 
 def test_simt_default_build_refuses_flagged_treelet_roots(simt_lib):

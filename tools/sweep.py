@@ -23,6 +23,11 @@ from build_variants import path as variant           # noqa: E402
 STAGES = {
     1: (["knot64", "soup4k"], [
         ("default", None, {}),
+        ("256-bit pair loads", "ldg256", {}),
+        ("256-bit pair loads + 64-byte triangles", "ldg256_tri64", {}),
+        ("256-bit pair loads + 64-byte triangles, no_allocate", "ldg256_tri64_na", {}),
+        ("256-bit pair loads + vote 1/3/2", "ldg256_vote132", {}),
+        ("256-bit loads + 64-byte triangles + vote 1/3/2 + prefetch cur", "ldg256_tri64_vote132_pfcur", {}),
         ("vote 1/3/2", "vote132", {}),
         ("vote 1/4/2", "vote142", {}),
         ("vote 2/7/4", "vote274", {}),
