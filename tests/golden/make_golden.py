@@ -7,6 +7,12 @@
                       rendered by the CPU oracle: SHA-256 of the float32 SUM buffer + 64 probe pixels.
                       A regression fixture of the oracle itself — the reference has no golden images.
 
+  soup_small.json     the config-5 shape at a size the oracle renders in a second (20,000 random triangles in three models — diffuse,
+                      glass, emissive — + 300 spheres, sky and sun, 96x96, 8 bounces, 2 spp, 2 frames): SHA-256 of both buffers, the
+                      reference's traversal counters and 32 probe pixels.  Pins the BVH builder, the traversal order (counters), the
+                      model loop, glass and sky against drift of the oracle; its inputs come from exact arithmetic on a Mersenne-
+                      twister stream (no transcendental numpy call), so the scene is the same on every host.
+
 Run from the repo root:  python tests/golden/make_golden.py
 """
 import hashlib
@@ -58,7 +64,28 @@ def make_cornell():
     json.dump(fix, open(os.path.join(HERE, "cornell_c1.json"), "w"), indent=1)
 
 
+def soup_scene():
+    from ray_tracing_b200 import scenes
+    return scenes.random_soup(96, 96, max_bounces=8, rays_per_pixel=2, triangles=20000, spheres=300)
+
+
+def make_soup():
+    from conftest import render, ORACLE_LIB
+    frame, accum, st = render(ORACLE_LIB, soup_scene(), frames=2, want_stats=True)
+    rng = np.random.RandomState(2)
+    probes = [(int(y), int(x)) for y, x in zip(rng.randint(0, 96, 32), rng.randint(0, 96, 32))]
+    fix = {
+        "config": "random_soup(96,96,max_bounces=8,rays_per_pixel=2,triangles=20000,spheres=300), renderSeed 12345, 2 frames",
+        "accum_sha256": hashlib.sha256(accum.tobytes()).hexdigest(),
+        "frame_sha256": hashlib.sha256(frame.tobytes()).hexdigest(),
+        "rays": int(st["rays"]), "boxTests": int(st["boxTests"]), "triTests": int(st["triTests"]), "sphereTests": int(st["sphereTests"]),
+        "probes": [{"y": y, "x": x, "accum_bits": [int(v) for v in accum[y, x].view(np.uint32)]} for y, x in probes],
+    }
+    json.dump(fix, open(os.path.join(HERE, "soup_small.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
     make_pcg()
     make_cornell()
+    make_soup()
     print("golden fixtures written to", HERE)

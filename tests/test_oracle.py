@@ -160,6 +160,19 @@ def test_cornell_golden_fixture():
     assert np.all(accum[..., 3] == 2.0)                         # quirk Q9: alpha of the SUM buffer = frame count
 
 
+def test_soup_golden_fixture():
+    """Mesh path of the oracle (BVH builder, traversal order and culling via the counters, model loop, glass, sky) against the committed fixture."""
+    sys.path.insert(0, GOLDEN)
+    from make_golden import soup_scene
+    fix = json.load(open(os.path.join(GOLDEN, "soup_small.json")))
+    frame, accum, st = render(ORACLE_LIB, soup_scene(), frames=2, want_stats=True)
+    assert all(st[k] == fix[k] for k in ("rays", "boxTests", "triTests", "sphereTests"))
+    for p in fix["probes"]:
+        assert [int(v) for v in accum[p["y"], p["x"]].view(np.uint32)] == p["accum_bits"]
+    assert hashlib.sha256(accum.tobytes()).hexdigest() == fix["accum_sha256"]
+    assert hashlib.sha256(frame.tobytes()).hexdigest() == fix["frame_sha256"]
+
+
 def _furnace(emission_strength, diffuse, spp, bounces):
     s = np.zeros(1, dtype=scenes.SPHERE_DTYPE)
     s["centre"] = (0, 0, 0)

@@ -147,3 +147,21 @@ def test_tlas_with_sphere_accelerator_and_a_model_without_world_bounds(kernel):
     for tlas in (-1, 0):
         fg, ag = render(CUDA_LIB, sc, frames=2, options={"kernel": kernel, "tlas": tlas})
         assert_bit_equal(ag, ao, f"kernel {kernel} tlas {tlas}")
+
+
+def test_golden_soup_fixture_on_the_kernels():
+    """The committed mesh-path fixture (tests/golden/soup_small.json, written by the oracle): all three kernels reproduce its hashes, and
+    the instrumented launches its traversal counters."""
+    import hashlib
+    import json
+    import os
+    import sys
+    from conftest import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    from make_golden import soup_scene
+    fix = json.load(open(os.path.join(GOLDEN, "soup_small.json")))
+    for kernel in (0, 1, 2):
+        frame, accum, st = render(CUDA_LIB, soup_scene(), frames=2, options={"kernel": kernel, "countStats": 1}, want_stats=True)
+        assert hashlib.sha256(accum.tobytes()).hexdigest() == fix["accum_sha256"], f"kernel {kernel}"
+        assert hashlib.sha256(frame.tobytes()).hexdigest() == fix["frame_sha256"], f"kernel {kernel}"
+        assert all(st[k] == fix[k] for k in ("rays", "boxTests", "triTests")), f"kernel {kernel}"
