@@ -53,6 +53,7 @@ STAGES = {
     2: (["knot64", "cluster4k", "soup4k"], [
         ("default", None, {}),
         ("leaf2", "leaf2", {}), ("ir1", "ir1", {}), ("ir3", "ir3", {}), ("rayinv", "rayinv", {}), ("pw20", "pw20", {}), ("pw16", "pw16", {}),
+        ("glass branch out of line (instruction footprint)", "glassool", {}),
         ("l2Persist", None, {"l2Persist": 1}), ("pairOrder 4", None, {"pairOrder": 4}), ("pairOrder 6", None, {"pairOrder": 6}),
         ("poolSlots 96 + treelet", "treelet", {"treeletPrefetch": 1, "poolSlots": 96}),
     ]),
