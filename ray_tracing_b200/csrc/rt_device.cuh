@@ -143,20 +143,9 @@ static_assert(sizeof(DevModel) == 144, "DevModel layout");
 #define RT_DEV_PROF(i, v) do { } while (0)
 #endif
 
-// true when model record `mr` cannot change the current result: its padded world box is missed or lies beyond bestDst
-RT_DI bool ModelOutOfReach(const float4* __restrict__ mr, f3 rayPos, f3 rayInv, float bestDst)
-{
-    RT_DEV_PROF(25, 1);
-    const float4 b0 = __ldg(mr + 7), b1 = __ldg(mr + 8);
-    const f3 tMin = (make_f3(b0.x, b0.y, b0.z) - rayPos) * rayInv;
-    const f3 tMax = (make_f3(b0.w, b1.x, b1.y) - rayPos) * rayInv;
-    const float tNear = fmaxf(fmaxf(fminf(tMin.x, tMax.x), fminf(tMin.y, tMax.y)), fminf(tMin.z, tMax.z));
-    const float tFar  = fminf(fminf(fmaxf(tMin.x, tMax.x), fmaxf(tMin.y, tMax.y)), fmaxf(tMin.z, tMax.z));
-    const bool hit = tFar >= tNear && tFar > 0.0f;
-    return !hit || (tNear * 0.99999619f - 1e-6f) > bestDst;
-}
-
-// The same test on a box of the TLAS (a box that encloses the padded world boxes of a set of models).
+// true when nothing inside the padded world-space box [bmin, bmax] can change the current result: the ray misses the box or
+// enters it beyond bestDst (with a relative 2^-18 and an absolute 1e-6 of slack on the entry distance).  Used on a model's own
+// box and on the TLAS boxes that enclose the boxes of several models.
 RT_DI bool WorldBoxOutOfReach(f3 bmin, f3 bmax, f3 rayPos, f3 rayInv, float bestDst)
 {
     const f3 tMin = (bmin - rayPos) * rayInv;
@@ -165,6 +154,14 @@ RT_DI bool WorldBoxOutOfReach(f3 bmin, f3 bmax, f3 rayPos, f3 rayInv, float best
     const float tFar  = fminf(fminf(fmaxf(tMin.x, tMax.x), fmaxf(tMin.y, tMax.y)), fmaxf(tMin.z, tMax.z));
     const bool hit = tFar >= tNear && tFar > 0.0f;
     return !hit || (tNear * 0.99999619f - 1e-6f) > bestDst;
+}
+
+// true when model record `mr` cannot change the current result (its padded world box, DevModel::wmin .. wmaxz)
+RT_DI bool ModelOutOfReach(const float4* __restrict__ mr, f3 rayPos, f3 rayInv, float bestDst)
+{
+    RT_DEV_PROF(25, 1);
+    const float4 b0 = __ldg(mr + 7), b1 = __ldg(mr + 8);
+    return WorldBoxOutOfReach(make_f3(b0.x, b0.y, b0.z), make_f3(b0.w, b1.x, b1.y), rayPos, rayInv, bestDst);
 }
 
 // Sphere with r*r precomputed (the exact product of HL:299).  32 bytes.
