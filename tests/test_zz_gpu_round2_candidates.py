@@ -165,3 +165,26 @@ def test_golden_soup_fixture_on_the_kernels():
         assert hashlib.sha256(accum.tobytes()).hexdigest() == fix["accum_sha256"], f"kernel {kernel}"
         assert hashlib.sha256(frame.tobytes()).hexdigest() == fix["frame_sha256"], f"kernel {kernel}"
         assert all(st[k] == fix[k] for k in ("rays", "boxTests", "triTests")), f"kernel {kernel}"
+
+
+def test_tlas_at_the_capacity_of_the_candidate_mask():
+    """4,096 models is what the per-lane candidate mask holds (128 words): the TLAS is used; 4,097 models fall back to the linear
+    per-model test.  Small quads scattered in a room, every tenth one glass; both counts must give the oracle's bits."""
+    import numpy as np
+    rng = np.random.RandomState(77)
+    meshes = [scenes.quad_mesh((-0.5, 0, -0.5), (0.5, 0, -0.5), (0.5, 0, 0.5), (-0.5, 0, 0.5)), scenes.room_mesh()]
+    room = scenes.ModelDesc(1, np.eye(4), np.eye(4), scenes.material(diffuse=(0.75, 0.75, 0.75), specularProbability=0.0))
+    quads = []
+    for i in range(4096):
+        l2w, w2l = scenes.trs(position=(rng.uniform(-2.5, 2.5), rng.uniform(0.2, 3.8), rng.uniform(-2.5, 2.5)), euler_deg=tuple(rng.uniform(0, 360, 3)),
+                              scale=tuple(rng.uniform(0.05, 0.25, 3)))
+        mat = (scenes.material(flag=scenes.MAT_GLASS, ior=1.4, smoothness=0.9, specularProbability=0.9) if i % 10 == 0 else
+               scenes.material(diffuse=tuple(rng.uniform(0.2, 0.9, 3)), emission=(1, 1, 1), emissionStrength=float(i % 7 == 0) * 4.0, specularProbability=0.1))
+        quads.append(scenes.ModelDesc(0, l2w, w2l, mat))
+    for models in ([room] + quads[:4095], [room] + quads):
+        sc = scenes.Scene(name="quads", width=64, height=36, meshes=meshes, models=models, cam_local_to_world=scenes.trs(position=(0, 1.9, -5.67))[0],
+                          fov=54.5, settings=dict(maxBounceCount=4, numRaysPerPixel=2))
+        fo, ao = render(ORACLE_LIB, sc, frames=1)
+        for kernel in (2, 1):
+            fg, ag = render(CUDA_LIB, sc, frames=1, options={"kernel": kernel})
+            assert_bit_equal(ag, ao, f"{len(models)} models kernel {kernel}")
