@@ -422,15 +422,9 @@ static int prepareScene(RtContext* c)
         if (!msg.empty()) return fail(c, RT_E_STATE, "rtDispatch: " + msg);
         c->sceneDirty = false; c->modelsDirty = true;
     }
-    if (c->modelsDirty)
     {
-        cudaError_t e = c->repack.buildModels(c->hModels, c->hNodes, c->P.modelCount, c->stream, c->optTlas);
-        if (e != cudaSuccess) return failCuda(c, e, "repack models");
-        c->modelsDirty = false;
-    }
-    {
-        // box containing every possible ray origin: the camera (with its defocus disc) and all geometry; it sizes the padding
-        // of the sphere accelerator, which is rebuilt when the box outgrows the one it was built for
+        // box containing every possible ray origin: the camera (with its defocus disc) and all geometry; it sizes the padding of
+        // the models' world boxes and of the sphere accelerator, which are rebuilt when the box outgrows the one they were built for
         float lo[3], hi[3];
         const float jitter = fabsf(c->P.DefocusStrength) / (float)(c->P.W ? c->P.W : 1u) *
                              (fabsf(c->P.cam[0]) + fabsf(c->P.cam[1]) + fabsf(c->P.cam[2]) + fabsf(c->P.cam[4]) + fabsf(c->P.cam[5]) + fabsf(c->P.cam[6]));
@@ -439,21 +433,22 @@ static int prepareScene(RtContext* c)
         for (int i = 0; i < c->P.modelCount; i++)
         {
             const RtModel& m = c->hModels[i];
-            const RtNode& root = c->hNodes[m.nodeOffset];
-            for (int k = 0; k < 8; k++)
-            {
-                const float v[3] = {k & 1 ? root.boundsMax[0] : root.boundsMin[0], k & 2 ? root.boundsMax[1] : root.boundsMin[1], k & 4 ? root.boundsMax[2] : root.boundsMin[2]};
-                for (int a = 0; a < 3; a++)
-                {
-                    const float w = m.localToWorld[a] * v[0] + m.localToWorld[4 + a] * v[1] + m.localToWorld[8 + a] * v[2] + m.localToWorld[12 + a];
-                    lo[a] = fminf(lo[a], w); hi[a] = fmaxf(hi[a], w);
-                }
-            }
+            double mlo[3], mhi[3];
+            if (!RepackState::worldBoxOfModel(m, c->hNodes[m.nodeOffset], mlo, mhi)) { for (int a = 0; a < 3; a++) { lo[a] = -INFINITY; hi[a] = INFINITY; } break; }
+            for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], std::nextafterf((float)mlo[a], -INFINITY)); hi[a] = fmaxf(hi[a], std::nextafterf((float)mhi[a], INFINITY)); }
         }
+        if (!c->modelsDirty && !c->repack.modelBoundCovers(lo, hi)) c->modelsDirty = true;
         if (!c->spheresDirty && c->repack.sphBvh && !c->repack.sphereBoundCovers(lo, hi)) c->spheresDirty = true;
+        if (c->modelsDirty || c->spheresDirty)      // some room, so that a moving camera does not rebuild every frame
+            for (int a = 0; a < 3; a++) { const float ext = 0.25f * (hi[a] - lo[a]) + 0.01f; lo[a] -= ext; hi[a] += ext; }
+        if (c->modelsDirty)
+        {
+            cudaError_t e = c->repack.buildModels(c->hModels, c->hNodes, c->P.modelCount, c->stream, c->optTlas, lo, hi);
+            if (e != cudaSuccess) return failCuda(c, e, "repack models");
+            c->modelsDirty = false;
+        }
         if (c->spheresDirty)
         {
-            for (int a = 0; a < 3; a++) { const float ext = 0.25f * (hi[a] - lo[a]) + 0.01f; lo[a] -= ext; hi[a] += ext; }
             cudaError_t e = c->repack.buildSpheres(c->hSpheres, lo, hi, c->stream);
             if (e != cudaSuccess) return failCuda(c, e, "repack spheres");
             c->spheresDirty = false;

@@ -46,7 +46,7 @@ for _name in sorted(dir(G)):
 
 # the TLAS tests of the round-2 GPU file run here too (the other tests of that file have interpreter versions of their own below)
 for _name in sorted(dir(Z)):
-    if _name.startswith("test_tlas_") or _name.startswith("test_golden_"):
+    if _name.startswith(("test_tlas_", "test_golden_", "test_model_", "test_moving_")):
         globals()["test_simt_" + _name[5:]] = getattr(Z, _name)
 
 
