@@ -49,6 +49,11 @@ def random_scene(rng):
         base = 0.05 if mesh == 3 else 1.0
         scale = base * np.exp(rng.uniform(np.log(0.02), np.log(1.5), 3)) * (rng.choice([1, 1, 1, -1], 3) if rng.rand() < 0.2 else 1)
         l2w, w2l = scenes.trs(position=tuple(rng.uniform(-2.5, 2.5, 3) * spread + np.array([0, 2.0, 0])), euler_deg=tuple(rng.uniform(0, 360, 3)), scale=tuple(scale))
+        odd = rng.rand()
+        if odd < 0.04:                                # localToWorld of another transform: only the normals notice
+            l2w = scenes.trs(position=tuple(rng.uniform(-5, 5, 3)), euler_deg=tuple(rng.uniform(0, 360, 3)), scale=tuple(rng.uniform(0.1, 2, 3)))[0]
+        elif odd < 0.05:                              # singular worldToLocal
+            w2l = w2l.copy(); w2l[int(rng.randint(0, 3)), :] = 0.0
         models.append(scenes.ModelDesc(mesh, l2w, w2l, random_material(rng)))
     ns = int(rng.choice([0, 0, 1, 5, 40, 64, 65, 200]))
     sph = np.zeros(ns, dtype=scenes.SPHERE_DTYPE)
