@@ -8,8 +8,10 @@
 //   * one level of the tree per round; all nodes of the level in parallel, one thread per TRIANGLE POSITION (a node's
 //     triangles are a contiguous range, so most warps work for one node) — segmented warp reductions (shuffles) fold the
 //     left / right boxes and counts of a candidate plane; a node that fits inside one warp stores its result directly, a
-//     larger one combines warps with atomicMin / atomicMax on order-preserving integer images of the floats (min / max / count
-//     are exact in any order, so the cost is the serial EvaluateSplit's bit for bit);
+//     larger one combines warps with atomicMin / atomicMax on order-preserving 64-bit keys (value, position in the sequence):
+//     min / max / count are exact in any order, so the cost is the serial EvaluateSplit's bit for bit, and the key's position part
+//     makes the reduction return what the reference's sequential strict comparison (`if (tri.MinX < xMin) xMin = tri.MinX`,
+//     BVH.cs:53-58,285-300) keeps among equal values: the FIRST one — which only shows when +0 and -0 meet in one bound;
 //   * the reference's partition is a sequential swap loop whose ORDER is part of the result.  Its outcome has a closed form:
 //     triangles with centre < plane keep their order at the front; a position x behind them keeps its triangle if that one
 //     belongs right, otherwise it receives the triangle found by following q -> start + (#left before q) from q = start +
@@ -47,12 +49,35 @@ struct BNode
     int   blockSize, index, blockStart;
 };
 
-struct CandAcc { unsigned int lmin[3], lmax[3], rmin[3], rmax[3]; int nL, nR; };
+struct CandAcc { unsigned long long lmin[3], lmax[3], rmin[3], rmax[3]; int nL, nR; };
 
 // order-preserving integer image of a float (no NaNs reach it: triangle bounds of finite vertices)
 RT_DI unsigned int f2ord(float f) { const unsigned int b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
 RT_DI float ord2f(unsigned int u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
 #define RT_FLT_MAX 3.402823466e+38f
+
+// Keys of a running minimum / maximum that behave like the reference's sequential loops: `if (v < best) best = v` keeps the first
+// of equal values, and equal values with different bits exist (+0 and -0).  High word: the value with -0 folded onto +0; low word:
+// the position in the sequence (ascending for the minimum, descending for the maximum, so that min / max of the keys prefers the
+// earlier element) and, in bit 0, whether the element was a negative zero.  Position < 2^31 (one per triangle).
+RT_DI unsigned long long KeyMin(float f, unsigned int pos)
+{
+    const bool zero = f == 0.0f;
+    return ((unsigned long long)f2ord(zero ? 0.0f : f) << 32) | ((unsigned long long)pos << 1) | (unsigned long long)(zero && (__float_as_uint(f) >> 31));
+}
+RT_DI unsigned long long KeyMax(float f, unsigned int pos)
+{
+    const bool zero = f == 0.0f;
+    return ((unsigned long long)f2ord(zero ? 0.0f : f) << 32) | ((unsigned long long)(0x7fffffffu - pos) << 1) | (unsigned long long)(zero && (__float_as_uint(f) >> 31));
+}
+RT_DI float KeyValue(unsigned long long k)
+{
+    const float v = ord2f((unsigned int)(k >> 32));
+    return (v == 0.0f && (k & 1ull)) ? -0.0f : v;
+}
+// what an empty sequence leaves: float.MaxValue / float.MinValue (BVH.cs:37-42,258-270), later than every real element
+#define RT_KEY_MIN_EMPTY KeyMin(RT_FLT_MAX, 0x7fffffffu)
+#define RT_KEY_MAX_EMPTY KeyMax(-RT_FLT_MAX, 0x7fffffffu)
 
 RT_DI float NodeCostD(float x, float y, float z, int numTriangles)      // BVH.cs:313-318
 {
@@ -112,7 +137,7 @@ RT_DI float TriCentre(const BuildTriD& t, int axis) { return axis == 0 ? t.cx : 
 
 // BVH.cs:44-59: build records + the root box (warp-reduced, then one set of atomics per warp)
 __global__ void k_bvh_init(const float* __restrict__ verts, const int* __restrict__ indices, int triCount, BuildTriD* __restrict__ tris,
-                           int* __restrict__ posNode, unsigned int* __restrict__ rootBox /* 6: min xyz, max xyz */)
+                           int* __restrict__ posNode, unsigned long long* __restrict__ rootBox /* 6 keys: min xyz, max xyz */)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     float lo[3] = {RT_FLT_MAX, RT_FLT_MAX, RT_FLT_MAX}, hi[3] = {-RT_FLT_MAX, -RT_FLT_MAX, -RT_FLT_MAX};
@@ -134,10 +159,10 @@ __global__ void k_bvh_init(const float* __restrict__ verts, const int* __restric
     }
     for (int d = 0; d < 3; d++)
     {
-        unsigned int mn = f2ord(lo[d]), mx = f2ord(hi[d]);
+        unsigned long long mn = k < triCount ? KeyMin(lo[d], (unsigned int)k) : RT_KEY_MIN_EMPTY, mx = k < triCount ? KeyMax(hi[d], (unsigned int)k) : RT_KEY_MAX_EMPTY;
         for (int off = 16; off > 0; off >>= 1)
         {
-            const unsigned int omn = __shfl_down_sync(0xffffffffu, mn, off), omx = __shfl_down_sync(0xffffffffu, mx, off);
+            const unsigned long long omn = __shfl_down_sync(0xffffffffu, mn, off), omx = __shfl_down_sync(0xffffffffu, mx, off);
             if (omn < mn) mn = omn;
             if (omx > mx) mx = omx;
         }
@@ -145,11 +170,11 @@ __global__ void k_bvh_init(const float* __restrict__ verts, const int* __restric
     }
 }
 
-__global__ void k_bvh_root(BNode* nodes, const unsigned int* rootBox, int triCount, int* nodeCounter)
+__global__ void k_bvh_root(BNode* nodes, const unsigned long long* rootBox, int triCount, int* nodeCounter)
 {
     if (blockIdx.x * blockDim.x + threadIdx.x != 0) return;
     BNode r; memset(&r, 0, sizeof(r));
-    for (int d = 0; d < 3; d++) { r.bmin[d] = ord2f(rootBox[d]); r.bmax[d] = ord2f(rootBox[3 + d]); }
+    for (int d = 0; d < 3; d++) { r.bmin[d] = KeyValue(rootBox[d]); r.bmax[d] = KeyValue(rootBox[3 + d]); }
     r.start = 0; r.count = triCount; r.left = -1; r.depth = 0; r.state = BN_ACTIVE;
     nodes[0] = r;
     *nodeCounter = 1;
@@ -157,7 +182,7 @@ __global__ void k_bvh_root(BNode* nodes, const unsigned int* rootBox, int triCou
 
 RT_DI void ResetAcc(CandAcc& a)
 {
-    for (int d = 0; d < 3; d++) { a.lmin[d] = a.rmin[d] = f2ord(RT_FLT_MAX); a.lmax[d] = a.rmax[d] = f2ord(-RT_FLT_MAX); }
+    for (int d = 0; d < 3; d++) { a.lmin[d] = a.rmin[d] = RT_KEY_MIN_EMPTY; a.lmax[d] = a.rmax[d] = RT_KEY_MAX_EMPTY; }
     a.nL = a.nR = 0;
 }
 
@@ -184,8 +209,8 @@ __global__ void k_bvh_evaluate(const BNode* __restrict__ nodes, const BuildTriD*
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int lane = threadIdx.x & 31u;
     int node = -1;
-    unsigned int v[12]; int nL = 0, nR = 0;
-    for (int d = 0; d < 3; d++) { v[d] = v[6 + d] = f2ord(RT_FLT_MAX); v[3 + d] = v[9 + d] = f2ord(-RT_FLT_MAX); }
+    unsigned long long v[12]; int nL = 0, nR = 0;
+    for (int d = 0; d < 3; d++) { v[d] = v[6 + d] = RT_KEY_MIN_EMPTY; v[3 + d] = v[9 + d] = RT_KEY_MAX_EMPTY; }
     int nodeStart = 0, nodeCount = 0;
     if (x < triCount)
     {
@@ -197,10 +222,12 @@ __global__ void k_bvh_evaluate(const BNode* __restrict__ nodes, const BuildTriD*
             if (nd.state == BN_ACTIVE && cand < nd.numCand && CandidatePlane(nd, quality, cand, axis, pos))
             {
                 const BuildTriD t = tris[x];
-                const int o = TriCentre(t, axis) < pos ? 0 : 6;
-                v[o + 0] = f2ord(t.minX); v[o + 1] = f2ord(t.minY); v[o + 2] = f2ord(t.minZ);
-                v[o + 3] = f2ord(t.maxX); v[o + 4] = f2ord(t.maxY); v[o + 5] = f2ord(t.maxZ);
-                if (o == 0) nL = 1; else nR = 1;
+                const bool left = TriCentre(t, axis) < pos;
+                const unsigned int px = (unsigned int)x;                      // the reference's loop runs over ascending positions (BVH.cs:274)
+                const unsigned long long key[6] = {KeyMin(t.minX, px), KeyMin(t.minY, px), KeyMin(t.minZ, px), KeyMax(t.maxX, px), KeyMax(t.maxY, px), KeyMax(t.maxZ, px)};
+#pragma unroll
+                for (int k = 0; k < 6; k++) { if (left) v[k] = key[k]; else v[6 + k] = key[k]; }     // (constant indices: v stays in registers)
+                if (left) nL = 1; else nR = 1;
                 nodeStart = nd.start; nodeCount = nd.count;
             }
             else node = -1;
@@ -213,7 +240,7 @@ __global__ void k_bvh_evaluate(const BNode* __restrict__ nodes, const BuildTriD*
         const bool take = (lane + (unsigned)off < 32u) && other == node && node >= 0;
         for (int k = 0; k < 12; k++)
         {
-            const unsigned int ov = __shfl_down_sync(0xffffffffu, v[k], off);
+            const unsigned long long ov = __shfl_down_sync(0xffffffffu, v[k], off);
             const bool isMin = (k % 6) < 3;
             if (take && (isMin ? ov < v[k] : ov > v[k])) v[k] = ov;
         }
@@ -249,7 +276,7 @@ __global__ void k_bvh_best(BNode* nodes, CandAcc* acc, int levelStart, int level
     if (nd.state != BN_ACTIVE || cand >= nd.numCand) return;
     CandAcc& a = acc[s];
     float L[6], R[6];
-    for (int d = 0; d < 3; d++) { L[d] = ord2f(a.lmin[d]); L[3 + d] = ord2f(a.lmax[d]); R[d] = ord2f(a.rmin[d]); R[3 + d] = ord2f(a.rmax[d]); }
+    for (int d = 0; d < 3; d++) { L[d] = KeyValue(a.lmin[d]); L[3 + d] = KeyValue(a.lmax[d]); R[d] = KeyValue(a.rmin[d]); R[3 + d] = KeyValue(a.rmax[d]); }
     const float costA = NodeCostD(L[3] - L[0], L[4] - L[1], L[5] - L[2], a.nL);
     const float costB = NodeCostD(R[3] - R[0], R[4] - R[1], R[5] - R[2], a.nR);
     const float cost = costA + costB;
@@ -440,7 +467,7 @@ inline cudaError_t bvh_build_device(const float* dVerts, const float* dNormals, 
 {
     cudaError_t e = cudaSuccess;
     BuildTriD* tris[2] = {nullptr, nullptr}; int* posNode[2] = {nullptr, nullptr};
-    int *flags = nullptr, *prefix = nullptr, *tileSums = nullptr, *counters = nullptr; unsigned int* rootBox = nullptr;
+    int *flags = nullptr, *prefix = nullptr, *tileSums = nullptr, *counters = nullptr; unsigned long long* rootBox = nullptr;
     BNode* nodes = nullptr; CandAcc* acc = nullptr;
     const int nodeCapacity = 2 * triCount + 1;
     const int numTiles = (triCount + SCAN_TILE - 1) / SCAN_TILE;
@@ -452,11 +479,11 @@ inline cudaError_t bvh_build_device(const float* dVerts, const float* dNormals, 
     RT_BVH_CK(cudaMalloc(&prefix, (size_t)triCount * sizeof(int)));
     RT_BVH_CK(cudaMalloc(&tileSums, (size_t)numTiles * sizeof(int)));
     RT_BVH_CK(cudaMalloc(&counters, 2 * sizeof(int)));
-    RT_BVH_CK(cudaMalloc(&rootBox, 6 * sizeof(unsigned int)));
+    RT_BVH_CK(cudaMalloc(&rootBox, 6 * sizeof(unsigned long long)));
     RT_BVH_CK(cudaMalloc(&nodes, (size_t)nodeCapacity * sizeof(BNode)));
     RT_BVH_CK(cudaMalloc(&acc, (size_t)(triCount + 1) * sizeof(CandAcc)));           // one slot per node of a level; every node owns at least one triangle
     {
-        const unsigned int init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+        const unsigned long long init[6] = {~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull};      // above / below every key
         RT_BVH_CK(cudaMemcpyAsync(rootBox, init, sizeof(init), cudaMemcpyHostToDevice, stream));
         RT_BVH_CK(cudaMemsetAsync(counters, 0, 2 * sizeof(int), stream));
         RT_BVH_CK(cudaStreamSynchronize(stream));                           // `init` is a local

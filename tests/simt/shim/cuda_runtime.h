@@ -95,6 +95,11 @@ static inline int __shfl_sync(unsigned int mask, int v, int srcLane) { return (i
 static inline float __shfl_sync(unsigned int mask, float v, int srcLane) { return __uint_as_float((unsigned int)simt::collective(simt::OP_SHFL, mask, __float_as_uint(v), srcLane)); }
 static inline unsigned int __shfl_down_sync(unsigned int mask, unsigned int v, unsigned int delta) { const unsigned int l = simt::lane_id(); return (unsigned int)simt::collective(simt::OP_SHFL, mask, v, l + delta < 32u ? (int)(l + delta) : (int)l); }
 static inline int __shfl_down_sync(unsigned int mask, int v, unsigned int delta) { return (int)__shfl_down_sync(mask, (unsigned int)v, delta); }
+static inline unsigned long long __shfl_down_sync(unsigned int mask, unsigned long long v, unsigned int delta)      // two 32-bit exchanges, as the hardware does
+{
+    const unsigned int lo = __shfl_down_sync(mask, (unsigned int)v, delta), hi = __shfl_down_sync(mask, (unsigned int)(v >> 32), delta);
+    return ((unsigned long long)hi << 32) | lo;
+}
 static inline unsigned int __shfl_up_sync(unsigned int mask, unsigned int v, unsigned int delta) { const unsigned int l = simt::lane_id(); return (unsigned int)simt::collective(simt::OP_SHFL, mask, v, l >= delta ? (int)(l - delta) : (int)l); }
 static inline int __shfl_up_sync(unsigned int mask, int v, unsigned int delta) { return (int)__shfl_up_sync(mask, (unsigned int)v, delta); }
 static inline void __syncthreads() { simt::syncthreads(); }
@@ -104,6 +109,8 @@ static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __A
 static inline unsigned int atomicMin(unsigned int* p, unsigned int v) { unsigned int old = __atomic_load_n(p, __ATOMIC_RELAXED); while (v < old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { } return old; }
 static inline unsigned int atomicMax(unsigned int* p, unsigned int v) { unsigned int old = __atomic_load_n(p, __ATOMIC_RELAXED); while (v > old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { } return old; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) { unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED); while (v < old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { } return old; }
+static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED); while (v > old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { } return old; }
 
 // ---- runtime API (the subset rt_api.cu / rt_repack.cuh call) ---------------------------------------------------------------------
 typedef int cudaError_t;
