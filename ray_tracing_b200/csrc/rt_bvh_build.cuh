@@ -44,6 +44,7 @@ struct BNode
     float parentCost;
     // best candidate so far (BVH.cs:232-246: first strictly smaller cost wins)
     float bestCost, bestPos; int bestAxis, bestNL;
+    int   picked;               // some candidate was strictly cheaper than float.MaxValue (else ChooseSplit returns axis 0, pos 0: BVH.cs:204-206,248)
     float bestL[6], bestR[6];   // min xyz, max xyz of the two sides
     // numbering
     int   blockSize, index, blockStart;
@@ -51,7 +52,7 @@ struct BNode
 
 struct CandAcc { unsigned long long lmin[3], lmax[3], rmin[3], rmax[3]; int nL, nR; };
 
-// order-preserving integer image of a float (no NaNs reach it: triangle bounds of finite vertices)
+// order-preserving integer image of a float (NaNs are filtered before: KeyMin / KeyMax)
 RT_DI unsigned int f2ord(float f) { const unsigned int b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
 RT_DI float ord2f(unsigned int u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
 #define RT_FLT_MAX 3.402823466e+38f
@@ -60,13 +61,16 @@ RT_DI float ord2f(unsigned int u) { return __uint_as_float((u & 0x80000000u) ? (
 // of equal values, and equal values with different bits exist (+0 and -0).  High word: the value with -0 folded onto +0; low word:
 // the position in the sequence (ascending for the minimum, descending for the maximum, so that min / max of the keys prefers the
 // earlier element) and, in bit 0, whether the element was a negative zero.  Position < 2^31 (one per triangle).
+// A NaN element never replaces the running value (`NaN < best` is false) and the running value is never NaN: it is skipped.
 RT_DI unsigned long long KeyMin(float f, unsigned int pos)
 {
+    if (f != f) return ((unsigned long long)f2ord(RT_FLT_MAX) << 32) | 0xfffffffeull;             // = RT_KEY_MIN_EMPTY
     const bool zero = f == 0.0f;
     return ((unsigned long long)f2ord(zero ? 0.0f : f) << 32) | ((unsigned long long)pos << 1) | (unsigned long long)(zero && (__float_as_uint(f) >> 31));
 }
 RT_DI unsigned long long KeyMax(float f, unsigned int pos)
 {
+    if (f != f) return (unsigned long long)f2ord(-RT_FLT_MAX) << 32;                                // = RT_KEY_MAX_EMPTY
     const bool zero = f == 0.0f;
     return ((unsigned long long)f2ord(zero ? 0.0f : f) << 32) | ((unsigned long long)(0x7fffffffu - pos) << 1) | (unsigned long long)(zero && (__float_as_uint(f) >> 31));
 }
@@ -198,7 +202,7 @@ __global__ void k_bvh_level_begin(BNode* nodes, CandAcc* acc, int levelStart, in
     nd.numCand = total;
     nd.parentCost = NodeCostD(nd.bmax[0] - nd.bmin[0], nd.bmax[1] - nd.bmin[1], nd.bmax[2] - nd.bmin[2], nd.count);
     nd.bestCost = quality == 0 ? __uint_as_float(0x7f800000u) : RT_FLT_MAX;   // Low takes its single candidate whatever it costs; High starts from float.MaxValue
-    nd.bestAxis = 0; nd.bestPos = 0.0f; nd.bestNL = 0;
+    nd.bestAxis = 0; nd.bestPos = 0.0f; nd.bestNL = 0; nd.picked = 0;
     ResetAcc(acc[s]);
 }
 
@@ -219,7 +223,12 @@ __global__ void k_bvh_evaluate(const BNode* __restrict__ nodes, const BuildTriD*
         {
             const BNode& nd = nodes[node];
             int axis; float pos;
-            if (nd.state == BN_ACTIVE && cand < nd.numCand && CandidatePlane(nd, quality, cand, axis, pos))
+            // cand = -1: the plane ChooseSplit returns when no candidate was cheaper than float.MaxValue (costs that overflowed to
+            // inf or are NaN) — axis 0, position 0 (BVH.cs:204-206).  Split() then partitions by it whatever it is (BVH.cs:101-147).
+            bool use;
+            if (cand < 0) { use = nd.state == BN_ACTIVE && quality == 1 && nd.numCand > 0 && !nd.picked; axis = 0; pos = 0.0f; }
+            else use = nd.state == BN_ACTIVE && cand < nd.numCand && CandidatePlane(nd, quality, cand, axis, pos);
+            if (use)
             {
                 const BuildTriD t = tris[x];
                 const bool left = TriCentre(t, axis) < pos;
@@ -274,17 +283,24 @@ __global__ void k_bvh_best(BNode* nodes, CandAcc* acc, int levelStart, int level
     if (s >= levelCount) return;
     BNode& nd = nodes[levelStart + s];
     if (nd.state != BN_ACTIVE || cand >= nd.numCand) return;
+    if (cand < 0 && (quality != 1 || nd.numCand <= 0 || nd.picked)) return;
     CandAcc& a = acc[s];
     float L[6], R[6];
     for (int d = 0; d < 3; d++) { L[d] = KeyValue(a.lmin[d]); L[3 + d] = KeyValue(a.lmax[d]); R[d] = KeyValue(a.rmin[d]); R[3 + d] = KeyValue(a.rmax[d]); }
     const float costA = NodeCostD(L[3] - L[0], L[4] - L[1], L[5] - L[2], a.nL);
     const float costB = NodeCostD(R[3] - R[0], R[4] - R[1], R[5] - R[2], a.nR);
     const float cost = costA + costB;
-    if (cost < nd.bestCost || quality == 0)
+    if (cand < 0)
+    {
+        // no candidate won: the split — if float.MaxValue < parentCost lets it happen — is by (axis 0, pos 0); its sides were just evaluated
+        nd.bestAxis = 0; nd.bestPos = 0.0f; nd.bestNL = a.nL;
+        for (int k = 0; k < 6; k++) { nd.bestL[k] = L[k]; nd.bestR[k] = R[k]; }
+    }
+    else if (cost < nd.bestCost || quality == 0)
     {
         int axis; float pos;
         CandidatePlane(nd, quality, cand, axis, pos);
-        nd.bestCost = cost; nd.bestAxis = axis; nd.bestPos = pos; nd.bestNL = a.nL;
+        nd.bestCost = cost; nd.bestAxis = axis; nd.bestPos = pos; nd.bestNL = a.nL; nd.picked = 1;
         for (int k = 0; k < 6; k++) { nd.bestL[k] = L[k]; nd.bestR[k] = R[k]; }
     }
     ResetAcc(a);
@@ -382,7 +398,7 @@ __global__ void k_scan_add(int* out, int n, const int* __restrict__ tileSums)
 
 // the reference's swap loop (BVH.cs:118-147) in closed form; see the header of this file
 __global__ void k_bvh_partition(const BNode* __restrict__ nodes, const BuildTriD* __restrict__ src, const int* __restrict__ posNode, const int* __restrict__ flags,
-                                const int* __restrict__ prefix, int triCount, BuildTriD* __restrict__ dst, int* __restrict__ dstNode)
+                                const int* __restrict__ prefix, int triCount, BuildTriD* __restrict__ dst, int* __restrict__ dstNode, int* __restrict__ inconsistent)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= triCount) return;
@@ -399,7 +415,15 @@ __global__ void k_bvh_partition(const BNode* __restrict__ nodes, const BuildTriD
     if (x >= s + nL)
     {
         int q = x;
-        if (flags[x]) { q = s + (prefix[x] - g0); while (flags[q]) q = s + (prefix[q] - g0); }
+        if (flags[x])
+        {
+            // every step moves q to a strictly smaller position as long as nL is the number of set flags of the node (it is: both come
+            // from the same comparison); the bound turns a broken invariant into an error code instead of a kernel that never ends
+            q = s + (prefix[x] - g0);
+            int steps = 0;
+            while (flags[q] && steps <= nd.count) { q = s + (prefix[q] - g0); steps++; }
+            if (steps > nd.count) { *inconsistent = 1; return; }
+        }
         dst[x] = src[q]; dstNode[x] = nd.left + 1;
     }
 }
@@ -478,14 +502,14 @@ inline cudaError_t bvh_build_device(const float* dVerts, const float* dNormals, 
     RT_BVH_CK(cudaMalloc(&flags, (size_t)triCount * sizeof(int)));
     RT_BVH_CK(cudaMalloc(&prefix, (size_t)triCount * sizeof(int)));
     RT_BVH_CK(cudaMalloc(&tileSums, (size_t)numTiles * sizeof(int)));
-    RT_BVH_CK(cudaMalloc(&counters, 2 * sizeof(int)));
+    RT_BVH_CK(cudaMalloc(&counters, 3 * sizeof(int)));                      // [0] nodes allocated  [1] capacity exceeded  [2] partition invariant broken
     RT_BVH_CK(cudaMalloc(&rootBox, 6 * sizeof(unsigned long long)));
     RT_BVH_CK(cudaMalloc(&nodes, (size_t)nodeCapacity * sizeof(BNode)));
     RT_BVH_CK(cudaMalloc(&acc, (size_t)(triCount + 1) * sizeof(CandAcc)));           // one slot per node of a level; every node owns at least one triangle
     {
         const unsigned long long init[6] = {~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull};      // above / below every key
         RT_BVH_CK(cudaMemcpyAsync(rootBox, init, sizeof(init), cudaMemcpyHostToDevice, stream));
-        RT_BVH_CK(cudaMemsetAsync(counters, 0, 2 * sizeof(int), stream));
+        RT_BVH_CK(cudaMemsetAsync(counters, 0, 3 * sizeof(int), stream));
         RT_BVH_CK(cudaStreamSynchronize(stream));                           // `init` is a local
     }
     const unsigned int T = 256, gridTri = (unsigned int)((triCount + T - 1) / T);
@@ -506,18 +530,26 @@ inline cudaError_t bvh_build_device(const float* dVerts, const float* dNormals, 
             RT_LAUNCH(gridTri, T, 0, stream, k_bvh_evaluate, nodes, tris[cur], posNode[cur], triCount, acc, levelBegin, quality, c);
             RT_LAUNCH(gridLvl, T, 0, stream, k_bvh_best, nodes, acc, levelBegin, levelCount, quality, c);
         }
+        if (quality == 1)
+        {
+            // nodes none of whose candidates was cheaper than float.MaxValue (overflowed or NaN costs): the reference still splits them,
+            // by axis 0 / position 0, when float.MaxValue < parentCost.  Threads of every other node leave this pass at once.
+            RT_LAUNCH(gridTri, T, 0, stream, k_bvh_evaluate, nodes, tris[cur], posNode[cur], triCount, acc, levelBegin, quality, -1);
+            RT_LAUNCH(gridLvl, T, 0, stream, k_bvh_best, nodes, acc, levelBegin, levelCount, quality, -1);
+        }
         RT_LAUNCH(gridLvl, T, 0, stream, k_bvh_decide, nodes, levelBegin, levelCount, counters, nodeCapacity, counters + 1);
         RT_LAUNCH(gridTri, T, 0, stream, k_bvh_flags, nodes, tris[cur], posNode[cur], triCount, flags);
         RT_LAUNCH((unsigned int)numTiles, SCAN_THREADS, 0, stream, k_scan_tiles, flags, triCount, prefix, tileSums);
         RT_LAUNCH(1, SCAN_THREADS, 0, stream, k_scan_sums, tileSums, numTiles);
         RT_LAUNCH(gridTri, T, 0, stream, k_scan_add, prefix, triCount, tileSums);
-        RT_LAUNCH(gridTri, T, 0, stream, k_bvh_partition, nodes, tris[cur], posNode[cur], flags, prefix, triCount, tris[cur ^ 1], posNode[cur ^ 1]);
+        RT_LAUNCH(gridTri, T, 0, stream, k_bvh_partition, nodes, tris[cur], posNode[cur], flags, prefix, triCount, tris[cur ^ 1], posNode[cur ^ 1], counters + 2);
         RT_LAUNCH(gridLvl, T, 0, stream, k_bvh_finish_level, nodes, levelBegin, levelCount);
         cur ^= 1;
-        int h[2] = {0, 0};
+        int h[3] = {0, 0, 0};
         RT_BVH_CK(cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
         RT_BVH_CK(cudaStreamSynchronize(stream));
         if (h[1]) { msg = "BVH node capacity exceeded"; cleanup(); return cudaErrorInvalidValue; }
+        if (h[2]) { msg = "BVH partition: left count and flags disagree (internal error)"; cleanup(); return cudaErrorInvalidValue; }
         levelBegin = nodeCount; nodeCount = h[0];
         levelStart.push_back(levelBegin);
         res.levels = level + 1;

@@ -247,3 +247,40 @@ def test_moving_the_camera_out_of_the_padded_region_rebuilds_the_model_boxes():
     ref = run(ORACLE_LIB, {})
     for kernel in (1, 2):
         assert_bit_equal(run(CUDA_LIB, {"kernel": kernel}), ref, f"kernel {kernel}")
+
+
+def test_model_free_device_bvh_build_on_degenerate_and_non_finite_input():
+    """rtBuildBVH against host/BVH.cpp, byte for byte, where a level-synchronous build can go wrong (all found by tools/simt_fuzz_bvh.py):
+    bounds that see +0 and -0 (the reference's sequential strict comparison keeps the first), NaN vertices (never replace a running
+    bound), an infinite vertex and extents whose surface area overflows FP32 (every candidate costs inf, ChooseSplit returns its
+    defaults 'axis 0, position 0' and Split still splits — the first version of the device build never finished on that)."""
+    import numpy as np
+    import ray_tracing_b200 as rt
+    from ray_tracing_b200 import capi
+    gpu = capi.RtLib(CUDA_LIB).create(0)
+    rng = np.random.RandomState(4)
+    cases = []
+    cases.append(rng.choice([-1.0, -0.0, 0.0, 1.0, 0.5], (300, 3, 3)))                                        # exact zeros of both signs
+    soup = rng.uniform(-1, 1, (200, 1, 3)) + rng.uniform(-0.05, 0.05, (200, 3, 3))
+    for special in (np.nan, np.inf, -np.inf):
+        t = soup.copy(); t[17, 1, 0] = special; t[90, 2, 2] = special
+        cases.append(t)
+    cases.append(soup * 1e20)                                                                                   # area overflows to inf
+    k = 16; gx, gy = np.meshgrid(np.arange(k), np.arange(k))
+    cases.append(np.stack([gx.ravel(), gy.ravel(), np.zeros(k * k)], 1)[:, None, :] + np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=np.float64)[None])   # equal costs
+    for tri in cases:
+        v = np.ascontiguousarray(tri.reshape(-1, 3), dtype=np.float32)
+        idx = np.arange(len(v), dtype=np.int32)
+        nrm = np.ascontiguousarray(rng.uniform(-1, 1, v.shape), dtype=np.float32)
+        for q in (1, 0, 2):
+            th, nh, _ = rt.build_bvh(v, idx, nrm, q)
+            tg, ng = gpu.build_bvh(v, idx, nrm, q)
+            assert len(ng) == len(nh) and np.array_equal(ng.view(np.uint8), nh.view(np.uint8)) and np.array_equal(tg.view(np.uint8), th.view(np.uint8))
+    # a tree with more than 2n + 1 nodes (chains of empty children below an infinite box): both builders refuse, neither hangs
+    t = soup[:20].copy(); t[17, 1, 0] = np.inf
+    v = np.ascontiguousarray(t.reshape(-1, 3), dtype=np.float32); idx = np.arange(len(v), dtype=np.int32)
+    with pytest.raises(ValueError):
+        rt.build_bvh(v, idx, v, 1)
+    with pytest.raises(capi.RtError):
+        gpu.build_bvh(v, idx, v, 1)
+    gpu.destroy()

@@ -41,6 +41,12 @@ def random_mesh(rng):
     else:                                           # clusters far apart
         c = rng.choice([-100.0, 0.0, 100.0], (n, 1, 3)) + rng.uniform(-1, 1, (n, 1, 3)); tri = c + rng.uniform(-0.2, 0.2, (n, 3, 3))
     tri = tri * scale
+    odd = rng.rand()
+    if odd < 0.06:                                  # non-finite vertices: the reference builds *something*; the device build must build the same
+        for _ in range(int(rng.randint(1, 4))):
+            tri[int(rng.randint(0, n)), int(rng.randint(0, 3)), int(rng.randint(0, 3))] = rng.choice([np.nan, np.inf, -np.inf])
+    elif odd < 0.12:                                # extents whose surface area overflows FP32: every candidate costs inf, the reference
+        tri = tri * (1e20 / scale)                  # then splits by "axis 0, position 0" (ChooseSplit's defaults)
     order = int(rng.randint(0, 4))
     if order == 1:
         tri = tri[::-1]
@@ -65,7 +71,16 @@ def main():
         rng = np.random.RandomState(seed)
         v, idx, nrm = random_mesh(rng)
         q = int(rng.choice([1, 1, 0, 2]))
-        th, nh, _ = rt.build_bvh(v, idx, nrm, q)
+        try:
+            th, nh, _ = rt.build_bvh(v, idx, nrm, q)
+        except ValueError:                          # more than 2n + 1 nodes (chains of empty children): both sides must refuse
+            try:
+                gpu.build_bvh(v, idx, nrm, q)
+                bad += 1
+                print(f"case seed {seed}: the host refuses (node capacity), the device build does not", flush=True)
+            except capi.RtError:
+                pass
+            continue
         tg, ng = gpu.build_bvh(v, idx, nrm, q)
         same = len(ng) == len(nh) and np.array_equal(ng.view(np.uint8), nh.view(np.uint8)) and np.array_equal(tg.view(np.uint8), th.view(np.uint8))
         if not same:
