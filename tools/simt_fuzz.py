@@ -35,7 +35,7 @@ def random_material(rng):
                            specularProbability=float(rng.choice([0.0, 1.0, rng.uniform(0, 1)])))
 
 
-def random_scene(rng):
+def random_scene(rng, odd=0.06):
     meshes = [scenes.knot_mesh(nu=int(rng.randint(12, 60)), nv=int(rng.randint(4, 9))), scenes.room_mesh(),
               scenes.quad_mesh((-0.5, 0, -0.5), (0.5, 0, -0.5), (0.5, 0, 0.5), (-0.5, 0, 0.5))]
     soup = scenes.random_soup(8, 8, 1, 1, triangles=int(rng.randint(60, 1500)), spheres=0, seed=int(rng.randint(1, 1000)))
@@ -63,6 +63,24 @@ def random_scene(rng):
     cam = scenes.trs(position=(float(rng.uniform(-1, 1)), 1.9 + float(rng.uniform(-1, 1)), -dist), euler_deg=(float(rng.uniform(-8, 8)), float(rng.uniform(-8, 8)), float(rng.uniform(-30, 30))))[0]
     fov = float(np.clip(np.degrees(2 * np.arctan(3.0 * max(spread, 1.0) / max(dist, 3.0))), 1e-4, 100.0))
     w, h = int(rng.choice([1, 7, 16, 33, 48, 64])), int(rng.choice([1, 5, 9, 24, 36]))
+    if rng.rand() < odd:                              # non-finite and degenerate numbers where a scene can carry them
+        special = [np.nan, np.inf, -np.inf, 0.0, -1.0]
+        for _ in range(int(rng.randint(1, 4))):
+            what = int(rng.randint(0, 5))
+            if what == 0 and len(sph):
+                sph["radius"][int(rng.randint(0, len(sph)))] = rng.choice(special)
+            elif what == 1 and len(sph):
+                sph["centre"][int(rng.randint(0, len(sph)))][int(rng.randint(0, 3))] = rng.choice(special[:3])
+            elif what == 2 and models:
+                k = int(rng.randint(0, len(models))); m = models[k]
+                w2l = m.world_to_local.copy(); w2l[int(rng.randint(0, 3)), int(rng.randint(0, 4))] = rng.choice(special[:3])
+                models[k] = scenes.ModelDesc(m.mesh, m.local_to_world, w2l, m.material)
+            elif what == 3 and models:
+                k = int(rng.randint(0, len(models))); m = models[k]
+                mat = m.material.copy(); mat["ior" if rng.rand() < 0.5 else "smoothness"] = rng.choice(special)
+                models[k] = scenes.ModelDesc(m.mesh, m.local_to_world, m.world_to_local, mat)
+            else:
+                cam = cam.copy(); cam[int(rng.randint(0, 3)), int(rng.randint(0, 4))] = rng.choice(special[:3])
     used = sorted({m.mesh for m in models})
     remap = {old: new for new, old in enumerate(used)}
     models = [scenes.ModelDesc(remap[m.mesh], m.local_to_world, m.world_to_local, m.material) for m in models]
@@ -119,6 +137,7 @@ def main():
     ap.add_argument("--cases", type=int, default=200)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--lib", default=None)
+    ap.add_argument("--odd", type=float, default=0.06, help="share of cases with NaN / inf / zero / negative numbers in spheres, matrices, materials, camera")
     ap.add_argument("--far", type=float, default=0.05, help="share of cases of the many-small-models-from-afar class")
     args = ap.parse_args()
     lib = args.lib or simt_build.build()
@@ -127,7 +146,7 @@ def main():
         seed = args.seed * 100003 + case
         rng = np.random.RandomState(seed)
         far = rng.rand() < args.far
-        sc = far_scene(rng) if far else random_scene(rng)
+        sc = far_scene(rng) if far else random_scene(rng, args.odd)
         frames = int(rng.choice([1, 1, 2]))
         opts = {"kernel": 1, "tlas": int(rng.choice([0, 1]))} if far else random_options(rng)   # (the pooled kernel is slow on the interpreter with 1,000 models)
         tile = (int(rng.randint(0, 3)), 3, int(rng.choice([1, 4, 8]))) if rng.rand() < 0.15 else None
