@@ -106,6 +106,27 @@ def far_scene(rng):
                         settings=dict(maxBounceCount=int(rng.choice([0, 1, 2])), numRaysPerPixel=2, divergeStrength=0.0, renderSeed=int(rng.randint(0, 2 ** 31 - 1))))
 
 
+def sphere_scene(rng):
+    """Large Spheres buffers (the padded-box accelerator): nested, overlapping, duplicated, tiny and huge spheres, any camera distance."""
+    n = int(rng.choice([65, 200, 1000, 3000]))
+    spread = float(rng.choice([1.0, 10.0, 300.0]))
+    sph = np.zeros(n, dtype=scenes.SPHERE_DTYPE)
+    centres = rng.uniform(-3, 3, (n, 3)) * spread
+    radii = np.exp(rng.uniform(np.log(1e-3), np.log(2.0), n)) * spread
+    for i in range(n):
+        if i and rng.rand() < 0.1:
+            centres[i] = centres[int(rng.randint(0, i))]                   # concentric / duplicated
+            if rng.rand() < 0.5:
+                radii[i] = radii[int(rng.randint(0, i))]
+        sph[i] = scenes._sphere(tuple(centres[i]), float(radii[i]), random_material(rng))
+    dist = float(np.exp(rng.uniform(np.log(0.1), np.log(1e5)))) * spread
+    cam = scenes.trs(position=(float(rng.uniform(-1, 1)) * spread, float(rng.uniform(-1, 1)) * spread, -dist), euler_deg=(float(rng.uniform(-5, 5)), float(rng.uniform(-5, 5)), 0.0))[0]
+    fov = float(np.clip(np.degrees(2 * np.arctan(4.0 * spread / max(dist, spread))), 1e-4, 100.0))
+    return scenes.Scene(name="spheres", width=int(rng.choice([32, 64])), height=int(rng.choice([18, 36])), spheres=sph, cam_local_to_world=cam, fov=fov,
+                        settings=dict(maxBounceCount=int(rng.choice([1, 4, 8])), numRaysPerPixel=int(rng.choice([1, 2])), useSky=bool(rng.rand() < 0.5),
+                                      divergeStrength=float(rng.choice([0.0, 0.3])), renderSeed=int(rng.randint(0, 2 ** 31 - 1))), sun_forward=tuple(rng.uniform(-1, 1, 3)))
+
+
 def random_options(rng):
     o = {"kernel": int(rng.choice([1, 2, 2]))}
     if rng.rand() < 0.5:
@@ -138,6 +159,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--lib", default=None)
     ap.add_argument("--odd", type=float, default=0.06, help="share of cases with NaN / inf / zero / negative numbers in spheres, matrices, materials, camera")
+    ap.add_argument("--spheres", type=float, default=0.05, help="share of cases of the large-Spheres-buffer class")
     ap.add_argument("--far", type=float, default=0.05, help="share of cases of the many-small-models-from-afar class")
     args = ap.parse_args()
     lib = args.lib or simt_build.build()
@@ -146,7 +168,7 @@ def main():
         seed = args.seed * 100003 + case
         rng = np.random.RandomState(seed)
         far = rng.rand() < args.far
-        sc = far_scene(rng) if far else random_scene(rng, args.odd)
+        sc = far_scene(rng) if far else (sphere_scene(rng) if rng.rand() < args.spheres else random_scene(rng, args.odd))
         frames = int(rng.choice([1, 1, 2]))
         opts = {"kernel": 1, "tlas": int(rng.choice([0, 1]))} if far else random_options(rng)   # (the pooled kernel is slow on the interpreter with 1,000 models)
         tile = (int(rng.randint(0, 3)), 3, int(rng.choice([1, 4, 8]))) if rng.rand() < 0.15 else None
