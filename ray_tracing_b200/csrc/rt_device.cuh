@@ -126,10 +126,10 @@ struct __align__(16) DevModel
     int   rootCount;    // root node's triangleCount
     int   cullBackface; // material.flag != GLASS (HL:355)
     int   matIndex;     // index into ModelInfo (material is read from the 224-byte record)
-    // Padded world-space bounds of the model (image of its root box under localToWorld, grown by 1e-4 of its size and
-    // position).  A ray that misses this box, or enters it beyond the closest hit so far, cannot be changed by this model:
+    // Padded world-space bounds of the model (image of its root box under the inverse of worldToLocal; the padding is described at
+    // buildModels, rt_repack.cuh).  A ray that misses this box, or enters it beyond the closest hit so far, cannot be changed by this model:
     // the non-instrumented kernels skip the model without transforming the ray (the reference's per-model loop, HL:347-371,
-    // would traverse it and find nothing).  +-inf when the two matrices of the model are not inverses of each other.
+    // would traverse it and find nothing).  Placed through the inverse of worldToLocal (rt_repack.cuh); +-inf when that is singular.
     float wmin[3], wmaxx;
     float wmaxy, wmaxz; int pad[2];
 };

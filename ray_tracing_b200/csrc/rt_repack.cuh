@@ -273,7 +273,7 @@ struct RepackState
         return mode > 0 || (mode < 0 && modelCount > TLAS_AUTO_THRESHOLD);
     }
 
-    // Host only (no CUDA call).  A model whose matrices are not inverses of each other carries an infinite box (buildModels); it
+    // Host only (no CUDA call).  A model with a singular worldToLocal carries an infinite box (buildModels); it
     // makes every TLAS box above it infinite, so it is always marked — conservative, like the linear test.
     static void planTlas(const std::vector<DevModel>& dm, int modelCount, std::vector<NodePair>& pairsOut, std::vector<int>& order, int& rootStart, int& rootCount)
     {
