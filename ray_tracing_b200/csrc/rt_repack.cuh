@@ -264,6 +264,10 @@ struct RepackState
     // median-split tree over a few hundred to a few thousand boxes is microseconds of host work next to a frame.
     RBuf<NodePair> tlasPairs; RBuf<int> tlasLeaves;
     int tlas = 0, tlasRootStart = 0, tlasRootCount = 0;
+#ifndef RT_TLAS_LEAF
+#define RT_TLAS_LEAF 4                                               // models per TLAS leaf.  Box tests per ray segment counted on the interpreter (tree + per-model, 500 instanced
+                                                                     // models): leaf 1: 105.0, 2: 91.3, 4: 85.9, 8: 91.8
+#endif
     static constexpr int TLAS_AUTO_THRESHOLD = 64;                   // below this the linear test of resident 32-byte boxes is cheaper (shipped scenes: 10-28 models)
 
     // mode: 0 = off, 1 = on whenever it is possible, -1 = automatic (more than TLAS_AUTO_THRESHOLD models)
@@ -289,7 +293,7 @@ struct RepackState
                 cen[3 * i + a] = std::isfinite(c) ? c : 0.0f;
             }
         }
-        BuildMedianSplitPairs(lo, hi, cen, n, 4, order, pairsOut, rootStart, rootCount);
+        BuildMedianSplitPairs(lo, hi, cen, n, RT_TLAS_LEAF, order, pairsOut, rootStart, rootCount);
     }
 
     cudaError_t buildTlas(const std::vector<DevModel>& dm, int modelCount, int mode, cudaStream_t stream)
