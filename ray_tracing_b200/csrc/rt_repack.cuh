@@ -57,8 +57,13 @@ struct MeshRoot { int rootStart, rootCount; };
 // the tree is a function of the input alone), leaves of at most `leafSize` items, records emitted parent before children —
 // depth <= ceil(log2(n / leafSize)) + 1.  Used for the sphere accelerator and for the TLAS over the models' world boxes; both
 // only decide what a ray may skip, so its shape never changes a result.
+//
+// sahDepth > 0 (the TLAS): down to that depth a range is split where the surface-area heuristic is smallest — all three axes, every
+// position of the items sorted by centre, cost = area(left) x count + area(right) x count — which keeps the boxes of a level apart
+// much better than the median does when the items are scattered; below it the median split bounds the depth (<= sahDepth +
+// log2(n / leafSize) + 1, the device walk keeps a stack of RT_TLAS_STACK entries and marks everything if that ever overflowed).
 inline void BuildMedianSplitPairs(const std::vector<float>& lo, const std::vector<float>& hi, const std::vector<float>& cen, size_t n, int leafSize,
-                                  std::vector<int>& order, std::vector<NodePair>& pairsOut, int& rootStart, int& rootCount)
+                                  std::vector<int>& order, std::vector<NodePair>& pairsOut, int& rootStart, int& rootCount, int sahDepth = 0)
 {
     order.resize(n);
     for (size_t i = 0; i < n; i++) order[i] = (int)i;
@@ -67,8 +72,42 @@ inline void BuildMedianSplitPairs(const std::vector<float>& lo, const std::vecto
         for (int a = 0; a < 3; a++) { blo[a] = INFINITY; bhi[a] = -INFINITY; }
         for (int k = start; k < start + count; k++) for (int a = 0; a < 3; a++) { blo[a] = std::min(blo[a], lo[3 * order[k] + a]); bhi[a] = std::max(bhi[a], hi[3 * order[k] + a]); }
     };
-    struct Work { int pairIndex, side, start, count; };
+    struct Work { int pairIndex, side, start, count, depth; };
     std::vector<Work> work;
+    auto halfArea = [](const float blo[3], const float bhi[3]) -> double {
+        const double x = (double)bhi[0] - blo[0], y = (double)bhi[1] - blo[1], z = (double)bhi[2] - blo[2];
+        const double a = x * y + x * z + y * z;
+        return a == a ? a : INFINITY;                                      // infinite boxes (inf - inf, inf x 0): as bad as it gets
+    };
+    std::vector<double> suffixArea;
+    auto splitRangeSah = [&](int start, int count) -> int {
+        // returns the first index of the right part after sorting the range along the best axis, or -1 if no split separates anything
+        double best = INFINITY; int bestAxis = -1, bestK = -1;
+        suffixArea.resize((size_t)count + 1);
+        for (int axis = 0; axis < 3; axis++)
+        {
+            std::sort(order.begin() + start, order.begin() + start + count,
+                      [&](int x, int y) { return cen[3 * x + axis] < cen[3 * y + axis] || (cen[3 * x + axis] == cen[3 * y + axis] && x < y); });
+            float blo[3] = {INFINITY, INFINITY, INFINITY}, bhi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (int k = count - 1; k >= 1; k--)
+            {
+                for (int a = 0; a < 3; a++) { blo[a] = std::min(blo[a], lo[3 * order[start + k] + a]); bhi[a] = std::max(bhi[a], hi[3 * order[start + k] + a]); }
+                suffixArea[k] = halfArea(blo, bhi);
+            }
+            for (int a = 0; a < 3; a++) { blo[a] = INFINITY; bhi[a] = -INFINITY; }
+            for (int k = 1; k < count; k++)                               // left = first k items of the sorted range
+            {
+                for (int a = 0; a < 3; a++) { blo[a] = std::min(blo[a], lo[3 * order[start + k - 1] + a]); bhi[a] = std::max(bhi[a], hi[3 * order[start + k - 1] + a]); }
+                const double cost = halfArea(blo, bhi) * k + suffixArea[k] * (count - k);
+                if (cost < best) { best = cost; bestAxis = axis; bestK = k; }
+            }
+        }
+        if (bestAxis < 0) return -1;
+        if (bestAxis != 2)
+            std::sort(order.begin() + start, order.begin() + start + count,
+                      [&](int x, int y) { return cen[3 * x + bestAxis] < cen[3 * y + bestAxis] || (cen[3 * x + bestAxis] == cen[3 * y + bestAxis] && x < y); });
+        return start + bestK;
+    };
     auto splitRange = [&](int start, int count) -> int {
         float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
         for (int k = start; k < start + count; k++) for (int a = 0; a < 3; a++) { clo[a] = std::min(clo[a], cen[3 * order[k] + a]); chi[a] = std::max(chi[a], cen[3 * order[k] + a]); }
@@ -81,11 +120,12 @@ inline void BuildMedianSplitPairs(const std::vector<float>& lo, const std::vecto
     if ((int)n <= leafSize) { rootStart = 0; rootCount = (int)n; return; }
     rootStart = 0; rootCount = 0;
     pairsOut.push_back(NodePair());
-    work.push_back(Work{0, -1, 0, (int)n});
+    work.push_back(Work{0, -1, 0, (int)n, 0});
     for (size_t w = 0; w < work.size(); w++)
     {
         const Work cur = work[w];
-        const int mid = splitRange(cur.start, cur.count);
+        int mid = cur.depth < sahDepth ? splitRangeSah(cur.start, cur.count) : -1;
+        if (mid < 0) mid = splitRange(cur.start, cur.count);
         const int cs[2] = {cur.start, mid}, cc[2] = {mid - cur.start, cur.start + cur.count - mid};
         for (int side = 0; side < 2; side++)
         {
@@ -93,7 +133,7 @@ inline void BuildMedianSplitPairs(const std::vector<float>& lo, const std::vecto
             boundsOf(cs[side], cc[side], blo, bhi);
             int st, ct;
             if (cc[side] <= leafSize) { st = cs[side]; ct = cc[side]; }
-            else { st = (int)pairsOut.size(); ct = 0; pairsOut.push_back(NodePair()); work.push_back(Work{st, side, cs[side], cc[side]}); }
+            else { st = (int)pairsOut.size(); ct = 0; pairsOut.push_back(NodePair()); work.push_back(Work{st, side, cs[side], cc[side], cur.depth + 1}); }
             NodePair& q = pairsOut[cur.pairIndex];       // (push_back may have moved the vector)
             if (side == 0) { q.aMinX = blo[0]; q.aMinY = blo[1]; q.aMinZ = blo[2]; q.aMaxX = bhi[0]; q.aMaxY = bhi[1]; q.aMaxZ = bhi[2]; q.aStart = st; q.aCount = ct; }
             else           { q.bMinX = blo[0]; q.bMinY = blo[1]; q.bMinZ = blo[2]; q.bMaxX = bhi[0]; q.bMaxY = bhi[1]; q.bMaxZ = bhi[2]; q.bStart = st; q.bCount = ct; }
@@ -268,6 +308,9 @@ struct RepackState
 #define RT_TLAS_LEAF 4                                               // models per TLAS leaf.  Box tests per ray segment counted on the interpreter (tree + per-model, 500 instanced
                                                                      // models): leaf 1: 105.0, 2: 91.3, 4: 85.9, 8: 91.8
 #endif
+#ifndef RT_TLAS_SAH_DEPTH
+#define RT_TLAS_SAH_DEPTH 10                                         // levels split by the surface-area heuristic; below: median (depth <= 10 + 11 < RT_TLAS_STACK)
+#endif
     static constexpr int TLAS_AUTO_THRESHOLD = 64;                   // below this the linear test of resident 32-byte boxes is cheaper (shipped scenes: 10-28 models)
 
     // mode: 0 = off, 1 = on whenever it is possible, -1 = automatic (more than TLAS_AUTO_THRESHOLD models)
@@ -293,7 +336,7 @@ struct RepackState
                 cen[3 * i + a] = std::isfinite(c) ? c : 0.0f;
             }
         }
-        BuildMedianSplitPairs(lo, hi, cen, n, RT_TLAS_LEAF, order, pairsOut, rootStart, rootCount);
+        BuildMedianSplitPairs(lo, hi, cen, n, RT_TLAS_LEAF, order, pairsOut, rootStart, rootCount, RT_TLAS_SAH_DEPTH);
     }
 
     cudaError_t buildTlas(const std::vector<DevModel>& dm, int modelCount, int mode, cudaStream_t stream)

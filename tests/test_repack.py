@@ -192,7 +192,7 @@ def test_tlas_plan_encloses_every_model_exactly_once(n):
     seen, depths = set(), []
     below = _tlas_walk(pairs, leaves, boxes, (int(root[0]), int(root[1])), None, None, 0, seen, depths)
     assert sorted(below) == list(range(n)) and len(seen) == k
-    assert max(depths) <= 12, "the device walk keeps a stack of 24 entries"
+    assert max(depths) < 24, "the device walk keeps a stack of 24 entries (RT_TLAS_STACK)"
     if n <= 4:
         assert k == 0 and root[1] == n                       # the root is a leaf
 
