@@ -33,6 +33,7 @@ VARIANTS = {
     "ldg256_tri64_na": ("RT_LDG256", "RT_TRI_PAD64", "RT_TRI_LOAD_POLICY=1"),
     "ldg256_vote132": ("RT_LDG256", "RT_VOTE_WL=3", "RT_VOTE_WN=2"),
     "ldg256_tri64_vote132_pfcur": ("RT_LDG256", "RT_TRI_PAD64", "RT_VOTE_WL=3", "RT_VOTE_WN=2", "RT_PREFETCH_CUR"),
+    "sphsah": ("RT_SPHERE_SAH_DEPTH=14",),
     "leaf2": ("RT_LEAF_REPEAT=2",),
     "ir1": ("RT_INNER_REPEAT=1",),
     "ir3": ("RT_INNER_REPEAT=3",),

@@ -54,6 +54,7 @@ STAGES = {
         ("default", None, {}),
         ("leaf2", "leaf2", {}), ("ir1", "ir1", {}), ("ir3", "ir3", {}), ("rayinv", "rayinv", {}), ("pw20", "pw20", {}), ("pw16", "pw16", {}),
         ("glass branch out of line (instruction footprint)", "glassool", {}),
+        ("sphere tree: surface-area sweep on the top 14 levels", "sphsah", {}),
         ("l2Persist", None, {"l2Persist": 1}), ("pairOrder 4", None, {"pairOrder": 4}), ("pairOrder 6", None, {"pairOrder": 6}),
         ("poolSlots 96 + treelet", "treelet", {"treeletPrefetch": 1, "poolSlots": 96}),
     ]),
