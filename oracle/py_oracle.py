@@ -26,12 +26,18 @@ def _f(bits):   # uint32 bits -> float32
     return np.array(bits & 0xFFFFFFFF, dtype=np.uint32).view(np.float32)[()]
 
 
-def fmin(a, b):
-    return b if a != a else (a if b != b else (a if a < b else b))
+def fmin(a, b):     # NaN-ignoring, -0 below +0 (the contract of DESIGN.md section 2)
+    if a != a: return b
+    if b != b: return a
+    if a == b: return a if np.signbit(a) else b
+    return a if a < b else b
 
 
 def fmax(a, b):
-    return b if a != a else (a if b != b else (a if a > b else b))
+    if a != a: return b
+    if b != b: return a
+    if a == b: return b if np.signbit(a) else a
+    return a if a > b else b
 
 
 # ---- pinned transcendental routines (same published schemes as rt_oracle_math.h, re-derived here) -----------------------

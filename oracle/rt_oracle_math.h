@@ -5,7 +5,7 @@
  * not recoverable from /root/reference.  This header PINS them:
  *   - every + - * / sqrt is one IEEE-754 binary32 operation, round-to-nearest-even, evaluated in the
  *     order the HLSL source writes it (left to right), never fused (build with -ffp-contract=off);
- *   - min/max are NaN-ignoring (fminf/fmaxf), as HLSL's are;
+ *   - min/max are NaN-ignoring, as HLSL's are, and order -0 below +0 (the GPU's FMNMX; libm's fminf/fmaxf do not);
  *   - transcendentals are the polynomial routines below, built only from those IEEE operations so
  *     that any conforming FP32 machine (this CPU, the B200 with -fmad=false) returns the same bits.
  *     They follow well-known published minimax schemes (Cody–Waite reduction; fdlibm-style
@@ -32,13 +32,27 @@ static inline float rt_inf() { return u2f(0x7f800000u); }
 static inline float rt_nan() { return u2f(0x7fc00000u); }
 
 /* ---- HLSL scalar intrinsics ---------------------------------------------------------------------- */
-static inline float min(float a, float b) { return fminf(a, b); }
-static inline float max(float a, float b) { return fmaxf(a, b); }
+/* NaN-ignoring, and -0 ordered below +0 — what the GPU's FMNMX does (libm's fminf / fmaxf return their first argument for a pair
+ * of zeros, which would make the result depend on the operand order) */
+static inline float min(float a, float b)
+{
+    if (a != a) return b;
+    if (b != b) return a;
+    if (a == b) return (f2u(a) & 0x80000000u) ? a : b;        /* equal: only zeros differ in bits; the negative one is the smaller */
+    return a < b ? a : b;
+}
+static inline float max(float a, float b)
+{
+    if (a != a) return b;
+    if (b != b) return a;
+    if (a == b) return (f2u(a) & 0x80000000u) ? b : a;
+    return a > b ? a : b;
+}
 static inline float abs(float a) { return fabsf(a); }
 static inline float sqrt(float a) { return sqrtf(a); }
 static inline float floor(float a) { return floorf(a); }
 static inline float sign(float a) { return (float)((a > 0.0f) ? 1 : 0) - (float)((a < 0.0f) ? 1 : 0); } /* sign(0)=0, sign(NaN)=0 */
-static inline float saturate(float a) { return fminf(fmaxf(a, 0.0f), 1.0f); }
+static inline float saturate(float a) { return min(max(a, 0.0f), 1.0f); }
 static inline float lerp(float a, float b, float t) { return a + t * (b - a); }
 static inline float smoothstep(float a, float b, float x)
 {
@@ -168,8 +182,8 @@ static inline float3 cross(float3 a, float3 b)
 }
 /* normalize(v) pinned as v * (1 / sqrt(dot(v,v)))  — the rsq·mul shape GPUs lower it to */
 static inline float3 normalize(float3 v) { float inv = 1.0f / sqrtf(dot(v, v)); return v * inv; }
-static inline float3 min(float3 a, float3 b) { return mk3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
-static inline float3 max(float3 a, float3 b) { return mk3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
+static inline float3 min(float3 a, float3 b) { return mk3(min(a.x, b.x), min(a.y, b.y), min(a.z, b.z)); }
+static inline float3 max(float3 a, float3 b) { return mk3(max(a.x, b.x), max(a.y, b.y), max(a.z, b.z)); }
 static inline float3 lerp(float3 a, float3 b, float t) { return a + t * (b - a); }
 static inline float3 exp(float3 a) { return mk3(exp(a.x), exp(a.y), exp(a.z)); }
 /* HLSL reflect(i, n) = i - 2 * n * dot(i, n); pinned as i - (2*dot(n,i))*n */

@@ -69,6 +69,24 @@ static inline uchar4 make_uchar4(unsigned char x, unsigned char y, unsigned char
 #define gridDim (simt::tl_gridDim)
 
 // ---- intrinsics -----------------------------------------------------------------------------------------------------------
+// fminf / fmaxf as the GPU computes them (FMNMX): NaN-ignoring, and -0 ordered below +0.  libm's versions return their first argument
+// for a pair of zeros, so the device code would see a different sign of zero here than on the B200.
+static inline float simt_fminf(float a, float b)
+{
+    if (a != a) return b;
+    if (b != b) return a;
+    if (a == b) { unsigned int u; memcpy(&u, &a, 4); return (u & 0x80000000u) ? a : b; }
+    return a < b ? a : b;
+}
+static inline float simt_fmaxf(float a, float b)
+{
+    if (a != a) return b;
+    if (b != b) return a;
+    if (a == b) { unsigned int u; memcpy(&u, &a, 4); return (u & 0x80000000u) ? b : a; }
+    return a > b ? a : b;
+}
+#define fminf simt_fminf
+#define fmaxf simt_fmaxf
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline int __popc(unsigned int v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned int v) { return __builtin_ffs((int)v); }
