@@ -63,8 +63,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=300)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--lib", default=None)
     args = ap.parse_args()
-    gpu = capi.RtLib(simt_build.build()).create(0)
+    gpu = capi.RtLib(args.lib or simt_build.build()).create(0)
     bad = 0
     for case in range(args.cases):
         seed = args.seed * 100003 + case
