@@ -26,6 +26,12 @@ def _f(bits):   # uint32 bits -> float32
     return np.array(bits & 0xFFFFFFFF, dtype=np.uint32).view(np.float32)[()]
 
 
+def f2uint_rz(f):   # float -> uint as the GPU converts: truncation, NaN / negative -> 0, saturating
+    if not (f > 0):
+        return 0
+    return 0xFFFFFFFF if f >= 4294967296.0 else int(f)
+
+
 def fmin(a, b):     # NaN-ignoring, -0 below +0 (the contract of DESIGN.md section 2)
     if a != a: return b
     if b != b: return a
@@ -400,7 +406,7 @@ class PyShader:
         uv = (F(x) / (F(W) - ONE), F(y) / (F(H) - ONE))
         cam = self.CamLocalToWorldMatrix
         origin = mul_mat(cam, v3(0, 0, 0), 1.0)
-        px, py = int(uv[0] * F(W)), int(uv[1] * F(H))
+        px, py = f2uint_rz(uv[0] * F(W)), f2uint_rz(uv[1] * F(H))
         self.state = (py * W + px + self.Frame * 719393 + self.renderSeed) & 0xFFFFFFFF
         focus_local = mulv((uv[0] - HALF, uv[1] - HALF, ONE), self.ViewParams)
         focus = mul_mat(cam, focus_local, 1.0)

@@ -524,8 +524,8 @@ struct Shader
         float3 camOrigin = mul_xyz(CamLocalToWorldMatrix, mk4(mk3(0.0f, 0.0f, 0.0f), 1.0f));
 
         // (HL:549)
-        uint pixelCoordX = (uint)(uv.x * (float)numPixels[0]);
-        uint pixelCoordY = (uint)(uv.y * (float)numPixels[1]);
+        uint pixelCoordX = orc::f2uint_rz(uv.x * (float)numPixels[0]);
+        uint pixelCoordY = orc::f2uint_rz(uv.y * (float)numPixels[1]);
         uint pixelIndex = pixelCoordY * numPixels[0] + pixelCoordX;
         uint rngState = pixelIndex + (uint)Frame * 719393u + (uint)renderSeed;
 
@@ -785,7 +785,7 @@ static unsigned DisplayEncode(float v)
     if (!(v > 0.0f)) return 0u;
     if (v > 1.0f) v = 1.0f;
     const float e = v <= 0.0031308f ? 12.92f * v : 1.055f * orc::pow(v, 0.41666666f) - 0.055f;
-    return (unsigned)(orc::min(orc::max(e, 0.0f), 1.0f) * 255.0f + 0.5f);
+    return orc::f2uint_rz(orc::min(orc::max(e, 0.0f), 1.0f) * 255.0f + 0.5f);
 }
 
 int rtDisplay(RtContext* c, int useAccumulated, int Frame, uint8_t* dst, size_t bytes)

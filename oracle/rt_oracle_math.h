@@ -31,6 +31,15 @@ static inline float u2f(uint u)  { float f; memcpy(&f, &u, 4); return f; }
 static inline float rt_inf() { return u2f(0x7f800000u); }
 static inline float rt_nan() { return u2f(0x7fc00000u); }
 
+/* float -> uint as the GPU converts (cvt.rzi.u32.f32): truncation, NaN and negatives give 0, values from 2^32 up saturate.  In C++ the
+ * cast of such values is undefined; HLSL does not define them either (a 1-pixel-wide image makes uv = 0 / 0). */
+static inline uint f2uint_rz(float f)
+{
+    if (!(f > 0.0f)) return 0u;
+    if (f >= 4294967296.0f) return 0xffffffffu;
+    return (uint)f;
+}
+
 /* ---- HLSL scalar intrinsics ---------------------------------------------------------------------- */
 /* NaN-ignoring, and -0 ordered below +0 — what the GPU's FMNMX does (libm's fminf / fmaxf return their first argument for a pair
  * of zeros, which would make the result depend on the operand order) */
