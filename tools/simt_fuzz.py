@@ -170,7 +170,8 @@ def main():
         far = rng.rand() < args.far
         sc = far_scene(rng) if far else (sphere_scene(rng) if rng.rand() < args.spheres else random_scene(rng, args.odd))
         frames = int(rng.choice([1, 1, 2]))
-        opts = {"kernel": 1, "tlas": int(rng.choice([0, 1]))} if far else random_options(rng)   # (the pooled kernel is slow on the interpreter with 1,000 models)
+        # (the pooled kernel is slow on the interpreter with 1,000 models: it gets the smaller far scenes only)
+        opts = {"kernel": 2 if len(sc.models) <= 150 and rng.rand() < 0.5 else 1, "tlas": int(rng.choice([0, 1]))} if far else random_options(rng)
         tile = (int(rng.randint(0, 3)), 3, int(rng.choice([1, 4, 8]))) if rng.rand() < 0.15 else None
         try:
             fo, ao, so = render(ORACLE_LIB, sc, frames=frames, want_stats=True)
