@@ -1,6 +1,8 @@
-"""GPU parity of options added after the last GPU session of round 1 (they are bit-exact on the SIMT interpreter build,
-tests/test_simt_kernels.py; this file sorts last so that `pytest -x -m gpu` reaches it after everything already validated on
-the B200)."""
+"""GPU parity of everything written after the last GPU session of round 1: the round-2 options (pair order, grid fit, L2 window), the
+device BVH build, the forced RandomValue draws, the TLAS over the models, the golden mesh fixture, and the regressions of the three
+defects the randomised searches found (model boxes and distant ray origins, zero signs / non-finite input in the device BVH build).  All of
+it is bit-exact on the SIMT interpreter build (tests/test_simt_kernels.py runs these bodies too); this file sorts after
+test_gpu_parity.py so that `pytest -x -m gpu` reaches it after everything already validated on the B200."""
 import pytest
 
 from conftest import CUDA_LIB, ORACLE_LIB, assert_bit_equal, render
