@@ -1,8 +1,9 @@
-// Shipped as source (no C# toolchain in the build image): the P/Invoke host for librt_b200.so.
+// Shipped as source, NEVER COMPILED (no C# toolchain in the build image: dotnet, mono, mcs, csc are absent): the P/Invoke host for librt_b200.so.
 // Compiled twin: ray_tracing_b200/host/RayComputeManager.cpp.  See INTEGRATION.md.
 // Assets/Scripts/Tracer/RayTracingManager.cs — the reference's RayComputeManager with its ComputeShader calls swapped
 using System;
 using System.Collections.Generic;
+using System.Runtime.InteropServices;
 using Seb.AccelerationStructures;
 using UnityEngine;
 
@@ -22,6 +23,7 @@ public class RayTracingManager : MonoBehaviour
     public Vector4 debugParams;
     public int numAccumulatedFrames, renderSeed;
     public Sphere[] spheres = Array.Empty<Sphere>();            // north-star extension
+    public int gpuCount = 1;                                    // > 1: the image is row-tiled over that many GPUs of the box, one NCCL all-gather per frame inside rtDispatch
 
     [StructLayout(LayoutKind.Sequential)] public struct MeshInfo { public int NodeOffset, TriangleOffset; public Matrix4x4 WorldToLocalMatrix, LocalToWorldMatrix; public RayTracingMaterial Material; }   // 224 B
     [StructLayout(LayoutKind.Sequential)] public struct Sphere { public Vector3 centre; public float radius; public RayTracingMaterial material; }                                                // 104 B
@@ -29,7 +31,7 @@ public class RayTracingManager : MonoBehaviour
     IntPtr ctx; MeshInfo[] meshInfo; Model[] models; bool hasBVH; int width, height;
     const int kernelRayTrace = 0, kernelResetAccumulated = 1;
 
-    void OnEnable() { RtB200.Check(IntPtr.Zero, RtB200.rtCreate(out ctx, 0)); hasBVH = false; renderSeed = new System.Random().Next(); ResetAccumulatedRender(); }
+    void OnEnable() { RtB200.Check(IntPtr.Zero, gpuCount > 1 ? RtB200.rtCreateMulti(out ctx, null, gpuCount) : RtB200.rtCreate(out ctx, 0)); hasBVH = false; renderSeed = new System.Random().Next(); ResetAccumulatedRender(); }
     void OnDestroy() { if (ctx != IntPtr.Zero) RtB200.rtDestroy(ctx); ctx = IntPtr.Zero; }
     void Update() { Render(); }
 

@@ -1,8 +1,9 @@
-// Shipped as source (no C# toolchain in the build image): the P/Invoke host for librt_b200.so.
+// Shipped as source, NEVER COMPILED (no C# toolchain in the build image: dotnet, mono, mcs, csc are absent): the P/Invoke host for librt_b200.so.
 // Compiled twin: ray_tracing_b200/host/RayComputeManager.cpp.  See INTEGRATION.md.
 // Assets/Scripts/Tracer/RtB200.cs
 using System;
 using System.Runtime.InteropServices;
+using Seb.AccelerationStructures;     // BVH (Assets/Scripts/Types/BVH.cs declares it in this namespace)
 
 public static class RtB200
 {
@@ -37,10 +38,18 @@ public static class RtB200
     [DllImport(Lib)] public static extern int rtSetOption(IntPtr ctx, string name, int value);           // "kernel", "tlas", "modelSkip", ... (rt_b200.h)
     [DllImport(Lib)] public static extern int rtSetStream(IntPtr ctx, IntPtr cudaStream);
     [StructLayout(LayoutKind.Sequential)]
-    public struct Stats { public ulong rays, boxTests, triTests, sphereTests, dispatches; public double kernelMs; public ulong sphereBoxTests; }
+    public struct Stats { public ulong rays, boxTests, triTests, sphereTests, dispatches; public double kernelMs; public ulong sphereBoxTests; public double exchangeMs; }
     [DllImport(Lib)] public static extern int rtGetStats(IntPtr ctx, out Stats stats);
     [DllImport(Lib)] public static extern int rtResetStats(IntPtr ctx);
-    // multi-GPU row bands: one process per GPU; the all-gather of TileSend into TileRecv is the host's (NCCL)
+    // multi-GPU inside the boundary.  A Unity host is ONE process: rtCreateMulti(out ctx, null, 8) instead of rtCreate, and nothing else changes —
+    // every rtSet* / rtSetBuffer reaches all GPUs, rtDispatch(kernelRayTrace) traces tile r of 8 on GPU r and ends with the NCCL all-gather of the frame's
+    // tiles, rtReadback / rtDisplay read GPU 0.  One process per GPU instead: rtGetUniqueId on rank 0, rtCommInit on every rank.
+    [DllImport(Lib)] public static extern int rtCreateMulti(out IntPtr ctx, int[] devices, int nDevices);
+    [DllImport(Lib)] public static extern int rtGetUniqueId(byte[] id128, UIntPtr bytes);
+    [DllImport(Lib)] public static extern int rtCommInit(IntPtr ctx, byte[] id128, UIntPtr bytes, int rank, int worldSize);
+    [DllImport(Lib)] public static extern int rtCommDestroy(IntPtr ctx);
+    [DllImport(Lib)] public static extern int rtExchangeTiles(IntPtr ctx);
+    // row bands by hand (option "exchange" = 0): the caller owns the collective between rtPackTile and rtUnpackTiles
     [DllImport(Lib)] public static extern int rtSetTile(IntPtr ctx, int rank, int worldSize, int bandRows);
     [DllImport(Lib)] public static extern int rtPackTile(IntPtr ctx);
     [DllImport(Lib)] public static extern int rtUnpackTiles(IntPtr ctx);

@@ -129,6 +129,34 @@ int rtUnpackTiles(RtContext* ctx);
 int rtGetIpcHandles(RtContext* ctx, void* handles, size_t bytes);
 int rtSetPeers(RtContext* ctx, int nPeers, const void* handles, size_t bytes);
 
+/* ---- multi-GPU inside the boundary -----------------------------------------------------------------------
+ * The reference host is ONE object issuing ONE dispatch per frame (RayComputeManager.RenderFrame, RCM:84-95); it must reach all
+ * GPUs of the box without hand-rolling a collective.  Two ways, same exchange (pack this GPU's row bands -> one ncclAllGather
+ * over NVLink -> scatter into both full-size textures, issued by rtDispatch(RT_KERNEL_RAYTRACE) itself on the context's stream):
+ *
+ *  (a) one process, several GPUs — what a Unity / C# host is:
+ *        rtCreateMulti(&ctx, devices, n)   devices = n CUDA ordinals (NULL = 0 .. n-1).  The returned context LEADS a group: every
+ *        rtSet* / rtSetBuffer / rtResize / rtSetOption call on it reaches all n GPUs (each keeps the whole scene),
+ *        rtDispatch traces tile r of n on GPU r and exchanges, rtReadback / rtDisplay read GPU devices[0], whose textures are
+ *        complete after the exchange; rtGetStats sums the counters of the group (times: the slowest GPU).  rtDestroy frees all.
+ *        n = 1 is rtCreate.  The call sequence of RayComputeManager does not change at all.
+ *  (b) one process per GPU (torchrun, mpirun, N copies of a C++ host):
+ *        rank 0: rtGetUniqueId(id, 128); the host hands the 128 bytes to the other ranks by any means (file, socket, MPI,
+ *        torch.distributed store); every rank: rtCreate(&ctx, localDevice) + rtCommInit(ctx, id, 128, rank, world)  — collective,
+ *        returns when all ranks have joined; it also makes the context render tile `rank` of `world` (rtSetTile, bands of 8 rows;
+ *        call rtSetTile afterwards with the same rank / world to change bandRows).  rtCommDestroy returns to one GPU.
+ *
+ * NCCL is loaded at run time (the libnccl.so.2 already in the process, else the loader's; RT_B200_NCCL_LIB overrides): the
+ * library has no link-time NCCL dependency and single-GPU hosts never load it.  Option "exchange" = 0 leaves the exchange to the
+ * caller (rtExchangeTiles, or rtPackTile / own collective / rtUnpackTiles as in round 1). */
+#define RT_UNIQUE_ID_BYTES 128
+int rtCreateMulti(RtContext** out, const int* devices, int nDevices);
+int rtGetUniqueId(void* id, size_t bytes);
+int rtCommInit(RtContext* ctx, const void* id, size_t bytes, int rank, int worldSize);
+int rtCommDestroy(RtContext* ctx);
+/* The exchange alone (pack -> all-gather -> unpack), asynchronous on the context's stream(s).  rtDispatch calls it. */
+int rtExchangeTiles(RtContext* ctx);
+
 /* Device address + size of a named device object, for zero-copy plumbing (NCCL, torch views).
  * name ∈ {"FrameRender","AccumulatedRender","TileSend","TileRecv"}. */
 int rtGetDevicePointer(RtContext* ctx, const char* name, void** devPtr, size_t* bytes);
@@ -148,6 +176,8 @@ int rtBuildBVH(RtContext* ctx, const float* verts, int vertCount, const int* ind
  *                 2 = persistent-thread wavefront with per-warp path pools, sorting and ray compaction,
  *                 -1 = automatic (default): 2 when the scene has meshes, 1 for sphere-only scenes
  *   "countStats"  1 = also count box / triangle tests (HL:254,271) — slower, off by default
+ *   "exchange"    1 (default) = rtDispatch(RAYTRACE) on a context with a communicator (rtCommInit / rtCreateMulti) ends with the
+ *                 all-gather of the frame's tiles; 0 = the caller exchanges (rtExchangeTiles or its own collective)
  *   "smemNodes"   number of top-of-tree node pairs staged in shared memory by TMA bulk copy (0 = off; -1 = automatic, which
  *                 is currently 0: measured, the staging never beat leaving that shared memory to L1)
  *   "poolSlots"   paths per warp pool of kernel 2: 32, 64 (default) or 96
@@ -186,6 +216,8 @@ typedef struct RtStats {
     double   kernelMs;      /* CUDA-event time of the RAYTRACE kernels since the last reset (sum)          */
     uint64_t sphereBoxTests;/* box tests of the sphere accelerator (Spheres buffers above 64 entries), "countStats" = 1;
                                with the accelerator, sphereTests counts the sphere tests actually made               */
+    double   exchangeMs;    /* CUDA-event time of the per-frame tile exchanges (pack + ncclAllGather + unpack) issued by
+                               rtDispatch / rtExchangeTiles since the last reset (sum)                              */
 } RtStats;
 
 /* Synchronises, then reports the counters accumulated since the last rtResetStats. */
@@ -194,7 +226,7 @@ int rtResetStats(RtContext* ctx);
 
 /* ABI version of this header: (major << 16) | minor. */
 int rtGetVersion(void);
-#define RT_B200_VERSION ((1 << 16) | 0)
+#define RT_B200_VERSION ((1 << 16) | 1)
 
 #ifdef __cplusplus
 }

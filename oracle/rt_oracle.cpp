@@ -599,6 +599,32 @@ static std::string g_createErr;
 
 static int fail(RtContext* c, int code, const std::string& msg) { if (c) c->err = msg; else g_createErr = msg; return code; }
 
+// The traversal stack below is int stack[64] (the reference's is 32, RayCommon.hlsl:239); a Nodes buffer whose inner nodes nest deeper
+// than 63 levels would overflow it.  Same limit and same error as the product's rtDispatch (rt_repack.cuh planScene).
+static bool bvhTooDeepOrBroken(const RtContext* c, std::string& why)
+{
+    const long long nn = (long long)c->nodes.size();
+    for (int i = 0; i < c->sh.modelCount && i < (int)c->models.size(); i++)
+    {
+        const int off = c->models[i].nodeOffset;
+        if (off < 0 || off >= nn) { why = "model nodeOffset out of range"; return true; }
+        std::vector<std::pair<long long, int>> todo(1, std::make_pair((long long)off, 1));
+        size_t visited = 0;
+        while (!todo.empty())
+        {
+            const std::pair<long long, int> cur = todo.back(); todo.pop_back();
+            const RtNode& nd = c->nodes[(size_t)cur.first];
+            if (nd.triangleCount > 0) continue;
+            if (cur.second > 63) { why = "BVH too deep: more than 63 levels of inner nodes (the traversal stacks hold 64 entries; the reference's builder stops at 32)"; return true; }
+            if (++visited > c->nodes.size()) { why = "BVH has a cycle"; return true; }
+            const long long a = (long long)off + nd.startIndex;
+            if (a < 0 || a + 1 >= nn) { why = "BVH child index out of range"; return true; }
+            todo.push_back(std::make_pair(a, cur.second + 1)); todo.push_back(std::make_pair(a + 1, cur.second + 1));
+        }
+    }
+    return false;
+}
+
 extern "C" {
 
 int rtGetVersion(void) { return RT_B200_VERSION; }
@@ -741,6 +767,7 @@ int rtDispatch(RtContext* c, int kernelIndex, int gx, int gy, int gz)
     }
     if (kernelIndex != RT_KERNEL_RAYTRACE) return fail(c, RT_E_INVALID, "rtDispatch: kernelIndex must be 0 or 1");
     if (c->sh.modelCount > (int)c->models.size()) return fail(c, RT_E_STATE, "rtDispatch: modelCount exceeds ModelInfo length");
+    { std::string why; if (bvhTooDeepOrBroken(c, why)) return fail(c, RT_E_STATE, "rtDispatch: " + why); }
 
     auto t0 = std::chrono::steady_clock::now();
     std::atomic<uint> nextRow(0);
@@ -800,6 +827,16 @@ int rtDisplay(RtContext* c, int useAccumulated, int Frame, uint8_t* dst, size_t 
 }
 
 int rtSynchronize(RtContext* c) { return c ? RT_OK : RT_E_INVALID; }
+// multi-GPU entry points of the ABI: the oracle is one CPU "device"
+int rtCreateMulti(RtContext** out, const int* devices, int nDevices)
+{
+    if (nDevices != 1) return fail(nullptr, RT_E_STATE, "oracle: one device only");
+    return rtCreate(out, devices ? devices[0] : 0);
+}
+int rtGetUniqueId(void*, size_t) { return fail(nullptr, RT_E_STATE, "oracle: no NCCL"); }
+int rtCommInit(RtContext* c, const void*, size_t, int, int) { return fail(c, RT_E_STATE, "oracle: no NCCL"); }
+int rtCommDestroy(RtContext* c) { return fail(c, RT_E_STATE, "oracle: no NCCL"); }
+int rtExchangeTiles(RtContext* c) { return fail(c, RT_E_STATE, "oracle: no device tile staging"); }
 int rtSetStream(RtContext* c, void*) { return c ? RT_OK : RT_E_INVALID; }
 int rtPackTile(RtContext* c) { return fail(c, RT_E_STATE, "oracle: no device tile staging"); }
 int rtUnpackTiles(RtContext* c) { return fail(c, RT_E_STATE, "oracle: no device tile staging"); }
@@ -828,6 +865,8 @@ int rtResetStats(RtContext* c) { if (!c) return RT_E_INVALID; c->stats = RtStats
 int orRenderPixels(RtContext* c, const int* xy, int n, float* out)
 {
     if (!c || !xy || !out || n < 0) return fail(c, RT_E_INVALID, "orRenderPixels: bad argument");
+    if (c->sh.modelCount > (int)c->models.size()) return fail(c, RT_E_STATE, "orRenderPixels: modelCount exceeds ModelInfo length");
+    { std::string why; if (bvhTooDeepOrBroken(c, why)) return fail(c, RT_E_STATE, "orRenderPixels: " + why); }
     auto t0 = std::chrono::steady_clock::now();
     std::atomic<int> next(0);
     int nt = c->threads;

@@ -38,7 +38,7 @@ BUFFER_DTYPES = {"Triangles": TRIANGLE_DTYPE, "Nodes": NODE_DTYPE, "ModelInfo": 
 
 class RtStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("boxTests", C.c_uint64), ("triTests", C.c_uint64), ("sphereTests", C.c_uint64),
-                ("dispatches", C.c_uint64), ("kernelMs", C.c_double), ("sphereBoxTests", C.c_uint64)]
+                ("dispatches", C.c_uint64), ("kernelMs", C.c_double), ("sphereBoxTests", C.c_uint64), ("exchangeMs", C.c_double)]
 
 
 class RtError(RuntimeError):
@@ -86,10 +86,15 @@ class RtLib:
             "rtGetStats": ([vp, C.POINTER(RtStats)], ci),
             "rtResetStats": ([vp], ci),
             "rtBuildBVH": ([vp, vp, ci, vp, ci, vp, ci, vp, vp, ci, C.POINTER(ci)], ci),
+            "rtCreateMulti": ([C.POINTER(vp), C.POINTER(ci), ci], ci),
+            "rtGetUniqueId": ([vp, C.c_size_t], ci),
+            "rtCommInit": ([vp, vp, C.c_size_t, ci, ci], ci),
+            "rtCommDestroy": ([vp], ci),
+            "rtExchangeTiles": ([vp], ci),
         }
         for name, (args, res) in sig.items():
             if not hasattr(L, name):
-                if name in ("rtGetIpcHandles", "rtSetPeers", "rtBuildBVH"):      # absent from older experimental builds used in A/B runs
+                if name in ("rtGetIpcHandles", "rtSetPeers", "rtBuildBVH", "rtCreateMulti", "rtGetUniqueId", "rtCommInit", "rtCommDestroy", "rtExchangeTiles"):      # absent from older experimental builds used in A/B runs
                     continue
                 raise AttributeError(f"{self.path} does not export {name}")
             fn = getattr(L, name)
@@ -101,6 +106,24 @@ class RtLib:
         if rc != RT_OK:
             raise RtError(rc, (self.lib.rtLastError(None) or b"").decode())
         return RtContext(self, h)
+
+    def create_multi(self, devices) -> "RtContext":
+        """rtCreateMulti: ONE context that renders on all `devices` of this process (row-band tiles + the all-gather inside rtDispatch)."""
+        devices = list(devices)
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.lib.rtCreateMulti(C.byref(h), arr, len(devices))
+        if rc != RT_OK:
+            raise RtError(rc, (self.lib.rtLastError(None) or b"").decode())
+        return RtContext(self, h)
+
+    def unique_id(self) -> bytes:
+        """rtGetUniqueId: the 128 bytes rank 0 hands to every rank for rtCommInit."""
+        buf = C.create_string_buffer(128)
+        rc = self.lib.rtGetUniqueId(buf, 128)
+        if rc != RT_OK:
+            raise RtError(rc, (self.lib.rtLastError(None) or b"").decode())
+        return buf.raw
 
 
 class RtContext:
@@ -200,6 +223,18 @@ class RtContext:
 
     def set_tile(self, rank: int, world: int, band_rows: int):
         self._ck(self._L.rtSetTile(self._h, rank, world, band_rows))
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """rtCommInit (collective over all ranks): NCCL communicator inside the context; RayTrace dispatches then end with the
+        all-gather of the frame's tiles, and the context renders tile `rank` of `world`."""
+        assert len(unique_id) == 128
+        self._ck(self._L.rtCommInit(self._h, unique_id, 128, rank, world))
+
+    def comm_destroy(self):
+        self._ck(self._L.rtCommDestroy(self._h))
+
+    def exchange_tiles(self):
+        self._ck(self._L.rtExchangeTiles(self._h))
 
     def pack_tile(self):
         self._ck(self._L.rtPackTile(self._h))

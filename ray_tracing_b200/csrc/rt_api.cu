@@ -11,6 +11,7 @@
 #include "rt_kernel_pool.cuh"
 #include "rt_repack.cuh"
 #include "rt_bvh_build.cuh"
+#include "rt_comm.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -69,10 +70,16 @@ struct RtContext
     int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16, optSortRays = 0, optForceExt = 0, optModelSkip = 1, optPairOrder = 0, optGridFit = 0, optL2Persist = 0, optTreeletPrefetch = 0, optZeroDefocus = 1, optTlas = -1;
     int l2PersistApplied = 0; const void* l2PersistBase = nullptr; size_t l2PersistBytes = 0;   // kernel -1 = automatic   // smemPairs -1 = automatic
 
+    // exchange of finished tiles inside the ABI (rt_comm.cuh): a communicator over the ranks of a tiled render — one process per
+    // GPU (rtCommInit) or several GPUs in this process (rtCreateMulti: this context leads, `followers` render the other tiles)
+    NcclApi::Comm comm = nullptr; int commRank = 0, commWorld = 1;
+    int optExchange = 1;
+    std::vector<RtContext*> followers; RtContext* leader = nullptr;
+
     // counters / timing
     unsigned long long* dCounters = nullptr;   // 5
     unsigned int* dWork = nullptr;
-    std::vector<EventPair> pending, freeEvents;
+    std::vector<EventPair> pending, pendingX, freeEvents;
     RtStats stats;
 };
 
@@ -96,6 +103,14 @@ static int drainEvents(RtContext* c)
         c->freeEvents.push_back(ev);
     }
     c->pending.clear();
+    for (auto& ev : c->pendingX)
+    {
+        CK(cudaEventSynchronize(ev.b));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, ev.a, ev.b));
+        c->stats.exchangeMs += ms;
+        c->freeEvents.push_back(ev);
+    }
+    c->pendingX.clear();
     return RT_OK;
 }
 
@@ -106,6 +121,8 @@ static void closePeers(RtContext* c)
 }
 
 extern "C" {
+
+static void destroyComm(RtContext* c);
 
 int rtGetVersion(void) { return RT_B200_VERSION; }
 
@@ -154,6 +171,12 @@ int rtCreate(RtContext** out, int device)
 int rtDestroy(RtContext* c)
 {
     if (!c) return RT_E_INVALID;
+    if (c->leader) return fail(c, RT_E_STATE, "rtDestroy: this context belongs to a group; destroy the context rtCreateMulti returned");
+    {
+        std::vector<RtContext*> members; members.swap(c->followers);
+        destroyComm(c);
+        for (RtContext* m : members) { destroyComm(m); m->leader = nullptr; rtDestroy(m); }
+    }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->nodes.release(); c->tris.release(); c->models.release(); c->spheres.release();
@@ -161,6 +184,7 @@ int rtDestroy(RtContext* c)
     c->repack.release();
     closePeers(c);
     for (auto& ev : c->pending) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    for (auto& ev : c->pendingX) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (auto& ev : c->freeEvents) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     if (c->dCounters) cudaFree(c->dCounters);
     if (c->dWork) cudaFree(c->dWork);
@@ -180,7 +204,7 @@ int rtSetStream(RtContext* c, void* s)
     return RT_OK;
 }
 
-int rtSetBuffer(RtContext* c, const char* name, const void* data, int count, int stride)
+static int one_rtSetBuffer(RtContext* c, const char* name, const void* data, int count, int stride)
 {
     if (!c || !name || count < 0 || (count > 0 && !data)) return fail(c, RT_E_INVALID, "rtSetBuffer: bad argument");
     CK(cudaSetDevice(c->device));
@@ -208,6 +232,8 @@ int rtSetBuffer(RtContext* c, const char* name, const void* data, int count, int
         // the BVH repack depends only on the (nodeOffset, triOffset) pairs; matrices / materials change every frame (RCM:192-204)
         bool sameTopology = (size_t)count == c->hModels.size();
         const RtModel* m = (const RtModel*)data;
+        // the reference re-sends ModelInfo every frame (RCM:192-204), mostly with the bytes of the frame before: nothing to do then
+        if (sameTopology && count > 0 && c->models.count == (size_t)count && memcmp(m, c->hModels.data(), (size_t)count * sizeof(RtModel)) == 0) return RT_OK;
         for (int i = 0; sameTopology && i < count; i++)
             sameTopology = m[i].nodeOffset == c->hModels[i].nodeOffset && m[i].triOffset == c->hModels[i].triOffset;
         if (!sameTopology) c->sceneDirty = true;
@@ -220,6 +246,7 @@ int rtSetBuffer(RtContext* c, const char* name, const void* data, int count, int
     if (n == "Spheres")
     {
         if (stride != (int)sizeof(RtSphere)) return fail(c, RT_E_INVALID, "rtSetBuffer: Spheres stride must be 104");
+        if (count > 0 && c->spheres.count == (size_t)count && c->hSpheres.size() == (size_t)count && memcmp(data, c->hSpheres.data(), (size_t)count * sizeof(RtSphere)) == 0) return RT_OK;
         CK(c->spheres.ensure(count));
         c->hSpheres.assign((const RtSphere*)data, (const RtSphere*)data + count);
         if (count) CK(cudaMemcpyAsync(c->spheres.p, c->hSpheres.data(), (size_t)count * sizeof(RtSphere), cudaMemcpyHostToDevice, c->stream));
@@ -229,7 +256,7 @@ int rtSetBuffer(RtContext* c, const char* name, const void* data, int count, int
     return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetBuffer: unknown buffer ") + name);
 }
 
-int rtSetInt(RtContext* c, const char* name, int v)
+static int one_rtSetInt(RtContext* c, const char* name, int v)
 {
     if (!c || !name) return fail(c, RT_E_INVALID, "rtSetInt: bad argument");
     const std::string n(name);
@@ -238,13 +265,18 @@ int rtSetInt(RtContext* c, const char* name, int v)
     else if (n == "MaxBounceCount") c->P.MaxBounceCount = v;
     else if (n == "NumRaysPerPixel") c->P.NumRaysPerPixel = v;
     else if (n == "renderSeed") c->P.renderSeed = v;
-    else if (n == "modelCount") c->P.modelCount = v;
+    else if (n == "modelCount")
+    {
+        // the pair plan, the mesh roots, the DevModel records and the TLAS are all sized for the count they were built with
+        if (v != c->P.modelCount) c->sceneDirty = c->modelsDirty = true;
+        c->P.modelCount = v;
+    }
     else if (n == "triangleCount" || n == "visMode") { /* declared but never read by the shader (HL:24,120) */ }
     else return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetInt: unknown uniform ") + name);
     return RT_OK;
 }
 
-int rtSetInts(RtContext* c, const char* name, const int* v, int n)
+static int one_rtSetInts(RtContext* c, const char* name, const int* v, int n)
 {
     if (!c || !name || !v) return fail(c, RT_E_INVALID, "rtSetInts: bad argument");
     if (std::string(name) == "Resolution")
@@ -256,7 +288,7 @@ int rtSetInts(RtContext* c, const char* name, const int* v, int n)
     return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetInts: unknown uniform ") + name);
 }
 
-int rtSetFloat(RtContext* c, const char* name, float v)
+static int one_rtSetFloat(RtContext* c, const char* name, float v)
 {
     if (!c || !name) return fail(c, RT_E_INVALID, "rtSetFloat: bad argument");
     const std::string n(name);
@@ -269,7 +301,7 @@ int rtSetFloat(RtContext* c, const char* name, float v)
     return RT_OK;
 }
 
-int rtSetVector(RtContext* c, const char* name, const float v[4])
+static int one_rtSetVector(RtContext* c, const char* name, const float v[4])
 {
     if (!c || !name || !v) return fail(c, RT_E_INVALID, "rtSetVector: bad argument");
     const std::string n(name);
@@ -281,21 +313,21 @@ int rtSetVector(RtContext* c, const char* name, const float v[4])
     return RT_OK;
 }
 
-int rtSetMatrix(RtContext* c, const char* name, const float v[16])
+static int one_rtSetMatrix(RtContext* c, const char* name, const float v[16])
 {
     if (!c || !name || !v) return fail(c, RT_E_INVALID, "rtSetMatrix: bad argument");
     if (std::string(name) == "CamLocalToWorldMatrix") { memcpy(c->P.cam, v, 64); return RT_OK; }
     return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetMatrix: unknown uniform ") + name);
 }
 
-int rtSetBool(RtContext* c, const char* name, int v)
+static int one_rtSetBool(RtContext* c, const char* name, int v)
 {
     if (!c || !name) return fail(c, RT_E_INVALID, "rtSetBool: bad argument");
     if (std::string(name) == "accumulate") { c->P.accumulate = v != 0; return RT_OK; }
     return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetBool: unknown uniform ") + name);
 }
 
-int rtResize(RtContext* c, int w, int h)
+static int one_rtResize(RtContext* c, int w, int h)
 {
     if (!c || w <= 0 || h <= 0) return fail(c, RT_E_INVALID, "rtResize: bad size");
     CK(cudaSetDevice(c->device));
@@ -316,17 +348,26 @@ int rtResize(RtContext* c, int w, int h)
 int rtSetTile(RtContext* c, int rank, int world, int bandRows)
 {
     if (!c || world < 1 || rank < 0 || rank >= world || bandRows < 1) return fail(c, RT_E_INVALID, "rtSetTile: bad argument");
+    if (c->leader) return fail(c, RT_E_STATE, "rtSetTile: this context belongs to a group");
+    if (!c->followers.empty())
+    {
+        // a group's ranks are its GPUs; only the band height is the caller's
+        if (rank != 0 || world != (int)c->followers.size() + 1) return fail(c, RT_E_INVALID, "rtSetTile: a group renders as rank 0 of its own GPU count; only bandRows can change");
+        for (RtContext* m : c->followers) { if (bandRows != m->bandRows) { m->tileSend.release(); m->tileRecv.release(); } m->bandRows = bandRows; }
+    }
+    if (c->comm && (rank != c->commRank || world != c->commWorld)) return fail(c, RT_E_INVALID, "rtSetTile: rank / world differ from the communicator's (rtCommInit)");
     if (rank != c->tileRank || world != c->tileWorld || bandRows != c->bandRows) { c->tileSend.release(); c->tileRecv.release(); }
     c->tileRank = rank; c->tileWorld = world; c->bandRows = bandRows;
     return RT_OK;
 }
 
-int rtSetOption(RtContext* c, const char* name, int value)
+static int one_rtSetOption(RtContext* c, const char* name, int value)
 {
     if (!c || !name) return fail(c, RT_E_INVALID, "rtSetOption: bad argument");
     const std::string n(name);
     if (n == "kernel") { if (value < -1 || value > 2) return fail(c, RT_E_INVALID, "rtSetOption: kernel must be -1 (auto), 0, 1 or 2"); c->optKernel = value; }
     else if (n == "countStats") c->optCountStats = value != 0;
+    else if (n == "exchange") c->optExchange = value != 0;
     else if (n == "smemNodes") c->optSmemPairs = value;
     else if (n == "modelSkip") c->optModelSkip = value != 0;
     else if (n == "tlas")
@@ -351,6 +392,79 @@ int rtSetOption(RtContext* c, const char* name, int value)
     else if (n == "tailLanes") { if (value < 0 || value > 31) return fail(c, RT_E_INVALID, "rtSetOption: tailLanes must be in [0, 31]"); c->optTailLanes = value; }
     else if (n == "poolSlots") { if (value != 32 && value != 64 && value != 96) return fail(c, RT_E_INVALID, "rtSetOption: poolSlots must be 32, 64 or 96"); c->optPoolSlots = value; }
     else return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetOption: unknown option ") + name);
+    return RT_OK;
+}
+
+// ---- the setters of a context that leads a group (rtCreateMulti) reach every GPU of the group ----
+int rtSetBuffer(RtContext* c, const char* name, const void* data, int count, int stride)
+{
+    int rc = one_rtSetBuffer(c, name, data, count, stride);
+    if (rc != RT_OK || !c) return rc;
+    for (RtContext* m : c->followers) if ((rc = one_rtSetBuffer(m, name, data, count, stride)) != RT_OK) return fail(c, rc, "GPU " + std::to_string(m->device) + ": " + m->err);
+    return RT_OK;
+}
+
+int rtSetInt(RtContext* c, const char* name, int v)
+{
+    int rc = one_rtSetInt(c, name, v);
+    if (rc != RT_OK || !c) return rc;
+    for (RtContext* m : c->followers) if ((rc = one_rtSetInt(m, name, v)) != RT_OK) return fail(c, rc, "GPU " + std::to_string(m->device) + ": " + m->err);
+    return RT_OK;
+}
+
+int rtSetInts(RtContext* c, const char* name, const int* v, int n)
+{
+    int rc = one_rtSetInts(c, name, v, n);
+    if (rc != RT_OK || !c) return rc;
+    for (RtContext* m : c->followers) if ((rc = one_rtSetInts(m, name, v, n)) != RT_OK) return fail(c, rc, "GPU " + std::to_string(m->device) + ": " + m->err);
+    return RT_OK;
+}
+
+int rtSetFloat(RtContext* c, const char* name, float v)
+{
+    int rc = one_rtSetFloat(c, name, v);
+    if (rc != RT_OK || !c) return rc;
+    for (RtContext* m : c->followers) if ((rc = one_rtSetFloat(m, name, v)) != RT_OK) return fail(c, rc, "GPU " + std::to_string(m->device) + ": " + m->err);
+    return RT_OK;
+}
+
+int rtSetVector(RtContext* c, const char* name, const float v[4])
+{
+    int rc = one_rtSetVector(c, name, v);
+    if (rc != RT_OK || !c) return rc;
+    for (RtContext* m : c->followers) if ((rc = one_rtSetVector(m, name, v)) != RT_OK) return fail(c, rc, "GPU " + std::to_string(m->device) + ": " + m->err);
+    return RT_OK;
+}
+
+int rtSetMatrix(RtContext* c, const char* name, const float v[16])
+{
+    int rc = one_rtSetMatrix(c, name, v);
+    if (rc != RT_OK || !c) return rc;
+    for (RtContext* m : c->followers) if ((rc = one_rtSetMatrix(m, name, v)) != RT_OK) return fail(c, rc, "GPU " + std::to_string(m->device) + ": " + m->err);
+    return RT_OK;
+}
+
+int rtSetBool(RtContext* c, const char* name, int v)
+{
+    int rc = one_rtSetBool(c, name, v);
+    if (rc != RT_OK || !c) return rc;
+    for (RtContext* m : c->followers) if ((rc = one_rtSetBool(m, name, v)) != RT_OK) return fail(c, rc, "GPU " + std::to_string(m->device) + ": " + m->err);
+    return RT_OK;
+}
+
+int rtResize(RtContext* c, int w, int h)
+{
+    int rc = one_rtResize(c, w, h);
+    if (rc != RT_OK || !c) return rc;
+    for (RtContext* m : c->followers) if ((rc = one_rtResize(m, w, h)) != RT_OK) return fail(c, rc, "GPU " + std::to_string(m->device) + ": " + m->err);
+    return RT_OK;
+}
+
+int rtSetOption(RtContext* c, const char* name, int value)
+{
+    int rc = one_rtSetOption(c, name, value);
+    if (rc != RT_OK || !c) return rc;
+    for (RtContext* m : c->followers) if ((rc = one_rtSetOption(m, name, value)) != RT_OK) return fail(c, rc, "GPU " + std::to_string(m->device) + ": " + m->err);
     return RT_OK;
 }
 
@@ -411,6 +525,7 @@ static int prepareScene(RtContext* c)
     const bool treelets = c->optTreeletPrefetch && kernelSel != 0;      // two-level treelets with flagged roots; no shared-memory staging with it
     const int pairOrder = treelets ? 2 : c->optPairOrder;
     if (treelets) budget = 0;
+    if (budget > 3072) budget = 3072;                                   // planScene's own clamp (192 KB), so that budgetUsed compares equal
     if (kernelSel == 2) { const int mx = pool_max_smem_pairs(c->optPoolSlots, (int)c->spheres.count); if (budget > mx) budget = mx; }
     else if (kernelSel == 0) budget = 0;
     if (budget != c->repack.budgetUsed || pairOrder != c->repack.orderUsed || treelets != c->repack.flagsUsed) c->sceneDirty = true;
@@ -434,7 +549,7 @@ static int prepareScene(RtContext* c)
         {
             const RtModel& m = c->hModels[i];
             double mlo[3], mhi[3];
-            if (!RepackState::worldBoxOfModel(m, c->hNodes[m.nodeOffset], mlo, mhi)) { for (int a = 0; a < 3; a++) { lo[a] = -INFINITY; hi[a] = INFINITY; } break; }
+            if (!RepackState::worldBoxOfModel(m, c->repack.roots[std::make_pair(m.nodeOffset, m.triOffset)], mlo, mhi)) { for (int a = 0; a < 3; a++) { lo[a] = -INFINITY; hi[a] = INFINITY; } break; }
             for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], std::nextafterf((float)mlo[a], -INFINITY)); hi[a] = fmaxf(hi[a], std::nextafterf((float)mhi[a], INFINITY)); }
         }
         if (!c->modelsDirty && !c->repack.modelBoundCovers(lo, hi)) c->modelsDirty = true;
@@ -457,7 +572,8 @@ static int prepareScene(RtContext* c)
     return RT_OK;
 }
 
-int rtDispatch(RtContext* c, int kernelIndex, int gx, int gy, int gz)
+// One GPU's share of a dispatch: the RayTrace kernel over this context's tile (the whole image without rtSetTile).
+static int dispatchLocal(RtContext* c, int kernelIndex, int gx, int gy, int gz)
 {
     if (!c || gx < 0 || gy < 0 || gz < 0) return fail(c, RT_E_INVALID, "rtDispatch: bad argument");
     if (c->width == 0) return fail(c, RT_E_STATE, "rtDispatch: rtResize has not been called");
@@ -572,6 +688,7 @@ int rtDisplay(RtContext* c, int useAccumulated, int Frame, uint8_t* dst, size_t 
 int rtSynchronize(RtContext* c)
 {
     if (!c) return RT_E_INVALID;
+    for (RtContext* m : c->followers) { CK(cudaSetDevice(m->device)); CK(cudaStreamSynchronize(m->stream)); }
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     return RT_OK;
@@ -616,6 +733,189 @@ int rtUnpackTiles(RtContext* c)
     launch_unpack_tiles(c->tileRecv.p, c->frame.p, c->accum.p, c->width, c->height, c->tileWorld, c->bandRows,
                         (int)tileRows(c, 0), c->stream);
     CK(cudaGetLastError());
+    return RT_OK;
+}
+
+
+// ---- exchange of finished tiles inside the ABI (rtCommInit / rtCreateMulti) -----------------------------------------------------
+
+// true when a RayTrace dispatch on this context is followed by the all-gather of the frame's tiles
+static bool exchanges(const RtContext* c) { return c->optExchange && c->tileWorld > 1 && (c->comm || !c->followers.empty() || c->leader); }
+
+static int beginExchangeTiming(RtContext* c, EventPair& ev)
+{
+    if (!c->freeEvents.empty()) { ev = c->freeEvents.back(); c->freeEvents.pop_back(); }
+    else { CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b)); }
+    CK(cudaEventRecord(ev.a, c->stream));
+    return RT_OK;
+}
+
+static int ncclFail(RtContext* c, NcclApi* api, int r, const char* what)
+{
+    return fail(c, RT_E_CUDA, std::string(what) + ": " + (api && api->GetErrorString ? api->GetErrorString(r) : "NCCL error") + " (" + std::to_string(r) + ")");
+}
+
+// pack -> ncclAllGather -> unpack on the streams of `n` contexts (one per GPU; n > 1 only for a single-process group, whose
+// collectives are issued as one NCCL group).  Under the SIMT interpreter the group's all-gather is the copy it stands for.
+static int exchangeTiles(RtContext* const* cs, int n)
+{
+    RtContext* lead = cs[0];
+    std::vector<EventPair> evs((size_t)n);
+    for (int i = 0; i < n; i++)
+    {
+        RtContext* c = cs[i];
+        CK(cudaSetDevice(c->device));
+        int rc = beginExchangeTiming(c, evs[i]); if (rc != RT_OK) return rc;
+        rc = rtPackTile(c); if (rc != RT_OK) return i ? fail(lead, rc, c->err) : rc;
+    }
+#ifdef RT_SIMT_EMU
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++)
+        memcpy(cs[i]->tileRecv.p + (size_t)j * cs[j]->tileSend.count, cs[j]->tileSend.p, cs[j]->tileSend.count * sizeof(float4));
+#else
+    std::string why;
+    NcclApi* api = NcclApi::get(why);
+    if (!api) return fail(lead, RT_E_STATE, "tile exchange: " + why);
+    int r;
+    if (n > 1 && (r = api->GroupStart()) != NcclApi::Success) return ncclFail(lead, api, r, "ncclGroupStart");
+    for (int i = 0; i < n; i++)
+    {
+        RtContext* c = cs[i];
+        if (!c->comm) return fail(lead, RT_E_STATE, "tile exchange: no communicator (rtCommInit)");
+        CK(cudaSetDevice(c->device));
+        if ((r = api->AllGather(c->tileSend.p, c->tileRecv.p, c->tileSend.count * sizeof(float4), NcclApi::Char, c->comm, c->stream)) != NcclApi::Success)
+            return ncclFail(lead, api, r, "ncclAllGather");
+    }
+    if (n > 1 && (r = api->GroupEnd()) != NcclApi::Success) return ncclFail(lead, api, r, "ncclGroupEnd");
+#endif
+    for (int i = 0; i < n; i++)
+    {
+        RtContext* c = cs[i];
+        CK(cudaSetDevice(c->device));
+        int rc = rtUnpackTiles(c); if (rc != RT_OK) return i ? fail(lead, rc, c->err) : rc;
+        CK(cudaEventRecord(evs[i].b, c->stream));
+        c->pendingX.push_back(evs[i]);
+    }
+    { RtContext* c = lead; CK(cudaSetDevice(c->device)); }
+    return RT_OK;
+}
+
+int rtDispatch(RtContext* c, int kernelIndex, int gx, int gy, int gz)
+{
+    if (!c) return RT_E_INVALID;
+    if (c->leader) return fail(c, RT_E_STATE, "rtDispatch: this context belongs to a group; dispatch on the context rtCreateMulti returned");
+    int rc = dispatchLocal(c, kernelIndex, gx, gy, gz);
+    if (rc != RT_OK) return rc;
+    for (RtContext* m : c->followers)
+        if ((rc = dispatchLocal(m, kernelIndex, gx, gy, gz)) != RT_OK) return fail(c, rc, "GPU " + std::to_string(m->device) + ": " + m->err);
+    if (!c->followers.empty()) CK(cudaSetDevice(c->device));
+    const bool traced = kernelIndex == RT_KERNEL_RAYTRACE && gz != 0 && gx > 0 && gy > 0;
+    if (!traced || !exchanges(c)) return RT_OK;
+    std::vector<RtContext*> all(1, c);
+    all.insert(all.end(), c->followers.begin(), c->followers.end());
+    return exchangeTiles(all.data(), (int)all.size());
+}
+
+int rtExchangeTiles(RtContext* c)
+{
+    if (!c) return RT_E_INVALID;
+    if (c->leader) return fail(c, RT_E_STATE, "rtExchangeTiles: call it on the context rtCreateMulti returned");
+    if (c->tileWorld <= 1) return RT_OK;
+    if (!c->comm && c->followers.empty()) return fail(c, RT_E_STATE, "rtExchangeTiles: no communicator (rtCommInit / rtCreateMulti)");
+    std::vector<RtContext*> all(1, c);
+    all.insert(all.end(), c->followers.begin(), c->followers.end());
+    return exchangeTiles(all.data(), (int)all.size());
+}
+
+int rtGetUniqueId(void* id, size_t bytes)
+{
+    if (!id || bytes != RT_UNIQUE_ID_BYTES) return fail(nullptr, RT_E_INVALID, "rtGetUniqueId: id must hold 128 bytes");
+    std::string why;
+    NcclApi* api = NcclApi::get(why);
+    if (!api) return fail(nullptr, RT_E_STATE, "rtGetUniqueId: " + why);
+    NcclApi::UniqueId u;
+    const int r = api->GetUniqueId(&u);
+    if (r != NcclApi::Success) return ncclFail(nullptr, api, r, "ncclGetUniqueId");
+    memcpy(id, &u, RT_UNIQUE_ID_BYTES);
+    return RT_OK;
+}
+
+static void destroyComm(RtContext* c)
+{
+    if (!c->comm) return;
+    std::string why;
+    NcclApi* api = NcclApi::get(why);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (api) api->CommDestroy(c->comm);
+    c->comm = nullptr; c->commRank = 0; c->commWorld = 1;
+}
+
+int rtCommInit(RtContext* c, const void* id, size_t bytes, int rank, int world)
+{
+    if (!c || !id || bytes != RT_UNIQUE_ID_BYTES || world < 1 || rank < 0 || rank >= world) return fail(c, RT_E_INVALID, "rtCommInit: bad argument");
+    if (c->leader || !c->followers.empty()) return fail(c, RT_E_STATE, "rtCommInit: the context belongs to a single-process group (rtCreateMulti), which has its communicator");
+    std::string why;
+    NcclApi* api = NcclApi::get(why);
+    if (!api) return fail(c, RT_E_STATE, "rtCommInit: " + why);
+    CK(cudaSetDevice(c->device));
+    destroyComm(c);
+    NcclApi::UniqueId u; memcpy(&u, id, RT_UNIQUE_ID_BYTES);
+    const int r = api->CommInitRank(&c->comm, world, u, rank);
+    if (r != NcclApi::Success) { c->comm = nullptr; return ncclFail(c, api, r, "ncclCommInitRank"); }
+    c->commRank = rank; c->commWorld = world;
+    return rtSetTile(c, rank, world, c->tileWorld == world && c->tileRank == rank ? c->bandRows : 8);
+}
+
+int rtCommDestroy(RtContext* c)
+{
+    if (!c) return RT_E_INVALID;
+    if (c->leader || !c->followers.empty()) return fail(c, RT_E_STATE, "rtCommDestroy: a group's communicator lives as long as the group (rtDestroy)");
+    destroyComm(c);
+    return rtSetTile(c, 0, 1, c->bandRows);
+}
+
+int rtCreateMulti(RtContext** out, const int* devices, int nDevices)
+{
+    if (!out) return fail(nullptr, RT_E_INVALID, "rtCreateMulti: out is NULL");
+    *out = nullptr;
+    if (nDevices < 1 || nDevices > 64) return fail(nullptr, RT_E_INVALID, "rtCreateMulti: between 1 and 64 devices");
+    for (int i = 0; i < nDevices; i++) for (int j = 0; j < i; j++)
+        if (devices && devices[i] == devices[j]) return fail(nullptr, RT_E_INVALID, "rtCreateMulti: a device is listed twice (NCCL needs one rank per GPU)");
+    std::vector<RtContext*> cs;
+    auto undo = [&](int code) { for (RtContext* m : cs) { destroyComm(m); m->leader = nullptr; m->followers.clear(); rtDestroy(m); } return code; };
+    for (int i = 0; i < nDevices; i++)
+    {
+        RtContext* m = nullptr;
+        const int rc = rtCreate(&m, devices ? devices[i] : i);
+        if (rc != RT_OK) return undo(rc);
+        cs.push_back(m);
+    }
+    if (nDevices > 1)
+    {
+#ifndef RT_SIMT_EMU
+        std::string why;
+        NcclApi* api = NcclApi::get(why);
+        if (!api) { fail(nullptr, RT_E_STATE, "rtCreateMulti: " + why); return undo(RT_E_STATE); }
+        NcclApi::UniqueId u;
+        int r = api->GetUniqueId(&u);
+        if (r == NcclApi::Success) r = api->GroupStart();
+        for (int i = 0; i < nDevices && r == NcclApi::Success; i++)
+        {
+            cudaSetDevice(cs[i]->device);
+            r = api->CommInitRank(&cs[i]->comm, nDevices, u, i);
+        }
+        if (r == NcclApi::Success) r = api->GroupEnd();
+        if (r != NcclApi::Success) { ncclFail(nullptr, api, r, "rtCreateMulti: NCCL communicator"); return undo(RT_E_CUDA); }
+#endif
+        for (int i = 0; i < nDevices; i++)
+        {
+            cs[i]->commRank = i; cs[i]->commWorld = nDevices;
+            cs[i]->tileRank = i; cs[i]->tileWorld = nDevices; cs[i]->bandRows = 8;
+            if (i) { cs[i]->leader = cs[0]; cs[0]->followers.push_back(cs[i]); }
+        }
+        cudaSetDevice(cs[0]->device);
+    }
+    *out = cs[0];
     return RT_OK;
 }
 
@@ -787,7 +1087,24 @@ int rtxPlanTlas(const float* boxes, int modelCount, void* pairsOut, int pairCap,
     return (int)out.size();
 }
 
+static int one_rtGetStats(RtContext* c, RtStats* out);
 int rtGetStats(RtContext* c, RtStats* out)
+{
+    // a group reports the work of all its GPUs: counters summed, times = the slowest GPU's (they run side by side)
+    int rc = one_rtGetStats(c, out);
+    if (rc != RT_OK || !c) return rc;
+    for (RtContext* m : c->followers)
+    {
+        RtStats s;
+        if ((rc = one_rtGetStats(m, &s)) != RT_OK) return fail(c, rc, "GPU " + std::to_string(m->device) + ": " + m->err);
+        out->rays += s.rays; out->boxTests += s.boxTests; out->triTests += s.triTests; out->sphereTests += s.sphereTests; out->sphereBoxTests += s.sphereBoxTests;
+        if (s.kernelMs > out->kernelMs) out->kernelMs = s.kernelMs;
+        if (s.exchangeMs > out->exchangeMs) out->exchangeMs = s.exchangeMs;
+    }
+    if (!c->followers.empty()) CK(cudaSetDevice(c->device));
+    return RT_OK;
+}
+static int one_rtGetStats(RtContext* c, RtStats* out)
 {
     if (!c || !out) return fail(c, RT_E_INVALID, "rtGetStats: bad argument");
     CK(cudaSetDevice(c->device));
@@ -800,7 +1117,16 @@ int rtGetStats(RtContext* c, RtStats* out)
     return RT_OK;
 }
 
+static int one_rtResetStats(RtContext* c);
 int rtResetStats(RtContext* c)
+{
+    int rc = one_rtResetStats(c);
+    if (rc != RT_OK || !c) return rc;
+    for (RtContext* m : c->followers) if ((rc = one_rtResetStats(m)) != RT_OK) return fail(c, rc, m->err);
+    if (!c->followers.empty()) CK(cudaSetDevice(c->device));
+    return RT_OK;
+}
+static int one_rtResetStats(RtContext* c)
 {
     if (!c) return RT_E_INVALID;
     CK(cudaSetDevice(c->device));

@@ -174,6 +174,7 @@ struct __align__(16) DevSphere
 // ---- kernel parameter block (uniform names as in HL:5-21, RC:7-8) ---------------------------------------------
 
 constexpr int RT_MAX_PEERS = 7;
+constexpr int RT_MAX_BVH_DEPTH = 63;                     // levels of inner nodes a Nodes buffer may have: every traversal stack holds 64 entries (rtDispatch rejects deeper trees)
 
 struct DevParams
 {

@@ -50,7 +50,37 @@ template <class T> struct RBuf
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-struct MeshRoot { int rootStart, rootCount; };
+// geo: the box a ray must touch to hit anything of the mesh, in mesh space — the union of the root's two child boxes (the reference
+// tests only child boxes, HL:257-270, never the root's own bounds) or, for a root that is a leaf, the bounds of its triangles'
+// vertices; geoValid = false when any of those numbers is not finite (such a model is never skipped).
+// Host staging that outlives the call that fills it: pinned memory + an event recorded behind the copies that read it, so that a
+// per-frame rebuild (the reference re-sends ModelInfo every frame, RCM:192-204) waits for its own previous COPY only — never for
+// the trace kernel queued behind it, which a cudaStreamSynchronize on a local vector did.
+template <class T> struct PinnedStage
+{
+    T* p = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool pending = false;
+    cudaError_t acquire(size_t n)
+    {
+        cudaError_t e;
+        if (pending) { if ((e = cudaEventSynchronize(ev)) != cudaSuccess) return e; pending = false; }
+        if (n <= cap && p) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        if ((e = cudaMallocHost((void**)&p, std::max<size_t>(n, 1) * sizeof(T))) != cudaSuccess) return e;
+        cap = std::max<size_t>(n, 1);
+        return cudaSuccess;
+    }
+    cudaError_t commit(cudaStream_t stream)
+    {
+        cudaError_t e;
+        if (!ev && (e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(ev, stream)) != cudaSuccess) return e;
+        pending = true; return cudaSuccess;
+    }
+    void release() { if (pending && ev) cudaEventSynchronize(ev); pending = false; if (p) cudaFreeHost(p); p = nullptr; cap = 0; if (ev) cudaEventDestroy(ev); ev = nullptr; }
+};
+
+struct MeshRoot { int rootStart, rootCount; float geoLo[3], geoHi[3]; bool geoValid; int leafRootTriStart; };
 
 // Host only: binary tree over n axis-aligned boxes in NodePair records (two child boxes per record; count > 0 <=> leaf whose
 // items are order[start .. start + count)).  Median split of the item centres on the widest centre axis (ties by item index, so
@@ -151,7 +181,7 @@ struct RepackState
     int orderUsed = 0;                              // treeletDepth of the current pair layout
     size_t totalPairs = 0;
 
-    void release() { pairs.release(); triGeom.release(); triNormals.release(); models.release(); spheres.release(); sphPairs.release(); sphLeaves.release(); tlasPairs.release(); tlasLeaves.release(); tlas = 0; roots.clear(); }
+    void release() { pairs.release(); triGeom.release(); triNormals.release(); models.release(); spheres.release(); sphPairs.release(); sphLeaves.release(); tlasPairs.release(); tlasLeaves.release(); tlas = 0; roots.clear(); stageModels.release(); stageSpheres.release(); stageTlasPairs.release(); stageTlasLeaves.release(); }
 
     // Renumbering of every distinct mesh referenced by the first modelCount models.  Host only (no CUDA call):
     // fills `out`, `roots`, `smemPairs`, `totalPairs`; a non-empty `msg` reports a malformed BVH.
@@ -173,22 +203,24 @@ struct RepackState
         {
             const std::pair<int,int> key(mdl[i].nodeOffset, mdl[i].triOffset);
             if (roots.count(key)) continue;
-            roots[key] = MeshRoot{0, 0};
+            roots[key] = MeshRoot{};
             Mesh m; m.nodeOffset = key.first; m.triOffset = key.second;
             const RtNode& root = nodes[m.nodeOffset];
             if (root.triangleCount <= 0)
             {
                 // BFS over inner nodes; order[k] = global index of the first child of the k-th inner node met
-                std::vector<int> queue; queue.push_back(m.nodeOffset);
+                std::vector<int> queue, level; queue.push_back(m.nodeOffset); level.push_back(1);
                 for (size_t q = 0; q < queue.size(); q++)
                 {
                     const RtNode& nd = nodes[queue[q]];
                     const long long a = (long long)m.nodeOffset + nd.startIndex;
                     if (a < 0 || a + 1 >= (long long)nodes.size()) { msg = "BVH child index out of range"; return; }
                     if (queue.size() > nodes.size()) { msg = "BVH has a cycle"; return; }
+                    // every traversal stack of the kernels (and the oracle's) holds RT_MAX_BVH_DEPTH + 1 entries; the reference's builder stops at 32 (BVH.cs:91)
+                    if (level[q] > RT_MAX_BVH_DEPTH) { msg = "BVH too deep: more than 63 levels of inner nodes (the traversal stacks hold 64 entries; the reference's builder stops at 32)"; return; }
                     m.order.push_back((int)a);
-                    if (nodes[a].triangleCount <= 0) { m.kidA.push_back((int)queue.size()); queue.push_back((int)a); } else m.kidA.push_back(-1);
-                    if (nodes[a + 1].triangleCount <= 0) { m.kidB.push_back((int)queue.size()); queue.push_back((int)a + 1); } else m.kidB.push_back(-1);
+                    if (nodes[a].triangleCount <= 0) { m.kidA.push_back((int)queue.size()); queue.push_back((int)a); level.push_back(level[q] + 1); } else m.kidA.push_back(-1);
+                    if (nodes[a + 1].triangleCount <= 0) { m.kidB.push_back((int)queue.size()); queue.push_back((int)a + 1); level.push_back(level[q] + 1); } else m.kidB.push_back(-1);
                 }
             }
             meshes.push_back(std::move(m));
@@ -254,9 +286,24 @@ struct RepackState
             // second pass in BFS order: the k-th inner node met owns pair k; its inner children are the next ones the BFS met
             size_t nextChildPair = 1;       // pair 0 belongs to the root
             const RtNode& root = nodes[m.nodeOffset];
-            MeshRoot r;
-            if (root.triangleCount > 0) { r.rootStart = m.triOffset + root.startIndex; r.rootCount = root.triangleCount; }
-            else { r.rootStart = globalPair(0); r.rootCount = 0; }
+            MeshRoot r{};
+            r.leafRootTriStart = -1;
+            if (root.triangleCount > 0)
+            {
+                r.rootStart = m.triOffset + root.startIndex; r.rootCount = root.triangleCount;
+                r.leafRootTriStart = r.rootStart; r.geoValid = false;               // buildScene reads the triangles back and fills the box
+            }
+            else
+            {
+                r.rootStart = globalPair(0); r.rootCount = 0;
+                const RtNode& A = nodes[m.order[0]]; const RtNode& B = nodes[m.order[0] + 1];
+                r.geoValid = true;
+                for (int a = 0; a < 3; a++)
+                {
+                    r.geoLo[a] = std::min(A.boundsMin[a], B.boundsMin[a]); r.geoHi[a] = std::max(A.boundsMax[a], B.boundsMax[a]);
+                    if (!std::isfinite(A.boundsMin[a]) || !std::isfinite(B.boundsMin[a]) || !std::isfinite(A.boundsMax[a]) || !std::isfinite(B.boundsMax[a])) r.geoValid = false;
+                }
+            }
             roots[std::make_pair(m.nodeOffset, m.triOffset)] = r;
             for (size_t k = 0; k < m.order.size(); k++)
             {
@@ -289,6 +336,21 @@ struct RepackState
         if ((e = pairs.ensure(std::max<size_t>(totalPairs, 1))) != cudaSuccess) return e;
         if (totalPairs && (e = cudaMemcpyAsync(pairs.p, out.data(), totalPairs * sizeof(NodePair), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;      // `out` is a local
+        for (auto& kv : roots)                                                  // meshes whose root is a leaf: the box of its triangles' vertices
+        {
+            MeshRoot& r = kv.second;
+            if (r.leafRootTriStart < 0 || r.rootCount <= 0) continue;
+            std::vector<RtTriangle> t((size_t)r.rootCount);
+            if ((e = cudaMemcpyAsync(t.data(), dTris + r.leafRootTriStart, t.size() * sizeof(RtTriangle), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+            if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+            r.geoValid = true;
+            for (int a = 0; a < 3; a++) { r.geoLo[a] = INFINITY; r.geoHi[a] = -INFINITY; }
+            for (const RtTriangle& q : t) for (int a = 0; a < 3; a++)
+            {
+                const float v[3] = {q.posA[a], q.posB[a], q.posC[a]};
+                for (float x : v) { if (!std::isfinite(x)) r.geoValid = false; r.geoLo[a] = std::min(r.geoLo[a], x); r.geoHi[a] = std::max(r.geoHi[a], x); }
+            }
+        }
         if ((e = triGeom.ensure(std::max<size_t>(triCount, 1))) != cudaSuccess) return e;
         if ((e = triNormals.ensure(std::max<size_t>(triCount, 1))) != cudaSuccess) return e;
         if (triCount)
@@ -303,6 +365,7 @@ struct RepackState
     // Rebuilt with the model records, i.e. whenever ModelInfo is re-sent (the reference re-sends it every frame, RCM:192-204): a
     // median-split tree over a few hundred to a few thousand boxes is microseconds of host work next to a frame.
     RBuf<NodePair> tlasPairs; RBuf<int> tlasLeaves;
+    PinnedStage<DevModel> stageModels; PinnedStage<DevSphere> stageSpheres; PinnedStage<NodePair> stageTlasPairs; PinnedStage<int> stageTlasLeaves;
     int tlas = 0, tlasRootStart = 0, tlasRootCount = 0;
 #ifndef RT_TLAS_LEAF
 #define RT_TLAS_LEAF 4                                               // models per TLAS leaf.  Box tests per ray segment counted on the interpreter (tree + per-model, 500 instanced
@@ -348,9 +411,13 @@ struct RepackState
         cudaError_t e;
         if ((e = tlasPairs.ensure(std::max<size_t>(pairsOut.size(), 1))) != cudaSuccess) return e;
         if ((e = tlasLeaves.ensure(order.size())) != cudaSuccess) return e;
-        if (!pairsOut.empty() && (e = cudaMemcpyAsync(tlasPairs.p, pairsOut.data(), pairsOut.size() * sizeof(NodePair), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
-        if ((e = cudaMemcpyAsync(tlasLeaves.p, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
-        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;      // the vectors are locals
+        if ((e = stageTlasPairs.acquire(pairsOut.size())) != cudaSuccess) return e;
+        if ((e = stageTlasLeaves.acquire(order.size())) != cudaSuccess) return e;
+        if (!pairsOut.empty()) memcpy(stageTlasPairs.p, pairsOut.data(), pairsOut.size() * sizeof(NodePair));
+        memcpy(stageTlasLeaves.p, order.data(), order.size() * sizeof(int));
+        if (!pairsOut.empty() && (e = cudaMemcpyAsync(tlasPairs.p, stageTlasPairs.p, pairsOut.size() * sizeof(NodePair), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(tlasLeaves.p, stageTlasLeaves.p, order.size() * sizeof(int), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+        if ((e = stageTlasPairs.commit(stream)) != cudaSuccess || (e = stageTlasLeaves.commit(stream)) != cudaSuccess) return e;
         tlas = 1;
         return cudaSuccess;
     }
@@ -372,10 +439,12 @@ struct RepackState
 
     // Where a model's geometry is, as far as rays are concerned: the ray test only uses worldToLocal (HL:351-352) and a hit lies at
     // rayPos + rayDir * dst with dst found in the model's space, i.e. at inverse(worldToLocal) x (point of the mesh) — whatever
-    // localToWorld says (it only turns normals, HL:367-368).  World box of the root box's eight corners through that inverse (double);
+    // localToWorld says (it only turns normals, HL:367-368).  World box of the eight corners of the mesh's geometry box (MeshRoot::geo — the root's child boxes, not the root node's own bounds, which the
+    // reference never reads) through that inverse (double);
     // false when worldToLocal is singular or not finite (nothing can be said about such a model).
-    static bool worldBoxOfModel(const RtModel& m, const RtNode& root, double lo[3], double hi[3])
+    static bool worldBoxOfModel(const RtModel& m, const MeshRoot& root, double lo[3], double hi[3])
     {
+        if (!root.geoValid) return false;
         const float* W = m.worldToLocal;                              // column-major 4x4, affine: x_local = A x_world + t
         const double A[3][3] = {{W[0], W[4], W[8]}, {W[1], W[5], W[9]}, {W[2], W[6], W[10]}}, t[3] = {W[12], W[13], W[14]};
         const double c00 = A[1][1] * A[2][2] - A[1][2] * A[2][1], c01 = A[1][2] * A[2][0] - A[1][0] * A[2][2], c02 = A[1][0] * A[2][1] - A[1][1] * A[2][0];
@@ -390,8 +459,8 @@ struct RepackState
         for (int a = 0; a < 3; a++) { lo[a] = INFINITY; hi[a] = -INFINITY; }
         for (int k = 0; k < 8; k++)
         {
-            const double v[3] = {(k & 1 ? root.boundsMax[0] : root.boundsMin[0]) - t[0], (k & 2 ? root.boundsMax[1] : root.boundsMin[1]) - t[1],
-                                 (k & 4 ? root.boundsMax[2] : root.boundsMin[2]) - t[2]};
+            const double v[3] = {(k & 1 ? root.geoHi[0] : root.geoLo[0]) - t[0], (k & 2 ? root.geoHi[1] : root.geoLo[1]) - t[1],
+                                 (k & 4 ? root.geoHi[2] : root.geoLo[2]) - t[2]};
             for (int a = 0; a < 3; a++)
             {
                 const double w = inv[a][0] * v[0] + inv[a][1] * v[1] + inv[a][2] * v[2];
@@ -414,6 +483,7 @@ struct RepackState
                             const float originLo[3], const float originHi[3])
     {
         std::vector<DevModel> out(std::max(modelCount, 1));
+        memset(out.data(), 0, out.size() * sizeof(DevModel));
         double originExtent = 0;
         for (int a = 0; a < 3; a++)
         {
@@ -437,7 +507,7 @@ struct RepackState
             d.matIndex = i;
             {
                 double lo[3], hi[3];
-                const bool placed = worldBoxOfModel(mdl[i], nodes[mdl[i].nodeOffset], lo, hi);
+                const bool placed = worldBoxOfModel(mdl[i], r, lo, hi);
                 float bmin[3], bmax[3];
                 for (int a = 0; a < 3; a++)
                 {
@@ -451,8 +521,10 @@ struct RepackState
         }
         cudaError_t e;
         if ((e = models.ensure(out.size())) != cudaSuccess) return e;
-        if ((e = cudaMemcpyAsync(models.p, out.data(), out.size() * sizeof(DevModel), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
-        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+        if ((e = stageModels.acquire(out.size())) != cudaSuccess) return e;
+        memcpy(stageModels.p, out.data(), out.size() * sizeof(DevModel));
+        if ((e = cudaMemcpyAsync(models.p, stageModels.p, out.size() * sizeof(DevModel), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+        if ((e = stageModels.commit(stream)) != cudaSuccess) return e;
         return buildTlas(out, modelCount, tlasMode, stream);
     }
 
@@ -487,8 +559,10 @@ struct RepackState
         }
         cudaError_t e;
         if ((e = spheres.ensure(out.size())) != cudaSuccess) return e;
-        if ((e = cudaMemcpyAsync(spheres.p, out.data(), out.size() * sizeof(DevSphere), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
-        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+        if ((e = stageSpheres.acquire(out.size())) != cudaSuccess) return e;
+        memcpy(stageSpheres.p, out.data(), out.size() * sizeof(DevSphere));
+        if ((e = cudaMemcpyAsync(spheres.p, stageSpheres.p, out.size() * sizeof(DevSphere), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+        if ((e = stageSpheres.commit(stream)) != cudaSuccess) return e;
         sphBvh = 0;
         if (sp.size() <= SPHERE_BVH_THRESHOLD) return cudaSuccess;
 

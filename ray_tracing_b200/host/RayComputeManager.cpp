@@ -23,6 +23,7 @@ std::string RtApi::Load(const char* path)
     RESOLVE(Readback, "rtReadback") RESOLVE(Synchronize, "rtSynchronize")
 #undef RESOLVE
     BuildBVH = reinterpret_cast<decltype(BuildBVH)>(dlsym(dl, "rtBuildBVH"));
+    CreateMulti = reinterpret_cast<decltype(CreateMulti)>(dlsym(dl, "rtCreateMulti"));
     return "";
 }
 
@@ -37,6 +38,15 @@ RayComputeManager::RayComputeManager(const char* backendLibrary, int device)
     if (!lastError.empty()) return;
     const int rc = api.Create(&ctx, device);
     if (rc != RT_OK) { lastError = std::string("rtCreate: ") + api.LastError(nullptr); ctx = nullptr; }
+}
+
+RayComputeManager::RayComputeManager(const char* backendLibrary, const int* devices, int deviceCount)
+{
+    lastError = api.Load(backendLibrary);
+    if (!lastError.empty()) return;
+    if (!api.CreateMulti) { lastError = "the library does not export rtCreateMulti"; return; }
+    const int rc = api.CreateMulti(&ctx, devices, deviceCount);
+    if (rc != RT_OK) { lastError = std::string("rtCreateMulti: ") + api.LastError(nullptr); ctx = nullptr; }
 }
 
 RayComputeManager::~RayComputeManager() { OnDestroy(); api.Unload(); }

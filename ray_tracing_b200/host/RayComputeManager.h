@@ -53,6 +53,7 @@ struct RtApi
     decltype(&rtSetBool) SetBool = nullptr; decltype(&rtResize) Resize = nullptr; decltype(&rtDispatch) Dispatch = nullptr;
     decltype(&rtReadback) Readback = nullptr; decltype(&rtSynchronize) Synchronize = nullptr;
     decltype(&rtBuildBVH) BuildBVH = nullptr;   // optional: absent from older builds of the library
+    decltype(&rtCreateMulti) CreateMulti = nullptr;   // optional: several GPUs behind one context (the all-gather of tiles inside rtDispatch)
     std::string Load(const char* path);        // returns "" on success, else the error text
     void Unload();
 };
@@ -96,6 +97,9 @@ public:
     std::string lastError;
 
     RayComputeManager(const char* backendLibrary, int device);
+    // the same manager on several GPUs of this process: the image is row-tiled over `devices`, rtDispatch ends with one NCCL
+    // all-gather of the frame's tiles (rtCreateMulti); nothing else in the call sequence changes
+    RayComputeManager(const char* backendLibrary, const int* devices, int deviceCount);
     ~RayComputeManager();
     bool IsRendering() const { return rayTracingEnabled; }                  // :55 (Application.isPlaying is implied)
 

@@ -75,6 +75,22 @@ int rcmCreate(const char* backendLibrary, int device, void** out)
     return RT_OK;
 }
 
+int rcmCreateMulti(const char* backendLibrary, const int* devices, int deviceCount, void** out)
+{
+    if (!backendLibrary || !out || deviceCount < 1) { g_err = "rcmCreateMulti: bad argument"; return RT_E_INVALID; }
+    Handle* h = new Handle();
+    h->mgr = new RayComputeManager(backendLibrary, devices, deviceCount);
+    if (!h->mgr->Context())
+    {
+        g_err = h->mgr->lastError;
+        delete h->mgr; delete h;
+        *out = nullptr;
+        return RT_E_NO_DEVICE;
+    }
+    *out = h;
+    return RT_OK;
+}
+
 int rcmDestroy(void* hv) { Handle* h = (Handle*)hv; if (!h) return RT_E_INVALID; delete h->mgr; delete h; return RT_OK; }
 
 const char* rcmLastError(void* hv) { Handle* h = (Handle*)hv; return h && h->mgr ? h->mgr->lastError.c_str() : g_err.c_str(); }

@@ -38,6 +38,7 @@ def host_lib() -> C.CDLL:
         L.rthObjCopy.argtypes = [vp, vp, vp]
         L.rthObjLastError.restype = cp
         L.rcmCreate.argtypes = [cp, ci, C.POINTER(vp)]
+        L.rcmCreateMulti.argtypes = [cp, C.POINTER(ci), ci, C.POINTER(vp)]
         L.rcmDestroy.argtypes = [vp]
         L.rcmLastError.argtypes = [vp]
         L.rcmLastError.restype = cp
@@ -116,14 +117,20 @@ class RayComputeManager:
                    "rayTracingEnabled", "accumulate", "useSky", "randomizeSeedOnEnable", "buildBVHOnDevice")
     _FLOAT_FIELDS = ("defocusStrength", "divergeStrength", "focusDistance", "sunFocus", "sunIntensity")
 
-    def __init__(self, backend_library: Optional[str] = None, device: int = 0):
+    def __init__(self, backend_library: Optional[str] = None, device: int = 0, devices: Optional[Sequence[int]] = None):
+        """device: the CUDA ordinal to render on; devices: several GPUs of this process behind ONE manager (rtCreateMulti: the
+        image is row-tiled over them and every RenderFrame ends with one NCCL all-gather of the frame's tiles)."""
         object.__setattr__(self, "_h", None)
         L = host_lib()
         lib_path = backend_library or capi.DEFAULT_LIB
         if not os.path.exists(lib_path):
             raise FileNotFoundError(f"{lib_path} not found (librt_b200 is CUDA-only; there is no CPU fallback)")
         h = C.c_void_p()
-        rc = L.rcmCreate(lib_path.encode(), device, C.byref(h))
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = L.rcmCreateMulti(lib_path.encode(), arr, len(devices), C.byref(h))
+        else:
+            rc = L.rcmCreate(lib_path.encode(), device, C.byref(h))
         if rc != 0:
             raise capi.RtError(rc, L.rcmLastError(None).decode())
         object.__setattr__(self, "_L", L)

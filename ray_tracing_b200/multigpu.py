@@ -5,9 +5,13 @@ scene, traces only its bands (pixels keep their GLOBAL index, so seeds and there
 run), and after each frame ONE all-gather over NCCL/NVLink hands every rank the finished tiles of all ranks;
 a local scatter puts them back at their global position.
 
-`TiledRenderer` is the device path (C-ABI rtPackTile -> torch.distributed all_gather_into_tensor on views of
-the context's own device buffers -> rtUnpackTiles).  The host-side helpers (owned_rows, pack_rows,
-unpack_rows) state the same layout in numpy; the world_size-2 gloo test uses them with CPU tensors.
+`TiledRenderer` is one rank of the one-process-per-GPU form.  The exchange lives INSIDE the C-ABI: rank 0 draws an
+id (rtGetUniqueId), the launcher's rendezvous carries its 128 bytes to the other ranks (here: torch.distributed's
+store; any transport does), every rank calls rtCommInit, and from then on each RayTrace dispatch ends with
+pack -> ncclAllGather -> unpack on the context's stream — no Python, no torch in the data plane.  exchange="torch"
+keeps round 1's form (rtPackTile -> torch.distributed all_gather_into_tensor on views of the context's device
+buffers -> rtUnpackTiles) for A/B runs.  The host-side helpers (owned_rows, pack_rows, unpack_rows) state the tile
+layout in numpy; the world_size-2 gloo test uses them with CPU tensors.
 """
 from __future__ import annotations
 
@@ -58,14 +62,21 @@ class _DevView:
 class TiledRenderer:
     """One rank of a row-tiled render: manager + per-frame all-gather of finished tiles (NCCL)."""
 
-    def __init__(self, mgr, rank: int, world: int, band_rows: int = 8, device=None, fused: bool = False):
+    def __init__(self, mgr, rank: int, world: int, band_rows: int = 8, device=None, fused: bool = False, exchange: str = "abi"):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.mgr, self.rank, self.world, self.band_rows = mgr, rank, world, band_rows
         self.ctx = mgr.context
-        self.ctx.set_tile(rank, world, band_rows)
         self.device = device
+        self.exchange = "fused" if (fused and world > 1) else exchange
+        if world > 1 and self.exchange == "abi":
+            box = [mgr._lib.unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)                  # 128 bytes through the launcher's rendezvous
+            self.ctx.comm_init(box[0], rank, world)                 # collective: NCCL communicator owned by the context
+        self.ctx.set_tile(rank, world, band_rows)
+        if world > 1 and self.exchange != "abi":
+            self.ctx.set_option("exchange", 0)
         self._send = self._recv = None
         # one torch stream carries everything: trace -> pack -> all-gather -> unpack are ordered on it
         self.stream = torch.cuda.Stream(device=device)
@@ -108,8 +119,8 @@ class TiledRenderer:
                 self.mgr.RenderFrame()                              # pixels land in every rank's images as they finish
                 self.frame_fence()                                  # every rank's kernel is done: the images are complete
                 return
-            self.mgr.RenderFrame()
-            if self.world == 1:
+            self.mgr.RenderFrame()                                  # exchange "abi": the dispatch itself ends with the all-gather
+            if self.world == 1 or self.exchange == "abi":
                 return
             send, recv = self._views()
             self.ctx.pack_tile()

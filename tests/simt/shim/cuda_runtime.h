@@ -149,7 +149,7 @@ static inline const char* cudaGetErrorString(cudaError_t e)
                  case 801: return "not supported by the SIMT test build"; default: return "error"; }
 }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 8; return cudaSuccess; }          // eight "devices" sharing the host's memory: lets rtCreateMulti groups run here
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int)
 {
@@ -167,6 +167,8 @@ template <class T> static inline cudaError_t cudaMalloc(T** p, size_t bytes)
     *p = (T*)q; return cudaSuccess;
 }
 static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
@@ -177,6 +179,8 @@ static inline cudaError_t cudaMemset2DAsync(void* d, size_t pitch, int v, size_t
     return cudaSuccess;
 }
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new simtEvent(); return cudaSuccess; }
+enum { cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned int) { *e = new simtEvent(); return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }

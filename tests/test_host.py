@@ -118,7 +118,7 @@ def test_header_symbols_exported_by_cuda_library():
     for n in names:
         assert hasattr(lib, n), f"librt_b200.so does not export {n}"
     lib.rtGetVersion.restype = C.c_int
-    assert lib.rtGetVersion() == (1 << 16)
+    assert lib.rtGetVersion() == (1 << 16) | 1
 
 
 def test_oracle_exports_the_same_abi():

@@ -1,0 +1,271 @@
+"""Round 2 additions to the C-ABI, checked without a GPU on the SIMT interpreter build of the product's own sources (tests/simt)
+and on the oracle: the multi-GPU group context (rtCreateMulti: tiles + the per-frame exchange inside rtDispatch), and the
+hardening items of the round-1 review (modelCount set on its own, root bounds the reference never reads, trees deeper than the
+traversal stacks, unchanged per-frame uploads).  The same bodies run against librt_b200.so under `-m gpu`
+(tests/test_gpu_round2_abi.py)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ORACLE_LIB, REPO, assert_bit_equal, render
+import ray_tracing_b200 as rt
+from ray_tracing_b200 import capi, scenes
+from ray_tracing_b200.capi import NODE_DTYPE, TRIANGLE_DTYPE
+
+sys.path.insert(0, os.path.join(REPO, "tests", "simt"))
+import build as simt_build   # noqa: E402
+
+
+@pytest.fixture(scope="session")
+def simt_lib():
+    return simt_build.build()
+
+
+# ---- bodies shared with the GPU file (lib = any library with the ABI) -----------------------------------------------------------
+
+def group_equals_single(lib, devices, sc, frames=2, options=None):
+    """ONE manager on several devices (rtCreateMulti) renders the image one device renders, bit for bit; its statistics are the sums."""
+    fref, aref, sref = render(lib, sc, frames=frames, want_stats=True, options=options)
+    mgr = rt.RayComputeManager(lib, devices=devices)
+    scenes.apply(sc, mgr)
+    ctx = mgr.context
+    for k, v in (options or {}).items():
+        ctx.set_option(k, v)
+    mgr.OnEnable()
+    ctx.reset_stats()
+    for _ in range(frames):
+        mgr.RenderFrame()
+    st = ctx.stats()
+    assert_bit_equal(mgr.raytraceFrameTex, fref, f"group of {len(devices)}: FrameRender")
+    assert_bit_equal(mgr.accumulatedResult, aref, f"group of {len(devices)}: AccumulatedRender")
+    assert st["rays"] == sref["rays"]
+    # a different band height is a layout choice only
+    ctx.set_tile(0, len(devices), 3)
+    mgr.ResetAccumulatedRender()
+    for _ in range(frames):
+        mgr.RenderFrame()
+    assert_bit_equal(mgr.accumulatedResult, aref, "bands of 3 rows")
+    with pytest.raises(capi.RtError):
+        ctx.set_tile(1, len(devices), 8)                     # a group is rank 0 of its own GPU count
+    mgr.OnDestroy()
+
+
+def one_model_scene(width=48, height=32, nu=40, nv=8):
+    sc = scenes.knot_room(width, height, 3, 2, nu=nu, nv=nv)
+    sc.models = sc.models[:1]
+    sc.meshes = sc.meshes[:1]
+    sc.settings = dict(sc.settings, useSky=True)
+    return sc
+
+
+def model_count_alone(lib):
+    """ADVICE (high): rtSetInt("modelCount") without re-sending ModelInfo must re-plan the scene (pair plan, roots, DevModel array)."""
+    sc = scenes.knot_room(48, 32, 3, 1, nu=30, nv=6)
+    out = {}
+    for name, path in (("oracle", ORACLE_LIB), ("lib", lib)):
+        for kernel in ((None,) if name == "oracle" else (0, 1, 2)):
+            mgr = rt.RayComputeManager(path)
+            scenes.apply(sc, mgr)
+            ctx = mgr.context
+            if kernel is not None:
+                ctx.set_option("kernel", kernel)
+            mgr.OnEnable()
+            imgs = []
+            for count in (1, 3, 2, 3):
+                ctx.set_int("modelCount", count)
+                ctx.dispatch_full(0)
+                imgs.append(mgr.raytraceFrameTex.copy())
+            out[(name, kernel)] = imgs
+            mgr.OnDestroy()
+    for kernel in (0, 1, 2):
+        for i, (a, b) in enumerate(zip(out[("lib", kernel)], out[("oracle", None)])):
+            assert_bit_equal(a, b, f"kernel {kernel}, modelCount step {i}")
+    assert not np.array_equal(out[("oracle", None)][0], out[("oracle", None)][1])      # the count does change the picture
+
+
+def root_bounds_are_never_read(lib):
+    """ADVICE (medium): the reference pushes the root unconditionally and tests child boxes only (RayCommon.hlsl:241-270); a Nodes
+    buffer whose root carries a far-away placeholder box renders the same with model skipping and with the TLAS."""
+    sc = one_model_scene()
+    m = sc.meshes[0]
+    _, nodes, _ = rt.build_bvh(m.vertices, m.indices, m.normals, "High")
+    bad = nodes.copy()
+    bad["boundsMin"][0] = (1e6, 1e6, 1e6)
+    bad["boundsMax"][0] = (1e6 + 1, 1e6 + 1, 1e6 + 1)
+
+    def run(path, options):
+        mgr = rt.RayComputeManager(path)
+        scenes.apply(sc, mgr)
+        ctx = mgr.context
+        for k, v in options.items():
+            ctx.set_option(k, v)
+        mgr.OnEnable()
+        ctx.set_buffer("Nodes", bad)
+        mgr.ResetAccumulatedRender()
+        mgr.RenderFrame(); mgr.RenderFrame()
+        a = mgr.accumulatedResult.copy()
+        mgr.OnDestroy()
+        return a
+    ref = run(ORACLE_LIB, {})
+    good = render(ORACLE_LIB, sc, frames=2)[1]
+    assert_bit_equal(ref, good, "the oracle itself does not read the root's bounds")
+    assert (ref[..., :3] != good[..., :3]).sum() == 0 and np.count_nonzero(ref[..., :3]) > 0
+    for opts in ({"kernel": 0}, {"kernel": 1}, {"kernel": 2}, {"kernel": 1, "tlas": 1}, {"kernel": 2, "tlas": 1}, {"kernel": 2, "modelSkip": 0}):
+        assert_bit_equal(run(lib, opts), ref, f"placeholder root box, {opts}")
+
+
+def chain_bvh(depth):
+    """A degenerate tree: every inner node has a one-triangle leaf and the next inner node; `depth` levels of inner nodes."""
+    tris = np.zeros(depth + 1, dtype=TRIANGLE_DTYPE)
+    for i in range(depth + 1):
+        x = -2.0 + 4.0 * i / depth
+        tris["posA"][i] = (x, 0.2, 0.0); tris["posB"][i] = (x + 0.03, 1.8, 0.0); tris["posC"][i] = (x + 0.06, 0.2, 0.0)
+        tris["normA"][i] = tris["normB"][i] = tris["normC"][i] = (0, 0, -1)
+    nodes = np.zeros(2 * depth + 1, dtype=NODE_DTYPE)
+    lo = np.minimum(np.minimum(tris["posA"], tris["posB"]), tris["posC"]); hi = np.maximum(np.maximum(tris["posA"], tris["posB"]), tris["posC"])
+    for level in range(depth):                                   # inner node `level` at index 0 (root) or 2 * level
+        idx = 0 if level == 0 else 2 * level
+        nodes["startIndex"][idx] = 2 * level + 1                 # children at 2*level+1 (leaf), 2*level+2 (next inner / last leaf)
+        nodes["triangleCount"][idx] = 0
+        nodes["boundsMin"][idx] = lo[level:].min(axis=0); nodes["boundsMax"][idx] = hi[level:].max(axis=0)
+        leaf = 2 * level + 1
+        nodes["startIndex"][leaf] = level; nodes["triangleCount"][leaf] = 1
+        nodes["boundsMin"][leaf] = lo[level]; nodes["boundsMax"][leaf] = hi[level]
+    last = 2 * depth
+    nodes["startIndex"][last] = depth; nodes["triangleCount"][last] = 1
+    nodes["boundsMin"][last] = lo[depth]; nodes["boundsMax"][last] = hi[depth]
+    return tris, nodes
+
+
+def deep_trees(lib):
+    """Trees deeper than the traversal stacks are refused with RT_E_STATE (by the oracle too: its stack has the same 64 entries);
+    the deepest legal chain, 63 levels of inner nodes, renders like the oracle."""
+    sc = one_model_scene(40, 24)
+    sc.settings = dict(sc.settings, useSky=True)
+
+    def run(path, depth, options):
+        tris, nodes = chain_bvh(depth)
+        mgr = rt.RayComputeManager(path)
+        scenes.apply(sc, mgr)
+        ctx = mgr.context
+        for k, v in options.items():
+            ctx.set_option(k, v)
+        mgr.OnEnable()
+        ctx.set_buffer("Triangles", tris)
+        ctx.set_buffer("Nodes", nodes)
+        try:
+            mgr.ResetAccumulatedRender()
+            mgr.RenderFrame()
+            return mgr.accumulatedResult.copy()
+        finally:
+            mgr.OnDestroy()
+    ref = run(ORACLE_LIB, 63, {})
+    assert np.count_nonzero(ref[..., :3]) > 0
+    for opts in ({"kernel": 0}, {"kernel": 1}, {"kernel": 2}, {"kernel": 2, "countStats": 1}):
+        assert_bit_equal(run(lib, 63, opts), ref, f"chain of 63 inner levels, {opts}")
+    for path in (ORACLE_LIB, lib):
+        with pytest.raises(capi.RtError) as e:
+            run(path, 64, {})
+        assert e.value.code == capi.RT_E_STATE and "too deep" in str(e.value)
+
+
+def unchanged_uploads_are_skipped_but_changes_are_not(lib):
+    """Re-sending the same ModelInfo / Spheres bytes (what the reference does every frame, RCM:192-204) is a no-op; a changed byte is not."""
+    sc = scenes.knot_room(48, 32, 3, 1, nu=30, nv=6)
+    sc.spheres = scenes.cornell_spheres(8, 8, 1, 1).spheres[6:8]
+    fo, ao = render(ORACLE_LIB, sc, frames=3)
+    fg, ag = render(lib, sc, frames=3)                        # RenderFrame re-sends ModelInfo and Spheres before every dispatch
+    assert_bit_equal(ag, ao, "three frames with identical re-sent buffers")
+    # and a material that changes between frames is seen
+    def moving(path):
+        mgr = rt.RayComputeManager(path)
+        scenes.apply(sc, mgr)
+        mgr.OnEnable()
+        mgr.RenderFrame()
+        mat = sc.models[0].material.copy(); mat["diffuseCol"] = (0.1, 0.9, 0.1, 1.0)
+        mgr.set_model_material(0, mat)
+        sp = sc.spheres.copy(); sp["radius"][0] *= 0.5
+        mgr.set_spheres(sp)
+        mgr.RenderFrame()
+        a = mgr.accumulatedResult.copy()
+        mgr.OnDestroy()
+        return a
+    assert_bit_equal(moving(lib), moving(ORACLE_LIB), "material and sphere changed between frames")
+
+
+# ---- on the SIMT build -----------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_simt_group_context_renders_the_single_context_image(simt_lib, n):
+    sc = scenes.knot_room(64, 45, 3, 2, nu=30, nv=6, glass=True)
+    sc.spheres = scenes.cornell_spheres(8, 8, 1, 1).spheres[6:9]
+    group_equals_single(simt_lib, list(range(n)), sc)
+    group_equals_single(simt_lib, list(range(n)), scenes.cornell_spheres(50, 37, 3, 2), options={"kernel": 2})
+
+
+def test_simt_group_context_with_tlas_and_per_frame_updates(simt_lib):
+    sc = scenes.instanced_knots(56, 40, 3, 1, instances=70)
+    group_equals_single(simt_lib, [0, 1], sc, frames=1)
+
+
+def test_simt_model_count_alone_replans_the_scene(simt_lib):
+    model_count_alone(simt_lib)
+
+
+def test_simt_root_bounds_are_never_read(simt_lib):
+    root_bounds_are_never_read(simt_lib)
+
+
+def test_simt_deep_trees_are_refused_not_truncated(simt_lib):
+    deep_trees(simt_lib)
+
+
+def test_simt_unchanged_uploads(simt_lib):
+    unchanged_uploads_are_skipped_but_changes_are_not(simt_lib)
+
+
+def test_group_and_comm_error_paths(simt_lib, oracle_path):
+    L = capi.RtLib(simt_lib)
+    with pytest.raises(capi.RtError):
+        L.create_multi([0, 0])                                # one rank per GPU
+    with pytest.raises(capi.RtError):
+        L.create_multi([])
+    with pytest.raises(capi.RtError) as e:
+        L.unique_id()                                         # the interpreter build carries no NCCL and says so
+    assert "NCCL" in str(e.value)
+    ctx = L.create_multi([0])                                 # a group of one is a plain context
+    ctx.set_tile(0, 1, 8)
+    ctx.destroy()
+    O = capi.RtLib(oracle_path)
+    with pytest.raises(capi.RtError):
+        O.create_multi([0, 1])
+
+
+def _build_example(tmp_path, name):
+    exe = str(tmp_path / name)
+    src = [os.path.join(REPO, "examples", name + ".cpp"), os.path.join(REPO, "ray_tracing_b200", "host", "RayComputeManager.cpp"),
+           os.path.join(REPO, "ray_tracing_b200", "host", "BVH.cpp")]
+    cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O1", "-ffp-contract=off", "-I", os.path.join(REPO, "include"),
+           "-I", os.path.join(REPO, "ray_tracing_b200", "host")] + src + ["-ldl", "-pthread", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_cpp_tiled_example_on_the_interpreter_build(tmp_path, simt_lib, oracle_path):
+    """examples/render_tiled.cpp, the C++ host of the multi-GPU form: --gpus 3 (one process, rtCreateMulti) writes the bytes
+    --gpus 1 writes, and both equal the oracle's image."""
+    exe = _build_example(tmp_path, "render_tiled")
+    outs = {}
+    for tag, lib, extra in (("oracle", oracle_path, []), ("one", simt_lib, []), ("three", simt_lib, ["--gpus", "3"])):
+        out = str(tmp_path / f"{tag}.bin")
+        r = subprocess.run([exe, lib, out, "--frames", "2", "--size", "96x54"] + extra, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr + r.stdout
+        assert re.search(r"alpha=2 fnv1a=[0-9a-f]{16}", r.stdout), r.stdout
+        outs[tag] = open(out, "rb").read()
+    assert len(outs["one"]) == 96 * 54 * 16
+    assert outs["one"] == outs["oracle"] and outs["three"] == outs["one"]

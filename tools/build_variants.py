@@ -46,6 +46,15 @@ VARIANTS = {
     "cornell_all": ("RT_SKIP_ZERO_DEFOCUS", "RT_GLASS_OUT_OF_LINE", "RT_SPHERE_SKIP_SQRT"),
     "zerodefocus_skipsqrt": ("RT_SKIP_ZERO_DEFOCUS", "RT_SPHERE_SKIP_SQRT"),
     "mb5": ("RT_WAVE_MINBLOCKS=5",),
+    # round 2, second call: combinations of the first call's winners on soup4k (profiles/r02_a_sweep_first_call.jsonl)
+    "c1": ("RT_LDG256", "RT_VOTE_WL=3", "RT_VOTE_WN=2", "RT_SMEM_STACK=8"),
+    "c2": ("RT_LDG256", "RT_VOTE_WL=3", "RT_VOTE_WN=2", "RT_SMEM_STACK=8", "RT_LEAF_REPEAT=2"),
+    "c3": ("RT_LDG256", "RT_VOTE_WL=3", "RT_VOTE_WN=2", "RT_SMEM_STACK=8", "RT_LEAF_REPEAT=2", "RT_SPHERE_SAH_DEPTH=14"),
+    "c4": ("RT_VOTE_WL=3", "RT_VOTE_WN=2", "RT_SMEM_STACK=8", "RT_LEAF_REPEAT=2", "RT_SPHERE_SAH_DEPTH=14"),
+    "c5": ("RT_LDG256", "RT_VOTE_WI=2", "RT_VOTE_WL=7", "RT_VOTE_WN=4", "RT_SMEM_STACK=8", "RT_LEAF_REPEAT=2", "RT_SPHERE_SAH_DEPTH=14"),
+    "c6": ("RT_LDG256", "RT_VOTE_WL=3", "RT_VOTE_WN=2", "RT_SMEM_STACK=16", "RT_LEAF_REPEAT=2", "RT_SPHERE_SAH_DEPTH=14"),
+    "c7": ("RT_LDG256", "RT_VOTE_WL=3", "RT_VOTE_WN=2", "RT_STACK_TOP_REG", "RT_LEAF_REPEAT=2", "RT_SPHERE_SAH_DEPTH=14"),
+    "smemstack16": ("RT_SMEM_STACK=16",),
     "all_mesh": ("RT_TREELET_PREFETCH", "RT_STACK_TOP_REG", "RT_TRI_LOAD_POLICY=1", "RT_LEAF_REPEAT=2"),
 }
 OUT_DIR = os.path.join(build.PKG_DIR, "variants")
