@@ -33,6 +33,11 @@ public static class RtB200
     // Display.shader:42-47 (tex / Frame, sRGB 8-bit): RayTraceDisplay.OnRenderImage and the screenshot of RayComputeManager.cs:106-111
     [DllImport(Lib)] public static extern int rtDisplay(IntPtr ctx, int useAccumulated, int frame, byte[] rgba, UIntPtr bytes);
 
+    // pipelined forms: the copy of frame k travels while frame k+1 renders (dst pinned: GCHandle.Alloc(..., GCHandleType.Pinned))
+    [DllImport(Lib)] public static extern int rtReadbackAsync(IntPtr ctx, string tex, IntPtr dst, UIntPtr bytes);
+    [DllImport(Lib)] public static extern int rtDisplayAsync(IntPtr ctx, int useAccumulated, int frame, IntPtr rgba, UIntPtr bytes);
+    [DllImport(Lib)] public static extern int rtReadbackWait(IntPtr ctx);
+
     // ---- extensions (no counterpart in the reference) ----
     [DllImport(Lib)] public static extern int rtGetVersion();
     [DllImport(Lib)] public static extern int rtSetOption(IntPtr ctx, string name, int value);           // "kernel", "tlas", "modelSkip", ... (rt_b200.h)

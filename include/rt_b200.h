@@ -96,6 +96,15 @@ int rtReadback(RtContext* ctx, const char* tex, float* dst, size_t bytes);
  * dst receives W*H RGBA8 pixels in [y][x] order (row 0 = bottom), bytes must equal W*H*4.  Synchronises. */
 int rtDisplay(RtContext* ctx, int useAccumulated, int Frame, uint8_t* dst, size_t bytes);
 
+/* Pipelined forms of rtReadback / rtDisplay for hosts that read every frame: the call snapshots the texture (or encodes the
+ * display image) on the dispatch stream as it is after the work queued so far, starts the device -> host copy on a stream of
+ * its own and returns; the next rtDispatch runs while the copy is in flight.  dst (pinned memory for a real overlap) is valid
+ * after rtReadbackWait (or rtSynchronize).  One copy in flight per context: a second call waits — on the device — for the first
+ * copy to have read the snapshot. */
+int rtReadbackAsync(RtContext* ctx, const char* tex, float* dst, size_t bytes);
+int rtDisplayAsync(RtContext* ctx, int useAccumulated, int Frame, uint8_t* dst, size_t bytes);
+int rtReadbackWait(RtContext* ctx);
+
 /* Block until all work queued on this context has finished. */
 int rtSynchronize(RtContext* ctx);
 

@@ -827,6 +827,9 @@ int rtDisplay(RtContext* c, int useAccumulated, int Frame, uint8_t* dst, size_t 
 }
 
 int rtSynchronize(RtContext* c) { return c ? RT_OK : RT_E_INVALID; }
+int rtReadbackAsync(RtContext* c, const char* tex, float* dst, size_t bytes) { return rtReadback(c, tex, dst, bytes); }      // the CPU has nothing to overlap
+int rtDisplayAsync(RtContext* c, int useAccumulated, int Frame, uint8_t* dst, size_t bytes) { return rtDisplay(c, useAccumulated, Frame, dst, bytes); }
+int rtReadbackWait(RtContext* c) { return c ? RT_OK : RT_E_INVALID; }
 // multi-GPU entry points of the ABI: the oracle is one CPU "device"
 int rtCreateMulti(RtContext** out, const int* devices, int nDevices)
 {

@@ -91,10 +91,13 @@ class RtLib:
             "rtCommInit": ([vp, vp, C.c_size_t, ci, ci], ci),
             "rtCommDestroy": ([vp], ci),
             "rtExchangeTiles": ([vp], ci),
+            "rtReadbackAsync": ([vp, cp, vp, C.c_size_t], ci),
+            "rtDisplayAsync": ([vp, ci, ci, vp, C.c_size_t], ci),
+            "rtReadbackWait": ([vp], ci),
         }
         for name, (args, res) in sig.items():
             if not hasattr(L, name):
-                if name in ("rtGetIpcHandles", "rtSetPeers", "rtBuildBVH", "rtCreateMulti", "rtGetUniqueId", "rtCommInit", "rtCommDestroy", "rtExchangeTiles"):      # absent from older experimental builds used in A/B runs
+                if name in ("rtGetIpcHandles", "rtSetPeers", "rtBuildBVH", "rtCreateMulti", "rtGetUniqueId", "rtCommInit", "rtCommDestroy", "rtExchangeTiles", "rtReadbackAsync", "rtDisplayAsync", "rtReadbackWait"):      # absent from older experimental builds used in A/B runs
                     continue
                 raise AttributeError(f"{self.path} does not export {name}")
             fn = getattr(L, name)
@@ -223,6 +226,16 @@ class RtContext:
 
     def set_tile(self, rank: int, world: int, band_rows: int):
         self._ck(self._L.rtSetTile(self._h, rank, world, band_rows))
+
+    def readback_async(self, tex: str, host_ptr: int, nbytes: int):
+        """rtReadbackAsync into caller-owned (pinned) host memory; valid after readback_wait()."""
+        self._ck(self._L.rtReadbackAsync(self._h, tex.encode(), C.c_void_p(host_ptr), nbytes))
+
+    def display_async(self, use_accumulated: bool, frame: int, host_ptr: int, nbytes: int):
+        self._ck(self._L.rtDisplayAsync(self._h, 1 if use_accumulated else 0, int(frame), C.c_void_p(host_ptr), nbytes))
+
+    def readback_wait(self):
+        self._ck(self._L.rtReadbackWait(self._h))
 
     def comm_init(self, unique_id: bytes, rank: int, world: int):
         """rtCommInit (collective over all ranks): NCCL communicator inside the context; RayTrace dispatches then end with the

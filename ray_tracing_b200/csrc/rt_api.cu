@@ -76,6 +76,11 @@ struct RtContext
     int optExchange = 1;
     std::vector<RtContext*> followers; RtContext* leader = nullptr;
 
+    // pipelined readback (rtReadbackAsync / rtDisplayAsync): a snapshot on the dispatch stream, the device -> host copy on a stream of
+    // its own, so that the next frame's kernel runs while the previous frame's result travels over PCIe
+    cudaStream_t copyStream = nullptr; cudaEvent_t snapReady = nullptr, copyDone = nullptr; bool copyPending = false;
+    DevBuf<float4> snap;
+
     // counters / timing
     unsigned long long* dCounters = nullptr;   // 5
     unsigned int* dWork = nullptr;
@@ -180,6 +185,10 @@ int rtDestroy(RtContext* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->nodes.release(); c->tris.release(); c->models.release(); c->spheres.release();
+    if (c->copyStream) { cudaStreamSynchronize(c->copyStream); cudaStreamDestroy(c->copyStream); }
+    if (c->snapReady) cudaEventDestroy(c->snapReady);
+    if (c->copyDone) cudaEventDestroy(c->copyDone);
+    c->snap.release();
     c->frame.release(); c->accum.release(); c->tileSend.release(); c->tileRecv.release(); c->display.release();
     c->repack.release();
     closePeers(c);
@@ -333,6 +342,7 @@ static int one_rtResize(RtContext* c, int w, int h)
     CK(cudaSetDevice(c->device));
     if (w != c->width || h != c->height)
     {
+        if (c->copyPending) { CK(cudaEventSynchronize(c->copyDone)); c->copyPending = false; }
         const size_t n = (size_t)w * h;
         CK(c->frame.ensure(n)); CK(c->accum.ensure(n));
         CK(cudaMemsetAsync(c->frame.p, 0, n * 16, c->stream));
@@ -677,6 +687,7 @@ int rtDisplay(RtContext* c, int useAccumulated, int Frame, uint8_t* dst, size_t 
     const size_t n = (size_t)c->width * c->height;
     if (bytes != n * 4) return fail(c, RT_E_INVALID, "rtDisplay: bytes must equal W*H*4");
     CK(cudaSetDevice(c->device));
+    if (c->copyPending) { CK(cudaEventSynchronize(c->copyDone)); c->copyPending = false; }
     CK(c->display.ensure(n));
     RT_LAUNCH((unsigned)((n + 255) / 256), 256, 0, c->stream, k_display, useAccumulated ? c->accum.p : c->frame.p, c->display.p, n, (float)Frame);
     CK(cudaGetLastError());
@@ -685,9 +696,68 @@ int rtDisplay(RtContext* c, int useAccumulated, int Frame, uint8_t* dst, size_t 
     return RT_OK;
 }
 
+// ---- pipelined readback -------------------------------------------------------------------------------------------------------
+static int copyPipeline(RtContext* c)
+{
+    if (!c->copyStream) CK(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+    if (!c->snapReady) CK(cudaEventCreateWithFlags(&c->snapReady, cudaEventDisableTiming));
+    if (!c->copyDone) CK(cudaEventCreateWithFlags(&c->copyDone, cudaEventDisableTiming));
+    if (c->copyPending) CK(cudaStreamWaitEvent(c->stream, c->copyDone, 0));      // the snapshot buffer is free once the copy before has read it
+    return RT_OK;
+}
+static int copyOut(RtContext* c, void* dst, const void* src, size_t bytes)
+{
+    CK(cudaEventRecord(c->snapReady, c->stream));
+    CK(cudaStreamWaitEvent(c->copyStream, c->snapReady, 0));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->copyStream));
+    CK(cudaEventRecord(c->copyDone, c->copyStream));
+    c->copyPending = true;
+    return RT_OK;
+}
+
+int rtReadbackAsync(RtContext* c, const char* tex, float* dst, size_t bytes)
+{
+    if (!c || !tex || !dst) return fail(c, RT_E_INVALID, "rtReadbackAsync: bad argument");
+    const std::string n(tex);
+    if (n != "FrameRender" && n != "AccumulatedRender") return fail(c, RT_E_UNKNOWN_NAME, std::string("rtReadbackAsync: unknown texture ") + tex);
+    const float4* src = n == "FrameRender" ? c->frame.p : c->accum.p;
+    if (!src) return fail(c, RT_E_STATE, "rtReadbackAsync: rtResize has not been called");
+    if (bytes != (size_t)c->width * c->height * 16) return fail(c, RT_E_INVALID, "rtReadbackAsync: bytes must equal W*H*16");
+    CK(cudaSetDevice(c->device));
+    int rc = copyPipeline(c); if (rc != RT_OK) return rc;
+    CK(c->snap.ensure((size_t)c->width * c->height));
+    CK(cudaMemcpyAsync(c->snap.p, src, bytes, cudaMemcpyDeviceToDevice, c->stream));       // the texture as it is after the work queued so far
+    return copyOut(c, dst, c->snap.p, bytes);
+}
+
+int rtDisplayAsync(RtContext* c, int useAccumulated, int Frame, uint8_t* dst, size_t bytes)
+{
+    if (!c || !dst) return fail(c, RT_E_INVALID, "rtDisplayAsync: bad argument");
+    if (!c->frame.p) return fail(c, RT_E_STATE, "rtDisplayAsync: rtResize has not been called");
+    const size_t n = (size_t)c->width * c->height;
+    if (bytes != n * 4) return fail(c, RT_E_INVALID, "rtDisplayAsync: bytes must equal W*H*4");
+    CK(cudaSetDevice(c->device));
+    int rc = copyPipeline(c); if (rc != RT_OK) return rc;
+    CK(c->display.ensure(n));
+    RT_LAUNCH((unsigned)((n + 255) / 256), 256, 0, c->stream, k_display, useAccumulated ? c->accum.p : c->frame.p, c->display.p, n, (float)Frame);
+    CK(cudaGetLastError());
+    return copyOut(c, dst, c->display.p, bytes);
+}
+
+int rtReadbackWait(RtContext* c)
+{
+    if (!c) return RT_E_INVALID;
+    if (!c->copyPending) return RT_OK;
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventSynchronize(c->copyDone));
+    c->copyPending = false;
+    return RT_OK;
+}
+
 int rtSynchronize(RtContext* c)
 {
     if (!c) return RT_E_INVALID;
+    if (c->copyPending) { CK(cudaSetDevice(c->device)); CK(cudaEventSynchronize(c->copyDone)); c->copyPending = false; }
     for (RtContext* m : c->followers) { CK(cudaSetDevice(m->device)); CK(cudaStreamSynchronize(m->stream)); }
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));

@@ -1,0 +1,125 @@
+"""Round 2 additions to the C-ABI on the B200 (`-m gpu`): the bodies of tests/test_round2_abi.py against librt_b200.so, the
+pipelined readback, and — on a box with at least two GPUs — the multi-GPU forms with the real NCCL all-gather inside rtDispatch
+(one process: rtCreateMulti; one process per GPU: examples/render_tiled.cpp with rtCommInit, no Python in the data plane)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import CUDA_LIB, ORACLE_LIB, REPO, assert_bit_equal, render
+import ray_tracing_b200 as rt
+from ray_tracing_b200 import scenes
+import test_round2_abi as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+def test_model_count_alone_replans_the_scene_on_gpu():
+    R.model_count_alone(CUDA_LIB)
+
+
+def test_root_bounds_are_never_read_on_gpu():
+    R.root_bounds_are_never_read(CUDA_LIB)
+
+
+def test_deep_trees_are_refused_not_truncated_on_gpu():
+    R.deep_trees(CUDA_LIB)
+
+
+def test_unchanged_uploads_on_gpu():
+    R.unchanged_uploads_are_skipped_but_changes_are_not(CUDA_LIB)
+
+
+def test_group_of_one_and_error_paths_on_gpu():
+    from ray_tracing_b200 import capi
+    L = capi.RtLib(CUDA_LIB)
+    with pytest.raises(capi.RtError):
+        L.create_multi([0, 0])
+    sc = scenes.knot_room(96, 54, 3, 2, nu=40, nv=8)
+    fref, aref = render(CUDA_LIB, sc, frames=2)
+    mgr = rt.RayComputeManager(CUDA_LIB, devices=[0])
+    scenes.apply(sc, mgr)
+    mgr.OnEnable(); mgr.RenderFrame(); mgr.RenderFrame()
+    assert_bit_equal(mgr.accumulatedResult, aref, "group of one GPU")
+    mgr.OnDestroy()
+
+
+def test_pipelined_readback_returns_every_frame_on_gpu():
+    """rtReadbackAsync / rtDisplayAsync: the copy of frame k, taken while frame k+1 renders, is frame k's image."""
+    import torch
+    sc = scenes.knot_room(160, 90, 3, 1, nu=40, nv=8)
+    refs = []
+    mgr = rt.RayComputeManager(CUDA_LIB)
+    scenes.apply(sc, mgr); mgr.OnEnable()
+    for _ in range(4):
+        mgr.RenderFrame(); refs.append(mgr.accumulatedResult.copy())
+    mgr.OnDestroy()
+    mgr = rt.RayComputeManager(CUDA_LIB)
+    scenes.apply(sc, mgr); mgr.OnEnable()
+    ctx = mgr.context
+    bufs = [torch.empty((90, 160, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    got = []
+    for k in range(4):
+        mgr.RenderFrame()
+        ctx.readback_async("AccumulatedRender", bufs[k & 1].data_ptr(), bufs[k & 1].numel() * 4)
+        ctx.readback_wait()
+        got.append(bufs[k & 1].numpy().copy())
+    for k in range(4):
+        assert_bit_equal(got[k], refs[k], f"pipelined readback, frame {k}")
+    # two copies queued back to back without a host wait in between: the second waits for the first on the device
+    mgr.ResetAccumulatedRender()
+    mgr.RenderFrame()
+    ctx.readback_async("AccumulatedRender", bufs[0].data_ptr(), bufs[0].numel() * 4)
+    mgr.RenderFrame()
+    ctx.readback_async("AccumulatedRender", bufs[1].data_ptr(), bufs[1].numel() * 4)
+    ctx.readback_wait()
+    assert_bit_equal(bufs[1].numpy(), refs[1], "second of two queued copies")
+    rgba = torch.empty((90, 160, 4), dtype=torch.uint8).pin_memory()
+    ctx.display_async(True, 2, rgba.data_ptr(), rgba.numel())
+    ctx.synchronize()
+    assert np.array_equal(rgba.numpy(), ctx.display(True, 2))
+    mgr.OnDestroy()
+
+
+def test_group_context_over_real_gpus_equals_one_gpu():
+    n = _gpu_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs (gpurun --gpus 2)")
+    sc = scenes.knot_room(320, 180, 4, 2, nu=80, nv=8, glass=True)
+    sc.spheres = scenes.cornell_spheres(8, 8, 1, 1).spheres[6:9]
+    R.group_equals_single(CUDA_LIB, list(range(min(n, 4))), sc)
+    R.group_equals_single(CUDA_LIB, list(range(n)), scenes.cornell_spheres(200, 150, 4, 2))
+
+
+def test_cpp_tiled_example_ranks_equal_one_gpu(tmp_path):
+    """N copies of examples/render_tiled.cpp (one per GPU, rtCommInit with the id passed through a file — no Python, no torch) and
+    the one-process form (--gpus N, rtCreateMulti) write the bytes one GPU writes."""
+    n = min(_gpu_count(), 4)
+    if n < 2:
+        pytest.skip("needs at least two GPUs (gpurun --gpus 2)")
+    exe = R._build_example(tmp_path, "render_tiled")
+    def run_one(tag, extra):
+        out = str(tmp_path / f"{tag}.bin")
+        r = subprocess.run([exe, CUDA_LIB, out, "--frames", "3"] + extra, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr + r.stdout
+        return open(out, "rb").read(), r.stdout
+    one, _ = run_one("one", [])
+    multi, log = run_one("multi", ["--gpus", str(n)])
+    assert multi == one, log
+    idf = str(tmp_path / "nccl.id")
+    procs = []
+    for r in range(n):
+        out = str(tmp_path / f"rank{r}.bin")
+        procs.append(subprocess.Popen([exe, CUDA_LIB, out, "--frames", "3", "--rank", str(r), "--world", str(n), "--device", str(r), "--id-file", idf],
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    logs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    assert open(str(tmp_path / "rank0.bin"), "rb").read() == one, logs[0]
+    assert re.search(rf"world={n} ", logs[0])

@@ -343,4 +343,4 @@ def test_csharp_binding_declares_every_entry_point_of_the_header():
     assert declared <= bound, f"not bound in RtB200.cs: {sorted(declared - bound)}"
     m = re.search(r"public struct Stats \{([^}]*)\}", cs)
     fields = re.findall(r"(\w+)[,;]", m.group(1))
-    assert [f for f in fields if f not in ("ulong", "double", "public")] == ["rays", "boxTests", "triTests", "sphereTests", "dispatches", "kernelMs", "sphereBoxTests"]
+    assert [f for f in fields if f not in ("ulong", "double", "public")] == ["rays", "boxTests", "triTests", "sphereTests", "dispatches", "kernelMs", "sphereBoxTests", "exchangeMs"]

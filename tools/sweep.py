@@ -62,6 +62,19 @@ STAGES = {
         ("default", None, {}), ("tlas off", None, {"tlas": 0}), ("tlas on", None, {"tlas": 1}), ("tlas on, kernel 1", None, {"tlas": 1, "kernel": 1}),
         ("tlas off, kernel 1", None, {"tlas": 0, "kernel": 1}), ("no model skipping at all", None, {"modelSkip": 0}),
     ]),
+    5: (["soup4k", "cluster4k", "knot64"], [       # round 2, second call: combinations of the first call's winners
+        ("default", None, {}),
+        ("ldg256 + vote 1/3/2 + smem stack 8", "c1", {}),
+        ("ldg256 + vote 1/3/2 + smem stack 8 + leaf2", "c2", {}),
+        ("ldg256 + vote 1/3/2 + smem stack 8 + leaf2 + sphere SAH", "c3", {}),
+        ("vote 1/3/2 + smem stack 8 + leaf2 + sphere SAH (128-bit loads)", "c4", {}),
+        ("ldg256 + vote 2/7/4 + smem stack 8 + leaf2 + sphere SAH", "c5", {}),
+        ("ldg256 + vote 1/3/2 + smem stack 16 + leaf2 + sphere SAH", "c6", {}),
+        ("ldg256 + vote 1/3/2 + stack top in registers + leaf2 + sphere SAH", "c7", {}),
+        ("smem stack 8", "smemstack8", {}),
+        ("smem stack 16", "smemstack16", {}),
+        ("vote 1/3/2", "vote132", {}),
+    ]),
     3: (["cornell64", "cornell1"], [
         ("default", None, {}), ("glass out of line", "glassool", {}), ("zero-defocus + glass out of line + skipsqrt", "cornell_all", {}), ("zero-defocus shortcut", "zerodefocus", {}), ("zero-defocus + skipsqrt", "zerodefocus_skipsqrt", {}), ("skipsqrt", "skipsqrt", {}), ("mb5", "mb5", {}), ("gridFit", None, {"gridFit": 1}), ("kernel 2", None, {"kernel": 2}),
     ]),
