@@ -123,3 +123,18 @@ def test_cpp_tiled_example_ranks_equal_one_gpu(tmp_path):
     assert all(p.returncode == 0 for p in procs), "\n".join(logs)
     assert open(str(tmp_path / "rank0.bin"), "rb").read() == one, logs[0]
     assert re.search(rf"world={n} ", logs[0])
+
+
+def test_ingested_fixture_scene_all_kernels_on_gpu():
+    """SURVEY 8f #2 on the GPU: a scene read from Unity YAML + OBJ (instanced mesh, built-in Cube / Quad, glass, checker, emitter,
+    transform hierarchy) traced by all three kernels equals the oracle, traversal counters included."""
+    R.ingested_scene_equals_oracle(CUDA_LIB, R.load_fixture(320, 180), frames=2)
+    R.ingested_scene_equals_oracle(CUDA_LIB, R.load_fixture(), frames=1, kernels=(2,))
+
+
+@pytest.mark.skipif(not os.path.isdir(R.REFERENCE_SCENES), reason="the reference's assets are not on this box")
+@pytest.mark.parametrize("name", ["Glass Dragon", "Glass Balls", "Sphere Refract", "Splash", "Text"])
+def test_reference_scene_on_gpu(name):
+    from ray_tracing_b200 import unity_scene
+    sc = unity_scene.load_unity_scene(os.path.join(R.REFERENCE_SCENES, name + ".unity"), width=160, height=90)
+    R.ingested_scene_equals_oracle(CUDA_LIB, sc, frames=1, kernels=(1, 2))

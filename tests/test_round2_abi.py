@@ -269,3 +269,59 @@ def test_cpp_tiled_example_on_the_interpreter_build(tmp_path, simt_lib, oracle_p
         outs[tag] = open(out, "rb").read()
     assert len(outs["one"]) == 96 * 54 * 16
     assert outs["one"] == outs["oracle"] and outs["three"] == outs["one"]
+
+
+# ---- an ingested scene: the committed Unity-YAML + OBJ fixture -----------------------------------------------------
+
+FIXTURE_SCENE = os.path.join(REPO, "tests", "fixtures", "unity_project", "Assets", "Scenes", "Fixture.unity")
+REFERENCE_SCENES = "/root/reference/Assets/Scenes"
+
+
+def load_fixture(width=None, height=None):
+    from ray_tracing_b200 import unity_scene
+    return unity_scene.load_unity_scene(FIXTURE_SCENE, width=width, height=height)
+
+
+def ingested_scene_equals_oracle(lib, sc, frames=2, kernels=(0, 1, 2)):
+    fo, ao, so = render(ORACLE_LIB, sc, frames=frames, want_stats=True)
+    assert np.count_nonzero(ao[..., :3]) > 0
+    for k in kernels:
+        for opts in ({"kernel": k}, {"kernel": k, "countStats": 1}):
+            fg, ag, sg = render(lib, sc, frames=frames, options=opts, want_stats=True)
+            assert_bit_equal(ag, ao, f"{sc.name} {opts}")
+            assert sg["rays"] == so["rays"]
+            if opts.get("countStats"):
+                assert all(sg[key] == so[key] for key in ("boxTests", "triTests")), (sc.name, opts)
+
+
+def test_fixture_scene_is_read_like_a_reference_scene():
+    sc = load_fixture()
+    assert (sc.width, sc.height) == (480, 270) and abs(sc.fov - 52.0) < 1e-6
+    assert sc.settings["maxBounceCount"] == 10 and sc.settings["numRaysPerPixel"] == 1 and sc.settings["renderSeed"] == 20260923
+    assert abs(sc.settings["divergeStrength"] - 1.5) < 1e-6 and sc.settings["useSky"] is False
+    assert [m.triangle_count for m in sc.meshes] == [12, 2, 528]            # built-in Cube, built-in Quad, Blob.obj (quads fanned)
+    assert len(sc.models) == 9                                               # the inactive object and the disabled component are skipped
+    assert [m.mesh for m in sc.models] == [0, 0, 0, 0, 0, 1, 2, 2, 2]        # three instances share the OBJ mesh
+    flags = [int(m.material["flag"]) for m in sc.models]
+    assert flags.count(2) == 1 and flags.count(1) == 1
+    glass = next(m for m in sc.models if int(m.material["flag"]) == 2)
+    # parent (rotated 12 degrees about Y, scaled (1, 1.1, 1)) x child (rotated 25 degrees, scaled 0.9): non-uniform world scale
+    s = np.linalg.norm(np.asarray(glass.local_to_world)[:3, :3], axis=0)
+    assert np.allclose(s, (0.9, 0.99, 0.9), atol=1e-6)
+    assert np.allclose(np.asarray(glass.local_to_world) @ np.asarray(glass.world_to_local), np.eye(4), atol=1e-5)
+    assert np.allclose(sc.sun_forward, (0.0, -np.sin(np.radians(50)), np.cos(np.radians(50))), atol=1e-6)
+
+
+def test_simt_fixture_scene_equals_oracle(simt_lib):
+    ingested_scene_equals_oracle(simt_lib, load_fixture(64, 36), frames=2)
+
+
+def test_fixture_generator_reproduces_the_committed_files(tmp_path):
+    """tests/fixtures/make_unity_fixture.py is the script that made the fixture; its output is what is committed."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_unity_fixture", os.path.join(REPO, "tests", "fixtures", "make_unity_fixture.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    mod.ROOT = str(tmp_path / "Assets")
+    mod.main()
+    for rel in ("Scenes/Fixture.unity", "Graphics/Blob.obj", "Graphics/Blob.obj.meta"):
+        assert open(os.path.join(mod.ROOT, rel)).read() == open(os.path.join(REPO, "tests", "fixtures", "unity_project", "Assets", rel)).read(), rel

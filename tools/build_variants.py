@@ -55,6 +55,10 @@ VARIANTS = {
     "c6": ("RT_LDG256", "RT_VOTE_WL=3", "RT_VOTE_WN=2", "RT_SMEM_STACK=16", "RT_LEAF_REPEAT=2", "RT_SPHERE_SAH_DEPTH=14"),
     "c7": ("RT_LDG256", "RT_VOTE_WL=3", "RT_VOTE_WN=2", "RT_STACK_TOP_REG", "RT_LEAF_REPEAT=2", "RT_SPHERE_SAH_DEPTH=14"),
     "smemstack16": ("RT_SMEM_STACK=16",),
+    "pw28": ("RT_POOL_WARPS=28",),
+    "pw32": ("RT_POOL_WARPS=32",),
+    "pw28_c": ("RT_POOL_WARPS=28", "RT_LDG256", "RT_VOTE_WL=3", "RT_VOTE_WN=2", "RT_LEAF_REPEAT=2", "RT_SPHERE_SAH_DEPTH=14"),
+    "pw32_c": ("RT_POOL_WARPS=32", "RT_LDG256", "RT_VOTE_WL=3", "RT_VOTE_WN=2", "RT_LEAF_REPEAT=2", "RT_SPHERE_SAH_DEPTH=14"),
     "all_mesh": ("RT_TREELET_PREFETCH", "RT_STACK_TOP_REG", "RT_TRI_LOAD_POLICY=1", "RT_LEAF_REPEAT=2"),
 }
 OUT_DIR = os.path.join(build.PKG_DIR, "variants")

@@ -21,12 +21,25 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--lib", default=b.LIB_CUDA)
     ap.add_argument("--repeat", type=int, default=3)
+    ap.add_argument("--only", default=None, help="substring of the mesh name: run that mesh only (for an ncu launch list of one build)")
+    ap.add_argument("--gpu-only", action="store_true", help="skip the host builds (identical = null)")
     args = ap.parse_args()
     meshes = [("knot 87k", scenes.knot_mesh()),
               ("cluster 871k", max(scenes.knot_cluster(64, 36, 2, 1).meshes, key=lambda m: m.triangle_count)),
               ("soup 333k (one of the three models of config 5)", max(scenes.random_soup(16, 16, 2, 1, triangles=1_000_000, spheres=1).meshes, key=lambda m: m.triangle_count))]
     gpu = capi.RtLib(args.lib).create(0)
+    if args.only:
+        meshes = [(n, m) for n, m in meshes if args.only in n]
     for name, m in meshes:
+        if args.gpu_only:
+            row = {"mesh": name, "triangles": int(m.triangle_count)}
+            for q, qn in ((1, "High"),):
+                best = 1e9
+                for _ in range(args.repeat):
+                    t0 = time.perf_counter(); tg, ng = gpu.build_bvh(m.vertices, m.indices, m.normals, q); best = min(best, time.perf_counter() - t0)
+                row[qn] = {"nodes": int(len(ng)), "gpu_ms_incl_copies": round(1e3 * best, 1)}
+            print(json.dumps(row), flush=True)
+            continue
         row = {"mesh": name, "triangles": int(m.triangle_count)}
         for q, qn in ((1, "High"), (0, "Low")):
             rt.set_build_threads(1)

@@ -74,6 +74,10 @@ STAGES = {
         ("smem stack 8", "smemstack8", {}),
         ("smem stack 16", "smemstack16", {}),
         ("vote 1/3/2", "vote132", {}),
+        ("28 warps per SM (72 registers)", "pw28", {}),
+        ("32 warps per SM (64 registers)", "pw32", {}),
+        ("28 warps + ldg256 + vote 1/3/2 + leaf2 + sphere SAH", "pw28_c", {}),
+        ("32 warps + ldg256 + vote 1/3/2 + leaf2 + sphere SAH", "pw32_c", {}),
     ]),
     3: (["cornell64", "cornell1"], [
         ("default", None, {}), ("glass out of line", "glassool", {}), ("zero-defocus + glass out of line + skipsqrt", "cornell_all", {}), ("zero-defocus shortcut", "zerodefocus", {}), ("zero-defocus + skipsqrt", "zerodefocus_skipsqrt", {}), ("skipsqrt", "skipsqrt", {}), ("mb5", "mb5", {}), ("gridFit", None, {"gridFit": 1}), ("kernel 2", None, {"kernel": 2}),
