@@ -612,9 +612,29 @@ RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const uns
                     // (x*1 - 0 is x exactly, so the mesh comparison is unchanged; inf stays inf and never passes)
                     const float cs = sph ? 0.99999619f : 1.0f, cb = sph ? 1e-6f : 0.0f;
                     if ((dstFar * cs - cb) < bestDst && stackCount < WAVE_STACK) { RT_PUSH(farRef); RT_PROF(11, 1); RT_PROF(32 + (stackCount < 31 ? stackCount : 31), 1); }   // (prefetching the far record here was measured: -2 %)
+#if defined(RT_SMEM_STACK) && defined(RT_BRANCHLESS_POP)
+                    // The pop below ran with 2.4 of 32 lanes (ncu, profiles/r01_f_soup4k_*): few lanes miss both children in the same step.
+                    // With the stack top in shared memory every lane can afford to READ the top (a conflict-free 8-byte access) and
+                    // select: descend into the near child or take the top.  When the near child is out of reach so is the far one
+                    // (dstFar >= dstNear), so the stack was not pushed in this step and its top is exactly what a pop returns.
+                    {
+                        const bool goNear = (dstNear * cs - cb) < bestDst;
+                        const bool ringHas = stackCount > stackSpilled;
+                        const int w_ = ((stackCount - 1) & (RT_SMEM_STACK - 1)) * 64;
+                        NodeRef top; top.start = ring[w_ + (int)lane]; top.count = ring[w_ + 32 + (int)lane];
+                        if (!goNear && !ringHas && stackCount > 0) { top = stack[stackSpilled - 1]; --stackSpilled; }      // rare: the ring ran empty above spilled entries
+                        const bool pop = !goNear && stackCount > 0;
+                        cur = goNear ? nearRef : top;
+                        stackCount -= pop ? 1 : 0;
+                        leafK = 0;
+                        mode = (goNear || pop) ? (cur.count > 0 ? T_LEAF : T_INNER) : T_NEXT;
+                        RT_PF_CUR();
+                    }
+#else
                     if ((dstNear * cs - cb) < bestDst) { cur = nearRef; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; RT_PF_CUR(); }
                     else if (stackCount > 0) { RT_POP(cur); leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; RT_PF_CUR(); }
                     else mode = T_NEXT;
+#endif
                 }
             }
             else

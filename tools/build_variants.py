@@ -55,6 +55,7 @@ VARIANTS = {
     "c6": ("RT_LDG256", "RT_VOTE_WL=3", "RT_VOTE_WN=2", "RT_SMEM_STACK=16", "RT_LEAF_REPEAT=2", "RT_SPHERE_SAH_DEPTH=14"),
     "c7": ("RT_LDG256", "RT_VOTE_WL=3", "RT_VOTE_WN=2", "RT_STACK_TOP_REG", "RT_LEAF_REPEAT=2", "RT_SPHERE_SAH_DEPTH=14"),
     "smemstack16": ("RT_SMEM_STACK=16",),
+    "c8": ("RT_LDG256", "RT_VOTE_WL=3", "RT_VOTE_WN=2", "RT_SMEM_STACK=8", "RT_BRANCHLESS_POP", "RT_LEAF_REPEAT=2", "RT_SPHERE_SAH_DEPTH=14"),
     "pw28": ("RT_POOL_WARPS=28",),
     "pw32": ("RT_POOL_WARPS=32",),
     "pw28_c": ("RT_POOL_WARPS=28", "RT_LDG256", "RT_VOTE_WL=3", "RT_VOTE_WN=2", "RT_LEAF_REPEAT=2", "RT_SPHERE_SAH_DEPTH=14"),

@@ -38,6 +38,7 @@ STAGES = {
         ("treelet+stacktop", "treelet_stacktop", {"treeletPrefetch": 1}),
         ("stacktop", "stacktop", {}),
         ("smem stack 4", "smemstack4", {}),
+        ("c3 + branch-free pop from the shared-memory stack", "c8", {}),
         ("smem stack 8", "smemstack8", {}),
         ("prefetch cur", "pfcur", {}),
         ("prefetch cur, 1 inner visit per census", "pfcur_ir1", {}),
@@ -71,6 +72,7 @@ STAGES = {
         ("ldg256 + vote 2/7/4 + smem stack 8 + leaf2 + sphere SAH", "c5", {}),
         ("ldg256 + vote 1/3/2 + smem stack 16 + leaf2 + sphere SAH", "c6", {}),
         ("ldg256 + vote 1/3/2 + stack top in registers + leaf2 + sphere SAH", "c7", {}),
+        ("c3 + branch-free pop from the shared-memory stack", "c8", {}),
         ("smem stack 8", "smemstack8", {}),
         ("smem stack 16", "smemstack16", {}),
         ("vote 1/3/2", "vote132", {}),
