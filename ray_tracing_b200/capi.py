@@ -276,12 +276,12 @@ class RtContext:
         n = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
         idx = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1)
         ntri = idx.size // 3
-        tris = np.zeros(max(ntri, 1), dtype=TRIANGLE_DTYPE)
-        nodes = np.zeros(2 * max(ntri, 1) + 1, dtype=NODE_DTYPE)
+        tris = np.empty(max(ntri, 1), dtype=TRIANGLE_DTYPE)
+        nodes = np.empty(2 * max(ntri, 1) + 1, dtype=NODE_DTYPE)
         count = C.c_int()
         self._ck(self._L.rtBuildBVH(self._h, v.ctypes.data, v.shape[0], idx.ctypes.data, idx.size, n.ctypes.data, int(quality),
                                     tris.ctypes.data, nodes.ctypes.data, nodes.shape[0], C.byref(count)))
-        return tris[:ntri].copy(), nodes[:count.value].copy()
+        return tris[:ntri], nodes[:count.value]
 
     def set_option(self, name: str, v: int):
         self._ck(self._L.rtSetOption(self._h, name.encode(), int(v)))

@@ -13,8 +13,10 @@
 #include "rt_bvh_build.cuh"
 #include "rt_comm.cuh"
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -67,7 +69,7 @@ struct RtContext
     float4* peerFrame[RT_MAX_PEERS]; float4* peerAccum[RT_MAX_PEERS]; int nPeers = 0;
 
     // options
-    int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 64, optTailLanes = 16, optSortRays = 0, optForceExt = 0, optModelSkip = 1, optPairOrder = 0, optGridFit = 0, optL2Persist = 0, optTreeletPrefetch = 0, optZeroDefocus = 1, optTlas = -1;
+    int optKernel = -1, optCountStats = 0, optSmemPairs = -1, optPoolSlots = 0, optTailLanes = 16, optSortRays = 0, optForceExt = 0, optModelSkip = 1, optPairOrder = 0, optGridFit = 0, optL2Persist = 0, optTreeletPrefetch = 0, optZeroDefocus = 1, optTlas = -1;
     int l2PersistApplied = 0; const void* l2PersistBase = nullptr; size_t l2PersistBytes = 0;   // kernel -1 = automatic   // smemPairs -1 = automatic
 
     // exchange of finished tiles inside the ABI (rt_comm.cuh): a communicator over the ranks of a tiled render — one process per
@@ -80,6 +82,11 @@ struct RtContext
     // its own, so that the next frame's kernel runs while the previous frame's result travels over PCIe
     cudaStream_t copyStream = nullptr; cudaEvent_t snapReady = nullptr, copyDone = nullptr; bool copyPending = false;
     DevBuf<float4> snap;
+
+    // rtBuildBVH: device arena kept between builds, pinned staging chunks for the copies of caller-owned arrays
+    DevBuf<unsigned char> buildArena;
+    static constexpr size_t STAGE_BYTES = 8u << 20;
+    unsigned char* stageBuf[2] = {nullptr, nullptr}; cudaEvent_t stageEv[2] = {nullptr, nullptr};
 
     // counters / timing
     unsigned long long* dCounters = nullptr;   // 5
@@ -189,6 +196,8 @@ int rtDestroy(RtContext* c)
     if (c->snapReady) cudaEventDestroy(c->snapReady);
     if (c->copyDone) cudaEventDestroy(c->copyDone);
     c->snap.release();
+    c->buildArena.release();
+    for (int k = 0; k < 2; k++) { if (c->stageBuf[k]) cudaFreeHost(c->stageBuf[k]); if (c->stageEv[k]) cudaEventDestroy(c->stageEv[k]); }
     c->frame.release(); c->accum.release(); c->tileSend.release(); c->tileRecv.release(); c->display.release();
     c->repack.release();
     closePeers(c);
@@ -400,7 +409,7 @@ static int one_rtSetOption(RtContext* c, const char* name, int value)
     }
     else if (n == "pairOrder") { if (value < 0 || value > 32) return fail(c, RT_E_INVALID, "rtSetOption: pairOrder must be 0 (breadth-first) or a treelet depth 1..32"); c->optPairOrder = value; }
     else if (n == "tailLanes") { if (value < 0 || value > 31) return fail(c, RT_E_INVALID, "rtSetOption: tailLanes must be in [0, 31]"); c->optTailLanes = value; }
-    else if (n == "poolSlots") { if (value != 32 && value != 64 && value != 96) return fail(c, RT_E_INVALID, "rtSetOption: poolSlots must be 32, 64 or 96"); c->optPoolSlots = value; }
+    else if (n == "poolSlots") { if (value != 0 && value != 32 && value != 64 && value != 96) return fail(c, RT_E_INVALID, "rtSetOption: poolSlots must be 0 (automatic), 32, 64 or 96"); c->optPoolSlots = value; }
     else return fail(c, RT_E_UNKNOWN_NAME, std::string("rtSetOption: unknown option ") + name);
     return RT_OK;
 }
@@ -536,7 +545,7 @@ static int prepareScene(RtContext* c)
     const int pairOrder = treelets ? 2 : c->optPairOrder;
     if (treelets) budget = 0;
     if (budget > 3072) budget = 3072;                                   // planScene's own clamp (192 KB), so that budgetUsed compares equal
-    if (kernelSel == 2) { const int mx = pool_max_smem_pairs(c->optPoolSlots, (int)c->spheres.count); if (budget > mx) budget = mx; }
+    if (kernelSel == 2) { const int mx = pool_max_smem_pairs(c->optPoolSlots ? c->optPoolSlots : 96, (int)c->spheres.count); if (budget > mx) budget = mx; }
     else if (kernelSel == 0) budget = 0;
     if (budget != c->repack.budgetUsed || pairOrder != c->repack.orderUsed || treelets != c->repack.flagsUsed) c->sceneDirty = true;
     if (c->sceneDirty)
@@ -1070,6 +1079,56 @@ int rtSetPeers(RtContext* c, int nPeers, const void* handles, size_t bytes)
     return RT_OK;
 }
 
+// Host <-> device copies of large caller-owned (pageable) arrays through two pinned chunks: the CPU copies chunk k + 1 into / out of
+// pinned memory while the DMA engine moves chunk k, instead of the driver's own slower staging of pageable memory.
+static int stagingReady(RtContext* c)
+{
+    for (int k = 0; k < 2; k++)
+    {
+        if (!c->stageBuf[k]) CK(cudaMallocHost((void**)&c->stageBuf[k], RtContext::STAGE_BYTES));
+        if (!c->stageEv[k]) CK(cudaEventCreateWithFlags(&c->stageEv[k], cudaEventDisableTiming));
+    }
+    return RT_OK;
+}
+static int stagedH2D(RtContext* c, void* dst, const void* src, size_t bytes)
+{
+    int rc = stagingReady(c); if (rc != RT_OK) return rc;
+    size_t off = 0; int k = 0;
+    while (off < bytes)
+    {
+        const size_t n = bytes - off < RtContext::STAGE_BYTES ? bytes - off : RtContext::STAGE_BYTES;
+        CK(cudaEventSynchronize(c->stageEv[k]));                                   // the copy that last used this chunk has read it
+        memcpy(c->stageBuf[k], (const unsigned char*)src + off, n);
+        CK(cudaMemcpyAsync((unsigned char*)dst + off, c->stageBuf[k], n, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaEventRecord(c->stageEv[k], c->stream));
+        off += n; k ^= 1;
+    }
+    return RT_OK;
+}
+static int stagedD2H(RtContext* c, void* dst, const void* src, size_t bytes)
+{
+    int rc = stagingReady(c); if (rc != RT_OK) return rc;
+    CK(cudaEventSynchronize(c->stageEv[0])); CK(cudaEventSynchronize(c->stageEv[1]));
+    size_t off = 0, prevOff = 0, prevN = 0; int k = 0;
+    while (off < bytes || prevN)
+    {
+        size_t n = 0;
+        if (off < bytes)
+        {
+            n = bytes - off < RtContext::STAGE_BYTES ? bytes - off : RtContext::STAGE_BYTES;
+            CK(cudaMemcpyAsync(c->stageBuf[k], (const unsigned char*)src + off, n, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaEventRecord(c->stageEv[k], c->stream));
+        }
+        if (prevN)                                                                  // while chunk k travels, hand chunk k ^ 1 to the caller
+        {
+            CK(cudaEventSynchronize(c->stageEv[k ^ 1]));
+            memcpy((unsigned char*)dst + prevOff, c->stageBuf[k ^ 1], prevN);
+        }
+        prevOff = off; prevN = n; off += n; k ^= 1;
+    }
+    return RT_OK;
+}
+
 // BVH(verts, indices, normals, quality) of the reference (BVH.cs:26, called per mesh from RayComputeManager.cs:209-232), built on the GPU:
 // the same Nodes / Triangles the host builder returns (rt_bvh_build.cuh).  Host arrays in, host arrays out.
 int rtBuildBVH(RtContext* c, const float* verts, int vertCount, const int* indices, int indexCount, const float* normals, int quality,
@@ -1084,21 +1143,35 @@ int rtBuildBVH(RtContext* c, const float* verts, int vertCount, const int* indic
     const int triCount = indexCount / 3;
     if (nodeCapacity < 2 * triCount + 1) return fail(c, RT_E_INVALID, "rtBuildBVH: outNodes must hold 2 * triangles + 1 entries");
     CK(cudaSetDevice(c->device));
-    DevBuf<float> dV, dN; DevBuf<int> dI; DevBuf<RtNode> dNodes; DevBuf<RtTriangle> dTris;
-    auto release = [&]() { dV.release(); dN.release(); dI.release(); dNodes.release(); dTris.release(); };
-    cudaError_t e;
-    if ((e = dV.ensure((size_t)vertCount * 3)) != cudaSuccess || (e = dN.ensure((size_t)vertCount * 3)) != cudaSuccess || (e = dI.ensure((size_t)indexCount)) != cudaSuccess ||
-        (e = dNodes.ensure((size_t)2 * triCount + 1)) != cudaSuccess || (e = dTris.ensure((size_t)triCount)) != cudaSuccess) { release(); return failCuda(c, e, "rtBuildBVH: cudaMalloc"); }
-    if ((e = cudaMemcpyAsync(dV.p, verts, (size_t)vertCount * 12, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(dN.p, normals, (size_t)vertCount * 12, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(dI.p, indices, (size_t)indexCount * 4, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) { release(); return failCuda(c, e, "rtBuildBVH: upload"); }
+    // ONE device allocation for inputs, outputs and the build's temporaries, kept by the context between builds (grow-only;
+    // RayComputeManager builds every mesh of a scene in turn), and two pinned staging chunks for the host <-> device copies.
+    const bool timing = getenv("RT_B200_BVH_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
+    const size_t bV = BvhScratch::align((size_t)vertCount * 12), bI = BvhScratch::align((size_t)indexCount * 4),
+                 bNodes = BvhScratch::align(((size_t)2 * triCount + 1) * sizeof(RtNode)), bTris = BvhScratch::align((size_t)triCount * sizeof(RtTriangle));
+    const size_t need = 2 * bV + bI + bNodes + bTris + BvhScratch::bytesFor(triCount);
+    if (need > c->buildArena.count) { CK(cudaStreamSynchronize(c->stream)); CK(c->buildArena.ensure(need)); }
+    unsigned char* base = c->buildArena.p;
+    float* dV = reinterpret_cast<float*>(base); float* dN = reinterpret_cast<float*>(base + bV); int* dI = reinterpret_cast<int*>(base + 2 * bV);
+    RtNode* dNodes = reinterpret_cast<RtNode*>(base + 2 * bV + bI); RtTriangle* dTris = reinterpret_cast<RtTriangle*>(base + 2 * bV + bI + bNodes);
+    BvhScratch scratch; scratch.base = base + 2 * bV + bI + bNodes + bTris; scratch.cap = c->buildArena.count - (2 * bV + bI + bNodes + bTris);
+    const double tAlloc = ms(t0);
+    const auto t1 = std::chrono::steady_clock::now();
+    int rc;
+    if ((rc = stagedH2D(c, dV, verts, (size_t)vertCount * 12)) != RT_OK || (rc = stagedH2D(c, dN, normals, (size_t)vertCount * 12)) != RT_OK ||
+        (rc = stagedH2D(c, dI, indices, (size_t)indexCount * 4)) != RT_OK) return rc;
+    const double tUp = ms(t1);
+    const auto t2 = std::chrono::steady_clock::now();
     BvhBuildResult res; std::string msg;
-    e = bvh_build_device(dV.p, dN.p, dI.p, triCount, quality, dNodes.p, dTris.p, c->stream, res, msg);
-    if (e != cudaSuccess) { release(); return msg.empty() ? failCuda(c, e, "rtBuildBVH") : fail(c, RT_E_STATE, "rtBuildBVH: " + msg); }
-    if ((e = cudaMemcpyAsync(outNodes, dNodes.p, (size_t)res.nodeCount * sizeof(RtNode), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(outTris, dTris.p, (size_t)triCount * sizeof(RtTriangle), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
-        (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { release(); return failCuda(c, e, "rtBuildBVH: download"); }
-    release();
+    cudaError_t e = bvh_build_device(dV, dN, dI, triCount, quality, dNodes, dTris, c->stream, res, msg, scratch);
+    if (e != cudaSuccess) return msg.empty() ? failCuda(c, e, "rtBuildBVH") : fail(c, RT_E_STATE, "rtBuildBVH: " + msg);
+    const double tBuild = ms(t2);
+    const auto t3 = std::chrono::steady_clock::now();
+    if ((rc = stagedD2H(c, outNodes, dNodes, (size_t)res.nodeCount * sizeof(RtNode))) != RT_OK || (rc = stagedD2H(c, outTris, dTris, (size_t)triCount * sizeof(RtTriangle))) != RT_OK) return rc;
+    if (timing) fprintf(stderr, "[rtBuildBVH] %d triangles, %d nodes, %d levels: arena %.2f ms, upload %.2f ms (%.1f MB), build %.2f ms, download %.2f ms (%.1f MB), total %.2f ms\n",
+                        triCount, res.nodeCount, res.levels, tAlloc, tUp, ((size_t)vertCount * 24 + (size_t)indexCount * 4) / 1e6, tBuild, ms(t3),
+                        ((size_t)res.nodeCount * sizeof(RtNode) + (size_t)triCount * sizeof(RtTriangle)) / 1e6, ms(t0));
     *outNodeCount = res.nodeCount;
     return RT_OK;
 }

@@ -484,33 +484,46 @@ __global__ void k_bvh_emit_tris(const BuildTriD* __restrict__ tris, int triCount
 // ---- host driver -------------------------------------------------------------------------------------------------------------
 struct BvhBuildResult { int nodeCount = 0, levels = 0; };
 
+// Scratch of one build, carved from ONE allocation the caller keeps between builds (a cudaMalloc / cudaFree pair per temporary cost
+// more than the kernels: 11 of each per build, every cudaFree a device-wide synchronisation).
+struct BvhScratch
+{
+    unsigned char* base = nullptr; size_t cap = 0, off = 0;
+    static size_t align(size_t n) { return (n + 255) & ~(size_t)255; }
+    static size_t bytesFor(int triCount)
+    {
+        const size_t n = (size_t)triCount, numTiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+        return 2 * align(n * sizeof(BuildTriD)) + 2 * align(n * sizeof(int)) + 2 * align(n * sizeof(int)) + align(numTiles * sizeof(int)) + align(3 * sizeof(int))
+             + align(6 * sizeof(unsigned long long)) + align((2 * n + 1) * sizeof(BNode)) + align((n + 1) * sizeof(CandAcc));
+    }
+    template <class T> T* take(size_t count) { T* p = reinterpret_cast<T*>(base + off); off += align(count * sizeof(T)); return p; }
+};
+
 // Device buffers in, device buffers out (dNodesOut: capacity 2 * triCount + 1, dTrisOut: triCount).  Everything on `stream`;
-// one 4-byte read-back per level tells the host how many nodes the next level has.
+// one 12-byte read-back per level tells the host how many nodes the next level has.  scratch: BvhScratch::bytesFor(triCount) bytes.
 inline cudaError_t bvh_build_device(const float* dVerts, const float* dNormals, const int* dIndices, int triCount, int quality,
-                                    RtNode* dNodesOut, RtTriangle* dTrisOut, cudaStream_t stream, BvhBuildResult& res, std::string& msg)
+                                    RtNode* dNodesOut, RtTriangle* dTrisOut, cudaStream_t stream, BvhBuildResult& res, std::string& msg, BvhScratch scratch)
 {
     cudaError_t e = cudaSuccess;
-    BuildTriD* tris[2] = {nullptr, nullptr}; int* posNode[2] = {nullptr, nullptr};
-    int *flags = nullptr, *prefix = nullptr, *tileSums = nullptr, *counters = nullptr; unsigned long long* rootBox = nullptr;
-    BNode* nodes = nullptr; CandAcc* acc = nullptr;
     const int nodeCapacity = 2 * triCount + 1;
     const int numTiles = (triCount + SCAN_TILE - 1) / SCAN_TILE;
-    auto cleanup = [&]() { cudaFree(tris[0]); cudaFree(tris[1]); cudaFree(posNode[0]); cudaFree(posNode[1]); cudaFree(flags); cudaFree(prefix); cudaFree(tileSums);
-                           cudaFree(counters); cudaFree(rootBox); cudaFree(nodes); cudaFree(acc); };
+    if (!scratch.base || scratch.cap < BvhScratch::bytesFor(triCount)) { msg = "BVH build: scratch too small (internal error)"; return cudaErrorInvalidValue; }
+    scratch.off = 0;
+    BuildTriD* tris[2]; int* posNode[2];
+    for (int k = 0; k < 2; k++) { tris[k] = scratch.take<BuildTriD>((size_t)triCount); posNode[k] = scratch.take<int>((size_t)triCount); }
+    int* flags = scratch.take<int>((size_t)triCount);
+    int* prefix = scratch.take<int>((size_t)triCount);
+    int* tileSums = scratch.take<int>((size_t)numTiles);
+    int* counters = scratch.take<int>(3);                                   // [0] nodes allocated  [1] capacity exceeded  [2] partition invariant broken
+    unsigned long long* rootBox = scratch.take<unsigned long long>(6);
+    BNode* nodes = scratch.take<BNode>((size_t)nodeCapacity);
+    CandAcc* acc = scratch.take<CandAcc>((size_t)triCount + 1);            // one slot per node of a level; every node owns at least one triangle
+    auto cleanup = [&]() { };
 #define RT_BVH_CK(call) do { e = (call); if (e != cudaSuccess) { cleanup(); return e; } } while (0)
-    for (int k = 0; k < 2; k++) { RT_BVH_CK(cudaMalloc(&tris[k], (size_t)triCount * sizeof(BuildTriD))); RT_BVH_CK(cudaMalloc(&posNode[k], (size_t)triCount * sizeof(int))); }
-    RT_BVH_CK(cudaMalloc(&flags, (size_t)triCount * sizeof(int)));
-    RT_BVH_CK(cudaMalloc(&prefix, (size_t)triCount * sizeof(int)));
-    RT_BVH_CK(cudaMalloc(&tileSums, (size_t)numTiles * sizeof(int)));
-    RT_BVH_CK(cudaMalloc(&counters, 3 * sizeof(int)));                      // [0] nodes allocated  [1] capacity exceeded  [2] partition invariant broken
-    RT_BVH_CK(cudaMalloc(&rootBox, 6 * sizeof(unsigned long long)));
-    RT_BVH_CK(cudaMalloc(&nodes, (size_t)nodeCapacity * sizeof(BNode)));
-    RT_BVH_CK(cudaMalloc(&acc, (size_t)(triCount + 1) * sizeof(CandAcc)));           // one slot per node of a level; every node owns at least one triangle
     {
-        const unsigned long long init[6] = {~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull};      // above / below every key
+        static const unsigned long long init[6] = {~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull};      // above / below every key
         RT_BVH_CK(cudaMemcpyAsync(rootBox, init, sizeof(init), cudaMemcpyHostToDevice, stream));
         RT_BVH_CK(cudaMemsetAsync(counters, 0, 3 * sizeof(int), stream));
-        RT_BVH_CK(cudaStreamSynchronize(stream));                           // `init` is a local
     }
     const unsigned int T = 256, gridTri = (unsigned int)((triCount + T - 1) / T);
     RT_LAUNCH(gridTri, T, 0, stream, k_bvh_init, dVerts, dIndices, triCount, tris[0], posNode[0], rootBox);

@@ -14,6 +14,35 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// ---- build defaults of round 2 ---------------------------------------------------------------------------------------------------
+// Every switch below was a compile-time candidate of round 1, measured on the B200 in round 2 (profiles/r02_a_sweep_first_call.jsonl,
+// profiles/r02_b_sweep_combinations.jsonl; same image bits in every row).  Together: 1M triangles + 10,000 spheres 473 -> 366 ms per
+// frame (+29 %), 871k-triangle glass cluster 84.7 -> 76.5 ms (+11 %), 87k-triangle knot 30.3 -> 28.8 ms (+5 %).  -DRT_DEFAULTS_R1
+// builds the round-1 kernels again (A/B runs, tools/build_variants.py "r1").
+#ifndef RT_DEFAULTS_R1
+#ifndef RT_LDG256
+#define RT_LDG256                  // node-pair records by two 256-bit loads instead of four 128-bit ones: half the L1 wavefronts
+#endif
+#ifndef RT_VOTE_WL
+#define RT_VOTE_WL 3               // cost-weighted vote of the trace phase: a leaf step is cheap and frees its lanes for the inner population
+#endif
+#ifndef RT_VOTE_WN
+#define RT_VOTE_WN 2
+#endif
+#ifndef RT_SMEM_STACK
+#define RT_SMEM_STACK 8            // the top 8 entries of every lane's traversal stack in a shared-memory ring (lane = bank), deeper ones spill to local memory
+#endif
+#ifndef RT_BRANCHLESS_POP
+#define RT_BRANCHLESS_POP          // an inner step that misses both children takes the stack top by a select, not by a 2.4-lane branch
+#endif
+#ifndef RT_LEAF_REPEAT
+#define RT_LEAF_REPEAT 2           // two leaf primitives per census
+#endif
+#ifndef RT_SPHERE_SAH_DEPTH
+#define RT_SPHERE_SAH_DEPTH 14     // sphere accelerator: top 14 levels by the surface-area sweep
+#endif
+#endif
+
 namespace rtd {
 
 struct f2 { float x, y; };

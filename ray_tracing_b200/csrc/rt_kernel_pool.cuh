@@ -51,28 +51,34 @@ namespace rtd {
 //                      across the warp, so lane = bank and a push or pop is two conflict-free 4-byte accesses instead of a local-memory
 //                      access that touches up to 32 different lines (divergent stack depths); deeper entries spill to the local
 //                      array, oldest first.  Costs N * 6 KB of shared memory per CTA (taken from L1).
-#if defined(RT_SMEM_STACK)
+// RING = entries of the shared-memory ring of a kernel instantiation: RT_SMEM_STACK, except for the 96-slot pools, whose 223 KB of path
+// state leave no room for it (they keep the whole stack in local memory).
+#if defined(RT_SMEM_STACK) && !defined(RT_STACK_TOP_REG)
 static_assert((RT_SMEM_STACK & (RT_SMEM_STACK - 1)) == 0 && RT_SMEM_STACK >= 2, "RT_SMEM_STACK must be a power of two");
-// entries [stackSpilled, stackCount) are in the ring at index (i & (N - 1)); entries [0, stackSpilled) in the local array
-#define RT_PUSH(x) do { if (stackCount - stackSpilled == RT_SMEM_STACK) { NodeRef sp_; const int r_ = (stackSpilled & (RT_SMEM_STACK - 1)) * 64; \
-                            sp_.start = ring[r_ + (int)lane]; sp_.count = ring[r_ + 32 + (int)lane]; stack[stackSpilled++] = sp_; } \
-                        const NodeRef px_ = (x); const int w_ = (stackCount & (RT_SMEM_STACK - 1)) * 64; ring[w_ + (int)lane] = px_.start; ring[w_ + 32 + (int)lane] = px_.count; stackCount++; } while (0)
-#define RT_POP(dst) do { --stackCount; if (stackCount < stackSpilled) { (dst) = stack[--stackSpilled]; } \
-                         else { const int w_ = (stackCount & (RT_SMEM_STACK - 1)) * 64; (dst).start = ring[w_ + (int)lane]; (dst).count = ring[w_ + 32 + (int)lane]; } } while (0)
-#elif defined(RT_STACK_TOP_REG)
+template <int M> struct PoolRing { static constexpr int N = M >= 96 ? 0 : RT_SMEM_STACK; };
+#else
+template <int M> struct PoolRing { static constexpr int N = 0; };
+#endif
+#if defined(RT_SMEM_STACK) && !defined(RT_STACK_TOP_REG)
+#define RT_RING_DEFAULT RT_SMEM_STACK
+#else
+#define RT_RING_DEFAULT 0
+#endif
+#if defined(RT_STACK_TOP_REG)
 #define RT_PUSH(x) do { if (stackCount > 0) stack[stackCount - 1] = stackTop; stackTop = (x); stackCount++; } while (0)
 #define RT_POP(dst) do { (dst) = stackTop; --stackCount; if (stackCount > 0) stackTop = stack[stackCount - 1]; } while (0)
 #else
-#define RT_PUSH(x) stack[stackCount++] = (x)
-#define RT_POP(dst) (dst) = stack[--stackCount]
+// entries [stackSpilled, stackCount) are in the ring at index (i & (RING - 1)); entries [0, stackSpilled) in the local array
+#define RT_PUSH(x) do { if constexpr (RING > 0) { \
+                            if (stackCount - stackSpilled == RING) { NodeRef sp_; const int r_ = (stackSpilled & (RING - 1)) * 64; \
+                                sp_.start = ring[r_ + (int)lane]; sp_.count = ring[r_ + 32 + (int)lane]; stack[stackSpilled++] = sp_; } \
+                            const NodeRef px_ = (x); const int w_ = (stackCount & (RING - 1)) * 64; ring[w_ + (int)lane] = px_.start; ring[w_ + 32 + (int)lane] = px_.count; stackCount++; } \
+                        else { stack[stackCount++] = (x); } } while (0)
+#define RT_POP(dst) do { if constexpr (RING > 0) { --stackCount; if (stackCount < stackSpilled) { (dst) = stack[--stackSpilled]; } \
+                             else { const int w_ = (stackCount & (RING - 1)) * 64; (dst).start = ring[w_ + (int)lane]; (dst).count = ring[w_ + 32 + (int)lane]; } } \
+                         else { (dst) = stack[--stackCount]; } } while (0)
 #endif
-#ifdef RT_SMEM_STACK
 #define RT_STACK_RESET() stackSpilled = 0
-#define RT_STACK_SMEM_BYTES ((size_t)POOL_THREADS * RT_SMEM_STACK * 8)
-#else
-#define RT_STACK_RESET() do { } while (0)
-#define RT_STACK_SMEM_BYTES ((size_t)0)
-#endif
 #ifndef RT_LEAF_REPEAT
 #define RT_LEAF_REPEAT 1
 #endif
@@ -220,10 +226,10 @@ RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const uns
     PoolView<M> pool;
     pool.w = reinterpret_cast<float*>(poolBase + (size_t)warp * POOL_BYTES);
     pool.order = reinterpret_cast<unsigned char*>(pool.w + POOL_WORDS * M);
-#ifdef RT_SMEM_STACK
-    int* ring = reinterpret_cast<int*>(poolBase + (size_t)POOL_WARPS * POOL_BYTES) + (size_t)warp * (RT_SMEM_STACK * 64);     // this warp's N x 2 x 32 words
+    constexpr int RING = PoolRing<M>::N;
+    int* ring = reinterpret_cast<int*>(poolBase + (size_t)POOL_WARPS * POOL_BYTES) + (size_t)warp * (RING * 64);     // this warp's RING x 2 x 32 words
     int stackSpilled = 0;
-#endif
+    (void)ring; (void)stackSpilled;
 
     // ---- stage the tree tops (TMA bulk copy) and the spheres; initialise the pool -------------------------------------
     const uint32_t mbar = smem_u32(&hdr->mbar);
@@ -612,7 +618,9 @@ RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const uns
                     // (x*1 - 0 is x exactly, so the mesh comparison is unchanged; inf stays inf and never passes)
                     const float cs = sph ? 0.99999619f : 1.0f, cb = sph ? 1e-6f : 0.0f;
                     if ((dstFar * cs - cb) < bestDst && stackCount < WAVE_STACK) { RT_PUSH(farRef); RT_PROF(11, 1); RT_PROF(32 + (stackCount < 31 ? stackCount : 31), 1); }   // (prefetching the far record here was measured: -2 %)
-#if defined(RT_SMEM_STACK) && defined(RT_BRANCHLESS_POP)
+#if defined(RT_BRANCHLESS_POP) && !defined(RT_STACK_TOP_REG)
+                    if constexpr (RING > 0)
+                    {
                     // The pop below ran with 2.4 of 32 lanes (ncu, profiles/r01_f_soup4k_*): few lanes miss both children in the same step.
                     // With the stack top in shared memory every lane can afford to READ the top (a conflict-free 8-byte access) and
                     // select: descend into the near child or take the top.  When the near child is out of reach so is the far one
@@ -620,7 +628,7 @@ RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const uns
                     {
                         const bool goNear = (dstNear * cs - cb) < bestDst;
                         const bool ringHas = stackCount > stackSpilled;
-                        const int w_ = ((stackCount - 1) & (RT_SMEM_STACK - 1)) * 64;
+                        const int w_ = ((stackCount - 1) & (RING - 1)) * 64;
                         NodeRef top; top.start = ring[w_ + (int)lane]; top.count = ring[w_ + 32 + (int)lane];
                         if (!goNear && !ringHas && stackCount > 0) { top = stack[stackSpilled - 1]; --stackSpilled; }      // rare: the ring ran empty above spilled entries
                         const bool pop = !goNear && stackCount > 0;
@@ -630,11 +638,14 @@ RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const uns
                         mode = (goNear || pop) ? (cur.count > 0 ? T_LEAF : T_INNER) : T_NEXT;
                         RT_PF_CUR();
                     }
-#else
+                    }
+                    else
+#endif
+                    {
                     if ((dstNear * cs - cb) < bestDst) { cur = nearRef; leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; RT_PF_CUR(); }
                     else if (stackCount > 0) { RT_POP(cur); leafK = 0; mode = cur.count > 0 ? T_LEAF : T_INNER; RT_PF_CUR(); }
                     else mode = T_NEXT;
-#endif
+                    }
                 }
             }
             else
@@ -716,7 +727,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool_tlas(const __
 template <int M> inline size_t pool_smem_bytes(const DevParams& P)
 {
     const int nS = P.sphereCount < WAVE_MAX_SMEM_SPHERES ? P.sphereCount : WAVE_MAX_SMEM_SPHERES;
-    return sizeof(WaveSmemHeader) + (size_t)P.smemPairs * sizeof(NodePair) + (size_t)nS * sizeof(DevSphere) + (size_t)POOL_WARPS * (POOL_WORDS * M * 4 + M) + RT_STACK_SMEM_BYTES;
+    return sizeof(WaveSmemHeader) + (size_t)P.smemPairs * sizeof(NodePair) + (size_t)nS * sizeof(DevSphere) + (size_t)POOL_WARPS * (POOL_WORDS * M * 4 + M) + (size_t)POOL_THREADS * PoolRing<M>::N * 8;
 }
 
 template <int M> inline cudaError_t pool_configure_one()
@@ -741,7 +752,7 @@ inline int pool_max_smem_pairs(int M, int sphereCount)
 {
     const int nS = sphereCount < WAVE_MAX_SMEM_SPHERES ? sphereCount : WAVE_MAX_SMEM_SPHERES;
     const long long left = 227LL * 1024 - (long long)sizeof(WaveSmemHeader) - (long long)nS * (long long)sizeof(DevSphere)
-                         - (long long)POOL_WARPS * (POOL_WORDS * M * 4 + M) - (long long)RT_STACK_SMEM_BYTES - 1024;
+                         - (long long)POOL_WARPS * (POOL_WORDS * M * 4 + M) - (long long)POOL_THREADS * (M >= 96 ? 0 : RT_RING_DEFAULT) * 8 - 1024;
     return left <= 0 ? 0 : (int)(left / (long long)sizeof(NodePair));
 }
 
@@ -778,6 +789,16 @@ inline cudaError_t pool_launch(const DevParams& P, int M, int numSMs, cudaStream
     const unsigned long long jobs64 = (unsigned long long)tilesX * tileRows * 32ull;
     if (jobs64 >= 0xffff0000ull) return cudaErrorInvalidValue;
     const unsigned int totalJobs = (unsigned int)jobs64;
+    if (M == 0)
+    {
+        // automatic: 64 slots per warp, except when the image is so small for the machine (multi-GPU tiles) that every pixel fits
+        // in the pools at once with 96: then there is no second, mostly empty round of pixels (a pixel's samples are one
+        // sequential RNG chain and cannot be split), measured at N = 8 on 1920x1080
+        M = 64;
+        const unsigned long long warps = (unsigned long long)numSMs * POOL_WARPS;
+        const unsigned long long perWarp = (totalJobs + warps - 1) / warps;
+        if (perWarp > 64 && perWarp <= 96 && pool_smem_bytes<96>(P) <= 227 * 1024) M = 96;
+    }
     if (M == 32) return pool_launch_m<32>(P, numSMs, stream, evA, evB, totalJobs, tilesX, ownedRows);
     if (M == 64) return pool_launch_m<64>(P, numSMs, stream, evA, evB, totalJobs, tilesX, ownedRows);
     if (M == 96) return pool_launch_m<96>(P, numSMs, stream, evA, evB, totalJobs, tilesX, ownedRows);

@@ -11,6 +11,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ray_tracing_b200 import build   # noqa: E402
 
 VARIANTS = {
+    "r1": ("RT_DEFAULTS_R1",),                                   # the round-1 default kernels
+    # round 2, third call: on top of the promoted defaults
+    "pw28_m32": ("RT_POOL_WARPS=28",),                            # run with poolSlots 32 (28 warps x 64 slots + the stack ring exceed 227 KB)
+    "stack4": ("RT_SMEM_STACK=4",),
+    "stack16": ("RT_SMEM_STACK=16",),
+    "vote274": ("RT_VOTE_WI=2", "RT_VOTE_WL=7", "RT_VOTE_WN=4"),
+    "leaf3": ("RT_LEAF_REPEAT=3",),
+    "tri64": ("RT_TRI_PAD64",),
     "vote132": ("RT_VOTE_WL=3", "RT_VOTE_WN=2"),
     "vote142": ("RT_VOTE_WL=4", "RT_VOTE_WN=2"),
     "vote274": ("RT_VOTE_WI=2", "RT_VOTE_WL=7", "RT_VOTE_WN=4"),

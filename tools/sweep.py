@@ -81,6 +81,24 @@ STAGES = {
         ("28 warps + ldg256 + vote 1/3/2 + leaf2 + sphere SAH", "pw28_c", {}),
         ("32 warps + ldg256 + vote 1/3/2 + leaf2 + sphere SAH", "pw32_c", {}),
     ]),
+    7: (["soup4k", "cluster4k", "knot64"], [        # round 2, third call: on top of the promoted defaults (rt_devmath.cuh)
+        ("default (round-2 defaults)", None, {}),
+        ("round-1 kernels (RT_DEFAULTS_R1)", "r1", {}),
+        ("32 pool slots per warp (more L1)", None, {"poolSlots": 32}),
+        ("28 warps x 32 slots", "pw28_m32", {"poolSlots": 32}),
+        ("stack ring 4", "stack4", {}),
+        ("stack ring 16", "stack16", {}),
+        ("vote 2/7/4", "vote274", {}),
+        ("3 leaf primitives per census", "leaf3", {}),
+        ("64-byte triangle records", "tri64", {}),
+        ("l2Persist", None, {"l2Persist": 1}),
+        ("sortRays", None, {"sortRays": 1}),
+        ("tailLanes 8", None, {"tailLanes": 8}),
+        ("tailLanes 24", None, {"tailLanes": 24}),
+    ]),
+    6: (["instances62", "instances126", "instances250"], [       # where the TLAS starts to pay (automatic threshold)
+        ("tlas off", None, {"tlas": 0}), ("tlas on", None, {"tlas": 1}),
+    ]),
     3: (["cornell64", "cornell1"], [
         ("default", None, {}), ("glass out of line", "glassool", {}), ("zero-defocus + glass out of line + skipsqrt", "cornell_all", {}), ("zero-defocus shortcut", "zerodefocus", {}), ("zero-defocus + skipsqrt", "zerodefocus_skipsqrt", {}), ("skipsqrt", "skipsqrt", {}), ("mb5", "mb5", {}), ("gridFit", None, {"gridFit": 1}), ("kernel 2", None, {"kernel": 2}),
     ]),
