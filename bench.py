@@ -430,8 +430,45 @@ def measure(name, w, args, env, steps, warmup, full):
     e2e_s = time.perf_counter() - t0
     e2e_rays_local = ctx.stats()["rays"]
 
+    # ---- 1-spp workloads: end to end with what the reference's display pass consumes (Display.shader: tex / Frame, 8-bit sRGB) -----
+    e2e_disp_s = None
+    if w["spp"] == 1:
+        rgba = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory() for _ in range(2)] if rank == 0 else None
+
+        def step_display(k):
+            touched["i"] += 1
+            if model_count:
+                mat = sc.models[0].material.copy(); mat["absorptionStrength"] = float(touched["i"])
+                mgr.set_model_material(0, mat)
+            else:
+                sp = sc.spheres.copy(); sp["material"]["ior"][0] = 1.0 + 1e-3 * touched["i"]
+                mgr.set_spheres(sp)
+            tiled.render_frame()
+            if rank == 0:
+                with torch.cuda.stream(stream):
+                    ctx.display_async(True, mgr.numAccumulatedFrames - 1, rgba[k & 1].data_ptr(), rgba[k & 1].numel())
+        for k in range(warmup):
+            step_display(k)
+        ctx.readback_wait()
+        barrier()
+        ctx.reset_stats()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            step_display(k)
+        ctx.readback_wait()
+        barrier()
+        e2e_disp_s = time.perf_counter() - t0
+        disp_rays = ctx.stats()["rays"]
+
     # ---- reduce over ranks --------------------------------------------------------------------------------------------------
     if world > 1:
+        if e2e_disp_s is not None:
+            td = torch.tensor([e2e_disp_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+            e2e_disp_s = float(td.item())
+            tr = torch.tensor([disp_rays], dtype=torch.int64, device=dev)
+            dist.all_reduce(tr, op=dist.ReduceOp.SUM)
+            disp_rays = int(tr.item())
         t = torch.tensor([ms_total, e2e_s, kernel_ms, exchange_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, e2e_s, kernel_ms_max, exchange_ms = [float(x) for x in t.tolist()]
@@ -523,6 +560,11 @@ def measure(name, w, args, env, steps, warmup, full):
             "gpu_launches": steps * (1 + (2 if (world > 1 and not tiled.fused) else 0)),
             "roofline": roof,
         }
+        if e2e_disp_s is not None:
+            rec["e2e_display"] = {"value": round(disp_rays / e2e_disp_s / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(1e3 * e2e_disp_s / steps, 4),
+                                  "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": W * H * 4,
+                                  "how": "as e2e, but the host reads what the reference's display pass consumes: rtDisplayAsync = accumulated / Frame, sRGB, 8 bits per channel (Display.shader:42-47); "
+                                         "the reference itself never reads the float4 target back (RayTraceDisplay.cs:9-23)"}
     mgr.OnDestroy()
     del tiled, mgr
     return rec

@@ -242,11 +242,15 @@ __global__ void k_bvh_evaluate(const BNode* __restrict__ nodes, const BuildTriD*
             else node = -1;
         }
     }
-    // segmented reduction over runs of equal node id (a node's positions are contiguous)
+    if (__ballot_sync(0xffffffffu, node >= 0) == 0u) return;       // no position of this warp belongs to a node that is being evaluated (deep levels: most triangles are final)
+    // segmented reduction over runs of equal node id (a node's positions are contiguous).  A round in which no lane has its
+    // off-neighbour in its own run ends the reduction: runs are contiguous, so no longer offset can match either (small nodes
+    // of the deep levels need one or two rounds, not five).
     for (int off = 1; off < 32; off <<= 1)
     {
         const int other = __shfl_down_sync(0xffffffffu, node, off);
         const bool take = (lane + (unsigned)off < 32u) && other == node && node >= 0;
+        if (!__any_sync(0xffffffffu, take)) break;
         for (int k = 0; k < 12; k++)
         {
             const unsigned long long ov = __shfl_down_sync(0xffffffffu, v[k], off);
