@@ -75,7 +75,7 @@ WORKLOADS = {
                      desc="1,000,000 random triangles in 3 models + 10,000 spheres, sky on, 4096x4096, 16 bounces, 16 spp per frame (configs[4] shape, the R = 16 split of SURVEY 8d)"),
 }
 DEFAULT_WORKLOAD = "knot256"
-DEFAULT_EXTRA = ["cornell64", "soup4k", "cornell1", "knot1"]
+DEFAULT_EXTRA = ["cornell64", "soup4k", "cluster4k", "cornell1", "knot1"]
 # steps / warm-up of the extra workloads (the main workload uses --steps / --warmup): bounded so that the default run stays within minutes
 EXTRA_STEPS = {"soup4k": (3, 3), "soup4k16": (2, 3), "cluster4k": (4, 3), "cornell1": (64, 8), "knot1": (64, 8)}
 METRIC = "Mrays/s at 1920x1080, 8 bounces (ray = one CalculateRayCollision call)"

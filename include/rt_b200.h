@@ -197,7 +197,7 @@ int rtBuildBVH(RtContext* ctx, const float* verts, int vertCount, const int* ind
  *   "tlas"        kernels 1 and 2, with "modelSkip" = 1: a tree over the models' padded world boxes (the per-frame model loop of
  *                 RayCommon.hlsl:347 for many-Model scenes).  One walk per ray segment marks the models the ray can reach; they
  *                 are then processed in buffer order against the running result, exactly like the linear loop, so the output
- *                 is unchanged.  Rebuilt on the host whenever ModelInfo is re-sent.  -1 (default) = automatic: used above 64
+ *                 is unchanged.  Rebuilt on the host whenever ModelInfo is re-sent.  -1 (default) = automatic: used above 128
  *                 models; 0 = off; 1 = on for any model count (up to 4096 models; above that the linear test is used)
  *   "extInstantiation"  1 = launch the kernel instantiation that carries the extensions (peer stores, sphere accelerator)
  *                 even when none is active — for testing that instantiation on one GPU

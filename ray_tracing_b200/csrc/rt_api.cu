@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace rtd;
@@ -85,7 +86,7 @@ struct RtContext
 
     // rtBuildBVH: device arena kept between builds, pinned staging chunks for the copies of caller-owned arrays
     DevBuf<unsigned char> buildArena;
-    static constexpr size_t STAGE_BYTES = 8u << 20;
+    static constexpr size_t STAGE_BYTES = 16u << 20;
     unsigned char* stageBuf[2] = {nullptr, nullptr}; cudaEvent_t stageEv[2] = {nullptr, nullptr};
 
     // counters / timing
@@ -1081,6 +1082,30 @@ int rtSetPeers(RtContext* c, int nPeers, const void* handles, size_t bytes)
 
 // Host <-> device copies of large caller-owned (pageable) arrays through two pinned chunks: the CPU copies chunk k + 1 into / out of
 // pinned memory while the DMA engine moves chunk k, instead of the driver's own slower staging of pageable memory.
+// memcpy of one staging chunk on a few host threads: one core moves 5-10 GB/s (less into pages that are touched for the first time),
+// the DMA engine 25-50 GB/s
+static void hostCopy(void* dst, const void* src, size_t n)
+{
+#ifndef RT_SIMT_EMU
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int parts = n < (1u << 20) || hw < 4 ? 1 : 4;
+    if (parts > 1)
+    {
+        std::thread th[3];
+        const size_t each = ((n / parts) + 4095) & ~(size_t)4095;
+        for (int k = 1; k < parts; k++)
+        {
+            const size_t off = each * k, len = off >= n ? 0 : (k == parts - 1 ? n - off : (each < n - off ? each : n - off));
+            th[k - 1] = std::thread([=]() { if (len) memcpy((unsigned char*)dst + off, (const unsigned char*)src + off, len); });
+        }
+        memcpy(dst, src, each < n ? each : n);
+        for (int k = 1; k < parts; k++) th[k - 1].join();
+        return;
+    }
+#endif
+    memcpy(dst, src, n);
+}
+
 static int stagingReady(RtContext* c)
 {
     for (int k = 0; k < 2; k++)
@@ -1098,7 +1123,7 @@ static int stagedH2D(RtContext* c, void* dst, const void* src, size_t bytes)
     {
         const size_t n = bytes - off < RtContext::STAGE_BYTES ? bytes - off : RtContext::STAGE_BYTES;
         CK(cudaEventSynchronize(c->stageEv[k]));                                   // the copy that last used this chunk has read it
-        memcpy(c->stageBuf[k], (const unsigned char*)src + off, n);
+        hostCopy(c->stageBuf[k], (const unsigned char*)src + off, n);
         CK(cudaMemcpyAsync((unsigned char*)dst + off, c->stageBuf[k], n, cudaMemcpyHostToDevice, c->stream));
         CK(cudaEventRecord(c->stageEv[k], c->stream));
         off += n; k ^= 1;
@@ -1122,7 +1147,7 @@ static int stagedD2H(RtContext* c, void* dst, const void* src, size_t bytes)
         if (prevN)                                                                  // while chunk k travels, hand chunk k ^ 1 to the caller
         {
             CK(cudaEventSynchronize(c->stageEv[k ^ 1]));
-            memcpy((unsigned char*)dst + prevOff, c->stageBuf[k ^ 1], prevN);
+            hostCopy((unsigned char*)dst + prevOff, c->stageBuf[k ^ 1], prevN);
         }
         prevOff = off; prevN = n; off += n; k ^= 1;
     }

@@ -374,7 +374,7 @@ struct RepackState
 #ifndef RT_TLAS_SAH_DEPTH
 #define RT_TLAS_SAH_DEPTH 10                                         // levels split by the surface-area heuristic; below: median (depth <= 10 + 11 < RT_TLAS_STACK)
 #endif
-    static constexpr int TLAS_AUTO_THRESHOLD = 64;                   // below this the linear test of resident 32-byte boxes is cheaper (shipped scenes: 10-28 models)
+    static constexpr int TLAS_AUTO_THRESHOLD = 128;                  // measured on the B200 (profiles/r02_c_*): 62 models: linear test 57.3 ms vs TLAS 70.0; 126: 132.8 vs 128.2; 250: 303 vs 229; 500: 599 vs 383
 
     // mode: 0 = off, 1 = on whenever it is possible, -1 = automatic (more than TLAS_AUTO_THRESHOLD models)
     static bool tlasWanted(int mode, int modelCount)

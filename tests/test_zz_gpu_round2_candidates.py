@@ -75,7 +75,7 @@ def _tlas_scene(instances, width=96, height=54, bounces=5, spp=2):
 
 @pytest.mark.parametrize("kernel", [1, 2])
 def test_tlas_many_models_bitwise(kernel):
-    """152 Model components (instancing of one mesh + room + light): above 64 models the TLAS is used automatically; forced on, forced
+    """152 Model components (instancing of one mesh + room + light): above 128 models the TLAS is used automatically; forced on, forced
     off and automatic must all give the oracle's bits (the oracle walks every model like the reference)."""
     sc = _tlas_scene(150)
     fo, ao = render(ORACLE_LIB, sc, frames=2)
