@@ -96,6 +96,12 @@ STAGES = {
         ("tailLanes 8", None, {"tailLanes": 8}),
         ("tailLanes 24", None, {"tailLanes": 24}),
     ]),
+    8: (["soup4k", "cluster4k", "knot64"], [        # tree tops staged in shared memory by TMA bulk copy, now that the pools + the stack ring leave L1 ~20 KB
+        ("default", None, {}),
+        ("smemNodes 128 (TMA-staged tree tops)", None, {"smemNodes": 128}),
+        ("smemNodes 256 (TMA-staged tree tops)", None, {"smemNodes": 256}),
+        ("smemNodes 300 (TMA-staged tree tops)", None, {"smemNodes": 300}),
+    ]),
     6: (["instances62", "instances126", "instances250"], [       # where the TLAS starts to pay (automatic threshold)
         ("tlas off", None, {"tlas": 0}), ("tlas on", None, {"tlas": 1}),
     ]),
