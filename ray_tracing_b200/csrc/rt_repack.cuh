@@ -533,6 +533,9 @@ struct RepackState
     int sphBvh = 0, sphRootStart = 0, sphRootCount = 0;
     float sphBoundLo[3] = {0, 0, 0}, sphBoundHi[3] = {0, 0, 0};     // region of ray origins the current padding is valid for
     static constexpr size_t SPHERE_BVH_THRESHOLD = 64;               // below this a linear scan is cheaper
+#ifndef RT_SPHERE_LEAF
+#define RT_SPHERE_LEAF 4                                              // spheres per leaf of the accelerator
+#endif
 #ifndef RT_SPHERE_SAH_DEPTH
 #define RT_SPHERE_SAH_DEPTH 0                                        // round-2 candidate: top levels of the sphere tree by the surface-area sweep (see BuildMedianSplitPairs); 0 = the measured median tree
 #endif
@@ -596,7 +599,7 @@ struct RepackState
         // median split on the widest centroid axis, leaves of <= 4 spheres; pairs emitted parent-before-children
         std::vector<int> order;
         std::vector<NodePair> pairsOut;
-        BuildMedianSplitPairs(lo, hi, cen, n, 4, order, pairsOut, sphRootStart, sphRootCount, RT_SPHERE_SAH_DEPTH);
+        BuildMedianSplitPairs(lo, hi, cen, n, RT_SPHERE_LEAF, order, pairsOut, sphRootStart, sphRootCount, RT_SPHERE_SAH_DEPTH);
         std::vector<DevSphere> leaves(n);
         for (size_t k = 0; k < n; k++) leaves[k] = out[order[k]];
         if ((e = sphPairs.ensure(std::max<size_t>(pairsOut.size(), 1))) != cudaSuccess) return e;

@@ -11,7 +11,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ray_tracing_b200 import build   # noqa: E402
 
 VARIANTS = {
-    "r1": ("RT_DEFAULTS_R1",),                                   # the round-1 default kernels
+    "r1": ("RT_DEFAULTS_R1",),
+    "sphleaf1": ("RT_SPHERE_LEAF=1", "RT_SPHERE_SAH_DEPTH=20"),
+    "sphleaf2": ("RT_SPHERE_LEAF=2", "RT_SPHERE_SAH_DEPTH=18"),
+    "sphleaf8": ("RT_SPHERE_LEAF=8",),
+    "sphsah20": ("RT_SPHERE_SAH_DEPTH=20",),                                   # the round-1 default kernels
     # round 2, third call: on top of the promoted defaults
     "pw28_m32": ("RT_POOL_WARPS=28",),                            # run with poolSlots 32 (28 warps x 64 slots + the stack ring exceed 227 KB)
     "stack4": ("RT_SMEM_STACK=4",),

@@ -102,6 +102,13 @@ STAGES = {
         ("smemNodes 256 (TMA-staged tree tops)", None, {"smemNodes": 256}),
         ("smemNodes 300 (TMA-staged tree tops)", None, {"smemNodes": 300}),
     ]),
+    9: (["soup4k"], [        # sphere accelerator shape (config 5: 10,000 spheres)
+        ("default (leaves of 4, SAH top 14)", None, {}),
+        ("leaves of 1, SAH 20 levels", "sphleaf1", {}),
+        ("leaves of 2, SAH 18 levels", "sphleaf2", {}),
+        ("leaves of 8", "sphleaf8", {}),
+        ("leaves of 4, SAH 20 levels", "sphsah20", {}),
+    ]),
     6: (["instances62", "instances126", "instances250"], [       # where the TLAS starts to pay (automatic threshold)
         ("tlas off", None, {"tlas": 0}), ("tlas on", None, {"tlas": 1}),
     ]),
