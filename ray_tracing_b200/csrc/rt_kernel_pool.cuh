@@ -617,6 +617,20 @@ RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const uns
                     // meshes: the reference's push-time test dst < best (HL:280-281).  Sphere boxes: conservative slack, ties kept
                     // (x*1 - 0 is x exactly, so the mesh comparison is unchanged; inf stays inf and never passes)
                     const float cs = sph ? 0.99999619f : 1.0f, cb = sph ? 1e-6f : 0.0f;
+#if defined(RT_PUSH_PREDICATED) && !defined(RT_STACK_TOP_REG)
+                    if constexpr (RING > 0)
+                    {
+                        // the push ran with 9.2 of 32 lanes (ncu, profiles/r02_c_soup4k_*): only the spill of a full ring stays a branch,
+                        // the two ring stores are predicated
+                        const bool push = (dstFar * cs - cb) < bestDst && stackCount < WAVE_STACK;
+                        if (push && stackCount - stackSpilled == RING)
+                        { NodeRef sp_; const int r_ = (stackSpilled & (RING - 1)) * 64; sp_.start = ring[r_ + (int)lane]; sp_.count = ring[r_ + 32 + (int)lane]; stack[stackSpilled++] = sp_; }
+                        const int w_ = (stackCount & (RING - 1)) * 64;
+                        if (push) { ring[w_ + (int)lane] = farRef.start; ring[w_ + 32 + (int)lane] = farRef.count; }
+                        stackCount += push ? 1 : 0;
+                    }
+                    else
+#endif
                     if ((dstFar * cs - cb) < bestDst && stackCount < WAVE_STACK) { RT_PUSH(farRef); RT_PROF(11, 1); RT_PROF(32 + (stackCount < 31 ? stackCount : 31), 1); }   // (prefetching the far record here was measured: -2 %)
 #if defined(RT_BRANCHLESS_POP) && !defined(RT_STACK_TOP_REG)
                     if constexpr (RING > 0)

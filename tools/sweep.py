@@ -102,6 +102,7 @@ STAGES = {
         ("smemNodes 256 (TMA-staged tree tops)", None, {"smemNodes": 256}),
         ("smemNodes 300 (TMA-staged tree tops)", None, {"smemNodes": 300}),
     ]),
+    10: (["soup4k", "cluster4k", "knot64"], [ ("default", None, {}), ("predicated push", "pushpred", {}) ]),
     9: (["soup4k"], [        # sphere accelerator shape (config 5: 10,000 spheres)
         ("default (leaves of 4, SAH top 14)", None, {}),
         ("leaves of 1, SAH 20 levels", "sphleaf1", {}),
