@@ -259,6 +259,11 @@ RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const uns
 
     Counters cnt; cnt.rays = cnt.box = cnt.tri = cnt.sph = cnt.sbox = 0;
     bool exhausted = false;                     // warp-uniform: the global pixel queue is empty
+    // Fair share: when the image is small for the machine (multi-GPU tiles, small images) a warp fills at most its share of the
+    // pixels, so that every SM gets work and — a pixel's samples being one sequential chain — all pixels start in the first round
+    // instead of the first CTAs swallowing the queue.  With more pixels than slots (the usual case) the cap is the pool size.
+    const unsigned int fairShare = (totalJobs + gridDim.x * POOL_WARPS - 1u) / (gridDim.x * POOL_WARPS);
+    const int slotCap = fairShare < (unsigned int)M ? (int)(fairShare ? fairShare : 1u) : M;
 
     // per-lane ray state of the trace phase.  It lives across phases: a lane whose ray is still in flight when the phase
     // ends keeps it (slot state PS_FLIGHT) and continues in the next trace phase, so long rays never hold the warp back.
@@ -375,7 +380,7 @@ RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const uns
             for (int c = 0; c < M / 32; c++)
             {
                 const int e = c * 32 + (int)lane;
-                const bool need = info_state(pool.u(F_INFO, e)) == PS_EMPTY;
+                const bool need = info_state(pool.u(F_INFO, e)) == PS_EMPTY && e < slotCap;
                 const unsigned needMask = __ballot_sync(0xffffffffu, need);
                 if (needMask == 0u || exhausted) continue;
                 unsigned base = 0;
@@ -402,7 +407,7 @@ RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const uns
                     }
                 }
                 if (base + (unsigned)__popc(needMask) >= totalJobs) exhausted = true;        // warp-uniform
-                else if (__ballot_sync(0xffffffffu, info_state(pool.u(F_INFO, e)) == PS_EMPTY)) anyEmpty = true;   // padding jobs: try again
+                else if (__ballot_sync(0xffffffffu, info_state(pool.u(F_INFO, e)) == PS_EMPTY && e < slotCap)) anyEmpty = true;   // padding jobs: try again
             }
             if (!anyEmpty) break;
         }
@@ -777,7 +782,7 @@ template <int M> inline cudaError_t pool_launch_m(const DevParams& P, int numSMs
     if (smemBytes > 227 * 1024) return cudaErrorInvalidConfiguration;
     unsigned grid = (unsigned)numSMs;                                   // one persistent CTA per SM
     const unsigned slots = POOL_WARPS * M;
-    const unsigned ctasNeeded = (totalJobs + slots - 1) / slots;
+    const unsigned ctasNeeded = (totalJobs + POOL_WARPS - 1) / POOL_WARPS;   // at least one pixel per warp: small images spread over the SMs (fair share, pool_body)
     if (grid > ctasNeeded) grid = ctasNeeded ? ctasNeeded : 1;
     grid = fit_persistent_grid(P.gridFit, grid, slots, totalJobs);
     cudaError_t e;
