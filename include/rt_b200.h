@@ -189,8 +189,7 @@ int rtBuildBVH(RtContext* ctx, const float* verts, int vertCount, const int* ind
  *                 all-gather of the frame's tiles; 0 = the caller exchanges (rtExchangeTiles or its own collective)
  *   "smemNodes"   number of top-of-tree node pairs staged in shared memory by TMA bulk copy (0 = off; -1 = automatic, which
  *                 is currently 0: measured, the staging never beat leaving that shared memory to L1)
- *   "poolSlots"   paths per warp pool of kernel 2: 32, 64 or 96; 0 (default) = automatic: 64, or 96 when that makes every pixel of a
- *                 small tile (multi-GPU) resident at once
+ *   "poolSlots"   paths per warp pool of kernel 2: 32, 64 or 96; 0 (default) = automatic, which is 64 (measured)
  *   "modelSkip"   1 (default) = kernels 1 and 2 skip a model when the ray misses its padded world-space box or enters it beyond
  *                 the closest hit so far (exact: such a model cannot change the result); 0 = walk every model like the
  *                 reference.  Always 0 when "countStats" = 1, so that the test counts equal the reference's

@@ -47,6 +47,7 @@ struct RtContext
     int device = 0;
     cudaStream_t ownStream = nullptr, stream = nullptr;
     int numSMs = 0;
+    unsigned long long dispatchPixels = 0;     // pixels of the RayTrace dispatch being prepared (this rank's tile): enters the automatic kernel choice
     std::string err;
 
     // uniforms (host copy)
@@ -490,10 +491,19 @@ int rtSetOption(RtContext* c, const char* name, int value)
 
 // Automatic choice (measured, profiles/): with meshes the pooled wavefront kernel wins (BVH traversal needs the ray queue);
 // for sphere-only scenes every ray costs the same and one path per lane avoids the pool's shared-memory round trips.
+// Small tiles (multi-GPU, small images): a pixel's samples are one sequential chain, so with about one pixel per pool slot there is
+// nothing for the pools to balance and the chain's own latency decides; one path per lane has the shorter chain (no phase
+// boundaries).  Measured on rank 0's tile of 8 / 4 / 2 of the default workload (profiles/r02_g_tile_ab_*, r02_h_*): see RT_SMALL_TILE_PIXELS_PER_SLOT.
+#ifndef RT_SMALL_TILE_PIXELS_PER_SLOT
+#define RT_SMALL_TILE_PIXELS_PER_SLOT 1.5
+#endif
 static int effectiveKernel(const RtContext* c)
 {
     if (c->optKernel >= 0) return c->optKernel;
-    return c->P.modelCount > 0 ? 2 : 1;
+    if (c->P.modelCount <= 0) return 1;
+    const double slots = (double)c->numSMs * POOL_WARPS * 64.0;
+    if (c->dispatchPixels > 0 && (double)c->dispatchPixels < RT_SMALL_TILE_PIXELS_PER_SLOT * slots) return 1;
+    return 2;
 }
 
 // "l2Persist": ask the L2 to keep the node-pair records (persisting access-policy window on the dispatch stream; every ray walks
@@ -616,6 +626,12 @@ static int dispatchLocal(RtContext* c, int kernelIndex, int gx, int gy, int gz)
     if (c->P.MaxBounceCount > 200 || W > 65535u || H > 65535u) return fail(c, RT_E_STATE, "rtDispatch: MaxBounceCount > 200 or a resolution above 65535 is not supported");
     if (c->P.MaxBounceCount < 0) return fail(c, RT_E_STATE, "rtDispatch: MaxBounceCount is negative (the reference clamps it to [0, 32], RCM:15)");
 
+    {
+        unsigned long long rows = 0;
+        for (unsigned int y0 = 0, b = 0; y0 < limY; y0 += (unsigned int)c->bandRows, b++)
+            if ((int)(b % (unsigned int)c->tileWorld) == c->tileRank) rows += (limY - y0) < (unsigned int)c->bandRows ? (limY - y0) : (unsigned int)c->bandRows;
+        c->dispatchPixels = rows * limX;
+    }
     int rc = prepareScene(c);
     if (rc != RT_OK) return rc;
     applyL2Persistence(c);

@@ -39,7 +39,13 @@
 #define RT_LEAF_REPEAT 2           // two leaf primitives per census
 #endif
 #ifndef RT_SPHERE_SAH_DEPTH
-#define RT_SPHERE_SAH_DEPTH 14     // sphere accelerator: top 14 levels by the surface-area sweep
+#define RT_SPHERE_SAH_DEPTH 20     // sphere accelerator: top 20 levels by the surface-area sweep ...
+#endif
+#ifndef RT_SPHERE_LEAF
+#define RT_SPHERE_LEAF 1           // ... and one sphere per leaf (profiles/r02_g_*: leaves of 4 / 2 / 1: 364 / 342 / 332 ms on config 5; leaves of 8: 406)
+#endif
+#ifndef RT_PUSH_PREDICATED
+#define RT_PUSH_PREDICATED         // the far child's push as two predicated ring stores; only the spill of a full ring branches (+1 ... +2 %)
 #endif
 #endif
 

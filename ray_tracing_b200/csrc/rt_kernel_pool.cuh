@@ -808,16 +808,8 @@ inline cudaError_t pool_launch(const DevParams& P, int M, int numSMs, cudaStream
     const unsigned long long jobs64 = (unsigned long long)tilesX * tileRows * 32ull;
     if (jobs64 >= 0xffff0000ull) return cudaErrorInvalidValue;
     const unsigned int totalJobs = (unsigned int)jobs64;
-    if (M == 0)
-    {
-        // automatic: 64 slots per warp, except when the image is so small for the machine (multi-GPU tiles) that every pixel fits
-        // in the pools at once with 96: then there is no second, mostly empty round of pixels (a pixel's samples are one
-        // sequential RNG chain and cannot be split), measured at N = 8 on 1920x1080
-        M = 64;
-        const unsigned long long warps = (unsigned long long)numSMs * POOL_WARPS;
-        const unsigned long long perWarp = (totalJobs + warps - 1) / warps;
-        if (perWarp > 64 && perWarp <= 96 && pool_smem_bytes<96>(P) <= 227 * 1024) M = 96;
-    }
+    if (M == 0) M = 64;      // automatic.  (96 slots so that every pixel of a small tile is resident at once was measured and lost: 121 vs 101 ms on rank 0's
+                             // tile of 8 of the default workload, profiles/r02_g_tile_ab_*: the 96-slot pools have no room for the stack ring.)
     if (M == 32) return pool_launch_m<32>(P, numSMs, stream, evA, evB, totalJobs, tilesX, ownedRows);
     if (M == 64) return pool_launch_m<64>(P, numSMs, stream, evA, evB, totalJobs, tilesX, ownedRows);
     if (M == 96) return pool_launch_m<96>(P, numSMs, stream, evA, evB, totalJobs, tilesX, ownedRows);
