@@ -183,7 +183,8 @@ int rtBuildBVH(RtContext* ctx, const float* verts, int vertCount, const int* ind
 /* Tuning / instrumentation switches.  name ∈
  *   "kernel"      0 = reference-shaped per-pixel megakernel, 1 = persistent threads (one path per lane),
  *                 2 = persistent-thread wavefront with per-warp path pools, sorting and ray compaction,
- *                 -1 = automatic (default): 2 when the scene has meshes, 1 for sphere-only scenes
+ *                 -1 = automatic (default): 2 when the scene has meshes, 1 for sphere-only scenes and for tiles so small that
+ *                 a pool slot gets about one pixel (below 1.5 pixels per slot; 2.5 with NumRaysPerPixel = 1: multi-GPU tiles)
  *   "countStats"  1 = also count box / triangle tests (HL:254,271) — slower, off by default
  *   "exchange"    1 (default) = rtDispatch(RAYTRACE) on a context with a communicator (rtCommInit / rtCreateMulti) ends with the
  *                 all-gather of the frame's tiles; 0 = the caller exchanges (rtExchangeTiles or its own collective)

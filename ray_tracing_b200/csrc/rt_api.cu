@@ -491,18 +491,25 @@ int rtSetOption(RtContext* c, const char* name, int value)
 
 // Automatic choice (measured, profiles/): with meshes the pooled wavefront kernel wins (BVH traversal needs the ray queue);
 // for sphere-only scenes every ray costs the same and one path per lane avoids the pool's shared-memory round trips.
-// Small tiles (multi-GPU, small images): a pixel's samples are one sequential chain, so with about one pixel per pool slot there is
-// nothing for the pools to balance and the chain's own latency decides; one path per lane has the shorter chain (no phase
-// boundaries).  Measured on rank 0's tile of 8 / 4 / 2 of the default workload (profiles/r02_g_tile_ab_*, r02_h_*): see RT_SMALL_TILE_PIXELS_PER_SLOT.
+// Small tiles (multi-GPU, small images).  A pixel's samples are one sequential chain, so with about one pixel per pool slot the pools
+// have nothing to balance: the slots that get a second pixel run it on a mostly empty machine for another whole pixel-time.  One path
+// per lane then finishes earlier although its throughput is lower.  Measured on one GPU over rank 0's tile of 2 / 4 / 8 of the default
+// workload, kernel ms pooled vs one path per lane (profiles/r02_h_tile_ab_*): 256 spp 217.9 / 303.8, 127.5 / 156.6, 94.6 / 87.0 at
+// 4.6 / 2.3 / 1.1 pixels per pool slot; 1 spp 1.30 / 1.43, 0.88 / 0.81, 0.68 / 0.55.  Hence: below 1.5 pixels per slot (2.5 in the
+// 1-spp mode) the automatic choice is kernel 1.
 #ifndef RT_SMALL_TILE_PIXELS_PER_SLOT
 #define RT_SMALL_TILE_PIXELS_PER_SLOT 1.5
+#endif
+#ifndef RT_SMALL_TILE_PIXELS_PER_SLOT_1SPP
+#define RT_SMALL_TILE_PIXELS_PER_SLOT_1SPP 2.5
 #endif
 static int effectiveKernel(const RtContext* c)
 {
     if (c->optKernel >= 0) return c->optKernel;
     if (c->P.modelCount <= 0) return 1;
     const double slots = (double)c->numSMs * POOL_WARPS * 64.0;
-    if (c->dispatchPixels > 0 && (double)c->dispatchPixels < RT_SMALL_TILE_PIXELS_PER_SLOT * slots) return 1;
+    const double threshold = c->P.NumRaysPerPixel <= 1 ? RT_SMALL_TILE_PIXELS_PER_SLOT_1SPP : RT_SMALL_TILE_PIXELS_PER_SLOT;
+    if (c->dispatchPixels > 0 && (double)c->dispatchPixels < threshold * slots) return 1;
     return 2;
 }
 
