@@ -13,6 +13,8 @@ from ray_tracing_b200 import build   # noqa: E402
 VARIANTS = {
     "r1": ("RT_DEFAULTS_R1",),
     "pushpred": ("RT_PUSH_PREDICATED",),
+    "mb7": ("RT_WAVE_MINBLOCKS=7",),
+    "mb8": ("RT_WAVE_MINBLOCKS=8",),
     "sphleaf1": ("RT_SPHERE_LEAF=1", "RT_SPHERE_SAH_DEPTH=20"),
     "sphleaf2": ("RT_SPHERE_LEAF=2", "RT_SPHERE_SAH_DEPTH=18"),
     "sphleaf8": ("RT_SPHERE_LEAF=8",),

@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--world", type=int, nargs="*", default=[8])
     ap.add_argument("--workloads", nargs="*", default=["knot256", "cornell64"])
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--lib", default=None, help="alternative build of librt_b200.so")
+    ap.add_argument("--only", nargs="*", default=None, help="substrings of the configuration labels to run")
     args = ap.parse_args()
     import torch
     import ray_tracing_b200 as rt
@@ -34,8 +36,8 @@ def main():
         sc = bench.make_scene(w)
         full = None
         for world in [1] + list(args.world):
-            for label, opts in CONFIGS if world > 1 else CONFIGS[:1]:
-                mgr = rt.RayComputeManager(b.LIB_CUDA)
+            for label, opts in (CONFIGS if world > 1 else CONFIGS[:1]) if not args.only else [c for c in CONFIGS if any(o in c[0] for o in args.only)]:
+                mgr = rt.RayComputeManager(args.lib or b.LIB_CUDA)
                 scenes.apply(sc, mgr)
                 ctx = mgr.context
                 for k, v in opts.items():
@@ -53,7 +55,7 @@ def main():
                 mgr.OnDestroy()
                 if world == 1:
                     full = ms
-                row = {"workload": wl, "tile": f"rank 0 of {world}", "config": label, "kernel_ms": round(ms, 4), "ideal_ms": round(full / world, 4), "efficiency": round(full / world / ms, 3)}
+                row = {"lib": os.path.basename(args.lib or b.LIB_CUDA), "workload": wl, "tile": f"rank 0 of {world}", "config": label, "kernel_ms": round(ms, 4), "ideal_ms": round(full / world, 4), "efficiency": round(full / world / ms, 3)}
                 print(json.dumps(row), flush=True)
                 out.write(json.dumps(row) + "\n"); out.flush()
 
