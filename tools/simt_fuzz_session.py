@@ -38,8 +38,11 @@ def make_script(rng, sc, steps):
     nm = len(sc.models)
     for _ in range(steps):
         for _ in range(int(rng.randint(0, 4))):
-            a = int(rng.randint(0, 10))
-            if a == 0:
+            a = int(rng.randint(0, 11))
+            if a == 10:
+                # round 2: the ABI below the manager — modelCount set on its own (no ModelInfo re-send), then a dispatch
+                script.append(("rawframe", (int(rng.randint(0, nm + 1)), int(rng.randint(1, 1000)))))
+            elif a == 0:
                 d = float(rng.choice([0.0, 3.0, 5.67, 60.0, 4000.0, 3e5]))
                 script.append(("camera", (float(np.clip(np.degrees(2 * np.arctan(3.0 / max(d, 3.0))), 1e-3, 90.0)),
                                           scenes.trs(position=(float(rng.uniform(-1, 1)), 1.9, -d), euler_deg=(float(rng.uniform(-5, 5)), float(rng.uniform(-5, 5)), 0.0))[0])))
@@ -59,7 +62,7 @@ def make_script(rng, sc, steps):
                 script.append(("setting", (str(rng.choice(["maxBounceCount", "numRaysPerPixel", "useSky", "accumulate", "divergeStrength", "defocusStrength"])), rng.rand())))
             else:
                 name = str(rng.choice(["kernel", "tlas", "modelSkip", "poolSlots", "pairOrder", "smemNodes", "tailLanes", "sortRays", "gridFit", "extInstantiation", "countStats"]))
-                value = {"kernel": [0, 1, 2, -1], "tlas": [-1, 0, 1], "modelSkip": [0, 1], "poolSlots": [32, 64, 96], "pairOrder": [0, 1, 3], "smemNodes": [0, 9, 200, -1],
+                value = {"kernel": [0, 1, 2, -1], "tlas": [-1, 0, 1], "modelSkip": [0, 1], "poolSlots": [0, 32, 64, 96], "pairOrder": [0, 1, 3], "smemNodes": [0, 9, 200, -1],
                          "tailLanes": [0, 5, 16, 31], "sortRays": [0, 1], "gridFit": [0, 1], "extInstantiation": [0, 1], "countStats": [0, 1]}[name]
                 script.append(("option", (name, int(rng.choice(value)))))
         script.append(("frame", ()))
@@ -108,12 +111,21 @@ def main():
             scenes.apply(sc, m)
             m.OnEnable()
             mgrs.append(m)
-        frame_no, failed = 0, None
+        frame_no, failed, resized = 0, None, False
         try:
             for action, a in script:
+                if action == "screen":
+                    resized = True                      # the textures follow at the next RenderFrame (InitFrame): no raw dispatch in between
+                if action == "rawframe" and resized:
+                    continue
                 if action == "frame":
+                    resized = False
+                if action in ("frame", "rawframe"):
                     for m in mgrs:
-                        m.RenderFrame()
+                        if action == "frame":
+                            m.RenderFrame()
+                        else:
+                            m.context.set_int("modelCount", a[0]); m.context.set_int("Frame", a[1]); m.context.dispatch_full(0)
                     frame_no += 1
                     for what in ("accumulatedResult", "raytraceFrameTex"):
                         x, y = getattr(mgrs[1], what), getattr(mgrs[0], what)
