@@ -206,14 +206,14 @@ int rtBuildBVH(RtContext* ctx, const float* verts, int vertCount, const int* ind
  *   "tailLanes"   kernel 2 leaves its trace phase when the ray queue is empty and at most this many lanes still trace
  *   "gridFit"     kernels 1 and 2: 1 = shrink the persistent grid so that every lane (pool slot) gets a whole number of pixels
  *                 — fewer, fully occupied rounds instead of a last round of mostly empty warps when the image is small for the
- *                 machine (multi-GPU tiles); 0 = one CTA set filling the machine (default; not yet measured)
+ *                 machine (multi-GPU tiles); 0 = one CTA set filling the machine (default; measured in round 2: the fit is 2-20 % slower, kept as an option)
  *   "l2Persist"   1 = persisting L2 access-policy window over the node-pair records on the dispatch stream (0 = default; not yet
  *                 measured)
  *   "treeletPrefetch"  1 = two-level treelet layout with flagged treelet roots and an L1 prefetch of both possible next records
- *                 (only in a library built with -DRT_TREELET_PREFETCH; the default build returns RT_E_INVALID; not yet measured)
+ *                 (only in a library built with -DRT_TREELET_PREFETCH; the default build returns RT_E_INVALID; measured in round 2: -1 ... -30 %)
  *   "pairOrder"   order of the repacked node-pair records inside a mesh: 0 = breadth-first (default), d = 1..32 = treelets of d
  *                 levels laid out depth-first (1 = plain pre-order: child A's record follows its parent's).  Layout only: the
- *                 traversal visits the same nodes in the same order; not yet measured on the GPU
+ *                 traversal visits the same nodes in the same order; measured in round 2: +-0.4 %
  * Unknown names return RT_E_UNKNOWN_NAME. */
 int rtSetOption(RtContext* ctx, const char* name, int value);
 

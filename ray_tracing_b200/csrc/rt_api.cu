@@ -515,7 +515,7 @@ static int effectiveKernel(const RtContext* c)
 
 // "l2Persist": ask the L2 to keep the node-pair records (persisting access-policy window on the dispatch stream; every ray walks
 // them, the triangle stream is marked streaming by omission).  The scenes already hit L2 at 76-86 % (profiles/), so this is a
-// candidate for the misses' latency, not for bandwidth; off by default, not yet measured.
+// candidate for the misses' latency, not for bandwidth; off by default (measured in round 2: +-1 %).
 static void applyL2Persistence(RtContext* c)
 {
 #ifndef RT_SIMT_EMU

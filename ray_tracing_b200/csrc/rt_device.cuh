@@ -10,7 +10,7 @@
 
 namespace rtd {
 
-// ---- cache policy of the triangle stream (round-2 candidate, compiled out by default) --------------------------------------
+// ---- cache policy of the triangle stream (compiled out by default; measured in round 2: 0 ... -2 %) ------------------------
 // Leaf triangles (48-byte TriGeom records, the normals of a winner) are touched once per test and rarely again soon, while the
 // node-pair records of the upper tree are re-read by every ray: L1 capacity was the lever in round 1 (no shared-memory tree
 // tops, 64-slot pools).  RT_TRI_LOAD_POLICY = 1 loads triangle data with L1::no_allocate, 2 with L1::evict_first, so that they do
@@ -33,7 +33,7 @@ RT_DI float4 ldg_tri(const float4* p)
 #endif
 }
 
-// ---- 256-bit record loads (round-2 candidate RT_LDG256, compiled out by default) -----------------------------------------------
+// ---- 256-bit record loads (RT_LDG256: on by default since round 2, rt_devmath.cuh) -----------------------------------------------
 // The L1 serves a load instruction one 128-byte line at a time (B300_MICROARCH.md: ~2 cycles per line touched within one LDG), and
 // in the node loop every lane reads its own 64-byte record: the four LDG.128 of a record cost 4 x (lanes) passes of the L1 data
 // pipe, which the round-1 profiles show 57-73 % busy on the mesh scenes.  sm_100 has 256-bit global loads (LDG.E.256): the same
@@ -69,7 +69,7 @@ struct __align__(64) NodePair
 // Triangle geometry as the intersection test consumes it: vertex A, the two edges and the face vector
 // cross(AB, AC) — each the single IEEE operation sequence of HL:190-192, evaluated once at upload
 // instead of once per test (same bits).  48 bytes = 3 × float4.
-// Round-2 candidate RT_TRI_PAD64 (compiled out by default): the record padded to 64 bytes, 64-byte aligned — one LDG.E.256 + one
+// RT_TRI_PAD64 (compiled out by default; measured in round 2: -0.4 ... -2 %): the record padded to 64 bytes, 64-byte aligned — one LDG.E.256 + one
 // LDG.128 instead of three LDG.128 (the L1 works through a load one line at a time, see ldg_record64), and a record never straddles
 // a 128-byte line (a 48-byte one does in three of eight positions); costs a third more triangle bytes in L2 / HBM.
 #ifdef RT_TRI_PAD64
@@ -373,7 +373,7 @@ RT_DI bool RaySphereCore(f3 rayPos, f3 rayDir, f3 centre, float r2, float& dst, 
     if (discriminant >= 0.0f)
     {
 #ifdef RT_SPHERE_SKIP_SQRT
-        // Experimental (off by default, not yet measured): a sphere the ray is moving away from (b > 0) is hit only if
+        // Experimental (off by default; measured in round 2: -3.5 ... -4.5 % on the Cornell box): a sphere the ray is moving away from (b > 0) is hit only if
         // sqrt(disc) >= b.  With bb = fl(b*b) in b^2 (1 +- 2^-24):  disc < bb (1 - 2^-21)  =>  disc < b^2 (1 - 2^-22)  =>
         // sqrt_rn(disc) < b  =>  -b + s < 0  =>  the reference's dstFar < 0  =>  no hit.  Saves the sqrt; never changes an answer.
         {
@@ -592,7 +592,7 @@ struct PathState
 };
 
 #ifdef RT_GLASS_OUT_OF_LINE
-// Round-2 candidate (compiled out by default): the glass branch of ShadeSegment (HL:499-518) as one out-of-line function.  Three of 32
+// Compiled out by default (measured in round 2: -18 % on the Cornell box, -4 % on the mesh scenes): the glass branch of ShadeSegment (HL:499-518) as one out-of-line function.  Three of 32
 // lanes take it on config 2; inlined it is ~150 instructions of the per-iteration footprint, and instruction fetch is a fifth of the
 // stall cycles of that issue-bound kernel (profiles/r01_f_cornell_*).  Same operations in the same order.
 RT_DNI void ShadeGlass(const RtMaterial* material, float hitDst, bool isBackface, f3 normal, f3 hitPos, f3 diffuseDir, float v7, PathState& ray)
@@ -739,7 +739,7 @@ RT_DI void GenerateCameraRay(const DevParams& P, const PixelSetup& s, uint32_t& 
 {
     const float numPixelsX = __uint2float_rn(P.W);
 #ifdef RT_SKIP_ZERO_DEFOCUS
-    // Round-2 candidate (compiled out by default): with DefocusStrength == 0 — every shipped scene but one — the defocus jitter is
+    // Compiled out by default (measured in round 2: -1 ... -2.4 %): with DefocusStrength == 0 — every shipped scene but one — the defocus jitter is
     // (finite * +-0) / W = +-0 and origin + camRight * +-0 + camUp * +-0 is the origin bit for bit as long as no origin component is
     // itself a zero (whose sign could flip) and the camera axes are finite; the host checks that once per dispatch.  The two random
     // numbers are still drawn (the stream must advance), only the sine, cosine, square root and two IEEE divisions are not evaluated.

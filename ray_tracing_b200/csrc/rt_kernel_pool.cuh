@@ -38,7 +38,8 @@ namespace rtd {
 #ifndef RT_POOL_WARPS
 #define RT_POOL_WARPS 24      // measured (profiles/r01_sweeps.log): 16 -> 24 warps per SM: knot 33.8 -> 31.7 ms, 871k-triangle scene 109.8 -> 93.4 ms
 #endif
-// Round-2 candidates, compiled out by default (each is bit-exact on the SIMT interpreter build; none measured on the GPU yet):
+// Compile-time switches (each is bit-exact on the SIMT interpreter build; all measured in round 2 — the winners are on by default, rt_devmath.cuh,
+// the rest stays available for A/B runs; DESIGN.md 5 has the table):
 //   RT_STACK_TOP_REG   the top entry of the traversal stack lives in two registers: a pop hands it over at once and issues
 //                      the local-memory load of the entry below, which is only needed at the next pop / push — the pop's
 //                      load latency (17 % of the stall samples on the 1M-triangle scene, profiles/r01_f_soup4k_*) overlaps
@@ -87,7 +88,7 @@ template <int M> struct PoolRing { static constexpr int N = 0; };
 //                      population sooner; counted on the SIMT interpreter build (step counts are exact there, the instruction cost per
 //                      step kind is an estimate from the SASS line profile: census 20, inner 150, leaf 55, next 90), weights 1 / 3 / 2
 //                      cut the inner steps of the 200k-triangle soup by 22 % (they run with 20 lanes instead of 15.6) and the estimated
-//                      instruction count by 17 %; 5-7 % on the knot scenes and on 24 instanced models.  Default 1 / 1 / 1 until measured.
+//                      instruction count by 17 %; 5-7 % on the knot scenes and on 24 instanced models.  Measured: +4.7 % alone on the 1M-triangle scene; default 1 / 3 / 2 (rt_devmath.cuh).
 #ifndef RT_VOTE_WI
 #define RT_VOTE_WI 1
 #endif

@@ -537,7 +537,7 @@ struct RepackState
 #define RT_SPHERE_LEAF 4                                              // spheres per leaf of the accelerator
 #endif
 #ifndef RT_SPHERE_SAH_DEPTH
-#define RT_SPHERE_SAH_DEPTH 0                                        // round-2 candidate: top levels of the sphere tree by the surface-area sweep (see BuildMedianSplitPairs); 0 = the measured median tree
+#define RT_SPHERE_SAH_DEPTH 0                                        // top levels of the sphere tree by the surface-area sweep (see BuildMedianSplitPairs; 20 by default since round 2, rt_devmath.cuh); 0 = the measured median tree
 #endif
 
     bool sphereBoundCovers(const float lo[3], const float hi[3]) const
