@@ -85,6 +85,9 @@ struct RtContext
     cudaStream_t copyStream = nullptr; cudaEvent_t snapReady = nullptr, copyDone = nullptr; bool copyPending = false;
     DevBuf<float4> snap;
 
+    // kernel 1 on small tiles: hand-off of a pixel's chain between sample chunks (rt_kernel_wave.cuh)
+    DevBuf<uint4> handoff; DevBuf<int> handoffFlags; int optSampleChunks = -1;
+
     // rtBuildBVH: device arena kept between builds, pinned staging chunks for the copies of caller-owned arrays
     DevBuf<unsigned char> buildArena;
     static constexpr size_t STAGE_BYTES = 16u << 20;
@@ -198,7 +201,7 @@ int rtDestroy(RtContext* c)
     if (c->snapReady) cudaEventDestroy(c->snapReady);
     if (c->copyDone) cudaEventDestroy(c->copyDone);
     c->snap.release();
-    c->buildArena.release();
+    c->buildArena.release(); c->handoff.release(); c->handoffFlags.release();
     for (int k = 0; k < 2; k++) { if (c->stageBuf[k]) cudaFreeHost(c->stageBuf[k]); if (c->stageEv[k]) cudaEventDestroy(c->stageEv[k]); }
     c->frame.release(); c->accum.release(); c->tileSend.release(); c->tileRecv.release(); c->display.release();
     c->repack.release();
@@ -389,6 +392,7 @@ static int one_rtSetOption(RtContext* c, const char* name, int value)
     if (n == "kernel") { if (value < -1 || value > 2) return fail(c, RT_E_INVALID, "rtSetOption: kernel must be -1 (auto), 0, 1 or 2"); c->optKernel = value; }
     else if (n == "countStats") c->optCountStats = value != 0;
     else if (n == "exchange") c->optExchange = value != 0;
+    else if (n == "sampleChunks") { if (value < -1 || value > 64) return fail(c, RT_E_INVALID, "rtSetOption: sampleChunks must be -1 (automatic), 0 / 1 (whole pixels) or 2..64"); c->optSampleChunks = value; }
     else if (n == "smemNodes") c->optSmemPairs = value;
     else if (n == "modelSkip") c->optModelSkip = value != 0;
     else if (n == "tlas")
@@ -685,6 +689,15 @@ static int dispatchLocal(RtContext* c, int kernelIndex, int gx, int gy, int gz)
     }
     else if (kernel == 1)
     {
+        P.chunks = wave_chunks(c->optSampleChunks, c->numSMs, c->dispatchPixels, P.NumRaysPerPixel);
+        if (P.chunks > 1)
+        {
+            unsigned long long rows = limX ? c->dispatchPixels / limX : 0;
+            const size_t jobs = (size_t)((limX + 7u) / 8u) * (size_t)((rows + 3ull) / 4ull) * 32u;
+            CK(c->handoff.ensure(jobs)); CK(c->handoffFlags.ensure(jobs));
+            CK(cudaMemsetAsync(c->handoffFlags.p, 0, jobs * sizeof(int), c->stream));
+            P.handoff = c->handoff.p; P.handoffFlags = c->handoffFlags.p;
+        }
         cudaError_t e = wave_launch(P, c->numSMs, c->stream, ev.a, ev.b);
         if (e != cudaSuccess) return failCuda(c, e, "wavefront launch");
     }

@@ -228,6 +228,9 @@ struct DevParams
     const NodePair* tlasPairs;              // inner records: two child boxes each; count > 0 <=> leaf, start -> tlasLeaves
     const int*      tlasLeaves;             // model indices in leaf order
     int   tlas, tlasRootStart, tlasRootCount, pad8;
+    // kernel 1 on small tiles: a pixel's samples in `chunks` consecutive jobs (1 = whole pixels); the RNG state and the running sum travel
+    // from one chunk to the next through `handoff` (x = rng state, yzw = bits of the sum), `handoffFlags[pixel job]` = chunks completed
+    int   chunks, pad9; uint4* handoff; int* handoffFlags;
 };
 
 struct Counters { unsigned int rays, box, tri, sph, sbox; };

@@ -297,6 +297,15 @@ RT_DI void wave_body(const DevParams& P, const unsigned int totalJobs, const uns
     int sample = 0, bounce = 0;
     size_t pixelOffset = 0;
     PathState ray; ray.pos = ray.dir = ray.transmittance = ray.totalLight = splat3(0.0f);
+    // Sample chunks (small tiles, P.chunks > 1).  A pixel's samples are one sequential chain, but the chain may change lanes between
+    // samples: job j is chunk j / totalJobs of pixel job j % totalJobs — samples [c R / C, (c + 1) R / C) — so every chunk 0 is handed
+    // out before any chunk 1, and the lane that finishes a chunk leaves the RNG state and the running sum for the lane that takes the
+    // next one.  With 2.3 pixels per lane (8 GPUs, 1080p) the last round of whole pixels runs on a quarter-full machine; in chunks of
+    // an eighth the same work is 18.2 rounds.  A lane whose predecessor chunk is still running holds its job and idles (it keeps
+    // taking part in the warp's collectives); the predecessor was handed out a whole pass over the tile earlier, so that is rare.
+    const int chunks = P.chunks > 1 ? P.chunks : 1;
+    const unsigned int chunkJobs = totalJobs * (unsigned int)chunks;
+    int chunk = 0, sampleEnd = P.NumRaysPerPixel; unsigned int pixJob = 0; bool waiting = false;
 
     for (;;)
     {
@@ -311,10 +320,11 @@ RT_DI void wave_body(const DevParams& P, const unsigned int totalJobs, const uns
             base = __shfl_sync(0xffffffffu, base, leader);
             if (need)
             {
-                const unsigned int job = base + (unsigned int)__popc(needMask & laneMaskLt);
-                if (job >= totalJobs) exhausted = true;
+                const unsigned int jobAll = base + (unsigned int)__popc(needMask & laneMaskLt);
+                if (jobAll >= chunkJobs) exhausted = true;
                 else
                 {
+                    const unsigned int job = chunks > 1 ? jobAll % totalJobs : jobAll;
                     const unsigned int tile = job >> 5, l = job & 31u;
                     const unsigned int x = (tile % tilesX) * 8u + (l & 7u);
                     const unsigned int r = (tile / tilesX) * 4u + (l >> 3);
@@ -325,9 +335,16 @@ RT_DI void wave_body(const DevParams& P, const unsigned int totalJobs, const uns
                         px = SetupPixel(P, x, y);
                         rngState = px.rngState;
                         totalIncomingLight = splat3(0.0f);
-                        sample = 0;
+                        sample = 0; sampleEnd = P.NumRaysPerPixel;
                         pixelOffset = (size_t)y * P.W + x;
                         havePixel = true; pathActive = false;
+                        if (chunks > 1)
+                        {
+                            chunk = (int)(jobAll / totalJobs); pixJob = job;
+                            sample = (int)(((long long)chunk * P.NumRaysPerPixel) / chunks);
+                            sampleEnd = (int)(((long long)(chunk + 1) * P.NumRaysPerPixel) / chunks);
+                            waiting = chunk > 0;          // the state at `sample` comes from the lane that ran the chunk before
+                        }
                     }
                 }
             }
@@ -337,11 +354,22 @@ RT_DI void wave_body(const DevParams& P, const unsigned int totalJobs, const uns
             if (__ballot_sync(0xffffffffu, !exhausted) == 0u) break;
             continue;
         }
+        if (chunks > 1 && havePixel && waiting)
+        {
+            if (*reinterpret_cast<volatile int*>(P.handoffFlags + pixJob) >= chunk)
+            {
+                __threadfence();
+                const volatile uint4* h = reinterpret_cast<const volatile uint4*>(P.handoff + pixJob);
+                rngState = h->x;
+                totalIncomingLight = make_f3(__uint_as_float(h->y), __uint_as_float(h->z), __uint_as_float(h->w));
+                waiting = false;
+            }
+        }
 
         // (interpreter-only schedule profile, see rt_kernel_pool.cuh / tools/simt_schedule_profile.py)
         WAVE_PROF(20, 1); WAVE_PROF_LANES(21, havePixel && !pathActive && sample < P.NumRaysPerPixel); WAVE_PROF_LANES(22, pathActive || (havePixel && sample < P.NumRaysPerPixel));
         // [generate] start the pixel's next sample
-        if (havePixel && !pathActive && sample < P.NumRaysPerPixel)
+        if (havePixel && !waiting && !pathActive && sample < sampleEnd)
         {
             GenerateCameraRay(P, px, rngState, ray);
             bounce = 0;
@@ -363,11 +391,21 @@ RT_DI void wave_body(const DevParams& P, const unsigned int totalJobs, const uns
             }
         }
 
-        // [write] pixel finished (RC:18-23)
-        if (havePixel && !pathActive && sample >= P.NumRaysPerPixel)
+        // [write] pixel finished (RC:18-23) — or, in chunks, this part of its chain: leave the state for the next chunk's lane
+        if (havePixel && !waiting && !pathActive && sample >= sampleEnd)
         {
-            const f3 pixelCol = totalIncomingLight / __int2float_rn(P.NumRaysPerPixel);
-            WritePixel<EXT>(P, pixelOffset, pixelCol.x, pixelCol.y, pixelCol.z);
+            if (sampleEnd >= P.NumRaysPerPixel)
+            {
+                const f3 pixelCol = totalIncomingLight / __int2float_rn(P.NumRaysPerPixel);
+                WritePixel<EXT>(P, pixelOffset, pixelCol.x, pixelCol.y, pixelCol.z);
+            }
+            else
+            {
+                volatile uint4* h = reinterpret_cast<volatile uint4*>(P.handoff + pixJob);
+                h->x = rngState; h->y = __float_as_uint(totalIncomingLight.x); h->z = __float_as_uint(totalIncomingLight.y); h->w = __float_as_uint(totalIncomingLight.z);
+                __threadfence();
+                *reinterpret_cast<volatile int*>(P.handoffFlags + pixJob) = chunk + 1;
+            }
             havePixel = false;
         }
     }
@@ -410,6 +448,23 @@ inline unsigned int fit_persistent_grid(int enabled, unsigned int grid, unsigned
     return fit < grid ? (unsigned int)(fit ? fit : 1) : grid;
 }
 
+// Sample chunks per pixel for kernel 1 (wave_body): automatic = only where whole pixels quantise badly — more than one and fewer than
+// eight pixels per resident lane — and then about sixteen chunk-rounds per launch.  forced > 0 overrides (tests); always <= samples.
+inline int wave_chunks(int forced, int numSMs, unsigned long long pixels, int samples)
+{
+    if (samples < 2) return 1;
+    int c = 1;
+    if (forced > 0) c = forced;
+    else if (forced < 0)
+    {
+        const double lanes = (double)numSMs * RT_WAVE_MINBLOCKS * WAVE_THREADS;
+        const double perLane = (double)pixels / lanes;
+        if (perLane > 1.0 && perLane < 8.0) { c = (int)(16.0 / perLane + 0.999); if (c > 16) c = 16; }
+    }
+    if (c > samples) c = samples;
+    return c < 1 ? 1 : c;
+}
+
 template <bool S, bool X> inline cudaError_t wave_configure_one()
 {
     return cudaFuncSetAttribute(k_raytrace_wave<S, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
@@ -433,7 +488,7 @@ template <bool S, bool X, bool T = false> inline cudaError_t wave_launch_one(con
     if (e != cudaSuccess) return e;
     if (ctasPerSM < 1) return cudaErrorInvalidConfiguration;
     unsigned int grid = (unsigned int)(numSMs * ctasPerSM);                  // persistent: a multiple of the SM count
-    const unsigned int warpsNeeded = (totalJobs + 31u) / 32u;
+    const unsigned int warpsNeeded = (totalJobs + 31u) / 32u;      // (whole pixels: a chunk of a pixel cannot run beside the chunk before it)
     const unsigned int ctasNeeded = (warpsNeeded + (WAVE_THREADS / 32) - 1) / (WAVE_THREADS / 32);
     if (grid > ctasNeeded) grid = ctasNeeded ? ctasNeeded : 1;
     grid = fit_persistent_grid(P.gridFit, grid, WAVE_THREADS, totalJobs);

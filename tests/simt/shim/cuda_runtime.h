@@ -47,6 +47,7 @@
 // ---- vector types -----------------------------------------------------------------------------------------------------------
 struct __attribute__((aligned(16))) float4 { float x, y, z, w; };
 struct __attribute__((aligned(16))) int4 { int x, y, z, w; };
+struct __attribute__((aligned(16))) uint4 { unsigned int x, y, z, w; };
 struct __attribute__((aligned(8))) int2 { int x, y; };
 struct __attribute__((aligned(4))) uchar4 { unsigned char x, y, z, w; };
 struct uint3 { unsigned int x, y, z; };
@@ -121,6 +122,7 @@ static inline unsigned long long __shfl_down_sync(unsigned int mask, unsigned lo
 static inline unsigned int __shfl_up_sync(unsigned int mask, unsigned int v, unsigned int delta) { const unsigned int l = simt::lane_id(); return (unsigned int)simt::collective(simt::OP_SHFL, mask, v, l >= delta ? (int)(l - delta) : (int)l); }
 static inline int __shfl_up_sync(unsigned int mask, int v, unsigned int delta) { return (int)__shfl_up_sync(mask, (unsigned int)v, delta); }
 static inline void __syncthreads() { simt::syncthreads(); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 static inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }

@@ -138,3 +138,14 @@ def test_reference_scene_on_gpu(name):
     from ray_tracing_b200 import unity_scene
     sc = unity_scene.load_unity_scene(os.path.join(R.REFERENCE_SCENES, name + ".unity"), width=160, height=90)
     R.ingested_scene_equals_oracle(CUDA_LIB, sc, frames=1, kernels=(1, 2))
+
+
+def test_sample_chunks_are_schedule_only_on_gpu():
+    R.sample_chunks_are_schedule_only(CUDA_LIB, sizes=((160, 90), (9, 5)))
+    # and the automatic choice: a tile with about two pixels per resident lane (640 x 360 on one GPU) picks chunks by itself
+    sc = scenes.cornell_spheres(640, 360, 6, 16)
+    fo, ao = render(ORACLE_LIB, scenes.cornell_spheres(640, 360, 6, 16), frames=1)
+    fa, aa = render(CUDA_LIB, sc, frames=1)
+    fw, aw = render(CUDA_LIB, sc, frames=1, options={"sampleChunks": 0})
+    assert_bit_equal(aa, aw, "automatic chunks vs whole pixels")
+    assert_bit_equal(aa, ao, "automatic chunks vs the oracle")

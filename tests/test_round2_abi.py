@@ -325,3 +325,43 @@ def test_fixture_generator_reproduces_the_committed_files(tmp_path):
     mod.main()
     for rel in ("Scenes/Fixture.unity", "Graphics/Blob.obj", "Graphics/Blob.obj.meta"):
         assert open(os.path.join(mod.ROOT, rel)).read() == open(os.path.join(REPO, "tests", "fixtures", "unity_project", "Assets", rel)).read(), rel
+
+
+# ---- sample chunks: a pixel's chain changes lanes between samples (kernel 1 on small tiles) -----------------------------------------
+
+def sample_chunks_are_schedule_only(lib, sizes=((40, 24), (9, 5), (64, 36))):
+    """Option sampleChunks: the same samples in the same order whatever the number of chunks — including more chunks than samples,
+    one sample per chunk, images smaller than a warp (predecessor and successor chunk in the same warp), accumulation over frames,
+    the sphere accelerator, the TLAS instantiation, row-band tiles and the instrumented build."""
+    for (w, h) in sizes:
+        for sc, extra in ((scenes.cornell_spheres(w, h, 4, 7), {}), (scenes.knot_room(w, h, 4, 5, nu=30, nv=6, glass=True), {}),
+                          (scenes.random_soup(w, h, max_bounces=3, rays_per_pixel=6, triangles=500, spheres=90), {}),
+                          (scenes.instanced_knots(w, h, 3, 4, instances=8), {"tlas": 1})):
+            fo, ao, so = render(ORACLE_LIB, sc, frames=2, want_stats=True)
+            for chunks in (2, 3, 16, 64):
+                opts = dict(extra, kernel=1, sampleChunks=chunks)
+                fg, ag, sg = render(lib, sc, frames=2, options=opts, want_stats=True)
+                assert_bit_equal(ag, ao, f"{sc.name} {w}x{h} {opts}")
+                assert_bit_equal(fg, fo, f"{sc.name} {w}x{h} frame {opts}")
+                assert sg["rays"] == so["rays"]
+    sc = scenes.knot_room(48, 40, 4, 6, nu=30, nv=6)
+    fo, ao, so = render(ORACLE_LIB, sc, frames=1, want_stats=True)
+    fg, ag, sg = render(lib, sc, frames=1, options={"kernel": 1, "sampleChunks": 3, "countStats": 1}, want_stats=True)
+    assert_bit_equal(ag, ao, "instrumented, chunks of a third")
+    assert all(sg[k] == so[k] for k in ("rays", "boxTests", "triTests"))
+    ft, at = render(lib, sc, frames=1, options={"kernel": 1, "sampleChunks": 4}, tile=(1, 3, 8))
+    rows = [y for y in range(sc.height) if (y // 8) % 3 == 1]
+    assert_bit_equal(at[rows], ao[rows], "row bands of rank 1 of 3, four chunks")
+    # one sample per pixel: nothing to split
+    sc1 = scenes.cornell_spheres(24, 16, 3, 1)
+    assert_bit_equal(render(lib, sc1, frames=2, options={"kernel": 1, "sampleChunks": 8})[1], render(ORACLE_LIB, sc1, frames=2)[1], "1 spp")
+
+
+def test_simt_sample_chunks_are_schedule_only(simt_lib):
+    sample_chunks_are_schedule_only(simt_lib)
+
+
+@pytest.mark.parametrize("order", ["1", "2"])
+def test_simt_sample_chunks_under_other_lane_schedules(simt_lib, monkeypatch, order):
+    monkeypatch.setenv("RT_SIMT_ORDER", order)
+    sample_chunks_are_schedule_only(simt_lib, sizes=((33, 7),))

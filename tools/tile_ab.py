@@ -15,7 +15,9 @@ sys.path.insert(0, REPO)
 import bench                                         # noqa: E402
 
 CONFIGS = [("default (automatic)", {}), ("kernel 2 (pools of 64)", {"kernel": 2}), ("kernel 2, pools of 32", {"kernel": 2, "poolSlots": 32}), ("kernel 1 (one path per lane)", {"kernel": 1}),
-           ("kernel 1 + tree tops in shared memory (TMA)", {"kernel": 1, "smemNodes": 1024}), ("kernel 2 + tree tops in shared memory (TMA)", {"kernel": 2, "smemNodes": 300})]
+           ("kernel 1, whole pixels", {"kernel": 1, "sampleChunks": 0}), ("kernel 1, 4 sample chunks", {"kernel": 1, "sampleChunks": 4}),
+           ("kernel 1, 8 sample chunks", {"kernel": 1, "sampleChunks": 8}), ("kernel 1, 16 sample chunks", {"kernel": 1, "sampleChunks": 16}),
+           ("kernel 1, 32 sample chunks", {"kernel": 1, "sampleChunks": 32})]
 
 
 def main():
