@@ -188,8 +188,8 @@ int rtBuildBVH(RtContext* ctx, const float* verts, int vertCount, const int* ind
  *   "countStats"  1 = also count box / triangle tests (HL:254,271) — slower, off by default
  *   "sampleChunks"  kernel 1: a pixel's NumRaysPerPixel samples as this many consecutive jobs, the RNG state and the running sum
  *                 handed from the lane that finishes a chunk to the lane that takes the next (same samples in the same order:
- *                 same bits).  -1 (default) = automatic: only on small tiles (more than one and fewer than eight pixels per
- *                 resident lane: multi-GPU tiles), about sixteen chunk-rounds per launch; 0 / 1 = whole pixels; 2..64 forced
+ *                 same bits).  -1 (default) = automatic: mesh scenes on small tiles only (more than one and fewer than four
+ *                 pixels per resident lane: multi-GPU tiles), about eight chunk-rounds per launch; 0 / 1 = whole pixels; 2..64 forced
  *   "exchange"    1 (default) = rtDispatch(RAYTRACE) on a context with a communicator (rtCommInit / rtCreateMulti) ends with the
  *                 all-gather of the frame's tiles; 0 = the caller exchanges (rtExchangeTiles or its own collective)
  *   "smemNodes"   number of top-of-tree node pairs staged in shared memory by TMA bulk copy (0 = off; -1 = automatic, which

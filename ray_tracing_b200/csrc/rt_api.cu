@@ -689,7 +689,7 @@ static int dispatchLocal(RtContext* c, int kernelIndex, int gx, int gy, int gz)
     }
     else if (kernel == 1)
     {
-        P.chunks = wave_chunks(c->optSampleChunks, c->numSMs, c->dispatchPixels, P.NumRaysPerPixel);
+        P.chunks = wave_chunks(c->optSampleChunks, c->numSMs, c->dispatchPixels, P.NumRaysPerPixel, P.modelCount);
         if (P.chunks > 1)
         {
             unsigned long long rows = limX ? c->dispatchPixels / limX : 0;

@@ -247,7 +247,7 @@ RT_DI Hit Intersect(const DevParams& P, const float4* __restrict__ smemPairs, co
 #endif
 // The kernel body.  TLAS = the many-model instantiation (its own kernel, k_raytrace_wave_tlas, so that the kernels measured in
 // round 1 keep their code: the TLAS walk and its mask exist only there).
-template <bool STATS, bool EXT, bool TLAS>
+template <bool STATS, bool EXT, bool TLAS, bool CHUNKED>
 RT_DI void wave_body(const DevParams& P, const unsigned int totalJobs, const unsigned int tilesX, const unsigned int ownedRows)
 {
     RT_DYNAMIC_SMEM(smemRaw);
@@ -303,7 +303,8 @@ RT_DI void wave_body(const DevParams& P, const unsigned int totalJobs, const uns
     // next one.  With 2.3 pixels per lane (8 GPUs, 1080p) the last round of whole pixels runs on a quarter-full machine; in chunks of
     // an eighth the same work is 18.2 rounds.  A lane whose predecessor chunk is still running holds its job and idles (it keeps
     // taking part in the warp's collectives); the predecessor was handed out a whole pass over the tile earlier, so that is rare.
-    const int chunks = P.chunks > 1 ? P.chunks : 1;
+    // (CHUNKED is a template parameter: with the hand-off code merely present the whole-pixel kernel ran 7 % slower on config 2)
+    const int chunks = CHUNKED && P.chunks > 1 ? P.chunks : 1;
     const unsigned int chunkJobs = totalJobs * (unsigned int)chunks;
     int chunk = 0, sampleEnd = P.NumRaysPerPixel; unsigned int pixJob = 0; bool waiting = false;
 
@@ -324,7 +325,7 @@ RT_DI void wave_body(const DevParams& P, const unsigned int totalJobs, const uns
                 if (jobAll >= chunkJobs) exhausted = true;
                 else
                 {
-                    const unsigned int job = chunks > 1 ? jobAll % totalJobs : jobAll;
+                    const unsigned int job = CHUNKED && chunks > 1 ? jobAll % totalJobs : jobAll;
                     const unsigned int tile = job >> 5, l = job & 31u;
                     const unsigned int x = (tile % tilesX) * 8u + (l & 7u);
                     const unsigned int r = (tile / tilesX) * 4u + (l >> 3);
@@ -338,7 +339,7 @@ RT_DI void wave_body(const DevParams& P, const unsigned int totalJobs, const uns
                         sample = 0; sampleEnd = P.NumRaysPerPixel;
                         pixelOffset = (size_t)y * P.W + x;
                         havePixel = true; pathActive = false;
-                        if (chunks > 1)
+                        if (CHUNKED && chunks > 1)
                         {
                             chunk = (int)(jobAll / totalJobs); pixJob = job;
                             sample = (int)(((long long)chunk * P.NumRaysPerPixel) / chunks);
@@ -354,7 +355,7 @@ RT_DI void wave_body(const DevParams& P, const unsigned int totalJobs, const uns
             if (__ballot_sync(0xffffffffu, !exhausted) == 0u) break;
             continue;
         }
-        if (chunks > 1 && havePixel && waiting)
+        if (CHUNKED && chunks > 1 && havePixel && waiting)
         {
             if (*reinterpret_cast<volatile int*>(P.handoffFlags + pixJob) >= chunk)
             {
@@ -369,7 +370,7 @@ RT_DI void wave_body(const DevParams& P, const unsigned int totalJobs, const uns
         // (interpreter-only schedule profile, see rt_kernel_pool.cuh / tools/simt_schedule_profile.py)
         WAVE_PROF(20, 1); WAVE_PROF_LANES(21, havePixel && !pathActive && sample < P.NumRaysPerPixel); WAVE_PROF_LANES(22, pathActive || (havePixel && sample < P.NumRaysPerPixel));
         // [generate] start the pixel's next sample
-        if (havePixel && !waiting && !pathActive && sample < sampleEnd)
+        if (havePixel && !(CHUNKED && waiting) && !pathActive && sample < (CHUNKED ? sampleEnd : P.NumRaysPerPixel))
         {
             GenerateCameraRay(P, px, rngState, ray);
             bounce = 0;
@@ -392,9 +393,9 @@ RT_DI void wave_body(const DevParams& P, const unsigned int totalJobs, const uns
         }
 
         // [write] pixel finished (RC:18-23) — or, in chunks, this part of its chain: leave the state for the next chunk's lane
-        if (havePixel && !waiting && !pathActive && sample >= sampleEnd)
+        if (havePixel && !(CHUNKED && waiting) && !pathActive && sample >= (CHUNKED ? sampleEnd : P.NumRaysPerPixel))
         {
-            if (sampleEnd >= P.NumRaysPerPixel)
+            if (!CHUNKED || sampleEnd >= P.NumRaysPerPixel)
             {
                 const f3 pixelCol = totalIncomingLight / __int2float_rn(P.NumRaysPerPixel);
                 WritePixel<EXT>(P, pixelOffset, pixelCol.x, pixelCol.y, pixelCol.z);
@@ -420,18 +421,18 @@ RT_DI void wave_body(const DevParams& P, const unsigned int totalJobs, const uns
     }
 }
 
-template <bool STATS, bool EXT>
+template <bool STATS, bool EXT, bool CHUNKED = false>
 __global__ void __launch_bounds__(WAVE_THREADS, RT_WAVE_MINBLOCKS) k_raytrace_wave(const __grid_constant__ DevParams P, const unsigned int totalJobs,
                                                                const unsigned int tilesX, const unsigned int ownedRows)
 {
-    wave_body<STATS, EXT, false>(P, totalJobs, tilesX, ownedRows);
+    wave_body<STATS, EXT, false, CHUNKED>(P, totalJobs, tilesX, ownedRows);
 }
 
 // many-model scenes: every extension + the TLAS walk (never instrumented: the counting build walks every model like the reference)
 __global__ void __launch_bounds__(WAVE_THREADS, RT_WAVE_MINBLOCKS) k_raytrace_wave_tlas(const __grid_constant__ DevParams P, const unsigned int totalJobs,
                                                                     const unsigned int tilesX, const unsigned int ownedRows)
 {
-    wave_body<false, true, true>(P, totalJobs, tilesX, ownedRows);
+    wave_body<false, true, true, true>(P, totalJobs, tilesX, ownedRows);      // (the many-model kernel carries the chunk hand-off: it is never the Cornell-box kernel)
 }
 
 // "gridFit": a pixel's samples cannot be split (one RNG chain), so a persistent lane works through whole pixels.  When the image
@@ -448,18 +449,21 @@ inline unsigned int fit_persistent_grid(int enabled, unsigned int grid, unsigned
     return fit < grid ? (unsigned int)(fit ? fit : 1) : grid;
 }
 
-// Sample chunks per pixel for kernel 1 (wave_body): automatic = only where whole pixels quantise badly — more than one and fewer than
-// eight pixels per resident lane — and then about sixteen chunk-rounds per launch.  forced > 0 overrides (tests); always <= samples.
-inline int wave_chunks(int forced, int numSMs, unsigned long long pixels, int samples)
+// Sample chunks per pixel for kernel 1 (wave_body): automatic = mesh scenes on tiles where whole pixels quantise badly — more than one and
+// fewer than four pixels per resident lane — and then about eight chunk-rounds per launch.  forced > 0 overrides (tests); always <= samples.
+inline int wave_chunks(int forced, int numSMs, unsigned long long pixels, int samples, int modelCount)
 {
     if (samples < 2) return 1;
     int c = 1;
     if (forced > 0) c = forced;
-    else if (forced < 0)
+    else if (forced < 0 && modelCount > 0)
     {
+        // measured on rank 0's tile of 8 of the default workload (2.3 pixels per lane; profiles/r02_j_tile_ab_sample_chunks.jsonl): whole pixels
+        // 89.3 ms, 4 chunks 79.9, 8: 80.4, 16: 81.9, 32: 84.0.  On the sphere-only Cornell box a sample is too cheap for the hand-off
+        // (5.30 ms whole pixels, 5.47 with 4 chunks), so sphere-only scenes keep whole pixels.
         const double lanes = (double)numSMs * RT_WAVE_MINBLOCKS * WAVE_THREADS;
         const double perLane = (double)pixels / lanes;
-        if (perLane > 1.0 && perLane < 8.0) { c = (int)(16.0 / perLane + 0.999); if (c > 16) c = 16; }
+        if (perLane > 1.0 && perLane < 4.0) { c = (int)(8.0 / perLane + 0.999); if (c > 8) c = 8; }
     }
     if (c > samples) c = samples;
     return c < 1 ? 1 : c;
@@ -476,15 +480,17 @@ inline cudaError_t wave_configure()
     if ((e = wave_configure_one<true, false>()) != cudaSuccess) return e;
     if ((e = wave_configure_one<false, true>()) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_raytrace_wave_tlas, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_raytrace_wave<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_raytrace_wave<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)) != cudaSuccess) return e;
     return wave_configure_one<true, true>();
 }
 
-template <bool S, bool X, bool T = false> inline cudaError_t wave_launch_one(const DevParams& P, int numSMs, size_t smemBytes, unsigned totalJobs, unsigned tilesX, unsigned ownedRows,
+template <bool S, bool X, bool T = false, bool C = false> inline cudaError_t wave_launch_one(const DevParams& P, int numSMs, size_t smemBytes, unsigned totalJobs, unsigned tilesX, unsigned ownedRows,
                                                              cudaStream_t stream, cudaEvent_t evA, cudaEvent_t evB)
 {
     int ctasPerSM = 0;
     cudaError_t e = T ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, k_raytrace_wave_tlas, WAVE_THREADS, smemBytes)
-                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, k_raytrace_wave<S, X>, WAVE_THREADS, smemBytes);
+                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, k_raytrace_wave<S, X, C>, WAVE_THREADS, smemBytes);
     if (e != cudaSuccess) return e;
     if (ctasPerSM < 1) return cudaErrorInvalidConfiguration;
     unsigned int grid = (unsigned int)(numSMs * ctasPerSM);                  // persistent: a multiple of the SM count
@@ -495,7 +501,7 @@ template <bool S, bool X, bool T = false> inline cudaError_t wave_launch_one(con
     if ((e = cudaMemsetAsync(P.workCounter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(evA, stream)) != cudaSuccess) return e;
     if (T) RT_LAUNCH(grid, WAVE_THREADS, smemBytes, stream, k_raytrace_wave_tlas, P, totalJobs, tilesX, ownedRows);
-    else RT_LAUNCH(grid, WAVE_THREADS, smemBytes, stream, RT_K(k_raytrace_wave<S, X>), P, totalJobs, tilesX, ownedRows);
+    else RT_LAUNCH(grid, WAVE_THREADS, smemBytes, stream, RT_K(k_raytrace_wave<S, X, C>), P, totalJobs, tilesX, ownedRows);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     return cudaEventRecord(evB, stream);
 }
@@ -514,6 +520,10 @@ inline cudaError_t wave_launch(const DevParams& P, int numSMs, cudaStream_t stre
 
     const size_t smemBytes = sizeof(WaveSmemHeader) + (size_t)P.smemPairs * sizeof(NodePair) + (size_t)WAVE_MAX_SMEM_SPHERES * sizeof(DevSphere);
     const bool ext = P.nPeers > 0 || P.sphBvh != 0 || P.forceExt != 0;   // extensions compiled into their own instantiation
+    // sample chunks (P.chunks > 1, small tiles): the hand-off lives in instantiations of its own (the extension family and the TLAS kernel)
+    if (P.chunks > 1 && !(P.tlas && P.modelSkip && !P.countStats))
+        return P.countStats ? wave_launch_one<true, true, false, true>(P, numSMs, smemBytes, totalJobs, tilesX, ownedRows, stream, evA, evB)
+                            : wave_launch_one<false, true, false, true>(P, numSMs, smemBytes, totalJobs, tilesX, ownedRows, stream, evA, evB);
     if (P.countStats) return ext ? wave_launch_one<true, true>(P, numSMs, smemBytes, totalJobs, tilesX, ownedRows, stream, evA, evB)
                                  : wave_launch_one<true, false>(P, numSMs, smemBytes, totalJobs, tilesX, ownedRows, stream, evA, evB);
     if (P.tlas && P.modelSkip) return wave_launch_one<false, true, true>(P, numSMs, smemBytes, totalJobs, tilesX, ownedRows, stream, evA, evB);

@@ -142,9 +142,9 @@ def test_reference_scene_on_gpu(name):
 
 def test_sample_chunks_are_schedule_only_on_gpu():
     R.sample_chunks_are_schedule_only(CUDA_LIB, sizes=((160, 90), (9, 5)))
-    # and the automatic choice: a tile with about two pixels per resident lane (640 x 360 on one GPU) picks chunks by itself
-    sc = scenes.cornell_spheres(640, 360, 6, 16)
-    fo, ao = render(ORACLE_LIB, scenes.cornell_spheres(640, 360, 6, 16), frames=1)
+    # and the automatic choice: a mesh scene with about two pixels per resident lane (640 x 360 on one GPU) picks kernel 1 and chunks by itself
+    sc = scenes.knot_room(640, 360, max_bounces=5, rays_per_pixel=8, nu=120, nv=10)
+    fo, ao = render(ORACLE_LIB, sc, frames=1)
     fa, aa = render(CUDA_LIB, sc, frames=1)
     fw, aw = render(CUDA_LIB, sc, frames=1, options={"sampleChunks": 0})
     assert_bit_equal(aa, aw, "automatic chunks vs whole pixels")
