@@ -680,6 +680,18 @@ static int dispatchLocal(RtContext* c, int kernelIndex, int gx, int gy, int gz)
 
     int kernel = effectiveKernel(c);
     if (c->P.NumRaysPerPixel == 0) kernel = 0;       // 0 samples: the per-pixel kernel reproduces the reference's 0/0 directly
+    // sample chunks (small tiles): a pixel's chain may change lanes / slots between samples; the hand-off buffers belong to the context
+    P.chunks = kernel == 1 ? wave_chunks(c->optSampleChunks, c->numSMs, c->dispatchPixels, P.NumRaysPerPixel, P.modelCount)
+             : kernel == 2 ? pool_chunks(c->optSampleChunks, c->optPoolSlots, c->numSMs, c->dispatchPixels, P.NumRaysPerPixel, P.modelCount) : 1;
+    if (c->dispatchPixels == 0) P.chunks = 1;        // a rank whose tile is empty (an image lower than the band pattern)
+    if (P.chunks > 1)
+    {
+        unsigned long long rows = limX ? c->dispatchPixels / limX : 0;
+        const size_t jobs = (size_t)((limX + 7u) / 8u) * (size_t)((rows + 3ull) / 4ull) * 32u;
+        CK(c->handoff.ensure(jobs)); CK(c->handoffFlags.ensure(jobs));
+        CK(cudaMemsetAsync(c->handoffFlags.p, 0, jobs * sizeof(int), c->stream));
+        P.handoff = c->handoff.p; P.handoffFlags = c->handoffFlags.p;
+    }
     if (kernel == 0)
     {
         CK(cudaEventRecord(ev.a, c->stream));
@@ -689,15 +701,6 @@ static int dispatchLocal(RtContext* c, int kernelIndex, int gx, int gy, int gz)
     }
     else if (kernel == 1)
     {
-        P.chunks = wave_chunks(c->optSampleChunks, c->numSMs, c->dispatchPixels, P.NumRaysPerPixel, P.modelCount);
-        if (P.chunks > 1)
-        {
-            unsigned long long rows = limX ? c->dispatchPixels / limX : 0;
-            const size_t jobs = (size_t)((limX + 7u) / 8u) * (size_t)((rows + 3ull) / 4ull) * 32u;
-            CK(c->handoff.ensure(jobs)); CK(c->handoffFlags.ensure(jobs));
-            CK(cudaMemsetAsync(c->handoffFlags.p, 0, jobs * sizeof(int), c->stream));
-            P.handoff = c->handoff.p; P.handoffFlags = c->handoffFlags.p;
-        }
         cudaError_t e = wave_launch(P, c->numSMs, c->stream, ev.a, ev.b);
         if (e != cudaSuccess) return failCuda(c, e, "wavefront launch");
     }

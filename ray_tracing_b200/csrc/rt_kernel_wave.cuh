@@ -304,7 +304,7 @@ RT_DI void wave_body(const DevParams& P, const unsigned int totalJobs, const uns
     // an eighth the same work is 18.2 rounds.  A lane whose predecessor chunk is still running holds its job and idles (it keeps
     // taking part in the warp's collectives); the predecessor was handed out a whole pass over the tile earlier, so that is rare.
     // (CHUNKED is a template parameter: with the hand-off code merely present the whole-pixel kernel ran 7 % slower on config 2)
-    const int chunks = CHUNKED && P.chunks > 1 ? P.chunks : 1;
+    const int chunks = CHUNKED && P.chunks > 1 && totalJobs > 0u ? P.chunks : 1;
     const unsigned int chunkJobs = totalJobs * (unsigned int)chunks;
     int chunk = 0, sampleEnd = P.NumRaysPerPixel; unsigned int pixJob = 0; bool waiting = false;
 

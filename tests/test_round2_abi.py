@@ -338,20 +338,24 @@ def sample_chunks_are_schedule_only(lib, sizes=((40, 24), (9, 5), (64, 36))):
                           (scenes.random_soup(w, h, max_bounces=3, rays_per_pixel=6, triangles=500, spheres=90), {}),
                           (scenes.instanced_knots(w, h, 3, 4, instances=8), {"tlas": 1})):
             fo, ao, so = render(ORACLE_LIB, sc, frames=2, want_stats=True)
-            for chunks in (2, 3, 16, 64):
-                opts = dict(extra, kernel=1, sampleChunks=chunks)
-                fg, ag, sg = render(lib, sc, frames=2, options=opts, want_stats=True)
-                assert_bit_equal(ag, ao, f"{sc.name} {w}x{h} {opts}")
-                assert_bit_equal(fg, fo, f"{sc.name} {w}x{h} frame {opts}")
-                assert sg["rays"] == so["rays"]
+            for kernel in (1, 2):
+                for chunks in (2, 3, 16, 64):
+                    opts = dict(extra, kernel=kernel, sampleChunks=chunks)
+                    fg, ag, sg = render(lib, sc, frames=2, options=opts, want_stats=True)
+                    assert_bit_equal(ag, ao, f"{sc.name} {w}x{h} {opts}")
+                    assert_bit_equal(fg, fo, f"{sc.name} {w}x{h} frame {opts}")
+                    assert sg["rays"] == so["rays"]
     sc = scenes.knot_room(48, 40, 4, 6, nu=30, nv=6)
     fo, ao, so = render(ORACLE_LIB, sc, frames=1, want_stats=True)
-    fg, ag, sg = render(lib, sc, frames=1, options={"kernel": 1, "sampleChunks": 3, "countStats": 1}, want_stats=True)
-    assert_bit_equal(ag, ao, "instrumented, chunks of a third")
-    assert all(sg[k] == so[k] for k in ("rays", "boxTests", "triTests"))
-    ft, at = render(lib, sc, frames=1, options={"kernel": 1, "sampleChunks": 4}, tile=(1, 3, 8))
     rows = [y for y in range(sc.height) if (y // 8) % 3 == 1]
-    assert_bit_equal(at[rows], ao[rows], "row bands of rank 1 of 3, four chunks")
+    for kernel in (1, 2):
+        fg, ag, sg = render(lib, sc, frames=1, options={"kernel": kernel, "sampleChunks": 3, "countStats": 1}, want_stats=True)
+        assert_bit_equal(ag, ao, f"instrumented, chunks of a third, kernel {kernel}")
+        assert all(sg[k] == so[k] for k in ("rays", "boxTests", "triTests"))
+        ft, at = render(lib, sc, frames=1, options={"kernel": kernel, "sampleChunks": 4}, tile=(1, 3, 8))
+        assert_bit_equal(at[rows], ao[rows], f"row bands of rank 1 of 3, four chunks, kernel {kernel}")
+    # pools of another size keep whole pixels (the option is ignored there)
+    assert_bit_equal(render(lib, sc, frames=1, options={"kernel": 2, "poolSlots": 32, "sampleChunks": 4})[1], ao, "32-slot pools")
     # one sample per pixel: nothing to split
     sc1 = scenes.cornell_spheres(24, 16, 3, 1)
     assert_bit_equal(render(lib, sc1, frames=2, options={"kernel": 1, "sampleChunks": 8})[1], render(ORACLE_LIB, sc1, frames=2)[1], "1 spp")
@@ -365,3 +369,15 @@ def test_simt_sample_chunks_are_schedule_only(simt_lib):
 def test_simt_sample_chunks_under_other_lane_schedules(simt_lib, monkeypatch, order):
     monkeypatch.setenv("RT_SIMT_ORDER", order)
     sample_chunks_are_schedule_only(simt_lib, sizes=((33, 7),))
+
+
+def test_simt_sample_chunks_on_a_rank_without_rows(simt_lib):
+    """Found by tools/simt_fuzz.py (seed 515245772): a 7x1 image in bands of one row over three ranks leaves ranks 1 and 2 no pixel;
+    forced sample chunks then divided by a job count of zero."""
+    sc = scenes.knot_room(7, 1, 3, 2, nu=20, nv=6)
+    fo, ao = render(ORACLE_LIB, sc, frames=1)
+    for kernel in (1, 2):
+        for rank in (0, 1, 2):
+            ft, at = render(simt_lib, sc, frames=1, options={"kernel": kernel, "sampleChunks": 7}, tile=(rank, 3, 1))
+            if rank == 0:
+                assert_bit_equal(at, ao, f"kernel {kernel}")

@@ -150,6 +150,8 @@ def random_options(rng):
         o["extInstantiation"] = 1
     if rng.rand() < 0.15:
         o["countStats"] = 1
+    if rng.rand() < 0.35:
+        o["sampleChunks"] = int(rng.choice([0, 2, 3, 7]))       # round 2: a pixel's chain split over lanes / slots (scenes here have 1-3 samples per pixel)
     return o
 
 

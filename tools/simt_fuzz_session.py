@@ -61,9 +61,9 @@ def make_script(rng, sc, steps):
             elif a == 6:
                 script.append(("setting", (str(rng.choice(["maxBounceCount", "numRaysPerPixel", "useSky", "accumulate", "divergeStrength", "defocusStrength"])), rng.rand())))
             else:
-                name = str(rng.choice(["kernel", "tlas", "modelSkip", "poolSlots", "pairOrder", "smemNodes", "tailLanes", "sortRays", "gridFit", "extInstantiation", "countStats"]))
+                name = str(rng.choice(["kernel", "tlas", "modelSkip", "poolSlots", "pairOrder", "smemNodes", "tailLanes", "sortRays", "gridFit", "extInstantiation", "countStats", "sampleChunks"]))
                 value = {"kernel": [0, 1, 2, -1], "tlas": [-1, 0, 1], "modelSkip": [0, 1], "poolSlots": [0, 32, 64, 96], "pairOrder": [0, 1, 3], "smemNodes": [0, 9, 200, -1],
-                         "tailLanes": [0, 5, 16, 31], "sortRays": [0, 1], "gridFit": [0, 1], "extInstantiation": [0, 1], "countStats": [0, 1]}[name]
+                         "tailLanes": [0, 5, 16, 31], "sortRays": [0, 1], "gridFit": [0, 1], "extInstantiation": [0, 1], "countStats": [0, 1], "sampleChunks": [-1, 0, 2, 3]}[name]
                 script.append(("option", (name, int(rng.choice(value)))))
         script.append(("frame", ()))
     return script
