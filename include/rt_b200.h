@@ -186,7 +186,7 @@ int rtBuildBVH(RtContext* ctx, const float* verts, int vertCount, const int* ind
  *                 -1 = automatic (default): 2 when the scene has meshes, 1 for sphere-only scenes and for tiles so small that
  *                 a pool slot gets about one pixel (below 1.5 pixels per slot; 2.5 with NumRaysPerPixel = 1: multi-GPU tiles)
  *   "countStats"  1 = also count box / triangle tests (HL:254,271) — slower, off by default
- *   "sampleChunks"  kernels 1 and 2 (64-slot pools): a pixel's NumRaysPerPixel samples as this many consecutive jobs, the RNG state and the running sum
+ *   "sampleChunks"  kernel 1: a pixel's NumRaysPerPixel samples as this many consecutive jobs, the RNG state and the running sum
  *                 handed from the lane that finishes a chunk to the lane that takes the next (same samples in the same order:
  *                 same bits).  -1 (default) = automatic: mesh scenes on small tiles only (more than one and fewer than four
  *                 pixels per resident lane: multi-GPU tiles), about eight chunk-rounds per launch; 0 / 1 = whole pixels; 2..64 forced

@@ -681,8 +681,9 @@ static int dispatchLocal(RtContext* c, int kernelIndex, int gx, int gy, int gz)
     int kernel = effectiveKernel(c);
     if (c->P.NumRaysPerPixel == 0) kernel = 0;       // 0 samples: the per-pixel kernel reproduces the reference's 0/0 directly
     // sample chunks (small tiles): a pixel's chain may change lanes / slots between samples; the hand-off buffers belong to the context
-    P.chunks = kernel == 1 ? wave_chunks(c->optSampleChunks, c->numSMs, c->dispatchPixels, P.NumRaysPerPixel, P.modelCount)
-             : kernel == 2 ? pool_chunks(c->optSampleChunks, c->optPoolSlots, c->numSMs, c->dispatchPixels, P.NumRaysPerPixel, P.modelCount) : 1;
+    // (kernel 1 only: in the pooled kernel the same hand-off measured 14 % slower than whole pixels on rank 0's tile of 4 and 5 % slower on
+    // the tile of 8 — profiles/r02_k_tile_ab_pool_sample_chunks.jsonl — and was taken out again)
+    P.chunks = kernel == 1 ? wave_chunks(c->optSampleChunks, c->numSMs, c->dispatchPixels, P.NumRaysPerPixel, P.modelCount) : 1;
     if (c->dispatchPixels == 0) P.chunks = 1;        // a rank whose tile is empty (an image lower than the band pattern)
     if (P.chunks > 1)
     {

@@ -131,8 +131,7 @@ constexpr int POOL_WORDS = 24;                 // 32-bit words of state per path
 
 // slot state (low 4 bits of the info word)
 enum : unsigned { PS_EMPTY = 0, PS_GEN = 1, PS_RAY = 2, PS_HIT_MISS = 3, PS_HIT_OPAQUE = 4, PS_HIT_GLASS = 5, PS_DONE = 6,
-                  PS_FLIGHT = 7 /* a lane is tracing this slot's ray (possibly across phases) */,
-                  PS_WAIT = 8 /* sample chunks: the chunk before this one is still running on another slot (rt_kernel_wave.cuh) */ };
+                  PS_FLIGHT = 7 /* a lane is tracing this slot's ray (possibly across phases) */ };
 
 
 // word index of each field inside a pool (field-major: word f of slot e is pool[f * M + e], conflict-free for lane = e)
@@ -211,7 +210,7 @@ template <int M> RT_DI int CompactRaysByOctant(const PoolView<M>& pool, unsigned
 // The kernel body.  TLAS = the many-model instantiation (k_raytrace_pool_tlas): at the start of a ray's model loop one walk of the
 // TLAS marks the models the ray can reach (TlasCollect, rt_device.cuh); the T_NEXT step then jumps from marked model to marked model,
 // in buffer order, re-testing each against the running result.  The kernels measured in round 1 are the TLAS = false instantiations.
-template <bool STATS, bool EXT, bool TLAS, int M, bool CHUNKED = false>
+template <bool STATS, bool EXT, bool TLAS, int M>
 RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const unsigned int tilesX, const unsigned int ownedRows)
 {
     RT_DYNAMIC_SMEM(smemRaw);
@@ -266,18 +265,6 @@ RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const uns
     // instead of the first CTAs swallowing the queue.  With more pixels than slots (the usual case) the cap is the pool size.
     const unsigned int fairShare = (totalJobs + gridDim.x * POOL_WARPS - 1u) / (gridDim.x * POOL_WARPS);
     const int slotCap = fairShare < (unsigned int)M ? (int)(fairShare ? fairShare : 1u) : M;
-    // Sample chunks (CHUNKED instantiation, P.chunks > 1: small tiles, see wave_body): job j = chunk j / totalJobs of pixel job
-    // j % totalJobs; a slot runs samples [c R / C, (c + 1) R / C) of its pixel and hands the RNG state and the running sum to the
-    // slot that takes the next chunk (PS_WAIT until the chunk before has arrived).
-    const int chunks = CHUNKED && P.chunks > 1 && totalJobs > 0u ? P.chunks : 1;
-    const unsigned int chunkJobs = totalJobs * (unsigned int)chunks;
-    auto chunkStart = [&](int c) { return (int)(((long long)c * P.NumRaysPerPixel) / chunks); };
-    auto chunkOf = [&](int smp) { return (int)((((long long)smp + 1) * chunks + P.NumRaysPerPixel - 1) / P.NumRaysPerPixel) - 1; };   // the c with chunkStart(c) <= smp < chunkStart(c + 1)
-    auto pixelJob = [&](unsigned int xy) {                           // the pixel's job index inside this rank's tile (inverse of the refill's mapping)
-        const unsigned int x = xy & 0xffffu, y = xy >> 16;
-        const unsigned int band = (unsigned int)P.bandRows, r = (y / (band * (unsigned int)P.tileWorld)) * band + (y % band);
-        return ((r >> 2) * tilesX + (x >> 3)) * 32u + ((r & 3u) << 3) + (x & 7u);
-    };
 
     // per-lane ray state of the trace phase.  It lives across phases: a lane whose ray is still in flight when the phase
     // ends keeps it (slot state PS_FLIGHT) and continues in the next trace phase, so long rays never hold the warp back.
@@ -363,17 +350,7 @@ RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const uns
                     {
                         const f3 sum = pool.get3(F_SUM, e) + ray.totalLight;              // HL:578
                         sample++;
-                        if (CHUNKED && chunks > 1 && (int)sample < P.NumRaysPerPixel && chunkOf((int)sample) != chunkOf((int)sample - 1))
-                        {
-                            // end of this slot's chunk: leave the chain for the slot that takes the next one
-                            const unsigned int pj = pixelJob(pool.u(F_XY, e));
-                            volatile uint4* h = reinterpret_cast<volatile uint4*>(P.handoff + pj);
-                            h->x = rngState; h->y = __float_as_uint(sum.x); h->z = __float_as_uint(sum.y); h->w = __float_as_uint(sum.z);
-                            __threadfence();
-                            *reinterpret_cast<volatile int*>(P.handoffFlags + pj) = chunkOf((int)sample);
-                            state = PS_EMPTY; sample = 0;
-                        }
-                        else if ((int)sample >= P.NumRaysPerPixel)
+                        if ((int)sample >= P.NumRaysPerPixel)
                         {
                             // pixel finished (RC:18-23)
                             const unsigned xy = pool.u(F_XY, e);
@@ -413,9 +390,8 @@ RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const uns
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (need)
                 {
-                    const unsigned jobAll = base + (unsigned)__popc(needMask & ltMask);
-                    const unsigned job = CHUNKED && chunks > 1 ? jobAll % totalJobs : jobAll;
-                    if (jobAll < chunkJobs)
+                    const unsigned job = base + (unsigned)__popc(needMask & ltMask);
+                    if (job < totalJobs)
                     {
                         const unsigned tile = job >> 5, l = job & 31u;
                         const unsigned x = (tile % tilesX) * 8u + (l & 7u);
@@ -427,12 +403,11 @@ RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const uns
                             pool.u(F_XY, e) = (y << 16) | x;
                             pool.u(F_RNG, e) = SetupPixel(P, x, y).rngState;
                             pool.set3(F_SUM, e, splat3(0.0f));
-                            const int c0 = CHUNKED && chunks > 1 ? (int)(jobAll / totalJobs) : 0;
-                            pool.u(F_INFO, e) = info_pack((unsigned)chunkStart(c0), 0, c0 > 0 ? PS_WAIT : PS_GEN);
+                            pool.u(F_INFO, e) = info_pack(0, 0, PS_GEN);
                         }
                     }
                 }
-                if (base + (unsigned)__popc(needMask) >= chunkJobs) exhausted = true;        // warp-uniform
+                if (base + (unsigned)__popc(needMask) >= totalJobs) exhausted = true;        // warp-uniform
                 else if (__ballot_sync(0xffffffffu, info_state(pool.u(F_INFO, e)) == PS_EMPTY && e < slotCap)) anyEmpty = true;   // padding jobs: try again
             }
             if (!anyEmpty) break;
@@ -447,33 +422,6 @@ RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const uns
             }
         }
         __syncwarp();
-
-        // (2b) sample chunks: slots whose predecessor chunk has arrived pick up the chain
-        bool anyWaiting = false;
-        if (CHUNKED && chunks > 1)
-        {
-#pragma unroll
-            for (int c = 0; c < M / 32; c++)
-            {
-                const int e = c * 32 + (int)lane;
-                const unsigned info = pool.u(F_INFO, e);
-                if (info_state(info) == PS_WAIT)
-                {
-                    const unsigned int pj = pixelJob(pool.u(F_XY, e));
-                    if (*reinterpret_cast<volatile int*>(P.handoffFlags + pj) >= chunkOf((int)info_sample(info)))
-                    {
-                        __threadfence();
-                        const volatile uint4* h = reinterpret_cast<const volatile uint4*>(P.handoff + pj);
-                        pool.u(F_RNG, e) = h->x;
-                        pool.set3(F_SUM, e, make_f3(__uint_as_float(h->y), __uint_as_float(h->z), __uint_as_float(h->w)));
-                        pool.u(F_INFO, e) = info_pack(info_sample(info), 0, PS_GEN);
-                    }
-                    else anyWaiting = true;
-                }
-            }
-            anyWaiting = __any_sync(0xffffffffu, anyWaiting);
-            __syncwarp();
-        }
 
         // (3) camera rays for the slots that start a sample (HL:567-576), in compacted batches
         {
@@ -501,11 +449,7 @@ RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const uns
 
         // ================================================= TRACE phase =================================================
         const int nRays = P.sortRays ? CompactRaysByOctant<M>(pool, lane) : CompactByState<M>(pool, lane, PS_RAY, PS_RAY);
-        if (nRays == 0 && __ballot_sync(0xffffffffu, mode != T_IDLE) == 0u)
-        {
-            if (CHUNKED && anyWaiting) continue;                     // nothing to trace, but a chunk of ours waits for its predecessor on another warp
-            break;                                                   // every slot is DONE: this warp is finished
-        }
+        if (nRays == 0 && __ballot_sync(0xffffffffu, mode != T_IDLE) == 0u) break;   // every slot is DONE: this warp is finished
         int next = 0;                                                // warp-uniform queue head
         bool finishedAny = false;                                    // warp-uniform: some ray completed in this phase
 
@@ -785,11 +729,11 @@ RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const uns
     }
 }
 
-template <bool STATS, bool EXT, int M, bool CHUNKED = false>
+template <bool STATS, bool EXT, int M>
 __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool(const __grid_constant__ DevParams P, const unsigned int totalJobs,
                                                                   const unsigned int tilesX, const unsigned int ownedRows)
 {
-    pool_body<STATS, EXT, false, M, CHUNKED>(P, totalJobs, tilesX, ownedRows);
+    pool_body<STATS, EXT, false, M>(P, totalJobs, tilesX, ownedRows);
 }
 
 // many-model scenes: every extension + the TLAS (never instrumented: the counting build walks every model like the reference)
@@ -820,8 +764,6 @@ inline cudaError_t pool_configure()
     cudaError_t e;
     if ((e = pool_configure_one<32>()) != cudaSuccess) return e;
     if ((e = pool_configure_one<64>()) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_raytrace_pool<false, true, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_raytrace_pool<true, true, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
     return pool_configure_one<96>();
 }
 
@@ -848,13 +790,6 @@ template <int M> inline cudaError_t pool_launch_m(const DevParams& P, int numSMs
     if ((e = cudaMemsetAsync(P.workCounter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(evA, stream)) != cudaSuccess) return e;
     const bool ext = P.nPeers > 0 || P.sphBvh != 0 || P.forceExt != 0;   // extensions compiled into their own instantiation
-    if (M == 64 && P.chunks > 1 && !(P.tlas && P.modelSkip && !P.countStats))
-    {
-        // sample chunks: instantiations of their own (64-slot pools, extension family), so that the whole-pixel kernels keep their code
-        if (P.countStats) RT_LAUNCH(grid, POOL_THREADS, smemBytes, stream, RT_K(k_raytrace_pool<true, true, 64, true>), P, totalJobs, tilesX, ownedRows);
-        else RT_LAUNCH(grid, POOL_THREADS, smemBytes, stream, RT_K(k_raytrace_pool<false, true, 64, true>), P, totalJobs, tilesX, ownedRows);
-    }
-    else
     if (P.countStats) { if (ext) RT_LAUNCH(grid, POOL_THREADS, smemBytes, stream, RT_K(k_raytrace_pool<true, true, M>), P, totalJobs, tilesX, ownedRows);
                         else RT_LAUNCH(grid, POOL_THREADS, smemBytes, stream, RT_K(k_raytrace_pool<true, false, M>), P, totalJobs, tilesX, ownedRows); }
     else if (P.tlas && P.modelSkip) RT_LAUNCH(grid, POOL_THREADS, smemBytes, stream, RT_K(k_raytrace_pool_tlas<M>), P, totalJobs, tilesX, ownedRows);
@@ -862,22 +797,6 @@ template <int M> inline cudaError_t pool_launch_m(const DevParams& P, int numSMs
            else RT_LAUNCH(grid, POOL_THREADS, smemBytes, stream, RT_K(k_raytrace_pool<false, false, M>), P, totalJobs, tilesX, ownedRows); }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     return cudaEventRecord(evB, stream);
-}
-
-// Sample chunks per pixel for kernel 2 (see wave_chunks): automatic = mesh scenes with more than one and fewer than four pixels per pool slot
-// (rank 0's tile of 4 of the default workload: 2.3), about eight chunk-rounds per launch; 64-slot pools only.
-inline int pool_chunks(int forced, int M, int numSMs, unsigned long long pixels, int samples, int modelCount)
-{
-    if (samples < 2 || (M != 0 && M != 64)) return 1;
-    int c = 1;
-    if (forced > 0) c = forced;
-    else if (forced < 0 && modelCount > 0)
-    {
-        const double perSlot = (double)pixels / ((double)numSMs * POOL_WARPS * 64.0);
-        if (perSlot > 1.0 && perSlot < 4.0) { c = (int)(8.0 / perSlot + 0.999); if (c > 8) c = 8; }
-    }
-    if (c > samples) c = samples;
-    return c < 1 ? 1 : c;
 }
 
 inline cudaError_t pool_launch(const DevParams& P, int M, int numSMs, cudaStream_t stream, cudaEvent_t evA, cudaEvent_t evB)
