@@ -149,3 +149,8 @@ def test_sample_chunks_are_schedule_only_on_gpu():
     fw, aw = render(CUDA_LIB, sc, frames=1, options={"sampleChunks": 0})
     assert_bit_equal(aa, aw, "automatic chunks vs whole pixels")
     assert_bit_equal(aa, ao, "automatic chunks vs the oracle")
+
+
+@pytest.mark.parametrize("name", sorted(R.SHIPPED_SETTINGS))
+def test_fixture_under_the_settings_of_every_shipped_scene_on_gpu(name):
+    R.ingested_scene_equals_oracle(CUDA_LIB, R.fixture_with_shipped_settings(name, 0.2), frames=3)

@@ -380,3 +380,76 @@ def test_simt_sample_chunks_on_a_rank_without_rows(simt_lib):
             ft, at = render(simt_lib, sc, frames=1, options={"kernel": kernel, "sampleChunks": 7}, tile=(rank, 3, 1))
             if rank == 0:
                 assert_bit_equal(at, ao, f"kernel {kernel}")
+
+
+# ---- the parameter space of the reference's own scenes, applied to the fixture scene -----------------------------
+
+SHIPPED_SETTINGS = {   # manager block of each shipped scene: resolution, MaxBounce, BVH quality, defocus / focus distance, camera field of view
+    "Glass Dragon": dict(size=(1920, 1080), maxBounceCount=10, bvhQuality=1, defocusStrength=0.0, focusDistance=1.0, fov=54.5),
+    "Glass Balls": dict(size=(1388, 781), maxBounceCount=10, bvhQuality=1, defocusStrength=0.0, focusDistance=1.0, fov=60.0),
+    "Sphere Refract": dict(size=(1573, 885), maxBounceCount=32, bvhQuality=1, defocusStrength=100.0, focusDistance=5.3, fov=38.0),
+    "Splash": dict(size=(1388, 781), maxBounceCount=32, bvhQuality=0, defocusStrength=0.0, focusDistance=1.0, fov=60.0),
+    "Text": dict(size=(1280, 720), maxBounceCount=32, bvhQuality=1, defocusStrength=0.0, focusDistance=1.0, fov=60.0),
+}
+
+
+def fixture_with_shipped_settings(name, scale):
+    st = SHIPPED_SETTINGS[name]
+    w, h = max(8, int(st["size"][0] * scale)), max(6, int(st["size"][1] * scale))     # odd sizes on purpose (781, 885 rows: partial 8x8 groups)
+    sc = load_fixture(w, h)
+    sc.fov = st["fov"]
+    sc.settings = dict(sc.settings, maxBounceCount=st["maxBounceCount"], bvhQuality=st["bvhQuality"], defocusStrength=st["defocusStrength"],
+                       focusDistance=st["focusDistance"], numRaysPerPixel=1, divergeStrength=1.5, useSky=False, accumulate=True)
+    sc.name = f"fixture with the settings of {name}"
+    return sc
+
+
+@pytest.mark.parametrize("name", sorted(SHIPPED_SETTINGS))
+def test_simt_fixture_under_the_settings_of_every_shipped_scene(simt_lib, name):
+    """1 ray per pixel per frame over several accumulated frames (numRaysPerPixel: 1 in all five scenes), 10 or 32 bounces, the depth of
+    field of Sphere Refract, the Low-quality BVH of Splash: the kernels against the oracle, traversal counters included."""
+    ingested_scene_equals_oracle(simt_lib, fixture_with_shipped_settings(name, 1.0 / 24.0), frames=3)
+
+
+def test_simt_group_context_api_surface(simt_lib):
+    """What else a host may do with the context rtCreateMulti returns: resize, reset, options, statistics, pipelined readback, display,
+    BVH build, a second group beside the first; and what it may not (a communicator of its own)."""
+    import ctypes as C
+    sc = scenes.knot_room(40, 30, 3, 2, nu=30, nv=6)
+    fo, ao = render(simt_lib, sc, frames=2)
+    L = capi.RtLib(simt_lib)
+    mgr = rt.RayComputeManager(simt_lib, devices=[0, 1, 2])
+    other = rt.RayComputeManager(simt_lib, devices=[3, 4])
+    for m in (mgr, other):
+        scenes.apply(sc, m); m.OnEnable()
+    ctx = mgr.context
+    with pytest.raises(capi.RtError):
+        ctx.comm_init(b"\0" * 128, 0, 3)                     # a group has its communicator
+    with pytest.raises(capi.RtError):
+        ctx.comm_destroy()
+    mgr.RenderFrame(); other.RenderFrame(); mgr.RenderFrame(); other.RenderFrame()
+    assert_bit_equal(mgr.accumulatedResult, ao, "group of three"); assert_bit_equal(other.accumulatedResult, ao, "group of two beside it")
+    # pipelined readback and display read the leader's complete textures
+    buf = np.empty((30, 40, 4), dtype=np.float32)
+    ctx.readback_async("AccumulatedRender", buf.ctypes.data, buf.nbytes); ctx.readback_wait()
+    assert_bit_equal(buf, ao, "rtReadbackAsync on a group")
+    rgba = np.empty((30, 40, 4), dtype=np.uint8)
+    ctx.display_async(True, 2, rgba.ctypes.data, rgba.nbytes); ctx.synchronize()
+    assert np.array_equal(rgba, ctx.display(True, 2))
+    # statistics are sums over the group; reset reaches every member
+    st = ctx.stats()
+    assert st["rays"] == render(simt_lib, sc, frames=2, want_stats=True)[2]["rays"]
+    ctx.reset_stats()
+    assert ctx.stats()["rays"] == 0
+    # reset + resize + a kernel option, then the same image again at the new size
+    mgr.set_screen(24, 16)
+    mgr.ResetAccumulatedRender()
+    ctx.set_option("kernel", 1)
+    mgr.RenderFrame()
+    assert_bit_equal(mgr.accumulatedResult, render(simt_lib, sc, frames=1, width=24, height=16)[1], "after resize")
+    # rtBuildBVH through the group's context
+    m = scenes.knot_mesh(nu=30, nv=6)
+    th, nh, _ = rt.build_bvh(m.vertices, m.indices, m.normals, 1)
+    tg, ng = ctx.build_bvh(m.vertices, m.indices, m.normals, 1)
+    assert np.array_equal(ng.view(np.uint8), nh.view(np.uint8)) and np.array_equal(tg.view(np.uint8), th.view(np.uint8))
+    mgr.OnDestroy(); other.OnDestroy()
