@@ -87,6 +87,7 @@ struct RtContext
 
     // kernel 1 on small tiles: hand-off of a pixel's chain between sample chunks (rt_kernel_wave.cuh)
     DevBuf<uint4> handoff; DevBuf<int> handoffFlags; int optSampleChunks = -1;
+    DevBuf<float> poolCold;                    // kernel 2 (RT_POOL_COLD_GLOBAL builds): slot fields of the shade phase, one block per resident warp
 
     // rtBuildBVH: device arena kept between builds, pinned staging chunks for the copies of caller-owned arrays
     DevBuf<unsigned char> buildArena;
@@ -201,7 +202,7 @@ int rtDestroy(RtContext* c)
     if (c->snapReady) cudaEventDestroy(c->snapReady);
     if (c->copyDone) cudaEventDestroy(c->copyDone);
     c->snap.release();
-    c->buildArena.release(); c->handoff.release(); c->handoffFlags.release();
+    c->buildArena.release(); c->handoff.release(); c->handoffFlags.release(); c->poolCold.release();
     for (int k = 0; k < 2; k++) { if (c->stageBuf[k]) cudaFreeHost(c->stageBuf[k]); if (c->stageEv[k]) cudaEventDestroy(c->stageEv[k]); }
     c->frame.release(); c->accum.release(); c->tileSend.release(); c->tileRecv.release(); c->display.release();
     c->repack.release();
@@ -707,6 +708,11 @@ static int dispatchLocal(RtContext* c, int kernelIndex, int gx, int gy, int gz)
     }
     else
     {
+        if (POOL_COLD_WORDS > 0)
+        {
+            CK(c->poolCold.ensure((size_t)c->numSMs * POOL_WARPS * POOL_COLD_WORDS * 96));      // sized for the largest pools
+            P.poolCold = c->poolCold.p;
+        }
         cudaError_t e = pool_launch(P, c->optPoolSlots, c->numSMs, c->stream, ev.a, ev.b);
         if (e != cudaSuccess) return failCuda(c, e, "pool wavefront launch");
     }

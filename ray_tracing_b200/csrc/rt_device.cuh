@@ -231,6 +231,7 @@ struct DevParams
     // kernel 1 on small tiles: a pixel's samples in `chunks` consecutive jobs (1 = whole pixels); the RNG state and the running sum travel
     // from one chunk to the next through `handoff` (x = rng state, yzw = bits of the sum), `handoffFlags[pixel job]` = chunks completed
     int   chunks, pad9; uint4* handoff; int* handoffFlags;
+    float* poolCold;                        // kernel 2 built with RT_POOL_COLD_GLOBAL: the per-warp blocks of the slot fields kept out of shared memory
 };
 
 struct Counters { unsigned int rays, box, tri, sph, sbox; };

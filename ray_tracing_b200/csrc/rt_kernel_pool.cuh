@@ -56,7 +56,11 @@ namespace rtd {
 // state leave no room for it (they keep the whole stack in local memory).
 #if defined(RT_SMEM_STACK) && !defined(RT_STACK_TOP_REG)
 static_assert((RT_SMEM_STACK & (RT_SMEM_STACK - 1)) == 0 && RT_SMEM_STACK >= 2, "RT_SMEM_STACK must be a power of two");
+#ifdef RT_POOL_COLD_GLOBAL
+template <int M> struct PoolRing { static constexpr int N = RT_SMEM_STACK; };
+#else
 template <int M> struct PoolRing { static constexpr int N = M >= 96 ? 0 : RT_SMEM_STACK; };
+#endif
 #else
 template <int M> struct PoolRing { static constexpr int N = 0; };
 #endif
@@ -134,10 +138,23 @@ enum : unsigned { PS_EMPTY = 0, PS_GEN = 1, PS_RAY = 2, PS_HIT_MISS = 3, PS_HIT_
                   PS_FLIGHT = 7 /* a lane is tracing this slot's ray (possibly across phases) */ };
 
 
-// word index of each field inside a pool (field-major: word f of slot e is pool[f * M + e], conflict-free for lane = e)
+// word index of each field inside a pool (field-major: word f of slot e is pool[f * M + e], conflict-free for lane = e).
+// RT_POOL_COLD_GLOBAL: the first POOL_HOT_WORDS fields — what the trace phase touches: info, ray, hit record — stay in shared memory;
+// the others (pixel, RNG state, transmittance, light, running sum: read and written once per segment, in the shade phase) live in a
+// per-warp block of global memory (L2-resident, ~80 bytes per segment against ~10 KB of node records), which hands 66 KB of
+// shared memory per CTA back to L1.
+#ifdef RT_POOL_COLD_GLOBAL
+enum : int { F_INFO = 0, F_POS, F_DIR = F_POS + 3, F_HDST = F_DIR + 3, F_HPRIM, F_HU, F_HV, F_HDET, F_HMODEL,
+             F_XY, F_RNG, F_TRN, F_LGT = F_TRN + 3, F_SUM = F_LGT + 3 };
+constexpr int POOL_HOT_WORDS = F_XY;
+static_assert(F_SUM + 3 == POOL_WORDS && POOL_HOT_WORDS == 13, "pool layout");
+#else
 enum : int { F_XY = 0, F_RNG, F_INFO, F_POS, F_DIR = F_POS + 3, F_TRN = F_DIR + 3, F_LGT = F_TRN + 3, F_SUM = F_LGT + 3,
              F_HDST = F_SUM + 3, F_HPRIM, F_HU, F_HV, F_HDET, F_HMODEL };
+constexpr int POOL_HOT_WORDS = POOL_WORDS;
 static_assert(F_HMODEL == POOL_WORDS - 1, "pool layout");
+#endif
+constexpr int POOL_COLD_WORDS = POOL_WORDS - POOL_HOT_WORDS;
 
 RT_DI unsigned info_pack(unsigned sample, unsigned bounce, unsigned state) { return (sample << 12) | (bounce << 4) | state; }
 RT_DI unsigned info_state(unsigned i) { return i & 15u; }
@@ -146,13 +163,16 @@ RT_DI unsigned info_sample(unsigned i) { return i >> 12; }
 
 template <int M> struct PoolView
 {
-    float* w;                                   // POOL_WORDS * M words
+    float* w;                                   // POOL_HOT_WORDS * M words of shared memory
+    float* g;                                   // POOL_COLD_WORDS * M words of global memory (RT_POOL_COLD_GLOBAL)
     unsigned char* order;                       // M slot indices
-    RT_DI float& f(int field, int e) const { return w[field * M + e]; }
-    RT_DI unsigned& u(int field, int e) const { return reinterpret_cast<unsigned*>(w)[field * M + e]; }
-    RT_DI int& i(int field, int e) const { return reinterpret_cast<int*>(w)[field * M + e]; }
-    RT_DI f3 get3(int field, int e) const { return make_f3(w[field * M + e], w[(field + 1) * M + e], w[(field + 2) * M + e]); }
-    RT_DI void set3(int field, int e, f3 v) const { w[field * M + e] = v.x; w[(field + 1) * M + e] = v.y; w[(field + 2) * M + e] = v.z; }
+    // (`field` is a constant at every call site: after inlining each access is a plain shared or a plain global one)
+    RT_DI float* at(int field, int e) const { return field < POOL_HOT_WORDS ? w + field * M + e : g + (field - POOL_HOT_WORDS) * M + e; }
+    RT_DI float& f(int field, int e) const { return *at(field, e); }
+    RT_DI unsigned& u(int field, int e) const { return *reinterpret_cast<unsigned*>(at(field, e)); }
+    RT_DI int& i(int field, int e) const { return *reinterpret_cast<int*>(at(field, e)); }
+    RT_DI f3 get3(int field, int e) const { return make_f3(f(field, e), f(field + 1, e), f(field + 2, e)); }
+    RT_DI void set3(int field, int e, f3 v) const { f(field, e) = v.x; f(field + 1, e) = v.y; f(field + 2, e) = v.z; }
 };
 
 // Build in `order` the list of slots whose state is in [lo, hi], grouped by state (ascending); returns the count.
@@ -219,14 +239,15 @@ RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const uns
     DevSphere* smemSpheres = reinterpret_cast<DevSphere*>(smemRaw + sizeof(WaveSmemHeader) + (size_t)P.smemPairs * sizeof(NodePair));
     const int nSmemSpheres = P.sphereCount < WAVE_MAX_SMEM_SPHERES ? P.sphereCount : WAVE_MAX_SMEM_SPHERES;
     unsigned char* poolBase = reinterpret_cast<unsigned char*>(smemSpheres + nSmemSpheres);
-    constexpr int POOL_BYTES = POOL_WORDS * M * 4 + M;          // M is a multiple of 32, so every pool stays 16-byte aligned
+    constexpr int POOL_BYTES = POOL_HOT_WORDS * M * 4 + M;      // M is a multiple of 32, so every pool stays 16-byte aligned
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned warp = threadIdx.x >> 5;
     const unsigned ltMask = (1u << lane) - 1u;
     PoolView<M> pool;
     pool.w = reinterpret_cast<float*>(poolBase + (size_t)warp * POOL_BYTES);
-    pool.order = reinterpret_cast<unsigned char*>(pool.w + POOL_WORDS * M);
+    pool.order = reinterpret_cast<unsigned char*>(pool.w + POOL_HOT_WORDS * M);
+    pool.g = POOL_COLD_WORDS ? P.poolCold + ((size_t)blockIdx.x * POOL_WARPS + warp) * (size_t)(POOL_COLD_WORDS * M) : nullptr;
     constexpr int RING = PoolRing<M>::N;
     int* ring = reinterpret_cast<int*>(poolBase + (size_t)POOL_WARPS * POOL_BYTES) + (size_t)warp * (RING * 64);     // this warp's RING x 2 x 32 words
     int stackSpilled = 0;
@@ -747,7 +768,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) k_raytrace_pool_tlas(const __
 template <int M> inline size_t pool_smem_bytes(const DevParams& P)
 {
     const int nS = P.sphereCount < WAVE_MAX_SMEM_SPHERES ? P.sphereCount : WAVE_MAX_SMEM_SPHERES;
-    return sizeof(WaveSmemHeader) + (size_t)P.smemPairs * sizeof(NodePair) + (size_t)nS * sizeof(DevSphere) + (size_t)POOL_WARPS * (POOL_WORDS * M * 4 + M) + (size_t)POOL_THREADS * PoolRing<M>::N * 8;
+    return sizeof(WaveSmemHeader) + (size_t)P.smemPairs * sizeof(NodePair) + (size_t)nS * sizeof(DevSphere) + (size_t)POOL_WARPS * (POOL_HOT_WORDS * M * 4 + M) + (size_t)POOL_THREADS * PoolRing<M>::N * 8;
 }
 
 template <int M> inline cudaError_t pool_configure_one()
@@ -772,7 +793,7 @@ inline int pool_max_smem_pairs(int M, int sphereCount)
 {
     const int nS = sphereCount < WAVE_MAX_SMEM_SPHERES ? sphereCount : WAVE_MAX_SMEM_SPHERES;
     const long long left = 227LL * 1024 - (long long)sizeof(WaveSmemHeader) - (long long)nS * (long long)sizeof(DevSphere)
-                         - (long long)POOL_WARPS * (POOL_WORDS * M * 4 + M) - (long long)POOL_THREADS * (M >= 96 ? 0 : RT_RING_DEFAULT) * 8 - 1024;
+                         - (long long)POOL_WARPS * (POOL_HOT_WORDS * M * 4 + M) - (long long)POOL_THREADS * (M >= 96 && !POOL_COLD_WORDS ? 0 : RT_RING_DEFAULT) * 8 - 1024;
     return left <= 0 ? 0 : (int)(left / (long long)sizeof(NodePair));
 }
 

@@ -266,7 +266,7 @@ def test_simt_pair_record_order_is_layout_only(simt_lib):
 
 
 @pytest.mark.skipif(not os.environ.get("RT_SIMT_VARIANTS"), reason="four extra interpreter builds (~3 min): set RT_SIMT_VARIANTS=1")
-@pytest.mark.parametrize("defines", [("RT_STACK_TOP_REG",), ("RT_CACHE_RAYINV",), ("RT_LEAF_REPEAT=2",), ("RT_SPHERE_SKIP_SQRT",), ("RT_TREELET_PREFETCH",), ("RT_SMEM_STACK=2",), ("RT_SMEM_STACK=2", "RT_BRANCHLESS_POP"), ("RT_SMEM_STACK=2", "RT_PUSH_PREDICATED"), ("RT_PUSH_PREDICATED",), ("RT_SMEM_STACK=8", "RT_BRANCHLESS_POP", "RT_LDG256", "RT_VOTE_WL=3", "RT_VOTE_WN=2", "RT_LEAF_REPEAT=2", "RT_SPHERE_SAH_DEPTH=14"), ("RT_SKIP_ZERO_DEFOCUS", "RT_GLASS_OUT_OF_LINE"), ("RT_VOTE_WL=3", "RT_VOTE_WN=2"), ("RT_VOTE_WI=2", "RT_VOTE_WL=7", "RT_VOTE_WN=4", "RT_LEAF_REPEAT=2"), ("RT_SMEM_STACK=8", "RT_PREFETCH_CUR"), ("RT_LDG256", "RT_TRI_PAD64"),
+@pytest.mark.parametrize("defines", [("RT_STACK_TOP_REG",), ("RT_CACHE_RAYINV",), ("RT_LEAF_REPEAT=2",), ("RT_SPHERE_SKIP_SQRT",), ("RT_TREELET_PREFETCH",), ("RT_SMEM_STACK=2",), ("RT_SMEM_STACK=2", "RT_BRANCHLESS_POP"), ("RT_SMEM_STACK=2", "RT_PUSH_PREDICATED"), ("RT_PUSH_PREDICATED",), ("RT_POOL_COLD_GLOBAL",), ("RT_POOL_COLD_GLOBAL", "RT_SMEM_STACK=16"), ("RT_SMEM_STACK=8", "RT_BRANCHLESS_POP", "RT_LDG256", "RT_VOTE_WL=3", "RT_VOTE_WN=2", "RT_LEAF_REPEAT=2", "RT_SPHERE_SAH_DEPTH=14"), ("RT_SKIP_ZERO_DEFOCUS", "RT_GLASS_OUT_OF_LINE"), ("RT_VOTE_WL=3", "RT_VOTE_WN=2"), ("RT_VOTE_WI=2", "RT_VOTE_WL=7", "RT_VOTE_WN=4", "RT_LEAF_REPEAT=2"), ("RT_SMEM_STACK=8", "RT_PREFETCH_CUR"), ("RT_LDG256", "RT_TRI_PAD64"),
                                      ("RT_STACK_TOP_REG", "RT_CACHE_RAYINV", "RT_LEAF_REPEAT=2", "RT_INNER_REPEAT=1")])
 def test_simt_compile_time_variants_are_bit_exact(defines, tmp_path):
     """The A/B candidates of tools/round2_sweep.sh change scheduling / instruction selection only: same pixels, same counters."""
