@@ -344,3 +344,12 @@ def test_csharp_binding_declares_every_entry_point_of_the_header():
     m = re.search(r"public struct Stats \{([^}]*)\}", cs)
     fields = re.findall(r"(\w+)[,;]", m.group(1))
     assert [f for f in fields if f not in ("ulong", "double", "public")] == ["rays", "boxTests", "triTests", "sphereTests", "dispatches", "kernelMs", "sphereBoxTests", "exchangeMs"]
+
+
+def test_abi_header_is_plain_c(tmp_path):
+    """include/rt_b200.h promises plain C (no torch / CUDA types in any signature): gcc -std=c99 -pedantic must accept it."""
+    src = tmp_path / "h.c"
+    src.write_text('#include "rt_b200.h"\nint main(void) { return rtGetVersion() == RT_B200_VERSION ? 0 : 1; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(REPO, "include"), "-fsyntax-only", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

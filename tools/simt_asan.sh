@@ -46,4 +46,16 @@ for q in (1, 0, 2):
     tg, ng = gpu.build_bvh(m.vertices, m.indices, m.normals, q)
     assert np.array_equal(ng.view(np.uint8), nh.view(np.uint8)) and np.array_equal(tg.view(np.uint8), th.view(np.uint8))
 print("device BVH build clean")
+# round 2: sample chunks (hand-off buffers), the group context (rtCreateMulti: tile staging + the in-process exchange), pipelined readback,
+# deep-tree refusal, a rank without rows
+import test_round2_abi as R
+R.sample_chunks_are_schedule_only(LIB, sizes=((33, 7),))
+R.group_equals_single(LIB, [0, 1, 2], scenes.knot_room(40, 30, 3, 2, nu=30, nv=6, glass=True))
+R.deep_trees(LIB)
+R.model_count_alone(LIB)
+R.root_bounds_are_never_read(LIB)
+sc = scenes.knot_room(7, 1, 3, 2, nu=20, nv=6)
+for rank in (0, 1, 2):
+    render(LIB, sc, frames=1, options={"kernel": 1, "sampleChunks": 7}, tile=(rank, 3, 1))
+print("round-2 ABI paths clean")
 PY
