@@ -622,7 +622,7 @@ RT_DI void pool_body(const DevParams& P, const unsigned int totalJobs, const uns
                     }
                     else
                     {
-                        LoadPair(P, smemPairs, cur.start, q0, q1, q2, q3);
+                        LoadPair<EXT>(P, smemPairs, cur.start, q0, q1, q2, q3);
                         RT_PROF(13, 1);
 #if defined(RT_PREFETCH_NEXT_PAIR) && !defined(RT_SIMT_EMU)
                         // with "pairOrder" = 1 (pre-order records) the record of an inner child A is the next one: ask for it while this one is
@@ -810,7 +810,7 @@ template <int M> inline cudaError_t pool_launch_m(const DevParams& P, int numSMs
     cudaError_t e;
     if ((e = cudaMemsetAsync(P.workCounter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(evA, stream)) != cudaSuccess) return e;
-    const bool ext = P.nPeers > 0 || P.sphBvh != 0 || P.forceExt != 0;   // extensions compiled into their own instantiation
+    const bool ext = P.nPeers > 0 || P.sphBvh != 0 || P.forceExt != 0 || P.smemPairs > 0;   // extensions (peer stores, sphere accelerator, staged tree tops) compiled into their own instantiation
     if (P.countStats) { if (ext) RT_LAUNCH(grid, POOL_THREADS, smemBytes, stream, RT_K(k_raytrace_pool<true, true, M>), P, totalJobs, tilesX, ownedRows);
                         else RT_LAUNCH(grid, POOL_THREADS, smemBytes, stream, RT_K(k_raytrace_pool<true, false, M>), P, totalJobs, tilesX, ownedRows); }
     else if (P.tlas && P.modelSkip) RT_LAUNCH(grid, POOL_THREADS, smemBytes, stream, RT_K(k_raytrace_pool_tlas<M>), P, totalJobs, tilesX, ownedRows);

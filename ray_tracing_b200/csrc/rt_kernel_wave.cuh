@@ -65,14 +65,16 @@ struct NodeRef { int start, count; };
 // record in L1 instead of paying another trip to L2 — the dependent-fetch chain that stalls the mesh scenes (profiles/) is halved.
 constexpr int TREELET_ROOT_BIT = 0x40000000;
 
-// Fetch one 64-byte pair record: from the shared-memory copy of the tree tops, or from HBM/L2.
+// Fetch one 64-byte pair record: from the shared-memory copy of the tree tops (STAGED instantiations only: the test for it was 4.7 %
+// of the warp instructions of the plain pooled kernel, for an option that measured neutral-to-negative twice — profiles/r02_e_*), or from L2 / HBM.
+template <bool STAGED>
 RT_DI void LoadPair(const DevParams& P, const float4* __restrict__ smemPairs, int idx, float4& q0, float4& q1, float4& q2, float4& q3)
 {
 #ifdef RT_TREELET_PREFETCH
     const bool treeletRoot = (idx & TREELET_ROOT_BIT) != 0;
     idx &= ~TREELET_ROOT_BIT;
 #endif
-    if (idx < P.smemPairs)
+    if (STAGED && idx < P.smemPairs)
     {
         const float4* p = smemPairs + (size_t)idx * 4;
         q0 = p[0]; q1 = p[1]; q2 = p[2]; q3 = p[3];
@@ -92,7 +94,7 @@ RT_DI void LoadPair(const DevParams& P, const float4* __restrict__ smemPairs, in
 }
 
 // HL:234-287 on the repacked streams.  Same visiting order and culling as the reference.
-template <bool STATS>
+template <bool STATS, bool STAGED>
 RT_DI void TraverseMesh(const DevParams& P, const float4* __restrict__ smemPairs, f3 pos, f3 dir, f3 invDir, float rayLength,
                         NodeRef root, bool cullBackface,
                         float& bestDst, int& bestTri, float& bestU, float& bestV, float& bestDet, Counters& cnt)
@@ -122,7 +124,7 @@ RT_DI void TraverseMesh(const DevParams& P, const float4* __restrict__ smemPairs
         else
         {
             float4 q0, q1, q2, q3;
-            LoadPair(P, smemPairs, cur.start, q0, q1, q2, q3);
+            LoadPair<STAGED>(P, smemPairs, cur.start, q0, q1, q2, q3);
             const float dstA = RayBoundingBoxDst(pos, invDir, make_f3(q0.x, q0.y, q0.z), make_f3(q0.w, q1.x, q1.y));
             const float dstB = RayBoundingBoxDst(pos, invDir, make_f3(q2.x, q2.y, q2.z), make_f3(q2.w, q3.x, q3.y));
             if (STATS) cnt.box += 2;
@@ -210,7 +212,7 @@ RT_DI Hit Intersect(const DevParams& P, const float4* __restrict__ smemPairs, co
         const f3 invDir = rcp3(localDir);
         NodeRef root; root.start = meta.x; root.count = meta.y;
         float dst, u, v, det; int tri;
-        TraverseMesh<STATS>(P, smemPairs, localPos, localDir, invDir, result.dst, root, meta.z != 0, dst, tri, u, v, det, cnt);
+        TraverseMesh<STATS, EXT>(P, smemPairs, localPos, localDir, invDir, result.dst, root, meta.z != 0, dst, tri, u, v, det, cnt);
         if (dst < result.dst)
         {
             const float4* nq = reinterpret_cast<const float4*>(P.triNormals + tri);
@@ -519,7 +521,7 @@ inline cudaError_t wave_launch(const DevParams& P, int numSMs, cudaStream_t stre
     const unsigned int totalJobs = (unsigned int)jobs64;
 
     const size_t smemBytes = sizeof(WaveSmemHeader) + (size_t)P.smemPairs * sizeof(NodePair) + (size_t)WAVE_MAX_SMEM_SPHERES * sizeof(DevSphere);
-    const bool ext = P.nPeers > 0 || P.sphBvh != 0 || P.forceExt != 0;   // extensions compiled into their own instantiation
+    const bool ext = P.nPeers > 0 || P.sphBvh != 0 || P.forceExt != 0 || P.smemPairs > 0;   // extensions (peer stores, sphere accelerator, staged tree tops) compiled into their own instantiation
     // sample chunks (P.chunks > 1, small tiles): the hand-off lives in instantiations of its own (the extension family and the TLAS kernel)
     if (P.chunks > 1 && !(P.tlas && P.modelSkip && !P.countStats))
         return P.countStats ? wave_launch_one<true, true, false, true>(P, numSMs, smemBytes, totalJobs, tilesX, ownedRows, stream, evA, evB)
