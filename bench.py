@@ -253,7 +253,7 @@ NCU_METRICS = ["dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.su
 _UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
 
 
-def ncu_probe(name, local, rank, world, band_rows, lib, timeout=600):
+def ncu_probe(name, local, rank, world, band_rows, lib, timeout=240):
     """Counters of ONE launch of the trace kernel on this workload (this rank's tile), from an ncu pass over a child process:
     the second RayTrace dispatch of `bench.py --probe`.  Returns a dict or {"unavailable": why}."""
     log = f"/tmp/rt_b200_probe_{os.getpid()}_{name}.csv"
@@ -483,9 +483,11 @@ def measure(name, w, args, env, steps, warmup, full):
     kernel_label = {2: "k_raytrace_pool (persistent wavefront, per-warp path pools)",
                     1: "k_raytrace_wave (persistent threads, one path per lane)", 0: "k_raytrace_mega (reference-shaped)"}[kernel_sel]
     probe = None
-    if full and rank == 0 and not args.no_probe:
+    if full and rank == 0 and not args.no_probe and not env.get("probe_broken"):
         mgr.context.synchronize()
         probe = ncu_probe(name, local, rank, world, args.band_rows, args.lib)
+        if "unavailable" in probe and ("Timeout" in probe["unavailable"] or "FileNotFound" in probe["unavailable"]):
+            env["probe_broken"] = True          # no ncu on this box, or it hangs: do not pay the timeout once per workload
     if world > 1:
         dist.barrier()                                               # the other ranks wait while rank 0's child uses GPU 0
 
