@@ -353,3 +353,23 @@ def test_abi_header_is_plain_c(tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(REPO, "include"), "-fsyntax-only", str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU arm: the oracle on this box's cores, no GPU): one JSON line with the contract's keys, the same
+    `config` the GPU arm prints for the workload, and e2e = value with zero copy bytes."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--workload", "cornell64", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    sys.path.insert(0, REPO)
+    import bench
+    assert line["impl"] == "reference" and line["unit"] == "Mrays/s" and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["config"] == bench.workload_config("cornell64", bench.WORKLOADS["cornell64"])
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"] > 0
+    assert line["e2e"] == {"value": line["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert bench.DEFAULT_WORKLOAD == "knot256" and bench.WORKLOADS["knot256"]["spp"] == 256 and (bench.WORKLOADS["knot256"]["width"], bench.WORKLOADS["knot256"]["height"]) == (1920, 1080)
+    # the algorithmic bytes are the SURVEY 8(d) formula
+    st = {"boxTests": 10, "sphereBoxTests": 2, "triTests": 3, "rays": 5, "sphereTests": 7}
+    assert bench.algorithmic_bytes(st, 4, 8, 2, 3) == 32 * 12 + 72 * 3 + 224 * 5 * 4 + 104 * 7 + 48 * 8 * 2 * 3
