@@ -13,6 +13,7 @@ from ray_tracing_b200 import build   # noqa: E402
 VARIANTS = {
     "r1": ("RT_DEFAULTS_R1",),
     "pushpred": ("RT_PUSH_PREDICATED",),
+    "stream": ("RT_STREAM_IMAGES",),
     "cold": ("RT_POOL_COLD_GLOBAL",),
     "cold_ring16": ("RT_POOL_COLD_GLOBAL", "RT_SMEM_STACK=16"),
     "mb7": ("RT_WAVE_MINBLOCKS=7",),

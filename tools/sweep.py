@@ -103,6 +103,7 @@ STAGES = {
         ("smemNodes 300 (TMA-staged tree tops)", None, {"smemNodes": 300}),
     ]),
     10: (["soup4k", "cluster4k", "knot64"], [ ("default", None, {}), ("predicated push", "pushpred", {}) ]),
+    13: (["soup4k", "cluster4k", "knot64", "cornell64"], [ ("default", None, {}), ("streaming loads / stores for the render targets", "stream", {}), ("the same + l2Persist", "stream", {"l2Persist": 1}) ]),
     12: (["soup4k", "cluster4k", "knot64", "knot256"], [ ("default", None, {}), ("smemNodes 256 (extension instantiation)", None, {"smemNodes": 256}) ]),
     11: (["soup4k", "cluster4k", "knot64"], [ ("default", None, {}), ("shade-phase slot fields in global memory (66 KB more L1)", "cold", {}),
                                               ("the same + stack ring of 16", "cold_ring16", {}), ("the same + 96 slots per warp", "cold", {"poolSlots": 96}) ]),
