@@ -24,6 +24,8 @@ std::string RtApi::Load(const char* path)
 #undef RESOLVE
     BuildBVH = reinterpret_cast<decltype(BuildBVH)>(dlsym(dl, "rtBuildBVH"));
     CreateMulti = reinterpret_cast<decltype(CreateMulti)>(dlsym(dl, "rtCreateMulti"));
+    ReadbackAsync = reinterpret_cast<decltype(ReadbackAsync)>(dlsym(dl, "rtReadbackAsync"));
+    ReadbackWait = reinterpret_cast<decltype(ReadbackWait)>(dlsym(dl, "rtReadbackWait"));
     return "";
 }
 
@@ -239,6 +241,24 @@ int RayComputeManager::ReadAccumulated(float* dst, size_t bytes)
 {
     if (!ctx) return RT_E_STATE;
     TRY(api.Readback(ctx, "AccumulatedRender", dst, bytes));
+    return RT_OK;
+}
+
+// Pipelined form for hosts that read every frame (rtReadbackAsync): the copy of this frame's image travels while the next frame renders;
+// dst (pinned memory for a real overlap) is valid after WaitReadback().
+int RayComputeManager::ReadAccumulatedAsync(float* dst, size_t bytes)
+{
+    if (!ctx) return RT_E_STATE;
+    if (!api.ReadbackAsync) return ReadAccumulated(dst, bytes);
+    TRY(api.ReadbackAsync(ctx, "AccumulatedRender", dst, bytes));
+    return RT_OK;
+}
+
+int RayComputeManager::WaitReadback()
+{
+    if (!ctx) return RT_E_STATE;
+    if (!api.ReadbackWait) return RT_OK;
+    TRY(api.ReadbackWait(ctx));
     return RT_OK;
 }
 

@@ -53,6 +53,7 @@ struct RtApi
     decltype(&rtSetBool) SetBool = nullptr; decltype(&rtResize) Resize = nullptr; decltype(&rtDispatch) Dispatch = nullptr;
     decltype(&rtReadback) Readback = nullptr; decltype(&rtSynchronize) Synchronize = nullptr;
     decltype(&rtBuildBVH) BuildBVH = nullptr;   // optional: absent from older builds of the library
+    decltype(&rtReadbackAsync) ReadbackAsync = nullptr; decltype(&rtReadbackWait) ReadbackWait = nullptr;   // optional: pipelined readback
     decltype(&rtCreateMulti) CreateMulti = nullptr;   // optional: several GPUs behind one context (the all-gather of tiles inside rtDispatch)
     std::string Load(const char* path);        // returns "" on success, else the error text
     void Unload();
@@ -113,6 +114,8 @@ public:
     // readback of the two render textures (raytraceFrameTex / accumulatedResult, :53-54)
     int ReadFrame(float* dst, size_t bytes);
     int ReadAccumulated(float* dst, size_t bytes);
+    int ReadAccumulatedAsync(float* dst, size_t bytes);      // returns at once; dst is valid after WaitReadback()
+    int WaitReadback();
     RtContext* Context() const { return ctx; }
     const RtApi& Api() const { return api; }
 
