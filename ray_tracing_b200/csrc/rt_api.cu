@@ -86,7 +86,7 @@ struct RtContext
     DevBuf<float4> snap;
 
     // kernel 1 on small tiles: hand-off of a pixel's chain between sample chunks (rt_kernel_wave.cuh)
-    DevBuf<uint4> handoff; DevBuf<int> handoffFlags; int optSampleChunks = -1;
+    DevBuf<unsigned long long> handoff; unsigned int chunkSerial = 0; int optSampleChunks = -1;
     DevBuf<float> poolCold;                    // kernel 2 (RT_POOL_COLD_GLOBAL builds): slot fields of the shade phase, one block per resident warp
 
     // rtBuildBVH: device arena kept between builds, pinned staging chunks for the copies of caller-owned arrays
@@ -202,7 +202,7 @@ int rtDestroy(RtContext* c)
     if (c->snapReady) cudaEventDestroy(c->snapReady);
     if (c->copyDone) cudaEventDestroy(c->copyDone);
     c->snap.release();
-    c->buildArena.release(); c->handoff.release(); c->handoffFlags.release(); c->poolCold.release();
+    c->buildArena.release(); c->handoff.release(); c->poolCold.release();
     for (int k = 0; k < 2; k++) { if (c->stageBuf[k]) cudaFreeHost(c->stageBuf[k]); if (c->stageEv[k]) cudaEventDestroy(c->stageEv[k]); }
     c->frame.release(); c->accum.release(); c->tileSend.release(); c->tileRecv.release(); c->display.release();
     c->repack.release();
@@ -690,9 +690,17 @@ static int dispatchLocal(RtContext* c, int kernelIndex, int gx, int gy, int gz)
     {
         unsigned long long rows = limX ? c->dispatchPixels / limX : 0;
         const size_t jobs = (size_t)((limX + 7u) / 8u) * (size_t)((rows + 3ull) / 4ull) * 32u;
-        CK(c->handoff.ensure(jobs)); CK(c->handoffFlags.ensure(jobs));
-        CK(cudaMemsetAsync(c->handoffFlags.p, 0, jobs * sizeof(int), c->stream));
-        P.handoff = c->handoff.p; P.handoffFlags = c->handoffFlags.p;
+        // four self-validating 64-bit words per pixel job; the tag carries a serial number of the dispatch, so nothing has to be cleared
+        // between frames (only a fresh allocation and the wrap of the 24-bit serial zero the buffer: tag 0 is never expected)
+        const size_t before = c->handoff.count;
+        CK(c->handoff.ensure(4 * jobs));
+        c->chunkSerial = (c->chunkSerial + 1u) & 0xffffffu;
+        if (c->handoff.count != before || c->chunkSerial == 0u)
+        {
+            CK(cudaMemsetAsync(c->handoff.p, 0, c->handoff.count * sizeof(unsigned long long), c->stream));
+            if (c->chunkSerial == 0u) c->chunkSerial = 1u;
+        }
+        P.handoff = c->handoff.p; P.handoffFlags = nullptr; P.chunkSerial = (int)c->chunkSerial;
     }
     if (kernel == 0)
     {

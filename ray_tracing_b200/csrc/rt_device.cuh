@@ -229,8 +229,9 @@ struct DevParams
     const int*      tlasLeaves;             // model indices in leaf order
     int   tlas, tlasRootStart, tlasRootCount, pad8;
     // kernel 1 on small tiles: a pixel's samples in `chunks` consecutive jobs (1 = whole pixels); the RNG state and the running sum travel
-    // from one chunk to the next through `handoff` (x = rng state, yzw = bits of the sum), `handoffFlags[pixel job]` = chunks completed
-    int   chunks, pad9; uint4* handoff; int* handoffFlags;
+    // from one chunk to the next through `handoff`: four 64-bit words per pixel job, each {tag, value} with tag = chunkSerial << 8 | chunks
+    // completed, so that every word validates itself (aligned 8-byte stores are single-copy atomic: no fence, no flag)
+    int   chunks, chunkSerial; unsigned long long* handoff; int* handoffFlags;
     float* poolCold;                        // kernel 2 built with RT_POOL_COLD_GLOBAL: the per-warp blocks of the slot fields kept out of shared memory
 };
 

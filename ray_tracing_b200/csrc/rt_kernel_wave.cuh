@@ -359,12 +359,14 @@ RT_DI void wave_body(const DevParams& P, const unsigned int totalJobs, const uns
         }
         if (CHUNKED && chunks > 1 && havePixel && waiting)
         {
-            if (*reinterpret_cast<volatile int*>(P.handoffFlags + pixJob) >= chunk)
+            // four self-validating words: {tag, value} with tag = this dispatch's serial and the number of chunks completed
+            const volatile unsigned long long* h = reinterpret_cast<const volatile unsigned long long*>(P.handoff + 4ull * pixJob);
+            const unsigned long long w0 = h[0], w1 = h[1], w2 = h[2], w3 = h[3];
+            const unsigned int tag = ((unsigned int)P.chunkSerial << 8) | (unsigned int)chunk;
+            if ((unsigned int)(w0 >> 32) == tag && (unsigned int)(w1 >> 32) == tag && (unsigned int)(w2 >> 32) == tag && (unsigned int)(w3 >> 32) == tag)
             {
-                __threadfence();
-                const volatile uint4* h = reinterpret_cast<const volatile uint4*>(P.handoff + pixJob);
-                rngState = h->x;
-                totalIncomingLight = make_f3(__uint_as_float(h->y), __uint_as_float(h->z), __uint_as_float(h->w));
+                rngState = (uint32_t)w0;
+                totalIncomingLight = make_f3(__uint_as_float((unsigned int)w1), __uint_as_float((unsigned int)w2), __uint_as_float((unsigned int)w3));
                 waiting = false;
             }
         }
@@ -404,10 +406,10 @@ RT_DI void wave_body(const DevParams& P, const unsigned int totalJobs, const uns
             }
             else
             {
-                volatile uint4* h = reinterpret_cast<volatile uint4*>(P.handoff + pixJob);
-                h->x = rngState; h->y = __float_as_uint(totalIncomingLight.x); h->z = __float_as_uint(totalIncomingLight.y); h->w = __float_as_uint(totalIncomingLight.z);
-                __threadfence();
-                *reinterpret_cast<volatile int*>(P.handoffFlags + pixJob) = chunk + 1;
+                volatile unsigned long long* h = reinterpret_cast<volatile unsigned long long*>(P.handoff + 4ull * pixJob);
+                const unsigned long long tag = (unsigned long long)(((unsigned int)P.chunkSerial << 8) | (unsigned int)(chunk + 1)) << 32;
+                h[0] = tag | rngState; h[1] = tag | __float_as_uint(totalIncomingLight.x);
+                h[2] = tag | __float_as_uint(totalIncomingLight.y); h[3] = tag | __float_as_uint(totalIncomingLight.z);
             }
             havePixel = false;
         }

@@ -16,7 +16,7 @@ import bench                                         # noqa: E402
 
 CONFIGS = [("default (automatic)", {}), ("kernel 2, whole pixels", {"kernel": 2, "sampleChunks": 0}), ("kernel 2, 2 sample chunks", {"kernel": 2, "sampleChunks": 2}),
            ("kernel 2, 4 sample chunks", {"kernel": 2, "sampleChunks": 4}), ("kernel 2, 8 sample chunks", {"kernel": 2, "sampleChunks": 8}), ("kernel 2, 16 sample chunks", {"kernel": 2, "sampleChunks": 16}),
-           ("kernel 1, whole pixels", {"kernel": 1, "sampleChunks": 0}), ("kernel 1, 4 sample chunks", {"kernel": 1, "sampleChunks": 4}),
+           ("kernel 1, whole pixels", {"kernel": 1, "sampleChunks": 0}), ("kernel 1, 2 sample chunks", {"kernel": 1, "sampleChunks": 2}), ("kernel 1, 4 sample chunks", {"kernel": 1, "sampleChunks": 4}),
            ("kernel 1, 8 sample chunks", {"kernel": 1, "sampleChunks": 8}), ("kernel 1, 16 sample chunks", {"kernel": 1, "sampleChunks": 16}),
            ("kernel 1, 32 sample chunks", {"kernel": 1, "sampleChunks": 32})]
 
