@@ -464,7 +464,7 @@ inline int wave_chunks(int forced, int numSMs, unsigned long long pixels, int sa
     {
         // measured on rank 0's tile of 8 of the default workload (2.3 pixels per lane; profiles/r02_j_tile_ab_sample_chunks.jsonl): whole pixels
         // 89.3 ms, 4 chunks 79.9, 8: 80.4, 16: 81.9, 32: 84.0.  On the sphere-only Cornell box a sample is too cheap for the hand-off
-        // (5.30 ms whole pixels, 5.47 with 4 chunks), so sphere-only scenes keep whole pixels.
+        // (4.93 ms whole pixels, 5.21 with 2 chunks, 5.32 with 4), so sphere-only scenes keep whole pixels.
         const double lanes = (double)numSMs * RT_WAVE_MINBLOCKS * WAVE_THREADS;
         const double perLane = (double)pixels / lanes;
         if (perLane > 1.0 && perLane < 4.0) { c = (int)(8.0 / perLane + 0.999); if (c > 8) c = 8; }
